@@ -1,0 +1,554 @@
+// api.cu — C ABI of libsurfel_b200.so (include/surfel_b200.h): the handle that replaces
+// class vis::CUDASurfelReconstruction (APP/cuda_surfel_reconstruction.{h,cc}), the host
+// wrappers that replace APP/cuda_surfel_reconstruction_kernels.cc and the RGB-D stream
+// runner that replaces the frame loop of APP/main.cc:885-1223.
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "sm_kernels.cuh"
+
+namespace smb {
+
+namespace {
+thread_local std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};
+}  // namespace
+
+int SetError(int code, const char* message) {
+  g_last_error = message ? message : "";
+  return code;
+}
+
+int CheckLaunch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return SM_OK;
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return SM_ERR_CUDA;
+}
+
+void CountLaunch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+}  // namespace smb
+
+using namespace smb;
+
+#define SM_CUDA(call)                                                                        \
+  do {                                                                                       \
+    const cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                                 \
+      g_last_error = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+      return SM_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+struct sm_reconstruction {
+  DeviceState d{};
+  int device = 0;
+  int sm_count = 0;
+  float fx = 0, fy = 0, cx = 0, cy = 0;
+  int parity = 0;                 // Counters::surfel_count slot holding the current count
+  bool rasters_cleared = false;   // the fused pre-processing tail already reset the rasters
+  IntegrateEvents events{};
+  // host mirror of the counters (pinned) for on-demand queries
+  Counters* host_counters = nullptr;
+  // pre-processing scratch (APP/main.cc filtered_depth_buffer_B)
+  u16* scratch_B = nullptr; size_t scratch_B_pitch = 0;
+  // stream-runner buffers
+  u16* run_depth = nullptr; size_t run_depth_pitch = 0;
+  float2* run_normals = nullptr; size_t run_normals_pitch = 0;
+  float* run_radius = nullptr; size_t run_radius_pitch = 0;
+  std::vector<u16*> ring_depth; size_t ring_depth_pitch = 0;
+  uchar3* ring_color[2] = {nullptr, nullptr}; size_t ring_color_pitch = 0;
+  cudaStream_t upload_stream = nullptr;
+  cudaEvent_t upload_done = nullptr, frame_done[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+int FetchCounters(sm_reconstruction* r, cudaStream_t stream) {
+  SM_CUDA(cudaMemcpyAsync(r->host_counters, r->d.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaStreamSynchronize(stream));
+  if (r->host_counters->capacity_overflow) {
+    return SetError(SM_ERR_CAPACITY, "surfel cap exceeded: new surfels of at least one frame were dropped "
+                                     "(the reference writes out of bounds here)");
+  }
+  return SM_OK;
+}
+
+FrameParams MakeFrameParams(const sm_reconstruction* r, u32 frame_index, const sm_integrate_params& p, u16* depth,
+                            size_t depth_pitch, const float* normals, size_t normals_pitch, const float* radius,
+                            size_t radius_pitch, const uint8_t* color, size_t color_pitch,
+                            const float* global_T_local, const float* local_T_global) {
+  FrameParams f;
+  f.frame_index = frame_index;
+  f.parity = r->parity;
+  f.active_window = p.surfel_integration_active_window_size;
+  f.fx = r->fx; f.fy = r->fy; f.cx = r->cx; f.cy = r->cy;
+  // Unprojection intrinsics for pixel center convention (kernels.cc:68-74).
+  f.fx_inv = 1.0f / r->fx;
+  f.fy_inv = 1.0f / r->fy;
+  const float cx_pixel_center = r->cx - 0.5f;
+  const float cy_pixel_center = r->cy - 0.5f;
+  f.cx_inv = -cx_pixel_center / r->fx;
+  f.cy_inv = -cy_pixel_center / r->fy;
+  f.sensor_noise_factor = p.sensor_noise_factor;
+  f.cos_normal_compatibility_threshold = cosf(M_PI / 180.0f * p.normal_compatibility_threshold_deg);  // kernels.cc:261
+  f.max_surfel_confidence = p.max_surfel_confidence;
+  f.inv_depth_scaling = 1.0f / p.depth_scaling;                 // cuda_surfel_reconstruction.cc:158
+  f.depth_scaling = 1.0f / f.inv_depth_scaling;                 // kernels.cc:179: 1.0f / depth_correction_factor
+  f.radius_factor_squared =
+      p.radius_factor_for_regularization_neighbors * p.radius_factor_for_regularization_neighbors;
+  f.blend_radius = p.measurement_blending_radius;
+  f.local_T_global = MakeMat3x4(local_T_global);
+  f.global_T_local = MakeMat3x4(global_T_local);
+  f.depth = depth; f.depth_pitch = depth_pitch;
+  f.normals = reinterpret_cast<const float2*>(normals); f.normals_pitch = normals_pitch;
+  f.radius = radius; f.radius_pitch = radius_pitch;
+  f.color = reinterpret_cast<const uchar3*>(color); f.color_pitch = color_pitch;
+  return f;
+}
+
+// CUDASurfelReconstruction::Integrate (cuda_surfel_reconstruction.cc:112-320).
+int IntegrateImpl(sm_reconstruction* r, cudaStream_t stream, u32 frame_index, const sm_integrate_params& p,
+                  u16* depth, size_t depth_pitch, const float* normals, size_t normals_pitch, const float* radius,
+                  size_t radius_pitch, const uint8_t* color, size_t color_pitch, const float* global_T_local,
+                  const float* local_T_global) {
+  const FrameParams f = MakeFrameParams(r, frame_index, p, depth, depth_pitch, normals, normals_pitch, radius,
+                                        radius_pitch, color, color_pitch, global_T_local, local_T_global);
+  int status = IntegrateFrame(stream, r->d, f, p.do_blending != 0, r->rasters_cleared, r->sm_count, &r->events);
+  r->rasters_cleared = false;
+  if (status != SM_OK) return status;
+  const int old_slot = r->parity;
+  r->parity ^= 1;  // k_new_surfel_scan wrote surfel_count[old ^ 1]
+  if (r->events.enabled) cudaEventRecord(r->events.ev[12], stream);
+  // cuda_surfel_reconstruction.cc:295-317; the detach-flag pass of UpdateNeighborsCUDA
+  // (kernels.cc:333-339) over the slots that existed before this frame rides on the first sweep.
+  const int iterations = p.regularization_iterations_per_integration_iteration;
+  if (iterations == 0) {
+    status = RegularizeSurfels(stream, r->d, /*disable_denoising*/ true, frame_index,
+                               p.radius_factor_for_regularization_neighbors, p.regularizer_weight,
+                               p.regularization_frame_window_size, r->parity, old_slot, r->sm_count);
+  } else {
+    for (int i = 0; i < iterations && status == SM_OK; ++i) {
+      status = RegularizeSurfels(stream, r->d, /*disable_denoising*/ false, frame_index,
+                                 p.radius_factor_for_regularization_neighbors, p.regularizer_weight,
+                                 p.regularization_frame_window_size, r->parity, i == 0 ? old_slot : -1, r->sm_count);
+    }
+  }
+  if (r->events.enabled) cudaEventRecord(r->events.ev[13], stream);
+  return status;
+}
+
+int EnsureRunBuffers(sm_reconstruction* r, int ring, bool on_host) {
+  const int W = r->d.width, H = r->d.height;
+  if (!r->run_depth) {
+    SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_depth), &r->run_depth_pitch, W * sizeof(u16), H));
+    SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_normals), &r->run_normals_pitch, W * sizeof(float2), H));
+    SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_radius), &r->run_radius_pitch, W * sizeof(float), H));
+    SM_CUDA(cudaMemset2D(r->run_radius, r->run_radius_pitch, 0, W * sizeof(float), H));
+  }
+  if (on_host && static_cast<int>(r->ring_depth.size()) != ring) {
+    for (u16* b : r->ring_depth) cudaFree(b);
+    r->ring_depth.assign(ring, nullptr);
+    for (auto& b : r->ring_depth) {
+      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&b), &r->ring_depth_pitch, W * sizeof(u16), H));
+    }
+    for (int i = 0; i < 2; ++i) {
+      if (!r->ring_color[i]) {
+        SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->ring_color[i]), &r->ring_color_pitch, W * 3, H));
+      }
+    }
+    if (!r->upload_stream) {
+      SM_CUDA(cudaStreamCreateWithFlags(&r->upload_stream, cudaStreamNonBlocking));
+      SM_CUDA(cudaEventCreateWithFlags(&r->upload_done, cudaEventDisableTiming));
+      SM_CUDA(cudaEventCreateWithFlags(&r->frame_done[0], cudaEventDisableTiming));
+      SM_CUDA(cudaEventCreateWithFlags(&r->frame_done[1], cudaEventDisableTiming));
+    }
+  }
+  return SM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void sm_default_integrate_params(sm_integrate_params* p) {
+  // APP/main.cc:279-371.
+  p->depth_scaling = 5000;
+  p->sensor_noise_factor = 0.05f;
+  p->max_surfel_confidence = 5.0f;
+  p->regularizer_weight = 10.0f;
+  p->regularization_frame_window_size = 30;
+  p->do_blending = 1;
+  p->measurement_blending_radius = 12;
+  p->regularization_iterations_per_integration_iteration = 1;
+  p->radius_factor_for_regularization_neighbors = 2;
+  p->normal_compatibility_threshold_deg = 40;
+  p->surfel_integration_active_window_size = std::numeric_limits<int>::max();
+}
+
+void sm_default_preprocess_params(sm_preprocess_params* p) {
+  // APP/main.cc:415-478.
+  p->depth_scaling = 5000;
+  p->max_depth = 3.0f;
+  p->depth_valid_region_radius = 333;
+  p->bilateral_filter_sigma_xy = 3;
+  p->bilateral_filter_radius_factor = 2.0f;
+  p->bilateral_filter_sigma_depth_factor = 0.05;
+  p->outlier_filtering_frame_count = 8;
+  p->outlier_filtering_required_inliers = -1;
+  p->outlier_filtering_depth_tolerance_factor = 0.02f;
+  p->depth_erosion_radius = 2;
+  p->observation_angle_threshold_deg = 85;
+  p->point_radius_extension_factor = 1.5f;
+  p->point_radius_clamp_factor = std::numeric_limits<float>::infinity();
+}
+
+const char* sm_last_error(void) { return g_last_error.c_str(); }
+const char* sm_version(void) { return "surfel_b200 0.1 (sm_100a)"; }
+uint64_t sm_kernel_launch_count(void) { return g_launches.load(); }
+
+int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width, int32_t height, float fx, float fy,
+              float cx, float cy) {
+  if (!out || width <= 0 || height <= 0 || max_surfel_count == 0 || max_surfel_count > 0x7FFFFFFFull - kSegment) {
+    return SetError(SM_ERR_INVALID_ARGUMENT, "sm_create: bad argument");
+  }
+  sm_reconstruction* r = new sm_reconstruction();
+  SM_CUDA(cudaGetDevice(&r->device));
+  cudaDeviceProp prop;
+  SM_CUDA(cudaGetDeviceProperties(&prop, r->device));
+  r->sm_count = prop.multiProcessorCount;
+  r->fx = fx; r->fy = fy; r->cx = cx; r->cy = cy;
+  DeviceState& d = r->d;
+  d.width = width; d.height = height;
+  d.capacity = static_cast<u32>(max_surfel_count);
+  const size_t padded = (max_surfel_count + kSegment - 1) / kSegment * kSegment;
+  d.stride = padded;
+  const size_t P = static_cast<size_t>(width) * height;
+  const size_t scan_tiles = (P + kSegment - 1) / kSegment;
+  SM_CUDA(cudaMalloc(&d.surfels, sizeof(float) * SM_ROW_COUNT * d.stride));
+  SM_CUDA(cudaMalloc(&d.assoc, sizeof(PixelAssoc) * P));
+  SM_CUDA(cudaMalloc(&d.first_depth, sizeof(float) * P));
+  SM_CUDA(cudaMalloc(&d.vis, sizeof(VisEntry) * padded));
+  SM_CUDA(cudaMalloc(&d.seg_count, sizeof(u32) * (padded / kSegment)));
+  SM_CUDA(cudaMalloc(&d.merge_flag, padded));
+  SM_CUDA(cudaMalloc(&d.new_flag, P));
+  SM_CUDA(cudaMalloc(&d.new_index, sizeof(u32) * P));
+  SM_CUDA(cudaMalloc(&d.scan_state, sizeof(unsigned long long) * scan_tiles));
+  SM_CUDA(cudaMalloc(&d.counters, sizeof(Counters)));
+  SM_CUDA(cudaMemset(d.counters, 0, sizeof(Counters)));
+  SM_CUDA(cudaMemset(d.new_flag, 0, P));
+  SM_CUDA(cudaMemset(d.new_index, 0, sizeof(u32) * P));
+  SM_CUDA(cudaMemset(d.scan_state, 0, sizeof(unsigned long long) * scan_tiles));
+  SM_CUDA(cudaMallocHost(&r->host_counters, sizeof(Counters)));
+  std::memset(r->host_counters, 0, sizeof(Counters));
+  SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->scratch_B), &r->scratch_B_pitch, width * sizeof(u16), height));
+  for (int i = 0; i < 14; ++i) SM_CUDA(cudaEventCreate(&r->events.ev[i]));
+  r->events.enabled = false;
+  int status = ClearAssociationRasters(nullptr, d);
+  if (status != SM_OK) return status;
+  SM_CUDA(cudaDeviceSynchronize());
+  *out = r;
+  return SM_OK;
+}
+
+int sm_destroy(sm_reconstruction* r) {
+  if (!r) return SM_OK;
+  cudaDeviceSynchronize();
+  DeviceState& d = r->d;
+  cudaFree(d.surfels); cudaFree(d.assoc); cudaFree(d.first_depth); cudaFree(d.vis); cudaFree(d.seg_count);
+  cudaFree(d.merge_flag); cudaFree(d.new_flag); cudaFree(d.new_index); cudaFree(d.scan_state); cudaFree(d.counters);
+  cudaFreeHost(r->host_counters);
+  cudaFree(r->scratch_B); cudaFree(r->run_depth); cudaFree(r->run_normals); cudaFree(r->run_radius);
+  for (u16* b : r->ring_depth) cudaFree(b);
+  cudaFree(r->ring_color[0]); cudaFree(r->ring_color[1]);
+  if (r->upload_stream) {
+    cudaStreamDestroy(r->upload_stream);
+    cudaEventDestroy(r->upload_done); cudaEventDestroy(r->frame_done[0]); cudaEventDestroy(r->frame_done[1]);
+  }
+  for (int i = 0; i < 14; ++i) cudaEventDestroy(r->events.ev[i]);
+  delete r;
+  return SM_OK;
+}
+
+int sm_reset(sm_reconstruction* r, void* stream) {
+  SM_CUDA(cudaMemsetAsync(r->d.counters, 0, sizeof(Counters), static_cast<cudaStream_t>(stream)));
+  r->parity = 0;
+  r->rasters_cleared = false;
+  return SM_OK;
+}
+
+int sm_preprocess(sm_reconstruction* r, void* stream, const sm_preprocess_params* p, const uint16_t* raw_depth,
+                  size_t raw_pitch, const uint16_t* const* other_depths, const size_t* other_pitches,
+                  const float* others_TR_reference, uint16_t* out_depth, size_t out_depth_pitch, float* out_normals,
+                  size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch) {
+  const int status = PreprocessFused(static_cast<cudaStream_t>(stream), *p, r->d.width, r->d.height, r->fx, r->fy,
+                                     r->cx, r->cy, raw_depth, raw_pitch, other_depths, other_pitches,
+                                     others_TR_reference, r->scratch_B, r->scratch_B_pitch, out_depth,
+                                     out_depth_pitch, reinterpret_cast<float2*>(out_normals), out_normals_pitch,
+                                     out_radius, out_radius_pitch, r->d.assoc, r->d.first_depth);
+  if (status == SM_OK) r->rasters_cleared = true;
+  return status;
+}
+
+int sm_bilateral_filter_and_depth_cutoff(void* stream, float sigma_xy, float sigma_value_factor,
+                                         uint16_t value_to_ignore, float radius_factor, uint16_t max_depth,
+                                         float depth_valid_region_radius, int32_t width, int32_t height,
+                                         const uint16_t* in_depth, size_t in_pitch, uint16_t* out_depth,
+                                         size_t out_pitch) {
+  return StageBilateral(static_cast<cudaStream_t>(stream), sigma_xy, sigma_value_factor, value_to_ignore,
+                        radius_factor, max_depth, depth_valid_region_radius, width, height, in_depth, in_pitch,
+                        out_depth, out_pitch);
+}
+
+int sm_outlier_depth_map_fusion(void* stream, int32_t other_count, int32_t required_count, float tolerance, float fx,
+                                float fy, float cx, float cy, int32_t width, int32_t height, const uint16_t* in_depth,
+                                size_t in_pitch, const uint16_t* const* other_depths, const size_t* other_pitches,
+                                const float* others_TR_reference, uint16_t* out_depth, size_t out_pitch) {
+  return StageOutlier(static_cast<cudaStream_t>(stream), other_count, required_count, tolerance, fx, fy, cx, cy,
+                      width, height, in_depth, in_pitch, other_depths, other_pitches, others_TR_reference, out_depth,
+                      out_pitch);
+}
+
+int sm_erode_depth_map(void* stream, int32_t radius, int32_t width, int32_t height, const uint16_t* in_depth,
+                       size_t in_pitch, uint16_t* out_depth, size_t out_pitch) {
+  return StageErode(static_cast<cudaStream_t>(stream), radius, width, height, in_depth, in_pitch, out_depth,
+                    out_pitch);
+}
+
+int sm_compute_normals_and_drop_bad_pixels(void* stream, float observation_angle_threshold_deg, float depth_scaling,
+                                           float fx, float fy, float cx, float cy, int32_t width, int32_t height,
+                                           const uint16_t* in_depth, size_t in_pitch, uint16_t* out_depth,
+                                           size_t out_pitch, float* out_normals, size_t normals_pitch) {
+  return StageNormals(static_cast<cudaStream_t>(stream), observation_angle_threshold_deg, depth_scaling, fx, fy, cx,
+                      cy, width, height, in_depth, in_pitch, out_depth, out_pitch,
+                      reinterpret_cast<float2*>(out_normals), normals_pitch);
+}
+
+int sm_compute_point_radii_and_remove_isolated_pixels(void* stream, float point_radius_extension_factor,
+                                                      float point_radius_clamp_factor, float depth_scaling, float fx,
+                                                      float fy, float cx, float cy, int32_t width, int32_t height,
+                                                      const uint16_t* in_depth, size_t in_pitch, float* out_radius,
+                                                      size_t radius_pitch, uint16_t* out_depth, size_t out_pitch) {
+  return StageRadii(static_cast<cudaStream_t>(stream), point_radius_extension_factor, point_radius_clamp_factor,
+                    depth_scaling, fx, fy, cx, cy, width, height, in_depth, in_pitch, out_radius, radius_pitch,
+                    out_depth, out_pitch);
+}
+
+int sm_integrate(sm_reconstruction* r, void* stream, uint32_t frame_index, const sm_integrate_params* p,
+                 uint16_t* depth, size_t depth_pitch, const float* normals, size_t normals_pitch, const float* radius,
+                 size_t radius_pitch, const uint8_t* color, size_t color_pitch, const float global_T_local[12],
+                 const float local_T_global[12]) {
+  return IntegrateImpl(r, static_cast<cudaStream_t>(stream), frame_index, *p, depth, depth_pitch, normals,
+                       normals_pitch, radius, radius_pitch, color, color_pitch, global_T_local, local_T_global);
+}
+
+int sm_regularize(sm_reconstruction* r, void* stream, uint32_t frame_index, float regularizer_weight,
+                  float radius_factor_for_regularization_neighbors, int32_t regularization_frame_window_size) {
+  return RegularizeSurfels(static_cast<cudaStream_t>(stream), r->d, /*disable_denoising*/ false, frame_index,
+                           radius_factor_for_regularization_neighbors, regularizer_weight,
+                           regularization_frame_window_size, r->parity, -1, r->sm_count);
+}
+
+int sm_surfel_count(sm_reconstruction* r, uint32_t* out) {
+  const int status = FetchCounters(r, nullptr);
+  *out = r->host_counters->surfel_count[r->parity] - r->host_counters->merge_count;
+  return status;
+}
+
+int sm_surfels_size(sm_reconstruction* r, uint32_t* out) {
+  const int status = FetchCounters(r, nullptr);
+  *out = r->host_counters->surfel_count[r->parity];
+  return status;
+}
+
+int sm_transfer_all_to_cpu(sm_reconstruction* r, void* stream_v, uint32_t /*frame_index*/, float* x, float* y,
+                           float* z, float* radius_squared, float* nx, float* ny, float* nz,
+                           uint32_t* last_update_stamp, uint64_t* out_count) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int status = FetchCounters(r, stream);
+  const u32 n = r->host_counters->surfel_count[r->parity];
+  if (out_count) *out_count = n;
+  if (n == 0) return status;
+  const size_t bytes = sizeof(float) * n;
+  const float* s = r->d.surfels;
+  const size_t st = r->d.stride;
+  SM_CUDA(cudaMemcpyAsync(x, s + SM_ROW_SMOOTH_X * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(y, s + SM_ROW_SMOOTH_Y * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(z, s + SM_ROW_SMOOTH_Z * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(radius_squared, s + SM_ROW_RADIUS_SQUARED * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(nx, s + SM_ROW_NORMAL_X * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(ny, s + SM_ROW_NORMAL_Y * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(nz, s + SM_ROW_NORMAL_Z * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(last_update_stamp, s + SM_ROW_LAST_UPDATE_STAMP * st, bytes, cudaMemcpyDeviceToHost, stream));
+  return status;
+}
+
+int sm_export_vertices(sm_reconstruction* r, void* stream, float* position_buffer, uint8_t* color_buffer) {
+  return ExportVertices(static_cast<cudaStream_t>(stream), r->d, r->parity, r->sm_count, position_buffer,
+                        color_buffer);
+}
+
+int sm_get_timings(sm_reconstruction* r, float out_ms[7]) {
+  if (!r->events.enabled) return SetError(SM_ERR_INVALID_ARGUMENT, "timings are not enabled (sm_enable_timings)");
+  SM_CUDA(cudaEventSynchronize(r->events.ev[13]));
+  for (int i = 0; i < 7; ++i) SM_CUDA(cudaEventElapsedTime(&out_ms[i], r->events.ev[2 * i], r->events.ev[2 * i + 1]));
+  return SM_OK;
+}
+
+int sm_enable_timings(sm_reconstruction* r, int32_t enable) {
+  r->events.enabled = enable != 0;
+  return SM_OK;
+}
+
+int sm_dump_state(sm_reconstruction* r, void* stream_v, float* host_rows, uint64_t host_row_stride_elems,
+                  uint32_t* surfels_size, uint32_t* merge_count) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int status = FetchCounters(r, stream);
+  const u32 n = r->host_counters->surfel_count[r->parity];
+  if (surfels_size) *surfels_size = n;
+  if (merge_count) *merge_count = r->host_counters->merge_count;
+  if (host_rows && n > 0) {
+    SM_CUDA(cudaMemcpy2DAsync(host_rows, host_row_stride_elems * sizeof(float), r->d.surfels,
+                              r->d.stride * sizeof(float), n * sizeof(float), SM_ROW_COUNT, cudaMemcpyDeviceToHost,
+                              stream));
+    SM_CUDA(cudaStreamSynchronize(stream));
+  }
+  return status;
+}
+
+int sm_load_state(sm_reconstruction* r, void* stream_v, const float* host_rows, uint64_t host_row_stride_elems,
+                  uint32_t surfels_size, uint32_t merge_count) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (surfels_size > r->d.capacity) return SetError(SM_ERR_CAPACITY, "sm_load_state: state larger than the surfel cap");
+  if (surfels_size > 0) {
+    SM_CUDA(cudaMemcpy2DAsync(r->d.surfels, r->d.stride * sizeof(float), host_rows,
+                              host_row_stride_elems * sizeof(float), surfels_size * sizeof(float), SM_ROW_COUNT,
+                              cudaMemcpyHostToDevice, stream));
+    // Invariant of regularize.cu: gradient rows and the weight row are zero between calls.
+    const int zero_rows[4] = {SM_ROW_GRADIENT_X, SM_ROW_GRADIENT_Y, SM_ROW_GRADIENT_Z, SM_ROW_GRADIENT_COUNT};
+    for (int row : zero_rows) {
+      SM_CUDA(cudaMemsetAsync(r->d.surfels + row * r->d.stride, 0, surfels_size * sizeof(float), stream));
+    }
+  }
+  Counters c{};
+  c.surfel_count[0] = c.surfel_count[1] = surfels_size;
+  c.merge_count = merge_count;
+  *r->host_counters = c;
+  SM_CUDA(cudaMemcpyAsync(r->d.counters, r->host_counters, sizeof(Counters), cudaMemcpyHostToDevice, stream));
+  SM_CUDA(cudaStreamSynchronize(stream));
+  r->parity = 0;
+  return SM_OK;
+}
+
+int sm_download_rasters(sm_reconstruction* r, void* stream_v, uint32_t* supporting_surfels,
+                        uint32_t* supporting_surfel_counts, float* supporting_surfel_depth_sums,
+                        uint32_t* conflicting_surfels, float* first_surfel_depth, uint8_t* new_surfel_flag_vector,
+                        uint32_t* new_surfel_indices) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const size_t P = static_cast<size_t>(r->d.width) * r->d.height;
+  std::vector<PixelAssoc> assoc(P);
+  SM_CUDA(cudaMemcpyAsync(assoc.data(), r->d.assoc, sizeof(PixelAssoc) * P, cudaMemcpyDeviceToHost, stream));
+  if (first_surfel_depth)
+    SM_CUDA(cudaMemcpyAsync(first_surfel_depth, r->d.first_depth, sizeof(float) * P, cudaMemcpyDeviceToHost, stream));
+  if (new_surfel_flag_vector)
+    SM_CUDA(cudaMemcpyAsync(new_surfel_flag_vector, r->d.new_flag, P, cudaMemcpyDeviceToHost, stream));
+  if (new_surfel_indices)
+    SM_CUDA(cudaMemcpyAsync(new_surfel_indices, r->d.new_index, sizeof(u32) * P, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaStreamSynchronize(stream));
+  for (size_t i = 0; i < P; ++i) {
+    if (supporting_surfels) supporting_surfels[i] = assoc[i].x;
+    if (conflicting_surfels) conflicting_surfels[i] = assoc[i].y;
+    if (supporting_surfel_counts) supporting_surfel_counts[i] = assoc[i].z;
+    if (supporting_surfel_depth_sums) std::memcpy(&supporting_surfel_depth_sums[i], &assoc[i].w, sizeof(float));
+  }
+  return SM_OK;
+}
+
+// The frame loop of APP/main.cc:885-1223 on a synthetic stream.
+int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s, const sm_preprocess_params* pp,
+                  const sm_integrate_params* ip, int32_t first_frame, int32_t last_frame, sm_stream_stats* stats) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int W = r->d.width, H = r->d.height;
+  if (s->width != W || s->height != H) return SetError(SM_ERR_INVALID_ARGUMENT, "stream size mismatch");
+  const int K = pp->outlier_filtering_frame_count;
+  const int half = K / 2;
+  if (K < 2 || K > 8 || first_frame < half || last_frame > s->frame_count - half || first_frame > last_frame) {
+    return SetError(SM_ERR_INVALID_ARGUMENT,
+                    "frame range needs outlier_filtering_frame_count/2 frames on both sides (main.cc:987-992)");
+  }
+  const size_t frame_elems = static_cast<size_t>(W) * H;
+  const int ring = K + 2;
+  int status = EnsureRunBuffers(r, ring, s->frames_on_host != 0);
+  if (status != SM_OK) return status;
+  const unsigned long long launches_before = g_launches.load();
+  uint64_t h2d = 0;
+
+  auto raw_ptr = [&](int frame, size_t* pitch) -> const u16* {
+    if (s->frames_on_host) { *pitch = r->ring_depth_pitch; return r->ring_depth[frame % ring]; }
+    *pitch = W * sizeof(u16);
+    return s->depth + frame_elems * frame;
+  };
+  int uploaded_until = first_frame - half - 1;
+  uint32_t integrated = 0;
+  for (int frame = first_frame; frame < last_frame; ++frame) {
+    const uint8_t* color = s->color + 3 * frame_elems * frame;
+    size_t color_pitch = static_cast<size_t>(W) * 3;
+    if (s->frames_on_host) {
+      // Upload stream (main.cc:902-984): the new raw depth map(s) and this frame's colour image.
+      // Ring slots written for frame f were last read by frame f - 2.
+      if (frame >= first_frame + 2) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->frame_done[frame % 2], 0));
+      for (int f = uploaded_until + 1; f <= frame + half; ++f) {
+        SM_CUDA(cudaMemcpy2DAsync(r->ring_depth[f % ring], r->ring_depth_pitch, s->depth + frame_elems * f,
+                                  W * sizeof(u16), W * sizeof(u16), H, cudaMemcpyHostToDevice, r->upload_stream));
+        h2d += frame_elems * sizeof(u16);
+      }
+      uploaded_until = frame + half;
+      SM_CUDA(cudaMemcpy2DAsync(r->ring_color[frame % 2], r->ring_color_pitch, color, static_cast<size_t>(W) * 3,
+                                static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, r->upload_stream));
+      h2d += frame_elems * 3;
+      SM_CUDA(cudaEventRecord(r->upload_done, r->upload_stream));
+      SM_CUDA(cudaStreamWaitEvent(stream, r->upload_done, 0));  // main.cc:995
+      color = reinterpret_cast<const uint8_t*>(r->ring_color[frame % 2]);
+      color_pitch = r->ring_color_pitch;
+    }
+    const u16* others[8];
+    size_t other_pitches[8];
+    for (int i = 0; i < half; ++i) {  // main.cc:1046-1059
+      others[i] = raw_ptr(frame - (i + 1), &other_pitches[i]);
+      others[half + i] = raw_ptr(frame + (i + 1), &other_pitches[half + i]);
+    }
+    size_t raw_pitch;
+    const u16* raw = raw_ptr(frame, &raw_pitch);
+    status = sm_preprocess(r, stream, pp, raw, raw_pitch, others, other_pitches,
+                           s->others_TR_reference + static_cast<size_t>(frame) * K * 12, r->run_depth,
+                           r->run_depth_pitch, reinterpret_cast<float*>(r->run_normals), r->run_normals_pitch,
+                           r->run_radius, r->run_radius_pitch);
+    if (status != SM_OK) return status;
+    status = IntegrateImpl(r, stream, static_cast<u32>(frame), *ip, r->run_depth, r->run_depth_pitch,
+                           reinterpret_cast<const float*>(r->run_normals), r->run_normals_pitch, r->run_radius,
+                           r->run_radius_pitch, color, color_pitch, s->global_T_frame + 12 * frame,
+                           s->frame_T_global + 12 * frame);
+    if (status != SM_OK) return status;
+    if (s->frames_on_host) SM_CUDA(cudaEventRecord(r->frame_done[frame % 2], stream));
+    ++integrated;
+  }
+  status = FetchCounters(r, stream);  // one 32-byte D2H + sync for the whole call
+  if (stats) {
+    stats->frames_integrated = integrated;
+    stats->surfels_size = r->host_counters->surfel_count[r->parity];
+    stats->surfel_count = stats->surfels_size - r->host_counters->merge_count;
+    stats->kernel_launches = g_launches.load() - launches_before;
+    stats->h2d_bytes = h2d;
+    stats->d2h_bytes = sizeof(Counters);
+  }
+  return status;
+}
+
+}  // extern "C"

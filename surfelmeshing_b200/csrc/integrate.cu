@@ -1,0 +1,880 @@
+// integrate.cu — per-frame surfel reconstruction kernels for sm_100a.
+//
+// Replaces the ~36 launches and 2 host synchronisations of
+// CUDASurfelReconstruction::Integrate() (APP/cuda_surfel_reconstruction.cc:112-291) by 9
+// stream-ordered launches with device-resident counters:
+//
+//   k_clear          a6   5 CUDABuffer::Clear launches -> one 128-bit store per pixel
+//   k_project        a7   RenderMinDepthCUDAKernel (kernels.cu:1466-1557): the only sweep over
+//                         ALL surfel slots (4 slots/thread, 128-bit SoA loads); splats min depth
+//                         and builds the segment-ordered list of surfels that project into the
+//                         image (block-local ballot/scan compaction, no global atomic)
+//   k_associate      a8   AssociateSurfelsCUDAKernel (:1586-1808) over the visible list
+//   k_merge          a9   MergeSurfelsCUDAKernel (:1857-2052) over the visible list; decisions
+//                         are taken on the pre-merge state and applied by k_integrate
+//   k_blend          a10  BlendMeasurements Start + (radius-2) Iteration kernels (:563-708) as
+//                         ONE kernel: every tile replays all wavefront iterations locally in
+//                         shared memory on a (radius-1)-pixel halo
+//   k_integrate      a11  IntegrateMeasurementsCUDAKernel (:741-1142) over the visible list
+//   k_update_neighbors a12 UpdateNeighborsCUDAKernel (:1197-1380) over the visible list
+//   k_new_surfel_scan  a13 CreateNewSurfelsCUDASerializingKernel (:90-111) + the CUB exclusive
+//                         scan (:2506-2520) fused: single-pass decoupled look-back scan in
+//                         raster order (stable: the k-th flagged pixel owns slot N + k)
+//   k_create_surfels   a13 CreateNewSurfelsCUDACreationKernel (:133-231)
+//
+// UpdateNeighborsCUDARemoveReplacedNeighborsKernel (:1420-1437) is folded into the first
+// regularisation sweep (regularize.cu). Arithmetic follows the reference SASS (sm_math.cuh).
+//
+// Deterministic where the reference is not (SURVEY §7 hard part 1): the supporting surfel
+// of a pixel is the MINIMUM supporting index (the reference: first atomicCAS wins), merge
+// decisions read the pre-merge state. Both are legal outcomes of the reference.
+
+#include "sm_kernels.cuh"
+
+namespace smb {
+
+namespace {
+
+#define SM_S(row, i) d.surfels[static_cast<size_t>(row) * d.stride + (i)]
+#define SM_SU(row, i) reinterpret_cast<u32*>(d.surfels)[static_cast<size_t>(row) * d.stride + (i)]
+
+constexpr int kBlock = 256;
+
+// IsSurfelActiveForIntegration (kernels.cu:77-87).
+__device__ __forceinline__ bool is_active(u32 last_update_stamp, u32 frame_index, int window) {
+  return static_cast<int>(last_update_stamp) > static_cast<int>(frame_index - static_cast<u32>(window));
+}
+
+struct Projection {
+  float u, v;
+  int px, py;
+  bool in_image;
+};
+
+// kernels.cu:1491-1500 (identical in a7/a8/a9/a11): inv = RCP(z); u = fma(x*inv, fx, cx).
+__device__ __forceinline__ Projection project(const FrameParams& f, int width, int height, float x, float y, float z) {
+  Projection p;
+  const float inv_z = frcp(z);
+  p.u = ffma(fmul(x, inv_z), f.fx, f.cx);
+  p.v = ffma(fmul(y, inv_z), f.fy, f.cy);
+  p.px = f2i_trunc(p.u);
+  p.py = f2i_trunc(p.v);
+  p.in_image = !(p.u < 0.f || p.v < 0.f || p.px < 0 || p.py < 0 || p.px >= width || p.py >= height);
+  return p;
+}
+
+// Secondary pixel by the sub-pixel triangle rule (kernels.cu:1506-1549; note `px > 1`).
+__device__ __forceinline__ bool secondary_pixel(const Projection& p, int width, int height, int* ox, int* oy) {
+  const float x_frac = fsub(p.u, i2f(p.px));
+  const float y_frac = fsub(p.v, i2f(p.py));
+  if (x_frac < y_frac) {
+    if (x_frac < fadd(-y_frac, 1.0f)) {
+      if (p.px > 1) { *ox = p.px - 1; *oy = p.py; return true; }
+      return false;
+    }
+    if (p.py < height - 1) { *ox = p.px; *oy = p.py + 1; return true; }
+    return false;
+  }
+  if (x_frac < fadd(-y_frac, 1.0f)) {
+    if (p.py > 0) { *ox = p.px; *oy = p.py - 1; return true; }
+    return false;
+  }
+  if (p.px < width - 1) { *ox = p.px + 1; *oy = p.py; return true; }
+  return false;
+}
+
+// -z of the measurement normal: sqrt(max(0, 1 - nx^2 - ny^2)) (kernels.cu:172,811,1656).
+__device__ __forceinline__ float normal_z_abs(float nx, float ny) {
+  return fsqrt_approx(fmaxf(0.f, ffma(-ny, ny, ffma(-nx, nx, 1.0f))));
+}
+
+// (1/|p|) * dot(p, R*n) > 0 test shared by a8/a9/a11/a12; returns the rotated normal.
+__device__ __forceinline__ float facing_dot(const FrameParams& f, float x, float y, float z, float nx, float ny,
+                                            float nz, float3* local_normal) {
+  const float rs = frsqrt_approx(squared_norm(x, y, z));
+  *local_normal = rotate_vec(f.local_T_global, nx, ny, nz);
+  return fmul(rs, ffma(z, local_normal->z, ffma(x, local_normal->x, fmul(y, local_normal->y))));
+}
+
+// ---------------------------------------------------------------------------------------
+// a6: clear
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_clear(DeviceState d) {
+  const int n = d.width * d.height;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    d.assoc[i] = make_uint4(kInvalidIndex, kInvalidIndex, 0u, 0u);
+    d.first_depth[i] = __int_as_float(0x7f800000);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// a7: projection sweep + min-depth splat + visible list
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_project(DeviceState d, FrameParams f) {
+  __shared__ u32 warp_totals[kBlock / 32];
+  const u32 n = d.counters->surfel_count[f.parity];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (blockIdx.x == 0) {
+    // Reset the state of this frame's new-surfel scan (runs after several kernel boundaries).
+    const int tiles = (d.width * d.height + kSegment - 1) / kSegment;
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) d.scan_state[t] = 0ull;
+    if (threadIdx.x == 0) d.counters->scan_ticket = 0;
+  }
+
+  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
+    const u32 base = seg * kSegment + threadIdx.x * 4;
+    VisEntry e[4];
+    int cnt = 0;
+    if (base < n) {
+      const float4 X = *reinterpret_cast<const float4*>(&SM_S(SM_ROW_X, base));
+      const float4 Y = *reinterpret_cast<const float4*>(&SM_S(SM_ROW_Y, base));
+      const float4 Z = *reinterpret_cast<const float4*>(&SM_S(SM_ROW_Z, base));
+      const uint4 T = *reinterpret_cast<const uint4*>(&SM_SU(SM_ROW_LAST_UPDATE_STAMP, base));
+      const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+      const u32 ts[4] = {T.x, T.y, T.z, T.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const u32 i = base + j;
+        if (i >= n) break;
+        const float z = transform_row(f.local_T_global.r2, xs[j], ys[j], zs[j]);
+        if (!(z > 0.f)) continue;
+        const float x = transform_row(f.local_T_global.r0, xs[j], ys[j], zs[j]);
+        const float y = transform_row(f.local_T_global.r1, xs[j], ys[j], zs[j]);
+        const Projection p = project(f, d.width, d.height, x, y, z);
+        if (!p.in_image) continue;
+        const bool active = is_active(ts[j], f.frame_index, f.active_window);
+        e[cnt++] = make_uint4(i | (active ? kActiveBit : 0u), __float_as_uint(x), __float_as_uint(y),
+                              __float_as_uint(z));
+        if (active) {
+          // RenderMinDepthAtPixel (kernels.cu:1458-1464): int-punned atomicMin, positive floats.
+          atomicMin(reinterpret_cast<int*>(&d.first_depth[p.py * d.width + p.px]), __float_as_int(z));
+          int ox, oy;
+          if (secondary_pixel(p, d.width, d.height, &ox, &oy)) {
+            atomicMin(reinterpret_cast<int*>(&d.first_depth[oy * d.width + ox]), __float_as_int(z));
+          }
+        }
+      }
+    }
+    // Block-wide exclusive scan of cnt (slot order is preserved inside the segment).
+    u32 incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_totals[warp] = incl;
+    __syncthreads();
+    u32 warp_base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) {
+      const u32 t = warp_totals[w];
+      if (w < warp) warp_base += t;
+      total += t;
+    }
+    VisEntry* out = d.vis + static_cast<size_t>(seg) * kSegment + warp_base + (incl - cnt);
+    for (int k = 0; k < cnt; ++k) out[k] = e[k];
+    if (threadIdx.x == 0) d.seg_count[seg] = total;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// a8: association
+// ---------------------------------------------------------------------------------------
+
+// Gates shared by association and merge up to the normal-compatibility test
+// (kernels.cu:1603-1668 / :1875-1936). Returns true if the measurement supports the surfel.
+// Writes the conflicting-surfel entry like the reference does.
+__device__ __forceinline__ bool supports_surfel(const DeviceState& d, const FrameParams& f, int x, int y, u32 idx,
+                                                float cx_, float cy_, float cz_) {
+  const int p = y * d.width + x;
+  const float measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
+  if (!(measurement_depth > 0.f)) return false;
+  const float first = d.first_depth[p];
+  if (first < fmul(measurement_depth, fadd(-f.sensor_noise_factor, 1.0f))) {
+    if (first == cz_) d.assoc[p].y = idx;  // this surfel is conflicting
+    return false;
+  }
+  const float occlusion_depth = fmul(fadd(f.sensor_noise_factor, 1.0f), measurement_depth);
+  if (cz_ > occlusion_depth) return false;
+  float3 ln;
+  const float dot_angle = facing_dot(f, cx_, cy_, cz_, SM_S(SM_ROW_NORMAL_X, idx), SM_S(SM_ROW_NORMAL_Y, idx),
+                                     SM_S(SM_ROW_NORMAL_Z, idx), &ln);
+  if (dot_angle > 0.f) return false;  // kSurfelNormalToViewingDirThreshold = 0
+  if (measurement_depth < cz_) {
+    const float2 nm = row_ptr(f.normals, f.normals_pitch, y)[x];
+    const float s = normal_z_abs(nm.x, nm.y);
+    const float dot2 = ffma(-ln.z, s, ffma(ln.x, nm.x, fmul(ln.y, nm.y)));
+    if (dot2 < f.cos_normal_compatibility_threshold) return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ void consider_association(const DeviceState& d, const FrameParams& f, int x, int y,
+                                                     u32 idx, float cx_, float cy_, float cz_) {
+  if (!supports_surfel(d, f, x, y, idx, cx_, cy_, cz_)) return;
+  const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+  if (!(surfel_radius_squared > 0.f)) return;
+  PixelAssoc* a = &d.assoc[y * d.width + x];
+  atomicMin(&a->x, idx);                                      // reference: atomicCAS(INV -> idx), first come
+  atomicAdd(&a->z, 1u);
+  atomicAdd(reinterpret_cast<float*>(&a->w), cz_);
+}
+
+__global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams f) {
+  const u32 n = d.counters->surfel_count[f.parity];
+  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
+    const u32 cnt = d.seg_count[seg];
+    const VisEntry* list = d.vis + static_cast<size_t>(seg) * kSegment;
+    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) {
+      const VisEntry e = list[k];
+      if (!(e.x & kActiveBit)) continue;
+      const u32 idx = e.x & ~kActiveBit;
+      const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
+      const Projection p = project(f, d.width, d.height, x, y, z);
+      consider_association(d, f, p.px, p.py, idx, x, y, z);
+      int ox, oy;
+      if (secondary_pixel(p, d.width, d.height, &ox, &oy)) consider_association(d, f, ox, oy, idx, x, y, z);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// a9: merge (decision only; applied in k_integrate)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool consider_merge(const DeviceState& d, const FrameParams& f, int x, int y, u32 idx,
+                                               float cx_, float cy_, float cz_, float surfel_radius_squared) {
+  if (!supports_surfel(d, f, x, y, idx, cx_, cy_, cz_)) return false;
+  const u32 supported_surfel = d.assoc[y * d.width + x].x;
+  if (supported_surfel == idx || supported_surfel == kInvalidIndex) return false;
+  // kernels.cu:1955-1984.
+  const float other_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, supported_surfel);
+  const float radius_diff = fmul(surfel_radius_squared, frcp(other_radius_squared));
+  if (radius_diff > 1.4400000572204589844f || radius_diff < 0.69444441795349121094f) return false;
+  const float dx = fsub(SM_S(SM_ROW_X, idx), SM_S(SM_ROW_X, supported_surfel));
+  const float dy = fsub(SM_S(SM_ROW_Y, idx), SM_S(SM_ROW_Y, supported_surfel));
+  const float dz = fsub(SM_S(SM_ROW_Z, idx), SM_S(SM_ROW_Z, supported_surfel));
+  const float distance_squared = squared_norm(dx, dy, dz);
+  if (distance_squared > fmul(fadd(surfel_radius_squared, other_radius_squared), 0.03125f)) return false;
+  const float dot_angle = dot3(SM_S(SM_ROW_NORMAL_X, idx), SM_S(SM_ROW_NORMAL_Y, idx), SM_S(SM_ROW_NORMAL_Z, idx),
+                               SM_S(SM_ROW_NORMAL_X, supported_surfel), SM_S(SM_ROW_NORMAL_Y, supported_surfel),
+                               SM_S(SM_ROW_NORMAL_Z, supported_surfel));
+  if (dot_angle < 0.93968999385833740234f) return false;  // cos 20 deg
+  return true;
+}
+
+__global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) {
+  const u32 n = d.counters->surfel_count[f.parity];
+  u32 merged_by_thread = 0;
+  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
+    const u32 cnt = d.seg_count[seg];
+    const size_t list_base = static_cast<size_t>(seg) * kSegment;
+    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) {
+      const VisEntry e = d.vis[list_base + k];
+      const u32 idx = e.x & ~kActiveBit;  // no active-window test here (kernels.cu:2016)
+      bool merged = false;
+      const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+      if (surfel_radius_squared >= 0.f) {
+        const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
+        const Projection p = project(f, d.width, d.height, x, y, z);
+        merged = consider_merge(d, f, p.px, p.py, idx, x, y, z, surfel_radius_squared);
+      }
+      d.merge_flag[list_base + k] = merged ? 1 : 0;
+      merged_by_thread += merged ? 1u : 0u;
+    }
+  }
+  // Block reduction of the merge count (reference: cub::BlockReduce + atomicAdd, :2045-2051).
+  merged_by_thread = __reduce_add_sync(0xffffffffu, merged_by_thread);
+  __shared__ u32 warp_sums[kBlock / 32];
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = merged_by_thread;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 total = 0;
+    for (int w = 0; w < kBlock / 32; ++w) total += warp_sums[w];
+    if (total > 0) atomicAdd(&d.counters->merge_count, total);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// a10: measurement blending, all iterations in one kernel
+// ---------------------------------------------------------------------------------------
+constexpr int kBlendTileW = 32, kBlendTileH = 16;
+
+__global__ void __launch_bounds__(512) k_blend(DeviceState d, FrameParams f) {
+  extern __shared__ __align__(16) unsigned char blend_smem[];
+  const int radius = f.blend_radius;
+  const int halo = max(radius - 1, 1);          // (radius - 2) iterations + the 3x3 start stencil
+  const int rw = kBlendTileW + 2 * halo, rh = kBlendTileH + 2 * halo;
+  const int rn = rw * rh;
+  float* s_delta = reinterpret_cast<float*>(blend_smem);
+  float* s_ndelta = s_delta + rn;
+  u16* s_depth0 = reinterpret_cast<u16*>(s_ndelta + rn);   // depth as handed in (start stencil reads this)
+  u16* s_depth = s_depth0 + rn;                             // working depth
+  u8* s_sup = reinterpret_cast<u8*>(s_depth + rn);
+  u8* s_dist = s_sup + rn;
+  u8* s_ndist = s_dist + rn;
+
+  const int tile_x = blockIdx.x * kBlendTileW, tile_y = blockIdx.y * kBlendTileH;
+  const int x0 = tile_x - halo, y0 = tile_y - halo;
+
+  for (int i = threadIdx.x; i < rn; i += blockDim.x) {
+    const int ly = i / rw, lx = i - ly * rw;
+    const int gx = x0 + lx, gy = y0 + ly;
+    u16 depth = 0;
+    u8 sup = 0;
+    if (gx >= 0 && gy >= 0 && gx < d.width && gy < d.height) {
+      depth = row_ptr(f.depth, f.depth_pitch, gy)[gx];
+      sup = d.assoc[gy * d.width + gx].x != kInvalidIndex;
+    }
+    s_depth0[i] = depth;
+    s_depth[i] = depth;
+    s_sup[i] = sup;
+    s_dist[i] = 0;
+    s_ndist[i] = 0;
+  }
+  __syncthreads();
+
+  const float depth_scaling = f.depth_scaling;  // the reference passes 1 / depth_correction_factor (kernels.cc:179)
+  const float rcp_scaling = frcp(depth_scaling);
+
+  // Start kernel (kernels.cu:563-615) on every region pixel whose 3x3 stencil is inside the
+  // region and that is an interior image pixel. The stencils read the depth as handed in
+  // (the reference's in-place write, flagged TODO at :610, can only matter if a blended depth
+  // rounds to 0).
+  int any_ring = 0;
+  {
+    for (int i = threadIdx.x; i < rn; i += blockDim.x) {
+      const int ly = i / rw, lx = i - ly * rw;
+      const int gx = x0 + lx, gy = y0 + ly;
+      if (lx < 1 || ly < 1 || lx >= rw - 1 || ly >= rh - 1) continue;
+      if (gx < 1 || gy < 1 || gx >= d.width - 1 || gy >= d.height - 1) continue;
+      if (s_depth0[i] == 0 || !s_sup[i]) continue;
+      bool measurement_border_pixel = false, surfel_border_pixel = false;
+#pragma unroll
+      for (int wy = -1; wy <= 1; ++wy) {
+#pragma unroll
+        for (int wx = -1; wx <= 1; ++wx) {
+          const int j = i + wy * rw + wx;
+          if (s_depth0[j] == 0) measurement_border_pixel = true;
+          else if (!s_sup[j]) surfel_border_pixel = true;
+        }
+      }
+      if (!measurement_border_pixel && !surfel_border_pixel) { s_dist[i] = 255; continue; }
+      const PixelAssoc a = d.assoc[gy * d.width + gx];
+      const float sum = __uint_as_float(a.w);
+      const float rcp_count = frcp(u2f(a.z));
+      const float depth_f = u2f(s_depth0[i]);
+      if (surfel_border_pixel) {
+        s_ndist[i] = 1;
+        s_ndelta[i] = ffma(sum, rcp_count, -fmul(depth_f, rcp_scaling));
+        any_ring = 1;
+      }
+      if (measurement_border_pixel) {
+        s_dist[i] = 1;
+        const float surfel_depth_average = fmul(sum, rcp_count);
+        s_delta[i] = ffma(-depth_f, rcp_scaling, surfel_depth_average);
+        s_depth[i] = static_cast<u16>(f2u_trunc(ffma(surfel_depth_average, depth_scaling, 0.5f)));
+        any_ring = 1;
+      } else {
+        s_dist[i] = 255;
+      }
+    }
+    const int block_any = __syncthreads_or(any_ring);
+    if (!block_any) return;  // no border ring reaches this tile: depth unchanged
+  }
+
+  // Iteration kernels (kernels.cu:647-708), iteration = 2 .. radius - 1 (kernels.cc:190).
+  const float interpolation_factor_term = 1.0f / (radius - 1.0f);   // host expression, kernels.cc:196
+  for (int iteration = 2; iteration < radius; ++iteration) {
+    const float scaled = fmul(ffma(-i2f(iteration - 1), interpolation_factor_term, 1.0f), depth_scaling);
+    for (int i = threadIdx.x; i < rn; i += blockDim.x) {
+      const int ly = i / rw, lx = i - ly * rw;
+      const int gx = x0 + lx, gy = y0 + ly;
+      if (lx < 1 || ly < 1 || lx >= rw - 1 || ly >= rh - 1) continue;
+      if (gx < 1 || gy < 1 || gx >= d.width - 1 || gy >= d.height - 1) continue;
+      if (s_dist[i] == 255) {
+        float delta_sum = 0.f;
+        int count = 0;
+#pragma unroll
+        for (int wy = -1; wy <= 1; ++wy) {
+#pragma unroll
+          for (int wx = -1; wx <= 1; ++wx) {
+            const int j = i + wy * rw + wx;
+            if (s_dist[j] == iteration - 1) { delta_sum = fadd(delta_sum, s_delta[j]); ++count; }
+          }
+        }
+        if (count > 0) {
+          s_dist[i] = iteration;
+          const float avg = fmul(frcp(i2f(count)), delta_sum);
+          s_delta[i] = avg;
+          s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
+        }
+      }
+      if (s_depth[i] != 0 && !s_sup[i] && s_ndist[i] == 0) {
+        float delta_sum = 0.f;
+        int count = 0;
+#pragma unroll
+        for (int wy = -1; wy <= 1; ++wy) {
+#pragma unroll
+          for (int wx = -1; wx <= 1; ++wx) {
+            const int j = i + wy * rw + wx;
+            if (s_ndist[j] == iteration - 1) { delta_sum = fadd(delta_sum, s_ndelta[j]); ++count; }
+          }
+        }
+        if (count > 0) {
+          s_ndist[i] = iteration;
+          const float avg = fmul(frcp(i2f(count)), delta_sum);
+          s_ndelta[i] = avg;
+          s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // Write back the tile interior.
+  {
+    const int lx = (threadIdx.x & 31) + halo, ly = (threadIdx.x >> 5) + halo;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx < d.width && gy < d.height) row_ptr(f.depth, f.depth_pitch, gy)[gx] = s_depth[ly * rw + lx];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// a11: integration / conflict handling
+// ---------------------------------------------------------------------------------------
+
+// IntegrateOrConflictSurfel (kernels.cu:741-982) for one (surfel, pixel) pair. The
+// reference serialises accesses to a surfel with a NaN spin-lock on its x coordinate; each
+// surfel is owned by exactly one thread here (and there), so the lock is never contended.
+__device__ __forceinline__ void integrate_or_conflict(const DeviceState& d, const FrameParams& f, int x, int y,
+                                                      u32 idx, float cx_, float cy_, float cz_) {
+  const int p = y * d.width + x;
+  const float measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
+  if (!(measurement_depth > 0.f)) return;
+  bool integrate = true, conflicting = false;
+  const float first = d.first_depth[p];
+  const PixelAssoc a = d.assoc[p];
+  if (first < fmul(measurement_depth, fadd(-f.sensor_noise_factor, 1.0f))) {
+    if (first == cz_ && a.y == idx) conflicting = true;
+    integrate = false;
+  }
+  if (!integrate && !conflicting) return;
+  if (cz_ > fmul(fadd(f.sensor_noise_factor, 1.0f), measurement_depth)) integrate = false;
+  if (!integrate && !conflicting) return;
+
+  // Read data (kernels.cu:804-814).
+  const float lx = fmul(measurement_depth, ffma(i2f(x), f.fx_inv, f.cx_inv));
+  const float ly = fmul(measurement_depth, ffma(i2f(y), f.fy_inv, f.cy_inv));
+  const float3 g = transform_point(f.global_T_local, lx, ly, measurement_depth);
+  const float2 nm = row_ptr(f.normals, f.normals_pitch, y)[x];
+  const float3 gn = rotate_vec(f.global_T_local, nm.x, nm.y, -normal_z_abs(nm.x, nm.y));
+  const uchar3 color = row_ptr(f.color, f.color_pitch, y)[x];
+
+  if (conflicting) {
+    const float confidence = fadd(SM_S(SM_ROW_CONFIDENCE, idx), -1.0f);
+    if (confidence <= 0.f) {
+      // Delete the old surfel by replacing it with a new one (kernels.cu:828-854).
+      SM_S(SM_ROW_X, idx) = g.x; SM_S(SM_ROW_Y, idx) = g.y; SM_S(SM_ROW_Z, idx) = g.z;
+      SM_S(SM_ROW_SMOOTH_X, idx) = g.x; SM_S(SM_ROW_SMOOTH_Y, idx) = g.y; SM_S(SM_ROW_SMOOTH_Z, idx) = g.z;
+      SM_S(SM_ROW_NORMAL_X, idx) = gn.x; SM_S(SM_ROW_NORMAL_Y, idx) = gn.y; SM_S(SM_ROW_NORMAL_Z, idx) = gn.z;
+      SM_SU(SM_ROW_COLOR, idx) = color.x | (color.y << 8) | (color.z << 16) | (1u << 24);  // detach flag set
+      SM_S(SM_ROW_RADIUS_SQUARED, idx) = row_ptr(f.radius, f.radius_pitch, y)[x];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) SM_SU(SM_ROW_NEIGHBOR0 + i, idx) = kInvalidIndex;
+      SM_S(SM_ROW_CONFIDENCE, idx) = 1.0f;
+      SM_SU(SM_ROW_CREATION_STAMP, idx) = f.frame_index;
+      SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
+    } else {
+      SM_S(SM_ROW_CONFIDENCE, idx) = confidence;
+    }
+  }
+  if (!integrate) return;
+
+  const float snx = SM_S(SM_ROW_NORMAL_X, idx), sny = SM_S(SM_ROW_NORMAL_Y, idx), snz = SM_S(SM_ROW_NORMAL_Z, idx);
+  float3 ln;
+  if (facing_dot(f, cx_, cy_, cz_, snx, sny, snz, &ln) > 0.f) return;
+  if (measurement_depth < cz_) {
+    if (ffma(gn.z, snz, ffma(gn.x, snx, fmul(gn.y, sny))) < f.cos_normal_compatibility_threshold) return;
+  }
+  const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+  if (surfel_radius_squared < 0.f) return;
+
+  // Integrate (kernels.cu:922-981).
+  const float weight = frcp(u2f(max(1u, a.z)));
+  if (SM_SU(SM_ROW_CREATION_STAMP, idx) < f.frame_index) {
+    const float confidence = SM_S(SM_ROW_CONFIDENCE, idx);
+    const float cw = fadd(weight, confidence);
+    SM_S(SM_ROW_CONFIDENCE, idx) = (cw < f.max_surfel_confidence) ? cw : f.max_surfel_confidence;
+    const float normalization_factor = frcp(cw);
+    SM_S(SM_ROW_X, idx) = fmul(normalization_factor, ffma(SM_S(SM_ROW_X, idx), confidence, fmul(g.x, weight)));
+    SM_S(SM_ROW_Y, idx) = fmul(normalization_factor, ffma(confidence, SM_S(SM_ROW_Y, idx), fmul(g.y, weight)));
+    SM_S(SM_ROW_Z, idx) = fmul(normalization_factor, ffma(g.z, weight, fmul(confidence, SM_S(SM_ROW_Z, idx))));
+    const float nx = ffma(gn.x, weight, fmul(confidence, snx));
+    const float ny = ffma(gn.y, weight, fmul(confidence, sny));
+    const float nz = ffma(gn.z, weight, fmul(confidence, snz));
+    const float normal_normalization = frsqrt_approx(ffma(nz, nz, ffma(nx, nx, fmul(ny, ny))));
+    SM_S(SM_ROW_NORMAL_X, idx) = fmul(nx, normal_normalization);
+    SM_S(SM_ROW_NORMAL_Y, idx) = fmul(ny, normal_normalization);
+    SM_S(SM_ROW_NORMAL_Z, idx) = fmul(nz, normal_normalization);
+    SM_S(SM_ROW_RADIUS_SQUARED, idx) = fminf(surfel_radius_squared, row_ptr(f.radius, f.radius_pitch, y)[x]);
+    const u32 old_color = SM_SU(SM_ROW_COLOR, idx);
+    const u32 r = f2u_trunc(ffma(normalization_factor,
+                                 ffma(u2f(color.x), weight, fmul(confidence, u2f(old_color & 0xFFu))), 0.5f));
+    const u32 gr = f2u_trunc(ffma(normalization_factor,
+                                  ffma(u2f(color.y), weight, fmul(confidence, u2f((old_color >> 8) & 0xFFu))), 0.5f));
+    const u32 b = f2u_trunc(ffma(normalization_factor,
+                                 ffma(u2f(color.z), weight, fmul(confidence, u2f((old_color >> 16) & 0xFFu))), 0.5f));
+    SM_SU(SM_ROW_COLOR, idx) = (r & 0xFFu) | ((gr & 0xFFu) << 8) | ((b & 0xFFu) << 16);  // unsets the detach flag
+    SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_integrate(DeviceState d, FrameParams f) {
+  const u32 n = d.counters->surfel_count[f.parity];
+  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
+    const u32 cnt = d.seg_count[seg];
+    const size_t list_base = static_cast<size_t>(seg) * kSegment;
+    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) {
+      const VisEntry e = d.vis[list_base + k];
+      const u32 idx = e.x & ~kActiveBit;
+      if (d.merge_flag[list_base + k]) {
+        // Apply the merge decided by k_merge (kernels.cu:1986-1989).
+        SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = 0;
+        SM_S(SM_ROW_RADIUS_SQUARED, idx) = -1.0f;
+        SM_SU(SM_ROW_COLOR, idx) = (SM_SU(SM_ROW_COLOR, idx) & 0x00FFFFFFu) | (1u << 24);
+        continue;
+      }
+      if (!(e.x & kActiveBit)) continue;
+      if (SM_S(SM_ROW_RADIUS_SQUARED, idx) < 0.f) continue;  // kernels.cu:1050
+      const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
+      const Projection p = project(f, d.width, d.height, x, y, z);
+      integrate_or_conflict(d, f, p.px, p.py, idx, x, y, z);
+      int ox, oy;
+      if (secondary_pixel(p, d.width, d.height, &ox, &oy)) integrate_or_conflict(d, f, ox, oy, idx, x, y, z);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// a12: neighbour update (kernels.cu:1197-1380)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, FrameParams f) {
+  const u32 n = d.counters->surfel_count[f.parity];
+  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
+    const u32 cnt = d.seg_count[seg];
+    const size_t list_base = static_cast<size_t>(seg) * kSegment;
+    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) {
+      const u32 idx = d.vis[list_base + k].x & ~kActiveBit;
+      if (!is_active(SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx), f.frame_index, f.active_window)) continue;
+      // The position may have been changed by the integration: project again.
+      const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
+      const float cz_ = transform_row(f.local_T_global.r2, gx, gy, gz);
+      if (!(cz_ > 0.f)) continue;
+      const float cx_ = transform_row(f.local_T_global.r0, gx, gy, gz);
+      const float cy_ = transform_row(f.local_T_global.r1, gx, gy, gz);
+      const float inv_z = frcp(cz_);
+      const int x = f2i_trunc(ffma(fmul(cx_, inv_z), f.fx, f.cx));
+      const int y = f2i_trunc(ffma(fmul(cy_, inv_z), f.fy, f.cy));
+      constexpr int kBorder = 1;
+      if (x < kBorder || y < kBorder || x >= d.width - kBorder || y >= d.height - kBorder) continue;
+
+      const float measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
+      if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) continue;
+      const float nx = SM_S(SM_ROW_NORMAL_X, idx), ny = SM_S(SM_ROW_NORMAL_Y, idx), nz = SM_S(SM_ROW_NORMAL_Z, idx);
+      float3 ln;
+      if (facing_dot(f, cx_, cy_, cz_, nx, ny, nz, &ln) > 0.f) continue;
+      const float radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+      if (radius_squared < 0.f) continue;
+      // kCheckScaleCompatibilityForNeighborAssignment, factor 1.5^2.
+      if (fmul(row_ptr(f.radius, f.radius_pitch, y)[x], frcp(radius_squared)) > 2.25f) continue;
+
+      float neighbor_distances_squared[4];
+      u32 neighbor_surfel_indices[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        neighbor_surfel_indices[m] = SM_SU(SM_ROW_NEIGHBOR0 + m, idx);
+        if (neighbor_surfel_indices[m] == kInvalidIndex) {
+          neighbor_distances_squared[m] = __int_as_float(0x7f800000);
+        } else {
+          const u32 q = neighbor_surfel_indices[m];
+          neighbor_distances_squared[m] = squared_norm(fsub(gx, SM_S(SM_ROW_X, q)), fsub(gy, SM_S(SM_ROW_Y, q)),
+                                                       fsub(gz, SM_S(SM_ROW_Z, q)));
+        }
+      }
+      const float max_distance_squared = fmul(radius_squared, f.radius_factor_squared);
+      const int kDirectionsX[4] = {-1, 1, 0, 0};
+      const int kDirectionsY[4] = {0, 0, -1, 1};
+#pragma unroll
+      for (int direction = 0; direction < 4; ++direction) {
+        const u32 q = d.assoc[(y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction]].x;
+        if (q == kInvalidIndex || q == idx) continue;
+        const float distance_squared = squared_norm(fsub(SM_S(SM_ROW_X, q), gx), fsub(SM_S(SM_ROW_Y, q), gy),
+                                                    fsub(SM_S(SM_ROW_Z, q), gz));
+        if (distance_squared > max_distance_squared) continue;
+        const float normal_dot = dot3(nx, ny, nz, SM_S(SM_ROW_NORMAL_X, q), SM_S(SM_ROW_NORMAL_Y, q),
+                                      SM_S(SM_ROW_NORMAL_Z, q));
+        if (normal_dot <= 0.f) continue;
+        // Already a neighbour, or best (farthest) slot to replace.
+        int best_n = -1;
+        float best_distance_squared = -1.f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (q == neighbor_surfel_indices[m]) { best_n = -1; break; }
+          if (neighbor_distances_squared[m] > best_distance_squared) {
+            best_n = m;
+            best_distance_squared = neighbor_distances_squared[m];
+          }
+        }
+        if (best_n >= 0 && distance_squared < best_distance_squared) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (m == best_n) { neighbor_surfel_indices[m] = q; neighbor_distances_squared[m] = distance_squared; }
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) SM_SU(SM_ROW_NEIGHBOR0 + m, idx) = neighbor_surfel_indices[m];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// a13: new-surfel flags + stable raster-order scan (single pass, decoupled look-back)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, FrameParams f) {
+  __shared__ u32 s_tile, s_prefix;
+  __shared__ u32 warp_totals[kBlock / 32];
+  const int total_pixels = d.width * d.height;
+  const int tiles = (total_pixels + kSegment - 1) / kSegment;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&d.counters->scan_ticket, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  if (tile >= static_cast<u32>(tiles)) return;
+
+  const int base = tile * kSegment + threadIdx.x * 4;
+  u32 flags[4];
+  u32 cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int seq = base + j;
+    u32 flag = 0;
+    if (seq < total_pixels) {
+      const int y = seq / d.width, x = seq - y * d.width;
+      constexpr int kBorder = 1;
+      if (x >= kBorder && y >= kBorder && x < d.width - kBorder && y < d.height - kBorder &&
+          row_ptr(f.depth, f.depth_pitch, y)[x] > 0) {
+        const PixelAssoc a = d.assoc[seq];
+        flag = (a.x == kInvalidIndex && a.y == kInvalidIndex) ? 1u : 0u;
+      }
+    }
+    flags[j] = flag;
+    cnt += flag;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_totals[warp] = incl;
+  __syncthreads();
+  u32 warp_base = 0, block_total = 0;
+#pragma unroll
+  for (int w = 0; w < kBlock / 32; ++w) {
+    const u32 t = warp_totals[w];
+    if (w < warp) warp_base += t;
+    block_total += t;
+  }
+  if (threadIdx.x == 0) {
+    u32 prefix = 0;
+    if (tile == 0) {
+      atomicExch(&d.scan_state[0], (2ull << 32) | block_total);
+    } else {
+      atomicExch(&d.scan_state[tile], (1ull << 32) | block_total);
+      for (int t = static_cast<int>(tile) - 1; t >= 0; --t) {
+        unsigned long long v;
+        do {
+          v = atomicAdd(&d.scan_state[t], 0ull);
+        } while ((v >> 32) == 0ull);
+        prefix += static_cast<u32>(v);
+        if ((v >> 32) == 2ull) break;
+      }
+      atomicExch(&d.scan_state[tile], (2ull << 32) | (prefix + block_total));
+    }
+    s_prefix = prefix;
+    if (tile == static_cast<u32>(tiles) - 1) {
+      // new_surfel_count = indices[P-1] + flag[P-1] (kernels.cc:116-125, cuda_surfel_reconstruction.cc:291).
+      const u32 n_old = d.counters->surfel_count[f.parity];
+      u32 new_count = prefix + block_total;
+      if (static_cast<u64>(n_old) + new_count > d.capacity) {
+        d.counters->capacity_overflow = 1;  // the reference would write past the buffer here
+        new_count = 0;
+      }
+      d.counters->new_surfel_count = new_count;
+      d.counters->surfel_count[f.parity ^ 1] = n_old + new_count;
+    }
+  }
+  __syncthreads();
+  u32 running = s_prefix + warp_base + (incl - cnt);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int seq = base + j;
+    if (seq < total_pixels) {
+      d.new_flag[seq] = static_cast<u8>(flags[j]);
+      d.new_index[seq] = running;
+    }
+    running += flags[j];
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameParams f) {
+  if (d.counters->new_surfel_count == 0) return;
+  const u32 surfel_count = d.counters->surfel_count[f.parity];
+  const int total_pixels = d.width * d.height;
+  for (int seq = blockIdx.x * blockDim.x + threadIdx.x; seq < total_pixels; seq += gridDim.x * blockDim.x) {
+    if (d.new_flag[seq] != 1) continue;
+    const int y = seq / d.width, x = seq - y * d.width;
+    const u32 idx = surfel_count + d.new_index[seq];
+    const float depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
+    const float lx = fmul(depth, ffma(i2f(x), f.fx_inv, f.cx_inv));
+    const float ly = fmul(depth, ffma(u2f(y), f.fy_inv, f.cy_inv));
+    const float3 g = transform_point(f.global_T_local, lx, ly, depth);
+    SM_S(SM_ROW_X, idx) = g.x; SM_S(SM_ROW_Y, idx) = g.y; SM_S(SM_ROW_Z, idx) = g.z;
+    const float2 nm = row_ptr(f.normals, f.normals_pitch, y)[x];
+    const float3 gn = rotate_vec(f.global_T_local, nm.x, nm.y, -normal_z_abs(nm.x, nm.y));
+    SM_S(SM_ROW_NORMAL_X, idx) = gn.x; SM_S(SM_ROW_NORMAL_Y, idx) = gn.y; SM_S(SM_ROW_NORMAL_Z, idx) = gn.z;
+    const uchar3 color = row_ptr(f.color, f.color_pitch, y)[x];
+    SM_SU(SM_ROW_COLOR, idx) = color.x | (color.y << 8) | (color.z << 16);
+    SM_S(SM_ROW_CONFIDENCE, idx) = 1.0f;
+    SM_SU(SM_ROW_CREATION_STAMP, idx) = f.frame_index;
+    SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
+    const float radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
+    SM_S(SM_ROW_RADIUS_SQUARED, idx) = radius_squared;
+    // The reference leaves rows 11-16 and 23 uninitialised; the regularisation of this
+    // library relies on rows 11-13 and 23 being zero between calls (regularize.cu).
+    SM_S(SM_ROW_GRADIENT_X, idx) = 0.f; SM_S(SM_ROW_GRADIENT_Y, idx) = 0.f; SM_S(SM_ROW_GRADIENT_Z, idx) = 0.f;
+    SM_S(SM_ROW_GRADIENT_COUNT, idx) = 0.f;
+
+    // Initial neighbours (kernels.cu:189-224).
+    const float max_distance_squared = fmul(radius_squared, f.radius_factor_squared);
+    float sum_x = 0.f, sum_y = 0.f, sum_z = 0.f;
+    int existing_neighbor_count_plus_1 = 1;
+    const int kDirectionsX[4] = {-1, 1, 0, 0};
+    const int kDirectionsY[4] = {0, 0, -1, 1};
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      const int nx_ = x + kDirectionsX[direction], ny_ = y + kDirectionsY[direction];
+      const int nseq = ny_ * d.width + nx_;
+      u32 neighbor_index = d.assoc[nseq].x;
+      if (neighbor_index != kInvalidIndex) {
+        const float distance_squared =
+            squared_norm(fsub(SM_S(SM_ROW_X, neighbor_index), g.x), fsub(SM_S(SM_ROW_Y, neighbor_index), g.y),
+                         fsub(SM_S(SM_ROW_Z, neighbor_index), g.z));
+        if (distance_squared > max_distance_squared) {
+          neighbor_index = kInvalidIndex;
+        } else {
+          sum_x = fadd(sum_x, SM_S(SM_ROW_SMOOTH_X, neighbor_index));
+          sum_y = fadd(sum_y, SM_S(SM_ROW_SMOOTH_Y, neighbor_index));
+          sum_z = fadd(sum_z, SM_S(SM_ROW_SMOOTH_Z, neighbor_index));
+          ++existing_neighbor_count_plus_1;
+        }
+      } else if (d.new_flag[nseq] == 1) {
+        const float diff = ffma(-u2f(row_ptr(f.depth, f.depth_pitch, ny_)[nx_]), f.inv_depth_scaling, depth);
+        if (!(fmul(diff, diff) > max_distance_squared)) neighbor_index = surfel_count + d.new_index[nseq];
+      }
+      SM_SU(SM_ROW_NEIGHBOR0 + direction, idx) = neighbor_index;
+    }
+    const float rcp_count = frcp(i2f(existing_neighbor_count_plus_1));
+    SM_S(SM_ROW_SMOOTH_X, idx) = fmul(fadd(g.x, sum_x), rcp_count);
+    SM_S(SM_ROW_SMOOTH_Y, idx) = fmul(fadd(g.y, sum_y), rcp_count);
+    SM_S(SM_ROW_SMOOTH_Z, idx) = fmul(fadd(g.z, sum_z), rcp_count);
+  }
+}
+
+// ExportVerticesCUDAKernel (kernels.cu:2412-2433).
+__global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int parity, float* position_buffer,
+                                                            u8* color_buffer) {
+  const u32 n = d.counters->surfel_count[parity];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool merged = SM_S(SM_ROW_RADIUS_SQUARED, i) < 0.f;
+    const float nan = __int_as_float(0x7fffffff);
+    position_buffer[3 * i + 0] = merged ? nan : SM_S(SM_ROW_SMOOTH_X, i);
+    position_buffer[3 * i + 1] = merged ? nan : SM_S(SM_ROW_SMOOTH_Y, i);
+    position_buffer[3 * i + 2] = merged ? nan : SM_S(SM_ROW_SMOOTH_Z, i);
+    const u32 c = SM_SU(SM_ROW_COLOR, i);
+    color_buffer[3 * i + 0] = c & 0xFF;
+    color_buffer[3 * i + 1] = (c >> 8) & 0xFF;
+    color_buffer[3 * i + 2] = (c >> 16) & 0xFF;
+  }
+}
+
+}  // namespace
+
+int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d) {
+  const int blocks = (d.width * d.height + kBlock * 4 - 1) / (kBlock * 4);
+  k_clear<<<blocks, kBlock, 0, stream>>>(d);
+  CountLaunch();
+  return CheckLaunch("clear");
+}
+
+int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams& f, bool do_blending,
+                   bool rasters_already_cleared, int sm_count, const IntegrateEvents* events) {
+  const bool timed = events && events->enabled;
+  auto record = [&](int i) { if (timed) cudaEventRecord(events->ev[i], stream); };
+  const int list_grid = sm_count * 8;  // persistent grid: 8 blocks of 256 threads per SM
+  const dim3 pixel_tiles((d.width + kBlendTileW - 1) / kBlendTileW, (d.height + kBlendTileH - 1) / kBlendTileH);
+  const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
+
+  record(0);
+  if (!rasters_already_cleared) {
+    const int status = ClearAssociationRasters(stream, d);
+    if (status != SM_OK) return status;
+  }
+  k_project<<<list_grid, kBlock, 0, stream>>>(d, f);
+  CountLaunch();
+  k_associate<<<list_grid, kBlock, 0, stream>>>(d, f);
+  CountLaunch();
+  record(1); record(2);
+  k_merge<<<list_grid, kBlock, 0, stream>>>(d, f);
+  CountLaunch();
+  record(3); record(4);
+  if (do_blending) {
+    const int halo = f.blend_radius - 1 > 1 ? f.blend_radius - 1 : 1;
+    const size_t rn = static_cast<size_t>(kBlendTileW + 2 * halo) * (kBlendTileH + 2 * halo);
+    const size_t smem = rn * (4 + 4 + 2 + 2 + 1 + 1 + 1) + 16;
+    if (smem > 200 * 1024) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
+    static size_t configured_smem = 0;
+    if (smem > 48 * 1024 && smem > configured_smem) {
+      if (cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend)");
+      configured_smem = smem;
+    }
+    k_blend<<<pixel_tiles, 512, smem, stream>>>(d, f);
+    CountLaunch();
+  }
+  record(5); record(6);
+  k_integrate<<<list_grid, kBlock, 0, stream>>>(d, f);
+  CountLaunch();
+  record(7); record(8);
+  k_update_neighbors<<<list_grid, kBlock, 0, stream>>>(d, f);
+  CountLaunch();
+  record(9); record(10);
+  k_new_surfel_scan<<<scan_tiles, kBlock, 0, stream>>>(d, f);
+  CountLaunch();
+  k_create_surfels<<<(d.width * d.height + kBlock - 1) / kBlock, kBlock, 0, stream>>>(d, f);
+  CountLaunch();
+  record(11);
+  return CheckLaunch("integrate");
+}
+
+int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm_count, float* position_buffer,
+                   u8* color_buffer) {
+  k_export_vertices<<<sm_count * 8, kBlock, 0, stream>>>(d, parity, position_buffer, color_buffer);
+  CountLaunch();
+  return CheckLaunch("export vertices");
+}
+
+}  // namespace smb

@@ -1,0 +1,743 @@
+// preprocess.cu — depth pre-processing kernels for sm_100a.
+//
+// Replaces the five launches of APP/main.cc:1015-1191
+//   BilateralFilteringAndDepthCutoffCUDA   APP/cuda_depth_processing.cu:50-158
+//   OutlierDepthMapFusionCUDA<K+1,u16>     :168-285 (all inliers) / :337-457 (>= required)
+//   ErodeDepthMapCUDA / CopyWithoutBorder  :514-579 / :589-633
+//   ComputeNormalsAndDropBadPixelsCUDA     :642-762
+//   ComputePointRadiiAndRemoveIsolatedPixelsCUDA :765-883
+// by two fused kernels:
+//   k_bilateral_outlier : raw u16 tile (+halo 6) staged in shared memory as fp32 with
+//                         128-bit global loads, 113-tap bilateral with both reciprocals
+//                         hoisted (1 MUFU per tap instead of the reference's 3), then the
+//                         multi-frame outlier test on the filtered value in registers.
+//   k_erode_normals_radii : erosion -> normals -> radii through three shared-memory tiles
+//                         (halo 4/2/1), optionally also clearing the association rasters
+//                         of the following Integrate().
+// plus one plain kernel per reference stage (used by the link-level shims and by the
+// per-stage parity tests). All arithmetic follows the reference's sm_100a SASS op for op
+// (see sm_math.cuh); the u16 outputs are bit-exact.
+
+#include "sm_kernels.cuh"
+
+namespace smb {
+
+namespace {
+
+constexpr int kTileW = 32;   // output tile
+constexpr int kTileH = 16;
+constexpr float kLog2e = 1.4426950216293334961f;  // 0x3FB8AA3B, the constant nvcc emits for exp()
+
+// ---------------------------------------------------------------------------------------
+// a1: bilateral filter + depth cutoff (cuda_depth_processing.cu:50-118)
+// ---------------------------------------------------------------------------------------
+
+struct BilateralArgs {
+  float denom_xy;             // 2 * sigma_xy^2
+  float sigma_value_factor;
+  int radius;
+  int radius_squared;
+  u16 value_to_ignore;
+  u16 max_depth;
+  float valid_radius_squared;
+  int width, height;
+  const u16* in;
+  size_t in_pitch;
+};
+
+// Cooperative fill of a (kTileH + 2R) x (tile_w_pad) fp32 tile from a pitched u16 raster.
+// The tile starts at x0 = tile_x - kPadX (kPadX = 8 >= R keeps x0 a multiple of 8 pixels so
+// that every 8-pixel group is one aligned 128-bit load); out-of-image pixels read as `fill`.
+template <int R, int PADX, int SW>
+__device__ __forceinline__ void load_depth_tile_f32(float* tile, const u16* in, size_t pitch, int width, int height,
+                                                    int tile_x, int tile_y, float fill) {
+  constexpr int kRows = kTileH + 2 * R;
+  constexpr int kVecPerRow = SW / 8;
+  const int x0 = tile_x - PADX;
+  const int y0 = tile_y - R;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) | pitch) & 15) == 0;
+  for (int v = threadIdx.x; v < kRows * kVecPerRow; v += blockDim.x) {
+    const int row = v / kVecPerRow;
+    const int col = (v - row * kVecPerRow) * 8;
+    const int gy = y0 + row;
+    const int gx = x0 + col;
+    float vals[8];
+    if (gy >= 0 && gy < height && gx >= 0 && gx + 8 <= width && aligned) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(row_ptr(in, pitch, gy) + gx));
+      vals[0] = u2f(q.x & 0xFFFFu); vals[1] = u2f(q.x >> 16);
+      vals[2] = u2f(q.y & 0xFFFFu); vals[3] = u2f(q.y >> 16);
+      vals[4] = u2f(q.z & 0xFFFFu); vals[5] = u2f(q.z >> 16);
+      vals[6] = u2f(q.w & 0xFFFFu); vals[7] = u2f(q.w >> 16);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int xx = gx + i;
+        vals[i] = (gy >= 0 && gy < height && xx >= 0 && xx < width) ? u2f(row_ptr(in, pitch, gy)[xx]) : fill;
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(tile + row * SW + col);
+    dst[0] = make_float4(vals[0], vals[1], vals[2], vals[3]);
+    dst[1] = make_float4(vals[4], vals[5], vals[6], vals[7]);
+  }
+}
+
+// One tap (cuda_depth_processing.cu:98-112; SASS: FMUL d*-d, FMUL *rcp_v, FFMA(-gd2, rcp_xy, .),
+// FMUL *log2e, MUFU.EX2, FFMA sum, FADD weight). c - s is exact in fp32 (both < 2^16).
+__device__ __forceinline__ void bilateral_tap(float s, float c, float neg_gd2, float rcp_xy, float rcp_v, float ignore,
+                                              float& sum, float& weight) {
+  const float d = fsub(c, s);
+  const float q = fmul(d, -d);
+  const float t = fmul(q, rcp_v);
+  const float e = ffma(neg_gd2, rcp_xy, t);
+  const float w = fex2_approx(fmul(e, kLog2e));
+  if (s != ignore) {
+    sum = ffma(w, s, sum);
+    weight = fadd(weight, w);
+  }
+}
+
+// Bilateral value of the pixel whose tile coordinates are (lx, ly) (tile origin includes
+// the halo). Returns the u16 result. R > 0: compile-time disc, fully unrolled.
+template <int R, int SW>
+__device__ __forceinline__ u16 bilateral_pixel(const float* tile, int lx, int ly, float c, const BilateralArgs& a,
+                                               float rcp_xy) {
+  const float ignore = u2f(a.value_to_ignore);
+  const float av = fmul(c, a.sigma_value_factor);   // adapted_sigma_value
+  const float denom_v = fmul(av, fadd(av, av));     // 2 * s * s as FADD + FMUL
+  const float rcp_v = frcp(denom_v);
+  float sum = 0.f, weight = 0.f;
+#pragma unroll
+  for (int dy = -R; dy <= R; ++dy) {
+#pragma unroll
+    for (int dx = -R; dx <= R; ++dx) {
+      if (dx * dx + dy * dy <= R * R) {
+        bilateral_tap(tile[(ly + dy) * SW + lx + dx], c, static_cast<float>(-(dx * dx + dy * dy)), rcp_xy, rcp_v,
+                      ignore, sum, weight);
+      }
+    }
+  }
+  if (weight != 0.f) {
+    return static_cast<u16>(f2u_trunc(ffma(frcp(weight), sum, 0.5f)));
+  }
+  return a.value_to_ignore;
+}
+
+// Circle mask + cutoff (cuda_depth_processing.cu:64-79). The reference evaluates the
+// squared centre distance in 32-bit unsigned arithmetic and converts it with I2FP.F32.U32.
+__device__ __forceinline__ bool bilateral_pixel_masked(unsigned x, unsigned y, const BilateralArgs& a) {
+  const unsigned hx = x - static_cast<unsigned>(a.width / 2);
+  const unsigned hy = y - static_cast<unsigned>(a.height / 2);
+  const float center_distance_squared = u2f(hx * hx + hy * hy);
+  return center_distance_squared > a.valid_radius_squared;
+}
+
+// ---------------------------------------------------------------------------------------
+// a2: multi-frame outlier fusion (cuda_depth_processing.cu:168-227 / :337-397)
+// ---------------------------------------------------------------------------------------
+
+constexpr int kMaxOthers = 8;
+
+struct OutlierArgs {
+  int other_count;      // K
+  int required_count;   // < 0: all K must agree (early break), else >= required_count
+  float max_tolerance_factor, min_tolerance_factor;
+  float fx, fy, cx, cy;
+  float fx_inv, fy_inv, cx_inv, cy_inv;
+  int width, height;
+  Mat3x4 other_TR_reference[kMaxOthers];
+  const u16* other_depths[kMaxOthers];
+  size_t other_pitches[kMaxOthers];
+};
+
+__device__ __forceinline__ bool outlier_check_one(const OutlierArgs& a, int k, float px, float py, float d) {
+  const Mat3x4& m = a.other_TR_reference[k];
+  const float oz = transform_row(m.r2, px, py, d);
+  if (oz <= 0.f) return false;
+  const float ox = transform_row(m.r0, px, py, d);
+  const float oy = transform_row(m.r1, px, py, d);
+  const float inv_z = frcp(oz);
+  const float u = ffma(fmul(ox, inv_z), a.fx, a.cx);
+  const float v = ffma(fmul(oy, inv_z), a.fy, a.cy);
+  const int ix = f2i_trunc(u);
+  const int iy = f2i_trunc(v);
+  if (ix < 0 || iy < 0 || ix >= a.width || iy >= a.height) return false;
+  const u16 od = row_ptr(a.other_depths[k], a.other_pitches[k], iy)[ix];
+  if (od == 0) return false;
+  const float odf = u2f(od);
+  if (fmul(a.max_tolerance_factor, oz) < odf) return false;
+  if (fmul(a.min_tolerance_factor, oz) > odf) return false;
+  return true;
+}
+
+// Returns the depth value to keep (depth_value or 0).
+__device__ __forceinline__ u16 outlier_pixel(const OutlierArgs& a, unsigned x, unsigned y, u16 depth_value) {
+  if (depth_value == 0) return 0;
+  const float d = u2f(depth_value);
+  const float px = fmul(ffma(a.fx_inv, u2f(x), a.cx_inv), d);
+  const float py = fmul(ffma(a.fy_inv, u2f(y), a.cy_inv), d);
+  if (a.required_count < 0) {
+    for (int k = 0; k < a.other_count; ++k) {
+      if (!outlier_check_one(a, k, px, py, d)) return 0;
+    }
+    return depth_value;
+  }
+  int ok_count = 0;
+  for (int k = 0; k < a.other_count; ++k) {
+    ok_count += outlier_check_one(a, k, px, py, d) ? 1 : 0;
+  }
+  return ok_count >= a.required_count ? depth_value : 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// fused a1+a2
+// ---------------------------------------------------------------------------------------
+
+template <int R, bool kWithOutlier>
+__global__ void __launch_bounds__(256)
+k_bilateral_outlier(BilateralArgs a, const __grid_constant__ OutlierArgs o, u16* out, size_t out_pitch) {
+  constexpr int PADX = 8;
+  constexpr int SW = kTileW + 2 * PADX;  // 48 floats per tile row
+  __shared__ __align__(16) float tile[(kTileH + 2 * R) * SW];
+
+  const int tile_x = blockIdx.x * kTileW;
+  const int tile_y = blockIdx.y * kTileH;
+
+  // Whole tile outside the valid circle? (cheap conservative test on the nearest tile point)
+  load_depth_tile_f32<R, PADX, SW>(tile, a.in, a.in_pitch, a.width, a.height, tile_x, tile_y,
+                                   u2f(a.value_to_ignore));
+  __syncthreads();
+
+  const float rcp_xy = frcp(a.denom_xy);
+  const int tx = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;  // 0..7
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int ly = ty + half * 8;
+    const unsigned x = tile_x + tx;
+    const unsigned y = tile_y + ly;
+    if (x >= static_cast<unsigned>(a.width) || y >= static_cast<unsigned>(a.height)) continue;
+    u16 result = a.value_to_ignore;
+    if (!bilateral_pixel_masked(x, y, a)) {
+      const float c = tile[(ly + R) * SW + tx + PADX];
+      const unsigned ci = f2u_trunc(c);
+      if (ci != a.value_to_ignore && ci <= a.max_depth) {
+        result = bilateral_pixel<R, SW>(tile, tx + PADX, ly + R, c, a, rcp_xy);
+      }
+    }
+    if (kWithOutlier) result = outlier_pixel(o, x, y, result);
+    row_ptr(out, out_pitch, y)[x] = result;
+  }
+}
+
+// Generic-radius fallback (any radius): one thread per pixel, taps read through L1/L2.
+__global__ void __launch_bounds__(256)
+k_bilateral_generic(BilateralArgs a, u16* out, size_t out_pitch) {
+  const unsigned x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const unsigned y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= static_cast<unsigned>(a.width) || y >= static_cast<unsigned>(a.height)) return;
+  u16 result = a.value_to_ignore;
+  if (!bilateral_pixel_masked(x, y, a)) {
+    const u16 center = row_ptr(a.in, a.in_pitch, y)[x];
+    if (center != a.value_to_ignore && center <= a.max_depth) {
+      const float c = u2f(center);
+      const float ignore = u2f(a.value_to_ignore);
+      const float rcp_xy = frcp(a.denom_xy);
+      const float av = fmul(c, a.sigma_value_factor);
+      const float rcp_v = frcp(fmul(av, fadd(av, av)));
+      float sum = 0.f, weight = 0.f;
+      const int min_y = max(0, static_cast<int>(y) - a.radius);
+      const int max_y = min(a.height - 1, static_cast<int>(y) + a.radius);
+      const int min_x = max(0, static_cast<int>(x) - a.radius);
+      const int max_x = min(a.width - 1, static_cast<int>(x) + a.radius);
+      for (int sy = min_y; sy <= max_y; ++sy) {
+        const int dy = sy - static_cast<int>(y);
+        const u16* row = row_ptr(a.in, a.in_pitch, sy);
+        for (int sx = min_x; sx <= max_x; ++sx) {
+          const int dx = sx - static_cast<int>(x);
+          const int gd2 = dx * dx + dy * dy;
+          if (gd2 > a.radius_squared) continue;
+          bilateral_tap(u2f(row[sx]), c, i2f(-gd2), rcp_xy, rcp_v, ignore, sum, weight);
+        }
+      }
+      if (weight != 0.f) result = static_cast<u16>(f2u_trunc(ffma(frcp(weight), sum, 0.5f)));
+    }
+  }
+  row_ptr(out, out_pitch, y)[x] = result;
+}
+
+__global__ void __launch_bounds__(256)
+k_outlier(const __grid_constant__ OutlierArgs o, const u16* in, size_t in_pitch, u16* out, size_t out_pitch) {
+  const unsigned x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const unsigned y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= static_cast<unsigned>(o.width) || y >= static_cast<unsigned>(o.height)) return;
+  row_ptr(out, out_pitch, y)[x] = outlier_pixel(o, x, y, row_ptr(in, in_pitch, y)[x]);
+}
+
+// ---------------------------------------------------------------------------------------
+// a3: erosion / border copy (cuda_depth_processing.cu:514-538 / :589-607)
+// ---------------------------------------------------------------------------------------
+
+// `get(y, x)` must return 0 outside the image.
+template <typename Get>
+__device__ __forceinline__ u16 erode_pixel(int radius, int x, int y, int width, int height, Get get) {
+  if (radius == 0) {
+    constexpr int kBorderSize = 1;
+    if (x < kBorderSize || y < kBorderSize || x >= width - kBorderSize || y >= height - kBorderSize) return 0;
+    return get(y, x);
+  }
+  if (x < radius || y < radius || x >= width - radius || y >= height - radius) return 0;
+  bool all_valid = true;
+  for (int dy = y - radius; dy <= y + radius; ++dy) {
+    for (int dx = x - radius; dx <= x + radius; ++dx) {
+      if (get(dy, dx) == 0) all_valid = false;
+    }
+  }
+  return all_valid ? get(y, x) : static_cast<u16>(0);
+}
+
+// ---------------------------------------------------------------------------------------
+// a4: normals (cuda_depth_processing.cu:642-718)
+// ---------------------------------------------------------------------------------------
+
+struct NormalsArgs {
+  float normal_dot_threshold;   // -cosf(M_PI / 180.f * angle)
+  float inv_depth_scaling;
+  float fx_inv, fy_inv, cx_inv, cy_inv;
+};
+
+// Precondition: centre and the four neighbours are non-zero. Returns the depth to keep.
+__device__ __forceinline__ u16 normals_pixel(const NormalsArgs& a, int x, int y, u16 center, u16 left, u16 right,
+                                             u16 top, u16 bottom, float2* normal_out) {
+  const float ids = a.inv_depth_scaling;
+  const float ld = fmul(u2f(left), ids);
+  const float bd = fmul(u2f(bottom), ids);
+  const float rd = fmul(u2f(right), ids);
+  const float td = fmul(u2f(top), ids);
+  const float fx_x = ffma(i2f(x), a.fx_inv, a.cx_inv);
+  const float fx_xp1 = ffma(i2f(x + 1), a.fx_inv, a.cx_inv);
+  const float fx_xm1 = ffma(i2f(x - 1), a.fx_inv, a.cx_inv);
+  const float fy_y = ffma(i2f(y), a.fy_inv, a.cy_inv);
+  const float fy_yp1 = ffma(i2f(y + 1), a.fy_inv, a.cy_inv);
+  const float fy_ym1 = ffma(i2f(y - 1), a.fy_inv, a.cy_inv);
+  const float left_x = fmul(ld, fx_xm1);
+  const float left_y = fmul(ld, fy_y);
+  const float bottom_x = fmul(fx_x, bd);
+  const float bottom_y = fmul(bd, fy_yp1);
+  // left_to_right = right - left, bottom_to_top = top - bottom; ptxas fuses the second
+  // product of every difference into the subtraction.
+  const float ax = ffma(rd, fx_xp1, -left_x);
+  const float ay = ffma(fy_y, rd, -left_y);
+  const float az = fsub(rd, ld);
+  const float bx = ffma(td, fx_x, -bottom_x);
+  const float by = ffma(td, fy_ym1, -bottom_y);
+  const float bz = fsub(td, bd);
+  // CrossProduct (cuda_util.cuh:69-73).
+  float nx = ffma(ay, bz, -fmul(az, by));
+  float ny = ffma(az, bx, -fmul(ax, bz));
+  float nz = ffma(ax, by, -fmul(ay, bx));
+  const float length = fsqrt_approx(ffma(nz, nz, ffma(nx, nx, fmul(ny, ny))));
+  // Viewing direction (normalised with MUFU.RSQ).
+  const float inv_dir_length = frsqrt_approx(fadd(ffma(fx_x, fx_x, fmul(fy_y, fy_y)), 1.0f));
+  const float vy = fmul(fy_y, inv_dir_length);
+  const float vx = fmul(fx_x, inv_dir_length);
+  if (length > 1e-6f) {
+    const float inv_length = fmul((a.fy_inv < 0.f) ? -1.0f : 1.0f, frcp(length));
+    nx = fmul(nx, inv_length);
+    ny = fmul(ny, inv_length);
+    nz = fmul(nz, inv_length);
+  } else {
+    nx = 0.f; ny = 0.f; nz = -1.f;
+  }
+  *normal_out = make_float2(nx, ny);
+  const float dot = ffma(inv_dir_length, nz, ffma(vx, nx, fmul(vy, ny)));
+  return (dot >= a.normal_dot_threshold) ? static_cast<u16>(0) : center;
+}
+
+// ---------------------------------------------------------------------------------------
+// a5: radii (cuda_depth_processing.cu:765-837)
+// ---------------------------------------------------------------------------------------
+
+struct RadiiArgs {
+  float point_radius_extension_factor_squared;
+  float clamp_factor_term;
+  float inv_depth_scaling;
+  float fx_inv, fy_inv, cx_inv, cy_inv;
+};
+
+// `get(y, x)`: normals-stage depth. Precondition: centre non-zero. Returns kept depth.
+template <typename Get>
+__device__ __forceinline__ u16 radii_pixel(const RadiiArgs& a, int x, int y, u16 center, Get get,
+                                           float* radius_squared_out) {
+  const float ids = a.inv_depth_scaling;
+  const float depth = fmul(u2f(center), ids);
+  const float local_x = fmul(depth, ffma(u2f(x), a.fx_inv, a.cx_inv));
+  const float local_y = fmul(depth, ffma(u2f(y), a.fy_inv, a.cy_inv));
+  int neighbor_count = 0;
+  float radius_squared = 0.f;
+  float min_neighbor_distance_squared = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int dy = y - 1; dy <= y + 1; ++dy) {
+#pragma unroll
+    for (int dx = x - 1; dx <= x + 1; ++dx) {
+      if (dx == x && dy == y) continue;
+      const float ddepth = fmul(u2f(get(dy, dx)), ids);
+      if (ddepth <= 0.f) continue;
+      ++neighbor_count;
+      const float oy = ffma(ffma(i2f(dy), a.fy_inv, a.cy_inv), ddepth, -local_y);
+      const float ox = ffma(ddepth, ffma(i2f(dx), a.fx_inv, a.cx_inv), -local_x);
+      const float oz = fsub(ddepth, depth);
+      const float distance_squared = ffma(oz, oz, ffma(ox, ox, fmul(oy, oy)));
+      if (distance_squared > radius_squared) radius_squared = distance_squared;
+      if (distance_squared < min_neighbor_distance_squared) min_neighbor_distance_squared = distance_squared;
+    }
+  }
+  radius_squared = fmul(radius_squared, a.point_radius_extension_factor_squared);
+  const float distance_squared_clamp = fmul(min_neighbor_distance_squared, a.clamp_factor_term);
+  if (radius_squared > distance_squared_clamp) radius_squared = distance_squared_clamp;
+  *radius_squared_out = radius_squared;
+  constexpr int kMinNeighborPixelsForRadiusComputation = 8;
+  return (neighbor_count < kMinNeighborPixelsForRadiusComputation) ? static_cast<u16>(0) : center;
+}
+
+// ---------------------------------------------------------------------------------------
+// fused a3+a4+a5 (+ clear of the association rasters, a6)
+// ---------------------------------------------------------------------------------------
+
+struct TailArgs {
+  int width, height;
+  int erosion_radius;
+  NormalsArgs normals;
+  RadiiArgs radii;
+  const u16* in; size_t in_pitch;         // outlier-filtered depth (B)
+  u16* out_depth; size_t out_depth_pitch;  // final depth (A)
+  float2* out_normals; size_t out_normals_pitch;
+  float* out_radius; size_t out_radius_pitch;
+  // Optional: association rasters to reset for the following Integrate().
+  uint4* assoc; float* first_depth;
+};
+
+constexpr int kMaxErode = 3;
+
+__global__ void __launch_bounds__(512)
+k_erode_normals_radii(TailArgs a) {
+  // B tile: halo r+2, E tile (eroded): halo 2, N tile (normals stage): halo 1.
+  constexpr int BW = kTileW + 2 * (kMaxErode + 2), BH = kTileH + 2 * (kMaxErode + 2);
+  constexpr int EW = kTileW + 4, EH = kTileH + 4;
+  constexpr int NW = kTileW + 2, NH = kTileH + 2;
+  __shared__ u16 sB[BH * BW];
+  __shared__ u16 sE[EH * EW];
+  __shared__ u16 sN[NH * NW];
+
+  const int r = a.erosion_radius;
+  const int hb = r + 2;  // halo of the B tile actually used
+  const int tile_x = blockIdx.x * kTileW;
+  const int tile_y = blockIdx.y * kTileH;
+  const int bw = kTileW + 2 * hb, bh = kTileH + 2 * hb;
+
+  for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
+    const int ly = i / bw, lx = i - ly * bw;
+    const int gx = tile_x - hb + lx, gy = tile_y - hb + ly;
+    u16 v = 0;
+    if (gx >= 0 && gy >= 0 && gx < a.width && gy < a.height) v = row_ptr(a.in, a.in_pitch, gy)[gx];
+    sB[ly * BW + lx] = v;
+  }
+  __syncthreads();
+
+  // Erode into the E tile (image coordinates tile - 2 .. tile + 2).
+  for (int i = threadIdx.x; i < EW * EH; i += blockDim.x) {
+    const int ly = i / EW, lx = i - ly * EW;
+    const int gx = tile_x - 2 + lx, gy = tile_y - 2 + ly;
+    u16 v = 0;
+    if (gx >= 0 && gy >= 0 && gx < a.width && gy < a.height) {
+      auto get = [&](int yy, int xx) -> u16 { return sB[(yy - tile_y + hb) * BW + (xx - tile_x + hb)]; };
+      v = erode_pixel(r, gx, gy, a.width, a.height, get);
+    }
+    sE[ly * EW + lx] = v;
+  }
+  __syncthreads();
+
+  // Normals stage on the N tile (image coordinates tile - 1 .. tile + 1).
+  for (int i = threadIdx.x; i < NW * NH; i += blockDim.x) {
+    const int ly = i / NW, lx = i - ly * NW;
+    const int gx = tile_x - 1 + lx, gy = tile_y - 1 + ly;
+    u16 v = 0;
+    if (gx >= 0 && gy >= 0 && gx < a.width && gy < a.height) {
+      const int ex = lx + 1, ey = ly + 1;  // position in the E tile
+      const u16 center = sE[ey * EW + ex];
+      float2 normal = make_float2(0.f, 0.f);
+      if (center != 0) {
+        // The reference reads the four neighbours without bounds checks and relies on the
+        // zero border left by the erosion (cuda_depth_processing.cuh:96-98); the E tile is
+        // zero outside the image, which is the same thing.
+        const u16 right = sE[ey * EW + ex + 1];
+        const u16 left = sE[ey * EW + ex - 1];
+        const u16 bottom = sE[(ey + 1) * EW + ex];
+        const u16 top = sE[(ey - 1) * EW + ex];
+        if (right != 0 && left != 0 && bottom != 0 && top != 0) {
+          v = normals_pixel(a.normals, gx, gy, center, left, right, top, bottom, &normal);
+        }
+      }
+      const bool interior = lx >= 1 && lx <= kTileW && ly >= 1 && ly <= kTileH;
+      if (interior) row_ptr(a.out_normals, a.out_normals_pitch, gy)[gx] = normal;
+    }
+    sN[ly * NW + lx] = v;
+  }
+  __syncthreads();
+
+  // Radii on the tile interior.
+  {
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int gx = tile_x + lx, gy = tile_y + ly;
+    if (gx < a.width && gy < a.height) {
+      const u16 center = sN[(ly + 1) * NW + lx + 1];
+      u16 kept = 0;
+      if (center != 0) {
+        auto get = [&](int yy, int xx) -> u16 { return sN[(yy - tile_y + 1) * NW + (xx - tile_x + 1)]; };
+        float radius_squared;
+        kept = radii_pixel(a.radii, gx, gy, center, get, &radius_squared);
+        row_ptr(a.out_radius, a.out_radius_pitch, gy)[gx] = radius_squared;
+      }
+      row_ptr(a.out_depth, a.out_depth_pitch, gy)[gx] = kept;
+      if (a.assoc) {
+        const size_t p = static_cast<size_t>(gy) * a.width + gx;
+        a.assoc[p] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+        a.first_depth[p] = __int_as_float(0x7f800000);
+      }
+    }
+  }
+}
+
+// ---- plain per-stage kernels (one thread per pixel) ------------------------------------
+
+__global__ void __launch_bounds__(256)
+k_erode(int radius, int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= width || y >= height) return;
+  auto get = [&](int yy, int xx) -> u16 { return row_ptr(in, in_pitch, yy)[xx]; };
+  row_ptr(out, out_pitch, y)[x] = erode_pixel(radius, x, y, width, height, get);
+}
+
+__global__ void __launch_bounds__(256)
+k_normals(NormalsArgs a, int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch,
+          float2* normals, size_t normals_pitch) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= width || y >= height) return;
+  const u16 center = row_ptr(in, in_pitch, y)[x];
+  u16 kept = 0;
+  float2 normal = make_float2(0.f, 0.f);
+  // Unlike the reference this kernel stays in bounds when the caller did not zero the border.
+  if (center != 0 && x >= 1 && y >= 1 && x < width - 1 && y < height - 1) {
+    const u16 right = row_ptr(in, in_pitch, y)[x + 1];
+    const u16 left = row_ptr(in, in_pitch, y)[x - 1];
+    const u16 bottom = row_ptr(in, in_pitch, y + 1)[x];
+    const u16 top = row_ptr(in, in_pitch, y - 1)[x];
+    if (right != 0 && left != 0 && bottom != 0 && top != 0) {
+      kept = normals_pixel(a, x, y, center, left, right, top, bottom, &normal);
+    }
+  }
+  row_ptr(out, out_pitch, y)[x] = kept;
+  row_ptr(normals, normals_pitch, y)[x] = normal;
+}
+
+__global__ void __launch_bounds__(256)
+k_radii(RadiiArgs a, int width, int height, const u16* in, size_t in_pitch, float* radius, size_t radius_pitch,
+        u16* out, size_t out_pitch) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= width || y >= height) return;
+  const u16 center = row_ptr(in, in_pitch, y)[x];
+  u16 kept = 0;
+  if (center != 0) {
+    auto get = [&](int yy, int xx) -> u16 {
+      return (xx >= 0 && yy >= 0 && xx < width && yy < height) ? row_ptr(in, in_pitch, yy)[xx] : static_cast<u16>(0);
+    };
+    float radius_squared;
+    kept = radii_pixel(a, x, y, center, get, &radius_squared);
+    row_ptr(radius, radius_pitch, y)[x] = radius_squared;
+  }
+  row_ptr(out, out_pitch, y)[x] = kept;
+}
+
+// ---- host-side argument construction (mirrors the reference's host wrappers) ------------
+
+BilateralArgs MakeBilateralArgs(float sigma_xy, float sigma_value_factor, u16 value_to_ignore, float radius_factor,
+                                u16 max_depth, float depth_valid_region_radius, int width, int height, const u16* in,
+                                size_t in_pitch) {
+  BilateralArgs a;
+  const int radius = radius_factor * sigma_xy + 0.5f;  // cuda_depth_processing.cu:135
+  a.denom_xy = 2.0f * sigma_xy * sigma_xy;             // :145
+  a.sigma_value_factor = sigma_value_factor;
+  a.radius = radius;
+  a.radius_squared = radius * radius;
+  a.value_to_ignore = value_to_ignore;
+  a.max_depth = max_depth;
+  a.valid_radius_squared = depth_valid_region_radius * depth_valid_region_radius;  // :151
+  a.width = width; a.height = height;
+  a.in = in; a.in_pitch = in_pitch;
+  return a;
+}
+
+void MakeUnprojection(float fx, float fy, float cx, float cy, float* fx_inv, float* fy_inv, float* cx_inv,
+                      float* cy_inv) {
+  // Unprojection intrinsics for pixel center convention (cuda_depth_processing.cu:258-264).
+  *fx_inv = 1.0f / fx;
+  *fy_inv = 1.0f / fy;
+  const float cx_pixel_center = cx - 0.5f;
+  const float cy_pixel_center = cy - 0.5f;
+  *cx_inv = -cx_pixel_center / fx;
+  *cy_inv = -cy_pixel_center / fy;
+}
+
+int MakeOutlierArgs(OutlierArgs* o, int other_count, int required_count, float tolerance, float fx, float fy,
+                    float cx, float cy, int width, int height, const u16* const* other_depths,
+                    const size_t* other_pitches, const float* others_TR_reference) {
+  if (other_count != 2 && other_count != 4 && other_count != 6 && other_count != 8) {
+    return SetError(SM_ERR_INVALID_ARGUMENT, "Unsupported value for outlier_filtering_frame_count (2,4,6,8)");
+  }
+  o->other_count = other_count;
+  o->required_count = (required_count == -1 || required_count == other_count) ? -1 : required_count;  // main.cc:1061
+  o->max_tolerance_factor = 1 + tolerance;  // cuda_depth_processing.cu:255-256
+  o->min_tolerance_factor = 1 - tolerance;
+  o->fx = fx; o->fy = fy; o->cx = cx; o->cy = cy;
+  MakeUnprojection(fx, fy, cx, cy, &o->fx_inv, &o->fy_inv, &o->cx_inv, &o->cy_inv);
+  o->width = width; o->height = height;
+  for (int i = 0; i < other_count; ++i) {
+    o->other_TR_reference[i] = MakeMat3x4(others_TR_reference + 12 * i);
+    o->other_depths[i] = other_depths[i];
+    o->other_pitches[i] = other_pitches[i];
+  }
+  return SM_OK;
+}
+
+NormalsArgs MakeNormalsArgs(float observation_angle_threshold_deg, float depth_scaling, float fx, float fy, float cx,
+                            float cy) {
+  NormalsArgs n;
+  n.normal_dot_threshold = -1 * cosf(M_PI / 180.f * observation_angle_threshold_deg);  // :752
+  n.inv_depth_scaling = 1.0f / depth_scaling;
+  MakeUnprojection(fx, fy, cx, cy, &n.fx_inv, &n.fy_inv, &n.cx_inv, &n.cy_inv);
+  return n;
+}
+
+RadiiArgs MakeRadiiArgs(float point_radius_extension_factor, float point_radius_clamp_factor, float depth_scaling,
+                        float fx, float fy, float cx, float cy) {
+  RadiiArgs r;
+  r.point_radius_extension_factor_squared = point_radius_extension_factor * point_radius_extension_factor;  // :872
+  r.clamp_factor_term = point_radius_clamp_factor * point_radius_clamp_factor * sqrtf(2) * sqrtf(2);       // :873
+  r.inv_depth_scaling = 1.0f / depth_scaling;
+  MakeUnprojection(fx, fy, cx, cy, &r.fx_inv, &r.fy_inv, &r.cx_inv, &r.cy_inv);
+  return r;
+}
+
+dim3 TileGrid(int width, int height) { return dim3((width + kTileW - 1) / kTileW, (height + kTileH - 1) / kTileH); }
+dim3 PixelGrid(int width, int height) { return dim3((width + 31) / 32, (height + 7) / 8); }
+
+int LaunchBilateral(cudaStream_t stream, const BilateralArgs& a, const OutlierArgs* o, u16* out, size_t out_pitch) {
+  static const OutlierArgs kNoOutlier = {};
+  if (a.radius == 6) {
+    if (o) k_bilateral_outlier<6, true><<<TileGrid(a.width, a.height), 256, 0, stream>>>(a, *o, out, out_pitch);
+    else k_bilateral_outlier<6, false><<<TileGrid(a.width, a.height), 256, 0, stream>>>(a, kNoOutlier, out, out_pitch);
+    CountLaunch();
+  } else {
+    if (a.radius < 0) return SetError(SM_ERR_INVALID_ARGUMENT, "negative bilateral radius");
+    k_bilateral_generic<<<PixelGrid(a.width, a.height), 256, 0, stream>>>(a, out, out_pitch);
+    CountLaunch();
+    if (o) {
+      k_outlier<<<PixelGrid(a.width, a.height), 256, 0, stream>>>(*o, out, out_pitch, out, out_pitch);
+      CountLaunch();
+    }
+  }
+  return CheckLaunch("bilateral/outlier");
+}
+
+}  // namespace
+
+// ---- entry points used by api.cu ----------------------------------------------------------
+
+int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int width, int height, float fx, float fy,
+                    float cx, float cy, const u16* raw, size_t raw_pitch, const u16* const* other_depths,
+                    const size_t* other_pitches, const float* others_TR_reference, u16* scratch_B,
+                    size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch, float2* out_normals,
+                    size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
+                    float* clear_first_depth) {
+  if (p.depth_erosion_radius < 0 || p.depth_erosion_radius > kMaxErode) {
+    return SetError(SM_ERR_INVALID_ARGUMENT, "depth_erosion_radius must be in [0, 3]");
+  }
+  const BilateralArgs b = MakeBilateralArgs(p.bilateral_filter_sigma_xy, p.bilateral_filter_sigma_depth_factor, 0,
+                                            p.bilateral_filter_radius_factor,
+                                            static_cast<u16>(p.depth_scaling * p.max_depth),  // main.cc:1021
+                                            p.depth_valid_region_radius, width, height, raw, raw_pitch);
+  OutlierArgs o;
+  int status = MakeOutlierArgs(&o, p.outlier_filtering_frame_count, p.outlier_filtering_required_inliers,
+                               p.outlier_filtering_depth_tolerance_factor, fx, fy, cx, cy, width, height,
+                               other_depths, other_pitches, others_TR_reference);
+  if (status != SM_OK) return status;
+  status = LaunchBilateral(stream, b, &o, scratch_B, scratch_B_pitch);
+  if (status != SM_OK) return status;
+
+  TailArgs t;
+  t.width = width; t.height = height;
+  t.erosion_radius = p.depth_erosion_radius;
+  t.normals = MakeNormalsArgs(p.observation_angle_threshold_deg, p.depth_scaling, fx, fy, cx, cy);
+  t.radii = MakeRadiiArgs(p.point_radius_extension_factor, p.point_radius_clamp_factor, p.depth_scaling, fx, fy, cx, cy);
+  t.in = scratch_B; t.in_pitch = scratch_B_pitch;
+  t.out_depth = out_depth; t.out_depth_pitch = out_depth_pitch;
+  t.out_normals = out_normals; t.out_normals_pitch = out_normals_pitch;
+  t.out_radius = out_radius; t.out_radius_pitch = out_radius_pitch;
+  t.assoc = clear_assoc; t.first_depth = clear_first_depth;
+  k_erode_normals_radii<<<TileGrid(width, height), 512, 0, stream>>>(t);
+  CountLaunch();
+  return CheckLaunch("erode/normals/radii");
+}
+
+int StageBilateral(cudaStream_t stream, float sigma_xy, float sigma_value_factor, u16 value_to_ignore,
+                   float radius_factor, u16 max_depth, float depth_valid_region_radius, int width, int height,
+                   const u16* in, size_t in_pitch, u16* out, size_t out_pitch) {
+  const BilateralArgs b = MakeBilateralArgs(sigma_xy, sigma_value_factor, value_to_ignore, radius_factor, max_depth,
+                                            depth_valid_region_radius, width, height, in, in_pitch);
+  return LaunchBilateral(stream, b, nullptr, out, out_pitch);
+}
+
+int StageOutlier(cudaStream_t stream, int other_count, int required_count, float tolerance, float fx, float fy,
+                 float cx, float cy, int width, int height, const u16* in, size_t in_pitch,
+                 const u16* const* other_depths, const size_t* other_pitches, const float* others_TR_reference,
+                 u16* out, size_t out_pitch) {
+  OutlierArgs o;
+  const int status = MakeOutlierArgs(&o, other_count, required_count, tolerance, fx, fy, cx, cy, width, height,
+                                     other_depths, other_pitches, others_TR_reference);
+  if (status != SM_OK) return status;
+  k_outlier<<<PixelGrid(width, height), 256, 0, stream>>>(o, in, in_pitch, out, out_pitch);
+  CountLaunch();
+  return CheckLaunch("outlier");
+}
+
+int StageErode(cudaStream_t stream, int radius, int width, int height, const u16* in, size_t in_pitch, u16* out,
+               size_t out_pitch) {
+  if (radius < 0 || radius > kMaxErode) return SetError(SM_ERR_INVALID_ARGUMENT, "radius value is not supported");
+  k_erode<<<PixelGrid(width, height), 256, 0, stream>>>(radius, width, height, in, in_pitch, out, out_pitch);
+  CountLaunch();
+  return CheckLaunch("erode");
+}
+
+int StageNormals(cudaStream_t stream, float observation_angle_threshold_deg, float depth_scaling, float fx, float fy,
+                 float cx, float cy, int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch,
+                 float2* normals, size_t normals_pitch) {
+  k_normals<<<PixelGrid(width, height), 256, 0, stream>>>(
+      MakeNormalsArgs(observation_angle_threshold_deg, depth_scaling, fx, fy, cx, cy), width, height, in, in_pitch, out,
+      out_pitch, normals, normals_pitch);
+  CountLaunch();
+  return CheckLaunch("normals");
+}
+
+int StageRadii(cudaStream_t stream, float point_radius_extension_factor, float point_radius_clamp_factor,
+               float depth_scaling, float fx, float fy, float cx, float cy, int width, int height, const u16* in,
+               size_t in_pitch, float* radius, size_t radius_pitch, u16* out, size_t out_pitch) {
+  k_radii<<<PixelGrid(width, height), 256, 0, stream>>>(
+      MakeRadiiArgs(point_radius_extension_factor, point_radius_clamp_factor, depth_scaling, fx, fy, cx, cy), width,
+      height, in, in_pitch, radius, radius_pitch, out, out_pitch);
+  CountLaunch();
+  return CheckLaunch("radii");
+}
+
+}  // namespace smb

@@ -1,0 +1,201 @@
+// regularize.cu — surfel regularisation for sm_100a (SURVEY §8 a14 + the second half of a12).
+//
+// Replaces RegularizeSurfelsCUDA (APP/cuda_surfel_reconstruction_kernels.cu:2099-2410: Clear,
+// Accumulate, Step, Update = 4 sweeps over all slots) and
+// UpdateNeighborsCUDARemoveReplacedNeighborsKernel (:1420-1437, a 5th sweep) by 3 sweeps:
+//
+//   k_reg_accumulate : [drop neighbour links to surfels with the detach flag] + Accumulate
+//   k_reg_step       : gradient step, staged in the gradient rows (:2197-2290)
+//   k_reg_update     : smooth <- staged, and the gradient rows / weight row are reset to zero
+//
+// Invariant that makes the Clear sweep unnecessary: rows 11-13 and 23 are zero between calls
+// (new surfels are created with zeros, Accumulate only adds into surfels inside the
+// regularisation window, and exactly those are reset by k_reg_update).
+// Float atomics make the accumulated gradients order-dependent, as in the reference.
+
+#include "sm_kernels.cuh"
+
+namespace smb {
+
+namespace {
+
+#define SM_S(row, i) d.surfels[static_cast<size_t>(row) * d.stride + (i)]
+#define SM_SU(row, i) reinterpret_cast<u32*>(d.surfels)[static_cast<size_t>(row) * d.stride + (i)]
+
+constexpr int kBlock = 256;
+
+struct RegParams {
+  u32 frame_index;
+  int window;                 // regularization_frame_window_size
+  float radius_factor_squared;
+  float regularizer_weight;
+  int count_slot;
+  int remove_below_slot;      // -1: no detach-flag pass
+};
+
+// `stamp < frame_index - window` evaluated like the reference: the subtraction in u32, the
+// comparison in int (kernels.cu:2132,2206).
+__device__ __forceinline__ bool outside_window(u32 stamp, const RegParams& p) {
+  return static_cast<int>(stamp) < static_cast<int>(p.frame_index - static_cast<u32>(p.window));
+}
+
+__global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegParams p) {
+  const u32 n = d.counters->surfel_count[p.count_slot];
+  const u32 n_remove = p.remove_below_slot >= 0 ? d.counters->surfel_count[p.remove_below_slot] : 0u;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    u32 nbr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nbr[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
+
+    if (i < n_remove) {
+      // UpdateNeighborsCUDARemoveReplacedNeighborsKernel (kernels.cu:1420-1437).
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (nbr[k] != kInvalidIndex && (SM_SU(SM_ROW_COLOR, nbr[k]) >> 24) == 1u) {
+          nbr[k] = kInvalidIndex;
+          SM_SU(SM_ROW_NEIGHBOR0 + k, i) = kInvalidIndex;
+        }
+      }
+    }
+
+    // Count neighbours inside the window (kernels.cu:2125-2139).
+    bool use[4];
+    int neighbor_count = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      use[k] = nbr[k] != kInvalidIndex && !outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, nbr[k]), p);
+      neighbor_count += use[k] ? 1 : 0;
+    }
+    if (neighbor_count == 0) continue;
+
+    const float sx = SM_S(SM_ROW_SMOOTH_X, i), sy = SM_S(SM_ROW_SMOOTH_Y, i), sz = SM_S(SM_ROW_SMOOTH_Z, i);
+    const float nx = SM_S(SM_ROW_NORMAL_X, i), ny = SM_S(SM_ROW_NORMAL_Y, i), nz = SM_S(SM_ROW_NORMAL_Z, i);
+    const float max_distance_squared = fmul(SM_S(SM_ROW_RADIUS_SQUARED, i), p.radius_factor_squared);
+    const float rcp_count = frcp(i2f(neighbor_count));
+    const float factor = fmul(fadd(p.regularizer_weight, p.regularizer_weight), rcp_count);  // 2 * w / count
+    const float weight_term = fmul(rcp_count, p.regularizer_weight);                         // w / count
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!use[k]) continue;
+      const u32 q = nbr[k];
+      const float dx = fsub(SM_S(SM_ROW_SMOOTH_X, q), sx);
+      const float dy = fsub(SM_S(SM_ROW_SMOOTH_Y, q), sy);
+      const float dz = fsub(SM_S(SM_ROW_SMOOTH_Z, q), sz);
+      const float f = fmul(factor, ffma(nz, dz, ffma(nx, dx, fmul(ny, dy))));
+      atomicAdd(&SM_S(SM_ROW_GRADIENT_X, q), fmul(nx, f));
+      atomicAdd(&SM_S(SM_ROW_GRADIENT_Y, q), fmul(ny, f));
+      atomicAdd(&SM_S(SM_ROW_GRADIENT_Z, q), fmul(nz, f));
+      atomicAdd(&SM_S(SM_ROW_GRADIENT_COUNT, q), weight_term);
+      // If the neighbour is too far away, remove it (kernels.cu:2184-2192).
+      if (squared_norm(dx, dy, dz) > max_distance_squared) SM_SU(SM_ROW_NEIGHBOR0 + k, i) = kInvalidIndex;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p) {
+  const u32 n = d.counters->surfel_count[p.count_slot];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
+    const float sx = SM_S(SM_ROW_SMOOTH_X, i), sy = SM_S(SM_ROW_SMOOTH_Y, i), sz = SM_S(SM_ROW_SMOOTH_Z, i);
+    const float nx = SM_S(SM_ROW_NORMAL_X, i), ny = SM_S(SM_ROW_NORMAL_Y, i), nz = SM_S(SM_ROW_NORMAL_Z, i);
+    // Data term (factor 2) + neighbour-induced terms.
+    float gx = ffma(fsub(sx, SM_S(SM_ROW_X, i)), 2.0f, SM_S(SM_ROW_GRADIENT_X, i));
+    float gy = ffma(fsub(sy, SM_S(SM_ROW_Y, i)), 2.0f, SM_S(SM_ROW_GRADIENT_Y, i));
+    float gz = ffma(fsub(sz, SM_S(SM_ROW_Z, i)), 2.0f, SM_S(SM_ROW_GRADIENT_Z, i));
+    int neighbor_count = 0;
+    float rx = 0.f, ry = 0.f, rz = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const u32 q = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
+      if (q == kInvalidIndex) continue;
+      ++neighbor_count;
+      const float dx = fsub(SM_S(SM_ROW_SMOOTH_X, q), sx);
+      const float dy = fsub(SM_S(SM_ROW_SMOOTH_Y, q), sy);
+      const float dz = fsub(SM_S(SM_ROW_SMOOTH_Z, q), sz);
+      const float normal_dot_difference = ffma(nz, dz, ffma(nx, dx, fmul(ny, dy)));
+      rx = ffma(-nx, normal_dot_difference, rx);
+      ry = ffma(-ny, normal_dot_difference, ry);
+      rz = ffma(-nz, normal_dot_difference, rz);
+    }
+    if (neighbor_count > 0) {
+      const float factor = fmul(fadd(p.regularizer_weight, p.regularizer_weight), frcp(i2f(neighbor_count)));
+      gx = ffma(factor, rx, gx);
+      gy = ffma(factor, ry, gy);
+      gz = ffma(factor, rz, gz);
+    }
+    const float gradient_length = fsqrt_approx(ffma(gz, gz, ffma(gx, gx, fmul(gy, gy))));
+    const float residual_terms_weight_sum = fadd(fadd(p.regularizer_weight, 1.0f), SM_S(SM_ROW_GRADIENT_COUNT, i));
+    float step_factor = fmul(frcp(residual_terms_weight_sum), 0.5f);
+    const float max_step_length = fsqrt_approx(SM_S(SM_ROW_RADIUS_SQUARED, i));
+    const float step_length = fmul(step_factor, gradient_length);
+    if (step_length > max_step_length) step_factor = fmul(step_factor, fmul(max_step_length, frcp(step_length)));
+    // Staged in the gradient rows; k_reg_update moves it to the smooth position.
+    SM_S(SM_ROW_GRADIENT_X, i) = ffma(step_factor, -gx, sx);
+    SM_S(SM_ROW_GRADIENT_Y, i) = ffma(step_factor, -gy, sy);
+    SM_S(SM_ROW_GRADIENT_Z, i) = ffma(step_factor, -gz, sz);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_reg_update(DeviceState d, RegParams p) {
+  const u32 n = d.counters->surfel_count[p.count_slot];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
+    SM_S(SM_ROW_SMOOTH_X, i) = SM_S(SM_ROW_GRADIENT_X, i);
+    SM_S(SM_ROW_SMOOTH_Y, i) = SM_S(SM_ROW_GRADIENT_Y, i);
+    SM_S(SM_ROW_SMOOTH_Z, i) = SM_S(SM_ROW_GRADIENT_Z, i);
+    SM_S(SM_ROW_GRADIENT_X, i) = 0.f;
+    SM_S(SM_ROW_GRADIENT_Y, i) = 0.f;
+    SM_S(SM_ROW_GRADIENT_Z, i) = 0.f;
+    SM_S(SM_ROW_GRADIENT_COUNT, i) = 0.f;
+  }
+}
+
+// RegularizeSurfelsCUDACopyOnlyKernel (kernels.cu:2310-2327) [+ detach-flag pass].
+__global__ void __launch_bounds__(kBlock) k_reg_copy_only(DeviceState d, RegParams p) {
+  const u32 n = d.counters->surfel_count[p.count_slot];
+  const u32 n_remove = p.remove_below_slot >= 0 ? d.counters->surfel_count[p.remove_below_slot] : 0u;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < n_remove) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const u32 q = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
+        if (q != kInvalidIndex && (SM_SU(SM_ROW_COLOR, q) >> 24) == 1u) SM_SU(SM_ROW_NEIGHBOR0 + k, i) = kInvalidIndex;
+      }
+    }
+    if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
+    SM_S(SM_ROW_SMOOTH_X, i) = SM_S(SM_ROW_X, i);
+    SM_S(SM_ROW_SMOOTH_Y, i) = SM_S(SM_ROW_Y, i);
+    SM_S(SM_ROW_SMOOTH_Z, i) = SM_S(SM_ROW_Z, i);
+  }
+}
+
+}  // namespace
+
+int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_denoising, u32 frame_index,
+                      float radius_factor_for_regularization_neighbors, float regularizer_weight,
+                      int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot,
+                      int sm_count) {
+  RegParams p;
+  p.frame_index = frame_index;
+  p.window = regularization_frame_window_size;
+  p.radius_factor_squared =
+      radius_factor_for_regularization_neighbors * radius_factor_for_regularization_neighbors;  // kernels.cu:2379
+  p.regularizer_weight = regularizer_weight;
+  p.count_slot = count_slot;
+  p.remove_below_slot = remove_replaced_below_slot;
+  const int grid = sm_count * 8;
+  if (disable_denoising) {
+    k_reg_copy_only<<<grid, kBlock, 0, stream>>>(d, p);
+    CountLaunch();
+    return CheckLaunch("regularize (copy only)");
+  }
+  k_reg_accumulate<<<grid, kBlock, 0, stream>>>(d, p);
+  CountLaunch();
+  k_reg_step<<<grid, kBlock, 0, stream>>>(d, p);
+  CountLaunch();
+  k_reg_update<<<grid, kBlock, 0, stream>>>(d, p);
+  CountLaunch();
+  return CheckLaunch("regularize");
+}
+
+}  // namespace smb

@@ -1,0 +1,137 @@
+// sm_kernels.cuh — declarations shared by the translation units of libsurfel_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/surfel_b200.h"
+#include "sm_math.cuh"
+
+namespace smb {
+
+// ---- error / bookkeeping (api.cu) ---------------------------------------------------------
+int SetError(int code, const char* message);
+int CheckLaunch(const char* what);   // cudaGetLastError() -> SM_OK / SM_ERR_CUDA
+void CountLaunch();                  // kernels launched by this library (sm_kernel_launch_count)
+
+inline Mat3x4 MakeMat3x4(const float* m) {
+  Mat3x4 r;
+  r.r0 = make_float4(m[0], m[1], m[2], m[3]);
+  r.r1 = make_float4(m[4], m[5], m[6], m[7]);
+  r.r2 = make_float4(m[8], m[9], m[10], m[11]);
+  return r;
+}
+
+// ---- device-side state shared by the Integrate kernels -------------------------------------
+
+constexpr u32 kInvalidIndex = 0xFFFFFFFFu;   // APP/surfel.h:63, kernels.cu:74
+constexpr int kSegment = 1024;               // surfel slots per list segment (one block-iteration)
+constexpr u32 kActiveBit = 0x80000000u;      // VisEntry.idx: surfel was active at projection time
+
+// Per-pixel association record (the reference keeps four separate rasters,
+// APP/cuda_surfel_reconstruction.h:138-142): one 128-bit load/store per pixel.
+//   x = supporting surfel, y = conflicting surfel, z = supporting count, w = depth sum (fp32 bits)
+typedef uint4 PixelAssoc;
+
+// Entry of the per-frame list of surfels that project into the image (z > 0, inside the
+// image): surfel index (| kActiveBit) and camera-space position. Segment s owns list
+// positions [s * kSegment, s * kSegment + seg_count[s]) and holds, in slot order, the visible
+// surfels of slots [s * kSegment, (s + 1) * kSegment): the list needs no global atomic and
+// is deterministic.
+typedef uint4 VisEntry;
+
+struct Counters {
+  u32 surfel_count[2];   // entries in use; [parity] is current, the scan of frame f writes [parity ^ 1]
+  u32 merge_count;
+  u32 new_surfel_count;  // of the last frame
+  u32 capacity_overflow; // sticky: a frame wanted more surfels than the cap (creation skipped)
+  u32 scan_ticket;       // dynamic tile ids of the new-surfel scan
+  u32 pad[2];
+};
+
+struct DeviceState {
+  // surfel SoA: row r, surfel i -> surfels[r * stride + i]
+  float* surfels;
+  size_t stride;         // elements per row (multiple of 64)
+  u32 capacity;
+  int width, height;
+  PixelAssoc* assoc;     // W*H
+  float* first_depth;    // W*H
+  VisEntry* vis;         // capacity (rounded up to kSegment)
+  u32* seg_count;        // capacity / kSegment
+  u8* merge_flag;        // per list position
+  u8* new_flag;          // W*H
+  u32* new_index;        // W*H
+  unsigned long long* scan_state;  // per scan tile: status << 32 | value
+  Counters* counters;
+};
+
+struct FrameParams {
+  u32 frame_index;
+  int parity;            // which Counters::surfel_count slot is current
+  int active_window;     // surfel_integration_active_window_size
+  float fx, fy, cx, cy;
+  float fx_inv, fy_inv, cx_inv, cy_inv;  // pixel-centre unprojection, kernels.cc:68-74
+  float sensor_noise_factor;
+  float cos_normal_compatibility_threshold;
+  float max_surfel_confidence;
+  float depth_scaling;
+  float inv_depth_scaling;               // 1.0f / depth_scaling (depth_correction_factor)
+  float radius_factor_squared;           // radius_factor_for_regularization_neighbors^2
+  int blend_radius;
+  Mat3x4 local_T_global;
+  Mat3x4 global_T_local;
+  // input rasters
+  u16* depth; size_t depth_pitch;
+  const float2* normals; size_t normals_pitch;
+  const float* radius; size_t radius_pitch;
+  const uchar3* color; size_t color_pitch;
+};
+
+// ---- preprocess.cu --------------------------------------------------------------------------
+int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int width, int height, float fx, float fy,
+                    float cx, float cy, const u16* raw, size_t raw_pitch, const u16* const* other_depths,
+                    const size_t* other_pitches, const float* others_TR_reference, u16* scratch_B,
+                    size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch, float2* out_normals,
+                    size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
+                    float* clear_first_depth);
+int StageBilateral(cudaStream_t stream, float sigma_xy, float sigma_value_factor, u16 value_to_ignore,
+                   float radius_factor, u16 max_depth, float depth_valid_region_radius, int width, int height,
+                   const u16* in, size_t in_pitch, u16* out, size_t out_pitch);
+int StageOutlier(cudaStream_t stream, int other_count, int required_count, float tolerance, float fx, float fy,
+                 float cx, float cy, int width, int height, const u16* in, size_t in_pitch,
+                 const u16* const* other_depths, const size_t* other_pitches, const float* others_TR_reference,
+                 u16* out, size_t out_pitch);
+int StageErode(cudaStream_t stream, int radius, int width, int height, const u16* in, size_t in_pitch, u16* out,
+               size_t out_pitch);
+int StageNormals(cudaStream_t stream, float observation_angle_threshold_deg, float depth_scaling, float fx, float fy,
+                 float cx, float cy, int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch,
+                 float2* normals, size_t normals_pitch);
+int StageRadii(cudaStream_t stream, float point_radius_extension_factor, float point_radius_clamp_factor,
+               float depth_scaling, float fx, float fy, float cx, float cy, int width, int height, const u16* in,
+               size_t in_pitch, float* radius, size_t radius_pitch, u16* out, size_t out_pitch);
+
+// ---- integrate.cu ---------------------------------------------------------------------------
+struct IntegrateEvents {
+  cudaEvent_t ev[14];
+  bool enabled;
+};
+int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams& f, bool do_blending,
+                   bool rasters_already_cleared, int sm_count, const IntegrateEvents* events);
+int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d);
+int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm_count, float* position_buffer,
+                   u8* color_buffer);
+
+// ---- regularize.cu --------------------------------------------------------------------------
+// `count_slot`: which Counters::surfel_count slot holds the surfel count to regularise.
+// `remove_replaced_below`: if >= 0, slot of the surfel count below which neighbour links to
+// surfels with the detach flag are dropped first (UpdateNeighborsCUDARemoveReplacedNeighbors
+// fused into the first sweep); -1 = no removal.
+int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_denoising, u32 frame_index,
+                      float radius_factor_for_regularization_neighbors, float regularizer_weight,
+                      int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot,
+                      int sm_count);
+
+}  // namespace smb
