@@ -274,6 +274,20 @@ int sm_stream_run(sm_reconstruction* r, void* stream, const sm_stream_desc* s,
 /* Number of kernel launches issued by this library since load (all handles). */
 uint64_t sm_kernel_launch_count(void);
 
+/* Per-kernel device timing for the roofline report of bench.py: while enabled, every kernel
+ * launch of the library is bracketed by CUDA events on its launching stream.
+ * sm_profile_report synchronises the device and returns, per kernel id, the accumulated
+ * elapsed milliseconds and the launch count since the last report. Never enabled inside a
+ * timed throughput region (the extra events serialise the launches). */
+int sm_profile_kernels(int32_t enable);
+int32_t sm_profile_kernel_count(void);
+const char* sm_profile_kernel_name(int32_t id);
+int sm_profile_report(double* total_ms, uint64_t* launches, int32_t n);
+
+/* Work counters of the last Integrate(): surfel slots swept (N), surfels that projected
+ * into the image (V), sum of the supporting counts (S), new surfels (M). Synchronises. */
+int sm_frame_counters(sm_reconstruction* r, void* stream, uint64_t out[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,6 +130,11 @@ _PRODUCT_ONLY = {
     "default_integrate_params": (None, [C.POINTER(IntegrateParams)]),
     "default_preprocess_params": (None, [C.POINTER(PreprocessParams)]),
     "kernel_launch_count": (C.c_uint64, []),
+    "profile_kernels": (C.c_int, [_I]),
+    "profile_kernel_count": (_I, []),
+    "profile_kernel_name": (C.c_char_p, [_I]),
+    "profile_report": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), _I]),
+    "frame_counters": (C.c_int, [_P, _P, C.POINTER(C.c_uint64 * 4)]),
 }
 
 EXPORTED_SYMBOLS = sorted(["sm_" + n for n in list(_SIGNATURES) + list(_PRODUCT_ONLY)])

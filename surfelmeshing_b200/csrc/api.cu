@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -32,7 +33,48 @@ int CheckLaunch(const char* what) {
   return SM_ERR_CUDA;
 }
 
-void CountLaunch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+namespace {
+// Per-kernel profiling (sm_profile_kernels): event pairs recorded around every launch.
+struct ProfileRecord { cudaEvent_t start, stop; int id; };
+std::mutex g_profile_mutex;
+bool g_profile_enabled = false;
+std::vector<ProfileRecord> g_profile_records;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t TakeEvent() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+const char* KernelName(int id) {
+  static const char* names[KID_COUNT] = {
+      "k_clear", "k_bilateral_outlier", "k_bilateral_generic", "k_outlier", "k_erode_normals_radii", "k_erode",
+      "k_normals", "k_radii", "k_project", "k_associate", "k_merge", "k_blend", "k_integrate", "k_update_neighbors",
+      "k_new_surfel_scan", "k_create_surfels", "k_reg_accumulate", "k_reg_step", "k_reg_update", "k_reg_copy_only",
+      "k_export_vertices"};
+  return (id >= 0 && id < KID_COUNT) ? names[id] : "?";
+}
+
+LaunchScope::LaunchScope(cudaStream_t stream, KernelId id) : stream_(stream), slot_(-1) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_profile_enabled) {
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    ProfileRecord r{TakeEvent(), TakeEvent(), static_cast<int>(id)};
+    cudaEventRecord(r.start, stream_);
+    slot_ = static_cast<int>(g_profile_records.size());
+    g_profile_records.push_back(r);
+  }
+}
+
+LaunchScope::~LaunchScope() {
+  if (slot_ >= 0) {
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    cudaEventRecord(g_profile_records[slot_].stop, stream_);
+  }
+}
 
 }  // namespace smb
 
@@ -213,6 +255,32 @@ void sm_default_preprocess_params(sm_preprocess_params* p) {
 const char* sm_last_error(void) { return g_last_error.c_str(); }
 const char* sm_version(void) { return "surfel_b200 0.1 (sm_100a)"; }
 uint64_t sm_kernel_launch_count(void) { return g_launches.load(); }
+
+int sm_profile_kernels(int32_t enable) {
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
+  g_profile_enabled = enable != 0;
+  return SM_OK;
+}
+
+int32_t sm_profile_kernel_count(void) { return KID_COUNT; }
+const char* sm_profile_kernel_name(int32_t id) { return KernelName(id); }
+
+int sm_profile_report(double* total_ms, uint64_t* launches, int32_t n) {
+  SM_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
+  for (int i = 0; i < n; ++i) { total_ms[i] = 0; launches[i] = 0; }
+  for (const ProfileRecord& r : g_profile_records) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess && r.id < n) {
+      total_ms[r.id] += ms;
+      launches[r.id] += 1;
+    }
+    g_event_pool.push_back(r.start);
+    g_event_pool.push_back(r.stop);
+  }
+  g_profile_records.clear();
+  return SM_OK;
+}
 
 int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width, int32_t height, float fx, float fy,
               float cx, float cy) {
@@ -463,12 +531,32 @@ int sm_download_rasters(sm_reconstruction* r, void* stream_v, uint32_t* supporti
     SM_CUDA(cudaMemcpyAsync(new_surfel_indices, r->d.new_index, sizeof(u32) * P, cudaMemcpyDeviceToHost, stream));
   SM_CUDA(cudaStreamSynchronize(stream));
   for (size_t i = 0; i < P; ++i) {
-    if (supporting_surfels) supporting_surfels[i] = assoc[i].x;
+    if (supporting_surfels) supporting_surfels[i] = supporting_index(assoc[i].x);
     if (conflicting_surfels) conflicting_surfels[i] = assoc[i].y;
     if (supporting_surfel_counts) supporting_surfel_counts[i] = assoc[i].z;
     if (supporting_surfel_depth_sums) std::memcpy(&supporting_surfel_depth_sums[i], &assoc[i].w, sizeof(float));
   }
   return SM_OK;
+}
+
+int sm_frame_counters(sm_reconstruction* r, void* stream_v, uint64_t out[4]) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int status = FetchCounters(r, stream);
+  // The last Integrate() swept the slots that existed before its new surfels were appended.
+  const u32 n_after = r->host_counters->surfel_count[r->parity];
+  const u32 n_swept = n_after - r->host_counters->new_surfel_count;
+  const size_t segments = (static_cast<size_t>(n_swept) + kSegment - 1) / kSegment;
+  std::vector<u32> seg(segments);
+  if (segments) SM_CUDA(cudaMemcpy(seg.data(), r->d.seg_count, sizeof(u32) * segments, cudaMemcpyDeviceToHost));
+  uint64_t visible = 0;
+  for (u32 c : seg) visible += c;
+  const size_t P = static_cast<size_t>(r->d.width) * r->d.height;
+  std::vector<PixelAssoc> assoc(P);
+  SM_CUDA(cudaMemcpy(assoc.data(), r->d.assoc, sizeof(PixelAssoc) * P, cudaMemcpyDeviceToHost));
+  uint64_t support = 0;
+  for (const PixelAssoc& a : assoc) support += a.z;
+  out[0] = n_swept; out[1] = visible; out[2] = support; out[3] = r->host_counters->new_surfel_count;
+  return status;
 }
 
 // The frame loop of APP/main.cc:885-1223 on a synthetic stream.

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kBlock) k_project(DeviceState d, FrameParams f
   for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
     const u32 base = seg * kSegment + threadIdx.x * 4;
     VisEntry e[4];
+    bool visible[4] = {false, false, false, false};
     int cnt = 0;
     if (base < n) {
       const float4 X = *reinterpret_cast<const float4*>(&SM_S(SM_ROW_X, base));
@@ -144,8 +145,9 @@ __global__ void __launch_bounds__(kBlock) k_project(DeviceState d, FrameParams f
         const Projection p = project(f, d.width, d.height, x, y, z);
         if (!p.in_image) continue;
         const bool active = is_active(ts[j], f.frame_index, f.active_window);
-        e[cnt++] = make_uint4(i | (active ? kActiveBit : 0u), __float_as_uint(x), __float_as_uint(y),
-                              __float_as_uint(z));
+        e[j] = make_uint4(i | (active ? kActiveBit : 0u), __float_as_uint(x), __float_as_uint(y), __float_as_uint(z));
+        visible[j] = true;
+        ++cnt;
         if (active) {
           // RenderMinDepthAtPixel (kernels.cu:1458-1464): int-punned atomicMin, positive floats.
           atomicMin(reinterpret_cast<int*>(&d.first_depth[p.py * d.width + p.px]), __float_as_int(z));
@@ -173,7 +175,10 @@ __global__ void __launch_bounds__(kBlock) k_project(DeviceState d, FrameParams f
       total += t;
     }
     VisEntry* out = d.vis + static_cast<size_t>(seg) * kSegment + warp_base + (incl - cnt);
-    for (int k = 0; k < cnt; ++k) out[k] = e[k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (visible[j]) *out++ = e[j];
+    }
     if (threadIdx.x == 0) d.seg_count[seg] = total;
     __syncthreads();
   }
@@ -212,12 +217,16 @@ __device__ __forceinline__ bool supports_surfel(const DeviceState& d, const Fram
 }
 
 __device__ __forceinline__ void consider_association(const DeviceState& d, const FrameParams& f, int x, int y,
-                                                     u32 idx, float cx_, float cy_, float cz_) {
+                                                     u32 idx, float cx_, float cy_, float cz_, bool secondary) {
   if (!supports_surfel(d, f, x, y, idx, cx_, cy_, cz_)) return;
   const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
   if (!(surfel_radius_squared > 0.f)) return;
   PixelAssoc* a = &d.assoc[y * d.width + x];
-  atomicMin(&a->x, idx);                                      // reference: atomicCAS(INV -> idx), first come
+  // Reference: atomicCAS(INV -> idx), first come wins. Every thread of the reference kernel
+  // handles its primary pixel before its secondary pixel, so primary associations typically
+  // arrive first; the deterministic rule here is "primary before secondary, then lowest
+  // index" (kSecondaryBit orders the keys), which is one of the reference's legal outcomes.
+  atomicMin(&a->x, idx | (secondary ? kSecondaryBit : 0u));
   atomicAdd(&a->z, 1u);
   atomicAdd(reinterpret_cast<float*>(&a->w), cz_);
 }
@@ -233,9 +242,9 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
       const u32 idx = e.x & ~kActiveBit;
       const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
       const Projection p = project(f, d.width, d.height, x, y, z);
-      consider_association(d, f, p.px, p.py, idx, x, y, z);
+      consider_association(d, f, p.px, p.py, idx, x, y, z, false);
       int ox, oy;
-      if (secondary_pixel(p, d.width, d.height, &ox, &oy)) consider_association(d, f, ox, oy, idx, x, y, z);
+      if (secondary_pixel(p, d.width, d.height, &ox, &oy)) consider_association(d, f, ox, oy, idx, x, y, z, true);
     }
   }
 }
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
 __device__ __forceinline__ bool consider_merge(const DeviceState& d, const FrameParams& f, int x, int y, u32 idx,
                                                float cx_, float cy_, float cz_, float surfel_radius_squared) {
   if (!supports_surfel(d, f, x, y, idx, cx_, cy_, cz_)) return false;
-  const u32 supported_surfel = d.assoc[y * d.width + x].x;
+  const u32 supported_surfel = supporting_index(d.assoc[y * d.width + x].x);
   if (supported_surfel == idx || supported_surfel == kInvalidIndex) return false;
   // kernels.cu:1955-1984.
   const float other_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, supported_surfel);
@@ -608,7 +617,7 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
       const int kDirectionsY[4] = {0, 0, -1, 1};
 #pragma unroll
       for (int direction = 0; direction < 4; ++direction) {
-        const u32 q = d.assoc[(y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction]].x;
+        const u32 q = supporting_index(d.assoc[(y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction]].x);
         if (q == kInvalidIndex || q == idx) continue;
         const float distance_squared = squared_norm(fsub(SM_S(SM_ROW_X, q), gx), fsub(SM_S(SM_ROW_Y, q), gy),
                                                     fsub(SM_S(SM_ROW_Z, q), gz));
@@ -768,7 +777,7 @@ __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameP
     for (int direction = 0; direction < 4; ++direction) {
       const int nx_ = x + kDirectionsX[direction], ny_ = y + kDirectionsY[direction];
       const int nseq = ny_ * d.width + nx_;
-      u32 neighbor_index = d.assoc[nseq].x;
+      u32 neighbor_index = supporting_index(d.assoc[nseq].x);
       if (neighbor_index != kInvalidIndex) {
         const float distance_squared =
             squared_norm(fsub(SM_S(SM_ROW_X, neighbor_index), g.x), fsub(SM_S(SM_ROW_Y, neighbor_index), g.y),
@@ -815,8 +824,7 @@ __global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int p
 
 int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d) {
   const int blocks = (d.width * d.height + kBlock * 4 - 1) / (kBlock * 4);
-  k_clear<<<blocks, kBlock, 0, stream>>>(d);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_CLEAR); k_clear<<<blocks, kBlock, 0, stream>>>(d); }
   return CheckLaunch("clear");
 }
 
@@ -833,13 +841,10 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
     const int status = ClearAssociationRasters(stream, d);
     if (status != SM_OK) return status;
   }
-  k_project<<<list_grid, kBlock, 0, stream>>>(d, f);
-  CountLaunch();
-  k_associate<<<list_grid, kBlock, 0, stream>>>(d, f);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_PROJECT); k_project<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_ASSOCIATE); k_associate<<<list_grid, kBlock, 0, stream>>>(d, f); }
   record(1); record(2);
-  k_merge<<<list_grid, kBlock, 0, stream>>>(d, f);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_MERGE); k_merge<<<list_grid, kBlock, 0, stream>>>(d, f); }
   record(3); record(4);
   if (do_blending) {
     const int halo = f.blend_radius - 1 > 1 ? f.blend_radius - 1 : 1;
@@ -852,28 +857,22 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
         return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend)");
       configured_smem = smem;
     }
-    k_blend<<<pixel_tiles, 512, smem, stream>>>(d, f);
-    CountLaunch();
+    { LaunchScope scope(stream, KID_BLEND); k_blend<<<pixel_tiles, 512, smem, stream>>>(d, f); }
   }
   record(5); record(6);
-  k_integrate<<<list_grid, kBlock, 0, stream>>>(d, f);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_INTEGRATE); k_integrate<<<list_grid, kBlock, 0, stream>>>(d, f); }
   record(7); record(8);
-  k_update_neighbors<<<list_grid, kBlock, 0, stream>>>(d, f);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_UPDATE_NEIGHBORS); k_update_neighbors<<<list_grid, kBlock, 0, stream>>>(d, f); }
   record(9); record(10);
-  k_new_surfel_scan<<<scan_tiles, kBlock, 0, stream>>>(d, f);
-  CountLaunch();
-  k_create_surfels<<<(d.width * d.height + kBlock - 1) / kBlock, kBlock, 0, stream>>>(d, f);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_NEW_SURFEL_SCAN); k_new_surfel_scan<<<scan_tiles, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_CREATE_SURFELS); k_create_surfels<<<(d.width * d.height + kBlock - 1) / kBlock, kBlock, 0, stream>>>(d, f); }
   record(11);
   return CheckLaunch("integrate");
 }
 
 int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm_count, float* position_buffer,
                    u8* color_buffer) {
-  k_export_vertices<<<sm_count * 8, kBlock, 0, stream>>>(d, parity, position_buffer, color_buffer);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_EXPORT_VERTICES); k_export_vertices<<<sm_count * 8, kBlock, 0, stream>>>(d, parity, position_buffer, color_buffer); }
   return CheckLaunch("export vertices");
 }
 

@@ -636,16 +636,14 @@ dim3 PixelGrid(int width, int height) { return dim3((width + 31) / 32, (height +
 int LaunchBilateral(cudaStream_t stream, const BilateralArgs& a, const OutlierArgs* o, u16* out, size_t out_pitch) {
   static const OutlierArgs kNoOutlier = {};
   if (a.radius == 6) {
+    LaunchScope scope(stream, KID_BILATERAL_OUTLIER);
     if (o) k_bilateral_outlier<6, true><<<TileGrid(a.width, a.height), 256, 0, stream>>>(a, *o, out, out_pitch);
     else k_bilateral_outlier<6, false><<<TileGrid(a.width, a.height), 256, 0, stream>>>(a, kNoOutlier, out, out_pitch);
-    CountLaunch();
   } else {
     if (a.radius < 0) return SetError(SM_ERR_INVALID_ARGUMENT, "negative bilateral radius");
-    k_bilateral_generic<<<PixelGrid(a.width, a.height), 256, 0, stream>>>(a, out, out_pitch);
-    CountLaunch();
+    { LaunchScope scope(stream, KID_BILATERAL_GENERIC); k_bilateral_generic<<<PixelGrid(a.width, a.height), 256, 0, stream>>>(a, out, out_pitch); }
     if (o) {
-      k_outlier<<<PixelGrid(a.width, a.height), 256, 0, stream>>>(*o, out, out_pitch, out, out_pitch);
-      CountLaunch();
+      { LaunchScope scope(stream, KID_OUTLIER); k_outlier<<<PixelGrid(a.width, a.height), 256, 0, stream>>>(*o, out, out_pitch, out, out_pitch); }
     }
   }
   return CheckLaunch("bilateral/outlier");
@@ -686,8 +684,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
   t.out_normals = out_normals; t.out_normals_pitch = out_normals_pitch;
   t.out_radius = out_radius; t.out_radius_pitch = out_radius_pitch;
   t.assoc = clear_assoc; t.first_depth = clear_first_depth;
-  k_erode_normals_radii<<<TileGrid(width, height), 512, 0, stream>>>(t);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_ERODE_NORMALS_RADII); k_erode_normals_radii<<<TileGrid(width, height), 512, 0, stream>>>(t); }
   return CheckLaunch("erode/normals/radii");
 }
 
@@ -707,36 +704,32 @@ int StageOutlier(cudaStream_t stream, int other_count, int required_count, float
   const int status = MakeOutlierArgs(&o, other_count, required_count, tolerance, fx, fy, cx, cy, width, height,
                                      other_depths, other_pitches, others_TR_reference);
   if (status != SM_OK) return status;
-  k_outlier<<<PixelGrid(width, height), 256, 0, stream>>>(o, in, in_pitch, out, out_pitch);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_OUTLIER); k_outlier<<<PixelGrid(width, height), 256, 0, stream>>>(o, in, in_pitch, out, out_pitch); }
   return CheckLaunch("outlier");
 }
 
 int StageErode(cudaStream_t stream, int radius, int width, int height, const u16* in, size_t in_pitch, u16* out,
                size_t out_pitch) {
   if (radius < 0 || radius > kMaxErode) return SetError(SM_ERR_INVALID_ARGUMENT, "radius value is not supported");
-  k_erode<<<PixelGrid(width, height), 256, 0, stream>>>(radius, width, height, in, in_pitch, out, out_pitch);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_ERODE); k_erode<<<PixelGrid(width, height), 256, 0, stream>>>(radius, width, height, in, in_pitch, out, out_pitch); }
   return CheckLaunch("erode");
 }
 
 int StageNormals(cudaStream_t stream, float observation_angle_threshold_deg, float depth_scaling, float fx, float fy,
                  float cx, float cy, int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch,
                  float2* normals, size_t normals_pitch) {
-  k_normals<<<PixelGrid(width, height), 256, 0, stream>>>(
+  { LaunchScope scope(stream, KID_NORMALS); k_normals<<<PixelGrid(width, height), 256, 0, stream>>>(
       MakeNormalsArgs(observation_angle_threshold_deg, depth_scaling, fx, fy, cx, cy), width, height, in, in_pitch, out,
-      out_pitch, normals, normals_pitch);
-  CountLaunch();
+      out_pitch, normals, normals_pitch); }
   return CheckLaunch("normals");
 }
 
 int StageRadii(cudaStream_t stream, float point_radius_extension_factor, float point_radius_clamp_factor,
                float depth_scaling, float fx, float fy, float cx, float cy, int width, int height, const u16* in,
                size_t in_pitch, float* radius, size_t radius_pitch, u16* out, size_t out_pitch) {
-  k_radii<<<PixelGrid(width, height), 256, 0, stream>>>(
+  { LaunchScope scope(stream, KID_RADII); k_radii<<<PixelGrid(width, height), 256, 0, stream>>>(
       MakeRadiiArgs(point_radius_extension_factor, point_radius_clamp_factor, depth_scaling, fx, fy, cx, cy), width,
-      height, in, in_pitch, radius, radius_pitch, out, out_pitch);
-  CountLaunch();
+      height, in, in_pitch, radius, radius_pitch, out, out_pitch); }
   return CheckLaunch("radii");
 }
 

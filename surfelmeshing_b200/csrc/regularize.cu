@@ -185,16 +185,12 @@ int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_de
   p.remove_below_slot = remove_replaced_below_slot;
   const int grid = sm_count * 8;
   if (disable_denoising) {
-    k_reg_copy_only<<<grid, kBlock, 0, stream>>>(d, p);
-    CountLaunch();
+    { LaunchScope scope(stream, KID_REG_COPY_ONLY); k_reg_copy_only<<<grid, kBlock, 0, stream>>>(d, p); }
     return CheckLaunch("regularize (copy only)");
   }
-  k_reg_accumulate<<<grid, kBlock, 0, stream>>>(d, p);
-  CountLaunch();
-  k_reg_step<<<grid, kBlock, 0, stream>>>(d, p);
-  CountLaunch();
-  k_reg_update<<<grid, kBlock, 0, stream>>>(d, p);
-  CountLaunch();
+  { LaunchScope scope(stream, KID_REG_ACCUMULATE); k_reg_accumulate<<<grid, kBlock, 0, stream>>>(d, p); }
+  { LaunchScope scope(stream, KID_REG_STEP); k_reg_step<<<grid, kBlock, 0, stream>>>(d, p); }
+  { LaunchScope scope(stream, KID_REG_UPDATE); k_reg_update<<<grid, kBlock, 0, stream>>>(d, p); }
   return CheckLaunch("regularize");
 }
 

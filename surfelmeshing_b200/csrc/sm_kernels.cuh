@@ -14,7 +14,26 @@ namespace smb {
 // ---- error / bookkeeping (api.cu) ---------------------------------------------------------
 int SetError(int code, const char* message);
 int CheckLaunch(const char* what);   // cudaGetLastError() -> SM_OK / SM_ERR_CUDA
-void CountLaunch();                  // kernels launched by this library (sm_kernel_launch_count)
+
+// Every kernel launch of the library goes through a LaunchScope: it counts the launch
+// (sm_kernel_launch_count) and, while sm_profile_kernels(1) is active, brackets it with CUDA
+// events on the launching stream so that bench.py can report per-kernel durations measured
+// live (never used inside a timed throughput region).
+enum KernelId {
+  KID_CLEAR = 0, KID_BILATERAL_OUTLIER, KID_BILATERAL_GENERIC, KID_OUTLIER, KID_ERODE_NORMALS_RADII, KID_ERODE,
+  KID_NORMALS, KID_RADII, KID_PROJECT, KID_ASSOCIATE, KID_MERGE, KID_BLEND, KID_INTEGRATE, KID_UPDATE_NEIGHBORS,
+  KID_NEW_SURFEL_SCAN, KID_CREATE_SURFELS, KID_REG_ACCUMULATE, KID_REG_STEP, KID_REG_UPDATE, KID_REG_COPY_ONLY,
+  KID_EXPORT_VERTICES, KID_COUNT
+};
+const char* KernelName(int id);
+class LaunchScope {
+ public:
+  LaunchScope(cudaStream_t stream, KernelId id);
+  ~LaunchScope();
+ private:
+  cudaStream_t stream_;
+  int slot_;
+};
 
 inline Mat3x4 MakeMat3x4(const float* m) {
   Mat3x4 r;
@@ -29,6 +48,13 @@ inline Mat3x4 MakeMat3x4(const float* m) {
 constexpr u32 kInvalidIndex = 0xFFFFFFFFu;   // APP/surfel.h:63, kernels.cu:74
 constexpr int kSegment = 1024;               // surfel slots per list segment (one block-iteration)
 constexpr u32 kActiveBit = 0x80000000u;      // VisEntry.idx: surfel was active at projection time
+
+// PixelAssoc.x while a frame is processed: supporting surfel index, with this bit set when the
+// association came through the surfel's secondary pixel (orders primary before secondary).
+constexpr u32 kSecondaryBit = 0x80000000u;
+__host__ __device__ __forceinline__ u32 supporting_index(u32 key) {
+  return key == kInvalidIndex ? kInvalidIndex : (key & ~kSecondaryBit);
+}
 
 // Per-pixel association record (the reference keeps four separate rasters,
 // APP/cuda_surfel_reconstruction.h:138-142): one 128-bit load/store per pixel.

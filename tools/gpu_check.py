@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--sigma", type=float, default=None)
     ap.add_argument("--cap", type=int, default=2_000_000)
+    ap.add_argument("--bench-frames", type=int, default=0)
     args = ap.parse_args()
 
     prod = _lib.load_product()
@@ -169,19 +170,43 @@ def main():
             cmp_exact("blended depth", depths[other], depths["a"])
             ro, ra_ = sts[other][0], sts["a"][0]
             if ro.shape == ra_.shape:
-                for row in range(25):
-                    if row in R.SCRATCH_ROWS:
-                        continue
-                    ne = int((ro[row].view(np.uint32) != ra_[row].view(np.uint32)).sum())
-                    if ne:
-                        if row < 17 or row == 23:
-                            dd = np.abs(ro[row] - ra_[row])
-                            extra = f" max abs {np.nanmax(dd):.3e}"
-                        else:
-                            extra = ""
-                        print(f"    row {row:2d} {R.ROW_NAMES[row]:18s} differs at {ne} surfels{extra}")
+                same_merge = (ro[7] < 0) == (ra_[7] < 0)
+                print(f"    surfels with different merge status: {int((~same_merge).sum())}")
+                det_rows = (0, 1, 2, 6, 7, 8, 9, 10, 17, 18, 24)
+                bad = 0
+                for row in det_rows:
+                    bad += int(((ro[row].view(np.uint32) != ra_[row].view(np.uint32)) & same_merge).sum())
+                print(f"    integrate rows (x,y,z,conf,r2,normal,stamps,color) diffs outside merge differences: {bad}"
+                      + ("" if bad == 0 else "   <-- DIFF"))
+                if other == "p":
+                    total += bad
+                for row in (3, 4, 5, 19, 20, 21, 22):
+                    ne = (ro[row].view(np.uint32) != ra_[row].view(np.uint32))
+                    extra = f" max abs {np.nanmax(np.abs(ro[row] - ra_[row])):.3e}" if row < 6 else ""
+                    print(f"    row {row:2d} {R.ROW_NAMES[row]:12s} differs at {int(ne.sum()):6d} (new surfels: {int(ne[n_a:].sum())}){extra}")
             else:
                 print("    state shapes differ", ro.shape, ra_.shape)
+
+    # ---- throughput probe ----
+    if args.bench_frames > 0:
+        print("[throughput probe]")
+        stb = S.make_stream(cam, args.bench_frames, device="cuda")
+        f0, f1 = stb.integrated_range()
+        for name, lib in (("reference", ref), ("product", prod)):
+            rec = R.CUDASurfelReconstruction(args.cap, W, H, cam.fx, cam.fy, cam.cx, cam.cy, lib=lib)
+            for rep in range(3):
+                rec.reset()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                stats = rec.stream_run(None, stb.depth, stb.color, stb.global_T_frame, stb.frame_T_global,
+                                       stb.others_TR_reference, pp, ip, f0, f1)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                print(f"  {name:9s} rep {rep}: {stats.frames_integrated} frames {ms:8.2f} ms -> {stats.frames_integrated / ms * 1e3:9.1f} fps;"
+                      f" surfels {stats.surfels_size} (count {stats.surfel_count}) launches {stats.kernel_launches}")
+            rec.close()
     print("TOTAL hard mismatches:", total)
 
 
