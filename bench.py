@@ -261,7 +261,7 @@ def main():
         rows_now, n_now, _ = rec.dump_state()
         stamps = rows_now[18].view(np.uint32)
         counters = {"P": cam.width * cam.height, "K": pp.outlier_filtering_frame_count,
-                    "valid": int((stream.depth[last - 1] > 0).sum()), "N": int(fc[0]), "V": int(fc[1]),
+                    "valid": int((stream.depth[last - 1].to(torch.int32) > 0).sum()), "N": int(fc[0]), "V": int(fc[1]),
                     "S": int(fc[2]), "M": int(fc[3]),
                     "A": int((stamps.astype(np.int64) >= (last - 1) - ip.regularization_frame_window_size).sum())}
         kernel_table = {}

@@ -303,6 +303,8 @@ int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width,
   SM_CUDA(cudaMalloc(&d.surfels, sizeof(float) * SM_ROW_COUNT * d.stride));
   SM_CUDA(cudaMalloc(&d.assoc, sizeof(PixelAssoc) * P));
   SM_CUDA(cudaMalloc(&d.first_depth, sizeof(float) * P));
+  SM_CUDA(cudaMalloc(&d.supported, P));
+  SM_CUDA(cudaMalloc(&d.new_list, sizeof(u32) * P));
   SM_CUDA(cudaMalloc(&d.vis, sizeof(VisEntry) * padded));
   SM_CUDA(cudaMalloc(&d.seg_count, sizeof(u32) * (padded / kSegment)));
   SM_CUDA(cudaMalloc(&d.merge_flag, padded));
@@ -330,7 +332,7 @@ int sm_destroy(sm_reconstruction* r) {
   if (!r) return SM_OK;
   cudaDeviceSynchronize();
   DeviceState& d = r->d;
-  cudaFree(d.surfels); cudaFree(d.assoc); cudaFree(d.first_depth); cudaFree(d.vis); cudaFree(d.seg_count);
+  cudaFree(d.surfels); cudaFree(d.assoc); cudaFree(d.first_depth); cudaFree(d.supported); cudaFree(d.new_list); cudaFree(d.vis); cudaFree(d.seg_count);
   cudaFree(d.merge_flag); cudaFree(d.new_flag); cudaFree(d.new_index); cudaFree(d.scan_state); cudaFree(d.counters);
   cudaFreeHost(r->host_counters);
   cudaFree(r->scratch_B); cudaFree(r->run_depth); cudaFree(r->run_normals); cudaFree(r->run_radius);
@@ -360,7 +362,7 @@ int sm_preprocess(sm_reconstruction* r, void* stream, const sm_preprocess_params
                                      r->cx, r->cy, raw_depth, raw_pitch, other_depths, other_pitches,
                                      others_TR_reference, r->scratch_B, r->scratch_B_pitch, out_depth,
                                      out_depth_pitch, reinterpret_cast<float2*>(out_normals), out_normals_pitch,
-                                     out_radius, out_radius_pitch, r->d.assoc, r->d.first_depth);
+                                     out_radius, out_radius_pitch, r->d.assoc, r->d.first_depth, r->d.supported);
   if (status == SM_OK) r->rasters_cleared = true;
   return status;
 }

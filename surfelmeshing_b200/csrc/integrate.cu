@@ -96,6 +96,19 @@ __device__ __forceinline__ float facing_dot(const FrameParams& f, float x, float
   return fmul(rs, ffma(z, local_normal->z, ffma(x, local_normal->x, fmul(y, local_normal->y))));
 }
 
+// Iterates the visible list with one entry per thread: a work item is one quarter (kBlock
+// positions) of a list segment; `body(pos)` runs for every occupied list position.
+template <typename Body>
+__device__ __forceinline__ void for_each_visible(const DeviceState& d, u32 n, Body&& body) {
+  constexpr u32 kItemsPerSegment = kSegment / kBlock;
+  const u32 items = ((n + kSegment - 1) / kSegment) * kItemsPerSegment;
+  for (u32 item = blockIdx.x; item < items; item += gridDim.x) {
+    const u32 seg = item / kItemsPerSegment;
+    const u32 k = (item % kItemsPerSegment) * kBlock + threadIdx.x;
+    if (k < d.seg_count[seg]) body(static_cast<size_t>(seg) * kSegment + k);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // a6: clear
 // ---------------------------------------------------------------------------------------
@@ -104,14 +117,17 @@ __global__ void __launch_bounds__(kBlock) k_clear(DeviceState d) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     d.assoc[i] = make_uint4(kInvalidIndex, kInvalidIndex, 0u, 0u);
     d.first_depth[i] = __int_as_float(0x7f800000);
+    d.supported[i] = 0;
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // a7: projection sweep + min-depth splat + visible list
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_project(DeviceState d, FrameParams f) {
-  __shared__ u32 warp_totals[kBlock / 32];
+constexpr int kProjectBlock = 512;  // 2 slots per thread, kSegment slots per block-iteration
+
+__global__ void __launch_bounds__(kProjectBlock) k_project(DeviceState d, FrameParams f) {
+  __shared__ u32 warp_totals[kProjectBlock / 32];
   const u32 n = d.counters->surfel_count[f.parity];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -123,19 +139,19 @@ __global__ void __launch_bounds__(kBlock) k_project(DeviceState d, FrameParams f
   }
 
   for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
-    const u32 base = seg * kSegment + threadIdx.x * 4;
-    VisEntry e[4];
-    bool visible[4] = {false, false, false, false};
-    int cnt = 0;
+    const u32 base = seg * kSegment + threadIdx.x * 2;
+    VisEntry e[2];
+    bool visible[2] = {false, false};
+    u32 cnt = 0;
     if (base < n) {
-      const float4 X = *reinterpret_cast<const float4*>(&SM_S(SM_ROW_X, base));
-      const float4 Y = *reinterpret_cast<const float4*>(&SM_S(SM_ROW_Y, base));
-      const float4 Z = *reinterpret_cast<const float4*>(&SM_S(SM_ROW_Z, base));
-      const uint4 T = *reinterpret_cast<const uint4*>(&SM_SU(SM_ROW_LAST_UPDATE_STAMP, base));
-      const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-      const u32 ts[4] = {T.x, T.y, T.z, T.w};
+      const float2 X = *reinterpret_cast<const float2*>(&SM_S(SM_ROW_X, base));
+      const float2 Y = *reinterpret_cast<const float2*>(&SM_S(SM_ROW_Y, base));
+      const float2 Z = *reinterpret_cast<const float2*>(&SM_S(SM_ROW_Z, base));
+      const uint2 T = *reinterpret_cast<const uint2*>(&SM_SU(SM_ROW_LAST_UPDATE_STAMP, base));
+      const float xs[2] = {X.x, X.y}, ys[2] = {Y.x, Y.y}, zs[2] = {Z.x, Z.y};
+      const u32 ts[2] = {T.x, T.y};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         const u32 i = base + j;
         if (i >= n) break;
         const float z = transform_row(f.local_T_global.r2, xs[j], ys[j], zs[j]);
@@ -169,14 +185,14 @@ __global__ void __launch_bounds__(kBlock) k_project(DeviceState d, FrameParams f
     __syncthreads();
     u32 warp_base = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < kBlock / 32; ++w) {
+    for (int w = 0; w < kProjectBlock / 32; ++w) {
       const u32 t = warp_totals[w];
       if (w < warp) warp_base += t;
       total += t;
     }
     VisEntry* out = d.vis + static_cast<size_t>(seg) * kSegment + warp_base + (incl - cnt);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2; ++j) {
       if (visible[j]) *out++ = e[j];
     }
     if (threadIdx.x == 0) d.seg_count[seg] = total;
@@ -185,114 +201,119 @@ __global__ void __launch_bounds__(kBlock) k_project(DeviceState d, FrameParams f
 }
 
 // ---------------------------------------------------------------------------------------
-// a8: association
+// a8 / a9: association and merge gates
 // ---------------------------------------------------------------------------------------
 
+// Everything a gate needs from one pixel, loaded up front so that all gathers of a list
+// entry are in flight together.
+struct PixelGate {
+  float measurement_depth;  // depth_correction_factor * depth
+  float first;              // first_surfel_depth
+  float2 normal;
+};
+
+__device__ __forceinline__ PixelGate load_pixel_gate(const DeviceState& d, const FrameParams& f, int x, int y) {
+  PixelGate g;
+  g.measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
+  g.first = d.first_depth[y * d.width + x];
+  g.normal = row_ptr(f.normals, f.normals_pitch, y)[x];
+  return g;
+}
+
 // Gates shared by association and merge up to the normal-compatibility test
-// (kernels.cu:1603-1668 / :1875-1936). Returns true if the measurement supports the surfel.
-// Writes the conflicting-surfel entry like the reference does.
-__device__ __forceinline__ bool supports_surfel(const DeviceState& d, const FrameParams& f, int x, int y, u32 idx,
-                                                float cx_, float cy_, float cz_) {
-  const int p = y * d.width + x;
-  const float measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
-  if (!(measurement_depth > 0.f)) return false;
-  const float first = d.first_depth[p];
-  if (first < fmul(measurement_depth, fadd(-f.sensor_noise_factor, 1.0f))) {
-    if (first == cz_) d.assoc[p].y = idx;  // this surfel is conflicting
+// (kernels.cu:1603-1668 / :1875-1936). `dot_angle` / `ln`: facing test of this surfel (pixel
+// independent). Returns true if the measurement supports the surfel; writes the
+// conflicting-surfel entry like the reference does.
+__device__ __forceinline__ bool supports_surfel(const DeviceState& d, const FrameParams& f, const PixelGate& g, int p,
+                                                u32 idx, float cz_, float dot_angle, const float3& ln) {
+  if (!(g.measurement_depth > 0.f)) return false;
+  if (g.first < fmul(g.measurement_depth, fadd(-f.sensor_noise_factor, 1.0f))) {
+    if (g.first == cz_) d.assoc[p].y = idx;  // this surfel is conflicting
     return false;
   }
-  const float occlusion_depth = fmul(fadd(f.sensor_noise_factor, 1.0f), measurement_depth);
-  if (cz_ > occlusion_depth) return false;
-  float3 ln;
-  const float dot_angle = facing_dot(f, cx_, cy_, cz_, SM_S(SM_ROW_NORMAL_X, idx), SM_S(SM_ROW_NORMAL_Y, idx),
-                                     SM_S(SM_ROW_NORMAL_Z, idx), &ln);
+  if (cz_ > fmul(fadd(f.sensor_noise_factor, 1.0f), g.measurement_depth)) return false;  // occluded
   if (dot_angle > 0.f) return false;  // kSurfelNormalToViewingDirThreshold = 0
-  if (measurement_depth < cz_) {
-    const float2 nm = row_ptr(f.normals, f.normals_pitch, y)[x];
-    const float s = normal_z_abs(nm.x, nm.y);
-    const float dot2 = ffma(-ln.z, s, ffma(ln.x, nm.x, fmul(ln.y, nm.y)));
+  if (g.measurement_depth < cz_) {
+    const float s = normal_z_abs(g.normal.x, g.normal.y);
+    const float dot2 = ffma(-ln.z, s, ffma(ln.x, g.normal.x, fmul(ln.y, g.normal.y)));
     if (dot2 < f.cos_normal_compatibility_threshold) return false;
   }
   return true;
 }
 
-__device__ __forceinline__ void consider_association(const DeviceState& d, const FrameParams& f, int x, int y,
-                                                     u32 idx, float cx_, float cy_, float cz_, bool secondary) {
-  if (!supports_surfel(d, f, x, y, idx, cx_, cy_, cz_)) return;
-  const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
-  if (!(surfel_radius_squared > 0.f)) return;
-  PixelAssoc* a = &d.assoc[y * d.width + x];
-  // Reference: atomicCAS(INV -> idx), first come wins. Every thread of the reference kernel
-  // handles its primary pixel before its secondary pixel, so primary associations typically
-  // arrive first; the deterministic rule here is "primary before secondary, then lowest
-  // index" (kSecondaryBit orders the keys), which is one of the reference's legal outcomes.
-  atomicMin(&a->x, idx | (secondary ? kSecondaryBit : 0u));
-  atomicAdd(&a->z, 1u);
-  atomicAdd(reinterpret_cast<float*>(&a->w), cz_);
-}
-
 __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams f) {
   const u32 n = d.counters->surfel_count[f.parity];
-  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
-    const u32 cnt = d.seg_count[seg];
-    const VisEntry* list = d.vis + static_cast<size_t>(seg) * kSegment;
-    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) {
-      const VisEntry e = list[k];
-      if (!(e.x & kActiveBit)) continue;
-      const u32 idx = e.x & ~kActiveBit;
-      const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
-      const Projection p = project(f, d.width, d.height, x, y, z);
-      consider_association(d, f, p.px, p.py, idx, x, y, z, false);
-      int ox, oy;
-      if (secondary_pixel(p, d.width, d.height, &ox, &oy)) consider_association(d, f, ox, oy, idx, x, y, z, true);
+  for_each_visible(d, n, [&](size_t pos) {
+    const VisEntry e = d.vis[pos];
+    if (!(e.x & kActiveBit)) return;
+    const u32 idx = e.x & ~kActiveBit;
+    const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
+    const Projection p = project(f, d.width, d.height, x, y, z);
+    int ox = p.px, oy = p.py;
+    const bool has2 = secondary_pixel(p, d.width, d.height, &ox, &oy);
+    // one batch of gathers
+    const PixelGate g0 = load_pixel_gate(d, f, p.px, p.py);
+    const PixelGate g1 = load_pixel_gate(d, f, ox, oy);
+    const float snx = SM_S(SM_ROW_NORMAL_X, idx), sny = SM_S(SM_ROW_NORMAL_Y, idx), snz = SM_S(SM_ROW_NORMAL_Z, idx);
+    const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+    float3 ln;
+    const float dot_angle = facing_dot(f, x, y, z, snx, sny, snz, &ln);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !has2) break;
+      const int pp = k == 0 ? p.py * d.width + p.px : oy * d.width + ox;
+      if (!supports_surfel(d, f, k == 0 ? g0 : g1, pp, idx, z, dot_angle, ln)) continue;
+      if (!(surfel_radius_squared > 0.f)) continue;
+      PixelAssoc* a = &d.assoc[pp];
+      // Reference: atomicCAS(INV -> idx), first come wins. Every thread of the reference kernel
+      // handles its primary pixel before its secondary pixel, so primary associations typically
+      // arrive first; the deterministic rule here is "primary before secondary, then lowest
+      // index" (kSecondaryBit orders the keys), which is one of the reference's legal outcomes.
+      atomicMin(&a->x, idx | (k == 1 ? kSecondaryBit : 0u));
+      atomicAdd(&a->z, 1u);
+      atomicAdd(reinterpret_cast<float*>(&a->w), z);
+      d.supported[pp] = 1;
     }
-  }
+  });
 }
 
-// ---------------------------------------------------------------------------------------
-// a9: merge (decision only; applied in k_integrate)
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ bool consider_merge(const DeviceState& d, const FrameParams& f, int x, int y, u32 idx,
-                                               float cx_, float cy_, float cz_, float surfel_radius_squared) {
-  if (!supports_surfel(d, f, x, y, idx, cx_, cy_, cz_)) return false;
-  const u32 supported_surfel = supporting_index(d.assoc[y * d.width + x].x);
-  if (supported_surfel == idx || supported_surfel == kInvalidIndex) return false;
-  // kernels.cu:1955-1984.
-  const float other_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, supported_surfel);
-  const float radius_diff = fmul(surfel_radius_squared, frcp(other_radius_squared));
-  if (radius_diff > 1.4400000572204589844f || radius_diff < 0.69444441795349121094f) return false;
-  const float dx = fsub(SM_S(SM_ROW_X, idx), SM_S(SM_ROW_X, supported_surfel));
-  const float dy = fsub(SM_S(SM_ROW_Y, idx), SM_S(SM_ROW_Y, supported_surfel));
-  const float dz = fsub(SM_S(SM_ROW_Z, idx), SM_S(SM_ROW_Z, supported_surfel));
-  const float distance_squared = squared_norm(dx, dy, dz);
-  if (distance_squared > fmul(fadd(surfel_radius_squared, other_radius_squared), 0.03125f)) return false;
-  const float dot_angle = dot3(SM_S(SM_ROW_NORMAL_X, idx), SM_S(SM_ROW_NORMAL_Y, idx), SM_S(SM_ROW_NORMAL_Z, idx),
-                               SM_S(SM_ROW_NORMAL_X, supported_surfel), SM_S(SM_ROW_NORMAL_Y, supported_surfel),
-                               SM_S(SM_ROW_NORMAL_Z, supported_surfel));
-  if (dot_angle < 0.93968999385833740234f) return false;  // cos 20 deg
-  return true;
-}
-
+// a9: merge decision (kernels.cu:1857-1992); applied by k_integrate.
 __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) {
   const u32 n = d.counters->surfel_count[f.parity];
   u32 merged_by_thread = 0;
-  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
-    const u32 cnt = d.seg_count[seg];
-    const size_t list_base = static_cast<size_t>(seg) * kSegment;
-    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) {
-      const VisEntry e = d.vis[list_base + k];
-      const u32 idx = e.x & ~kActiveBit;  // no active-window test here (kernels.cu:2016)
-      bool merged = false;
-      const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
-      if (surfel_radius_squared >= 0.f) {
-        const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
-        const Projection p = project(f, d.width, d.height, x, y, z);
-        merged = consider_merge(d, f, p.px, p.py, idx, x, y, z, surfel_radius_squared);
+  for_each_visible(d, n, [&](size_t pos) {
+    const VisEntry e = d.vis[pos];
+    const u32 idx = e.x & ~kActiveBit;  // no active-window test here (kernels.cu:2016)
+    const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
+    const Projection p = project(f, d.width, d.height, x, y, z);
+    const int pp = p.py * d.width + p.px;
+    // batch 1
+    const PixelGate g = load_pixel_gate(d, f, p.px, p.py);
+    const u32 supported_surfel = supporting_index(d.assoc[pp].x);
+    const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+    const float snx = SM_S(SM_ROW_NORMAL_X, idx), sny = SM_S(SM_ROW_NORMAL_Y, idx), snz = SM_S(SM_ROW_NORMAL_Z, idx);
+    const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
+    bool merged = false;
+    if (surfel_radius_squared >= 0.f) {
+      float3 ln;
+      const float dot_angle = facing_dot(f, x, y, z, snx, sny, snz, &ln);
+      if (supports_surfel(d, f, g, pp, idx, z, dot_angle, ln) && supported_surfel != idx &&
+          supported_surfel != kInvalidIndex) {
+        // batch 2: the supporting surfel (kernels.cu:1955-1984)
+        const u32 q = supported_surfel;
+        const float other_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, q);
+        const float qx = SM_S(SM_ROW_X, q), qy = SM_S(SM_ROW_Y, q), qz = SM_S(SM_ROW_Z, q);
+        const float qnx = SM_S(SM_ROW_NORMAL_X, q), qny = SM_S(SM_ROW_NORMAL_Y, q), qnz = SM_S(SM_ROW_NORMAL_Z, q);
+        const float radius_diff = fmul(surfel_radius_squared, frcp(other_radius_squared));
+        const float distance_squared = squared_norm(fsub(gx, qx), fsub(gy, qy), fsub(gz, qz));
+        merged = !(radius_diff > 1.4400000572204589844f || radius_diff < 0.69444441795349121094f) &&
+                 !(distance_squared > fmul(fadd(surfel_radius_squared, other_radius_squared), 0.03125f)) &&
+                 !(dot3(snx, sny, snz, qnx, qny, qnz) < 0.93968999385833740234f);  // cos 20 deg
       }
-      d.merge_flag[list_base + k] = merged ? 1 : 0;
-      merged_by_thread += merged ? 1u : 0u;
     }
-  }
+    d.merge_flag[pos] = merged ? 1 : 0;
+    merged_by_thread += merged ? 1u : 0u;
+  });
   // Block reduction of the merge count (reference: cub::BlockReduce + atomicAdd, :2045-2051).
   merged_by_thread = __reduce_add_sync(0xffffffffu, merged_by_thread);
   __shared__ u32 warp_sums[kBlock / 32];
@@ -309,32 +330,53 @@ __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) 
 // a10: measurement blending, all iterations in one kernel
 // ---------------------------------------------------------------------------------------
 constexpr int kBlendTileW = 32, kBlendTileH = 16;
+constexpr int kBlendBlock = 512;
+constexpr u32 kClaimed = 254;  // distance-map value of a pixel claimed in the running iteration
 
-__global__ void __launch_bounds__(512) k_blend(DeviceState d, FrameParams f) {
+// Claims byte `i` of a u8 map (4-byte CAS on the containing word) if it currently holds
+// `expected`; returns true for exactly one claimant.
+__device__ __forceinline__ bool claim_byte(u8* map, int i, u32 expected) {
+  u32* word = reinterpret_cast<u32*>(map) + (i >> 2);
+  const int shift = (i & 3) * 8;
+  u32 old = *reinterpret_cast<volatile u32*>(word);
+  while (((old >> shift) & 0xFFu) == expected) {
+    const u32 desired = (old & ~(0xFFu << shift)) | (kClaimed << shift);
+    const u32 seen = atomicCAS(word, old, desired);
+    if (seen == old) return true;
+    old = seen;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParams f) {
   extern __shared__ __align__(16) unsigned char blend_smem[];
+  __shared__ int s_count[2][2];  // [ring][ping-pong] frontier sizes
   const int radius = f.blend_radius;
   const int halo = max(radius - 1, 1);          // (radius - 2) iterations + the 3x3 start stencil
   const int rw = kBlendTileW + 2 * halo, rh = kBlendTileH + 2 * halo;
   const int rn = rw * rh;
+  const int rn4 = (rn + 3) & ~3;
   float* s_delta = reinterpret_cast<float*>(blend_smem);
-  float* s_ndelta = s_delta + rn;
-  u16* s_depth0 = reinterpret_cast<u16*>(s_ndelta + rn);   // depth as handed in (start stencil reads this)
-  u16* s_depth = s_depth0 + rn;                             // working depth
-  u8* s_sup = reinterpret_cast<u8*>(s_depth + rn);
-  u8* s_dist = s_sup + rn;
-  u8* s_ndist = s_dist + rn;
+  float* s_ndelta = s_delta + rn4;
+  u16* s_depth0 = reinterpret_cast<u16*>(s_ndelta + rn4);  // depth as handed in (start stencil reads this)
+  u16* s_depth = s_depth0 + rn4;                            // working depth
+  u16* s_front = s_depth + rn4;                             // frontier lists: [ring][ping-pong][rn4]
+  u8* s_sup = reinterpret_cast<u8*>(s_front + 4 * rn4);
+  u8* s_dist = s_sup + rn4;
+  u8* s_ndist = s_dist + rn4;
 
   const int tile_x = blockIdx.x * kBlendTileW, tile_y = blockIdx.y * kBlendTileH;
   const int x0 = tile_x - halo, y0 = tile_y - halo;
 
-  for (int i = threadIdx.x; i < rn; i += blockDim.x) {
+  if (threadIdx.x < 4) (&s_count[0][0])[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < rn4; i += blockDim.x) {
     const int ly = i / rw, lx = i - ly * rw;
     const int gx = x0 + lx, gy = y0 + ly;
     u16 depth = 0;
     u8 sup = 0;
-    if (gx >= 0 && gy >= 0 && gx < d.width && gy < d.height) {
+    if (i < rn && gx >= 0 && gy >= 0 && gx < d.width && gy < d.height) {
       depth = row_ptr(f.depth, f.depth_pitch, gy)[gx];
-      sup = d.assoc[gy * d.width + gx].x != kInvalidIndex;
+      sup = d.supported[gy * d.width + gx];
     }
     s_depth0[i] = depth;
     s_depth[i] = depth;
@@ -346,107 +388,129 @@ __global__ void __launch_bounds__(512) k_blend(DeviceState d, FrameParams f) {
 
   const float depth_scaling = f.depth_scaling;  // the reference passes 1 / depth_correction_factor (kernels.cc:179)
   const float rcp_scaling = frcp(depth_scaling);
+  auto processed = [&](int lx, int ly) {
+    // pixels whose 3x3 stencil lies inside the region and that are interior image pixels
+    const int gx = x0 + lx, gy = y0 + ly;
+    return lx >= 1 && ly >= 1 && lx < rw - 1 && ly < rh - 1 && gx >= 1 && gy >= 1 && gx < d.width - 1 &&
+           gy < d.height - 1;
+  };
 
-  // Start kernel (kernels.cu:563-615) on every region pixel whose 3x3 stencil is inside the
-  // region and that is an interior image pixel. The stencils read the depth as handed in
-  // (the reference's in-place write, flagged TODO at :610, can only matter if a blended depth
-  // rounds to 0).
-  int any_ring = 0;
-  {
-    for (int i = threadIdx.x; i < rn; i += blockDim.x) {
-      const int ly = i / rw, lx = i - ly * rw;
-      const int gx = x0 + lx, gy = y0 + ly;
-      if (lx < 1 || ly < 1 || lx >= rw - 1 || ly >= rh - 1) continue;
-      if (gx < 1 || gy < 1 || gx >= d.width - 1 || gy >= d.height - 1) continue;
-      if (s_depth0[i] == 0 || !s_sup[i]) continue;
-      bool measurement_border_pixel = false, surfel_border_pixel = false;
+  // Start kernel (kernels.cu:563-615). The stencils read the depth as handed in (the
+  // reference's in-place write, flagged TODO at :610, can only matter if a blended depth
+  // rounds to 0). Ring pixels (distance 1) become the first frontiers.
+  for (int i = threadIdx.x; i < rn; i += blockDim.x) {
+    const int ly = i / rw, lx = i - ly * rw;
+    if (!processed(lx, ly)) continue;
+    if (s_depth0[i] == 0 || !s_sup[i]) continue;
+    bool measurement_border_pixel = false, surfel_border_pixel = false;
 #pragma unroll
-      for (int wy = -1; wy <= 1; ++wy) {
+    for (int wy = -1; wy <= 1; ++wy) {
 #pragma unroll
-        for (int wx = -1; wx <= 1; ++wx) {
-          const int j = i + wy * rw + wx;
-          if (s_depth0[j] == 0) measurement_border_pixel = true;
-          else if (!s_sup[j]) surfel_border_pixel = true;
-        }
-      }
-      if (!measurement_border_pixel && !surfel_border_pixel) { s_dist[i] = 255; continue; }
-      const PixelAssoc a = d.assoc[gy * d.width + gx];
-      const float sum = __uint_as_float(a.w);
-      const float rcp_count = frcp(u2f(a.z));
-      const float depth_f = u2f(s_depth0[i]);
-      if (surfel_border_pixel) {
-        s_ndist[i] = 1;
-        s_ndelta[i] = ffma(sum, rcp_count, -fmul(depth_f, rcp_scaling));
-        any_ring = 1;
-      }
-      if (measurement_border_pixel) {
-        s_dist[i] = 1;
-        const float surfel_depth_average = fmul(sum, rcp_count);
-        s_delta[i] = ffma(-depth_f, rcp_scaling, surfel_depth_average);
-        s_depth[i] = static_cast<u16>(f2u_trunc(ffma(surfel_depth_average, depth_scaling, 0.5f)));
-        any_ring = 1;
-      } else {
-        s_dist[i] = 255;
+      for (int wx = -1; wx <= 1; ++wx) {
+        const int j = i + wy * rw + wx;
+        if (s_depth0[j] == 0) measurement_border_pixel = true;
+        else if (!s_sup[j]) surfel_border_pixel = true;
       }
     }
-    const int block_any = __syncthreads_or(any_ring);
-    if (!block_any) return;  // no border ring reaches this tile: depth unchanged
+    if (!measurement_border_pixel && !surfel_border_pixel) { s_dist[i] = 255; continue; }
+    const PixelAssoc a = d.assoc[(y0 + ly) * d.width + x0 + lx];
+    const float sum = __uint_as_float(a.w);
+    const float rcp_count = frcp(u2f(a.z));
+    const float depth_f = u2f(s_depth0[i]);
+    if (surfel_border_pixel) {
+      s_ndist[i] = 1;
+      s_ndelta[i] = ffma(sum, rcp_count, -fmul(depth_f, rcp_scaling));
+      s_front[2 * rn4 + atomicAdd(&s_count[1][0], 1)] = static_cast<u16>(i);
+    }
+    if (measurement_border_pixel) {
+      s_dist[i] = 1;
+      const float surfel_depth_average = fmul(sum, rcp_count);
+      s_delta[i] = ffma(-depth_f, rcp_scaling, surfel_depth_average);
+      s_depth[i] = static_cast<u16>(f2u_trunc(ffma(surfel_depth_average, depth_scaling, 0.5f)));
+      s_front[atomicAdd(&s_count[0][0], 1)] = static_cast<u16>(i);
+    } else {
+      s_dist[i] = 255;
+    }
   }
+  __syncthreads();
+  if (s_count[0][0] == 0 && s_count[1][0] == 0) return;  // no border ring reaches this tile: depth unchanged
 
-  // Iteration kernels (kernels.cu:647-708), iteration = 2 .. radius - 1 (kernels.cc:190).
+  // Iteration kernels (kernels.cu:647-708), iteration = 2 .. radius - 1 (kernels.cc:190), as a
+  // breadth-first wavefront: only the 8-neighbourhoods of the previous frontier are visited.
   const float interpolation_factor_term = 1.0f / (radius - 1.0f);   // host expression, kernels.cc:196
   for (int iteration = 2; iteration < radius; ++iteration) {
-    const float scaled = fmul(ffma(-i2f(iteration - 1), interpolation_factor_term, 1.0f), depth_scaling);
-    for (int i = threadIdx.x; i < rn; i += blockDim.x) {
-      const int ly = i / rw, lx = i - ly * rw;
-      const int gx = x0 + lx, gy = y0 + ly;
-      if (lx < 1 || ly < 1 || lx >= rw - 1 || ly >= rh - 1) continue;
-      if (gx < 1 || gy < 1 || gx >= d.width - 1 || gy >= d.height - 1) continue;
-      if (s_dist[i] == 255) {
-        float delta_sum = 0.f;
-        int count = 0;
+    const int cur = iteration & 1, nxt = cur ^ 1;   // iteration 2 reads lists [0], writes [1]
+    const int src = cur, dst = nxt;
+    // (lists of the start phase are in slot 0; `cur` for iteration 2 is 0)
+    if (threadIdx.x < 2) s_count[threadIdx.x][dst] = 0;
+    __syncthreads();
+    // claim phase
 #pragma unroll
-        for (int wy = -1; wy <= 1; ++wy) {
-#pragma unroll
-          for (int wx = -1; wx <= 1; ++wx) {
-            const int j = i + wy * rw + wx;
-            if (s_dist[j] == iteration - 1) { delta_sum = fadd(delta_sum, s_delta[j]); ++count; }
-          }
+    for (int ring = 0; ring < 2; ++ring) {
+      const int len = s_count[ring][src];
+      const u16* list = s_front + (2 * ring + src) * rn4;
+      u16* out = s_front + (2 * ring + dst) * rn4;
+      for (int t = threadIdx.x; t < len * 8; t += blockDim.x) {
+        const int q = list[t >> 3];
+        const int m = (t & 7) + ((t & 7) >= 4 ? 1 : 0);  // 0..8 without the centre
+        const int pidx = q + (m / 3 - 1) * rw + (m % 3 - 1);
+        const int ly = pidx / rw, lx = pidx - ly * rw;
+        if (!processed(lx, ly)) continue;
+        bool claimed;
+        if (ring == 0) {
+          claimed = claim_byte(s_dist, pidx, 255u);
+        } else {
+          claimed = s_depth[pidx] != 0 && !s_sup[pidx] && claim_byte(s_ndist, pidx, 0u);
         }
-        if (count > 0) {
-          s_dist[i] = iteration;
-          const float avg = fmul(frcp(i2f(count)), delta_sum);
-          s_delta[i] = avg;
-          s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
-        }
-      }
-      if (s_depth[i] != 0 && !s_sup[i] && s_ndist[i] == 0) {
-        float delta_sum = 0.f;
-        int count = 0;
-#pragma unroll
-        for (int wy = -1; wy <= 1; ++wy) {
-#pragma unroll
-          for (int wx = -1; wx <= 1; ++wx) {
-            const int j = i + wy * rw + wx;
-            if (s_ndist[j] == iteration - 1) { delta_sum = fadd(delta_sum, s_ndelta[j]); ++count; }
-          }
-        }
-        if (count > 0) {
-          s_ndist[i] = iteration;
-          const float avg = fmul(frcp(i2f(count)), delta_sum);
-          s_ndelta[i] = avg;
-          s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
-        }
+        if (claimed) out[atomicAdd(&s_count[ring][dst], 1)] = static_cast<u16>(pidx);
       }
     }
     __syncthreads();
+    // update phase
+    const float scaled = fmul(ffma(-i2f(iteration - 1), interpolation_factor_term, 1.0f), depth_scaling);
+#pragma unroll
+    for (int ring = 0; ring < 2; ++ring) {
+      const int len = s_count[ring][dst];
+      const u16* list = s_front + (2 * ring + dst) * rn4;
+      u8* dist = ring == 0 ? s_dist : s_ndist;
+      float* delta = ring == 0 ? s_delta : s_ndelta;
+      for (int t = threadIdx.x; t < len; t += blockDim.x) {
+        const int i = list[t];
+        float delta_sum = 0.f;
+        int count = 0;
+#pragma unroll
+        for (int wy = -1; wy <= 1; ++wy) {
+#pragma unroll
+          for (int wx = -1; wx <= 1; ++wx) {
+            const int j = i + wy * rw + wx;
+            if (dist[j] == iteration - 1) { delta_sum = fadd(delta_sum, delta[j]); ++count; }
+          }
+        }
+        // count > 0: the pixel was claimed through a neighbour at distance iteration - 1
+        const float avg = fmul(frcp(i2f(count)), delta_sum);
+        delta[i] = avg;
+        s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
+      }
+    }
+    __syncthreads();
+    // publish the new distances only after every update has read its stencil
+#pragma unroll
+    for (int ring = 0; ring < 2; ++ring) {
+      const int len = s_count[ring][dst];
+      const u16* list = s_front + (2 * ring + dst) * rn4;
+      u8* dist = ring == 0 ? s_dist : s_ndist;
+      for (int t = threadIdx.x; t < len; t += blockDim.x) dist[list[t]] = static_cast<u8>(iteration);
+    }
+    __syncthreads();
+    if (s_count[0][dst] == 0 && s_count[1][dst] == 0) break;  // both wavefronts died out
   }
 
   // Write back the tile interior.
   {
     const int lx = (threadIdx.x & 31) + halo, ly = (threadIdx.x >> 5) + halo;
     const int gx = x0 + lx, gy = y0 + ly;
-    if (gx < d.width && gy < d.height) row_ptr(f.depth, f.depth_pitch, gy)[gx] = s_depth[ly * rw + lx];
+    const int i = ly * rw + lx;
+    if (gx < d.width && gy < d.height && s_depth[i] != s_depth0[i]) row_ptr(f.depth, f.depth_pitch, gy)[gx] = s_depth[i];
   }
 }
 
@@ -454,116 +518,161 @@ __global__ void __launch_bounds__(512) k_blend(DeviceState d, FrameParams f) {
 // a11: integration / conflict handling
 // ---------------------------------------------------------------------------------------
 
+// The attributes of one surfel that Integrate reads and writes, held in registers while its
+// (up to two) pixels are processed; written back once.
+struct SurfelState {
+  float x, y, z, confidence, radius_squared, nx, ny, nz;
+  float smooth_x, smooth_y, smooth_z;  // only set by a replacement
+  u32 color, creation_stamp, last_update_stamp;
+  bool replaced, dirty, stamped;
+};
+
+struct PixelMeasurement {
+  float measurement_depth, first, radius_squared;
+  float2 normal;
+  u32 conflicting, count;
+  u32 r, g, b;
+};
+
+__device__ __forceinline__ PixelMeasurement load_pixel_measurement(const DeviceState& d, const FrameParams& f, int x,
+                                                                   int y) {
+  PixelMeasurement m;
+  const int p = y * d.width + x;
+  m.measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
+  m.first = d.first_depth[p];
+  const PixelAssoc a = d.assoc[p];
+  m.conflicting = a.y;
+  m.count = a.z;
+  m.normal = row_ptr(f.normals, f.normals_pitch, y)[x];
+  m.radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
+  const uchar3 c = row_ptr(f.color, f.color_pitch, y)[x];
+  m.r = c.x; m.g = c.y; m.b = c.z;
+  return m;
+}
+
 // IntegrateOrConflictSurfel (kernels.cu:741-982) for one (surfel, pixel) pair. The
 // reference serialises accesses to a surfel with a NaN spin-lock on its x coordinate; each
 // surfel is owned by exactly one thread here (and there), so the lock is never contended.
-__device__ __forceinline__ void integrate_or_conflict(const DeviceState& d, const FrameParams& f, int x, int y,
-                                                      u32 idx, float cx_, float cy_, float cz_) {
-  const int p = y * d.width + x;
-  const float measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
-  if (!(measurement_depth > 0.f)) return;
+__device__ __forceinline__ void integrate_or_conflict(const FrameParams& f, const PixelMeasurement& m, int x, int y,
+                                                      u32 idx, float cx_, float cy_, float cz_, SurfelState& s) {
+  if (!(m.measurement_depth > 0.f)) return;
   bool integrate = true, conflicting = false;
-  const float first = d.first_depth[p];
-  const PixelAssoc a = d.assoc[p];
-  if (first < fmul(measurement_depth, fadd(-f.sensor_noise_factor, 1.0f))) {
-    if (first == cz_ && a.y == idx) conflicting = true;
+  if (m.first < fmul(m.measurement_depth, fadd(-f.sensor_noise_factor, 1.0f))) {
+    if (m.first == cz_ && m.conflicting == idx) conflicting = true;
     integrate = false;
   }
   if (!integrate && !conflicting) return;
-  if (cz_ > fmul(fadd(f.sensor_noise_factor, 1.0f), measurement_depth)) integrate = false;
+  if (cz_ > fmul(fadd(f.sensor_noise_factor, 1.0f), m.measurement_depth)) integrate = false;
   if (!integrate && !conflicting) return;
 
   // Read data (kernels.cu:804-814).
-  const float lx = fmul(measurement_depth, ffma(i2f(x), f.fx_inv, f.cx_inv));
-  const float ly = fmul(measurement_depth, ffma(i2f(y), f.fy_inv, f.cy_inv));
-  const float3 g = transform_point(f.global_T_local, lx, ly, measurement_depth);
-  const float2 nm = row_ptr(f.normals, f.normals_pitch, y)[x];
-  const float3 gn = rotate_vec(f.global_T_local, nm.x, nm.y, -normal_z_abs(nm.x, nm.y));
-  const uchar3 color = row_ptr(f.color, f.color_pitch, y)[x];
+  const float lx = fmul(m.measurement_depth, ffma(i2f(x), f.fx_inv, f.cx_inv));
+  const float ly = fmul(m.measurement_depth, ffma(i2f(y), f.fy_inv, f.cy_inv));
+  const float3 g = transform_point(f.global_T_local, lx, ly, m.measurement_depth);
+  const float3 gn = rotate_vec(f.global_T_local, m.normal.x, m.normal.y, -normal_z_abs(m.normal.x, m.normal.y));
 
   if (conflicting) {
-    const float confidence = fadd(SM_S(SM_ROW_CONFIDENCE, idx), -1.0f);
+    const float confidence = fadd(s.confidence, -1.0f);
     if (confidence <= 0.f) {
       // Delete the old surfel by replacing it with a new one (kernels.cu:828-854).
-      SM_S(SM_ROW_X, idx) = g.x; SM_S(SM_ROW_Y, idx) = g.y; SM_S(SM_ROW_Z, idx) = g.z;
-      SM_S(SM_ROW_SMOOTH_X, idx) = g.x; SM_S(SM_ROW_SMOOTH_Y, idx) = g.y; SM_S(SM_ROW_SMOOTH_Z, idx) = g.z;
-      SM_S(SM_ROW_NORMAL_X, idx) = gn.x; SM_S(SM_ROW_NORMAL_Y, idx) = gn.y; SM_S(SM_ROW_NORMAL_Z, idx) = gn.z;
-      SM_SU(SM_ROW_COLOR, idx) = color.x | (color.y << 8) | (color.z << 16) | (1u << 24);  // detach flag set
-      SM_S(SM_ROW_RADIUS_SQUARED, idx) = row_ptr(f.radius, f.radius_pitch, y)[x];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) SM_SU(SM_ROW_NEIGHBOR0 + i, idx) = kInvalidIndex;
-      SM_S(SM_ROW_CONFIDENCE, idx) = 1.0f;
-      SM_SU(SM_ROW_CREATION_STAMP, idx) = f.frame_index;
-      SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
+      s.x = g.x; s.y = g.y; s.z = g.z;
+      s.smooth_x = g.x; s.smooth_y = g.y; s.smooth_z = g.z;
+      s.nx = gn.x; s.ny = gn.y; s.nz = gn.z;
+      s.color = m.r | (m.g << 8) | (m.b << 16) | (1u << 24);  // detach flag set
+      s.radius_squared = m.radius_squared;
+      s.confidence = 1.0f;
+      s.creation_stamp = f.frame_index;
+      s.stamped = true;
+      s.replaced = true;
     } else {
-      SM_S(SM_ROW_CONFIDENCE, idx) = confidence;
+      s.confidence = confidence;
     }
+    s.dirty = true;
   }
   if (!integrate) return;
 
-  const float snx = SM_S(SM_ROW_NORMAL_X, idx), sny = SM_S(SM_ROW_NORMAL_Y, idx), snz = SM_S(SM_ROW_NORMAL_Z, idx);
   float3 ln;
-  if (facing_dot(f, cx_, cy_, cz_, snx, sny, snz, &ln) > 0.f) return;
-  if (measurement_depth < cz_) {
-    if (ffma(gn.z, snz, ffma(gn.x, snx, fmul(gn.y, sny))) < f.cos_normal_compatibility_threshold) return;
+  if (facing_dot(f, cx_, cy_, cz_, s.nx, s.ny, s.nz, &ln) > 0.f) return;
+  if (m.measurement_depth < cz_) {
+    if (ffma(gn.z, s.nz, ffma(gn.x, s.nx, fmul(gn.y, s.ny))) < f.cos_normal_compatibility_threshold) return;
   }
-  const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
-  if (surfel_radius_squared < 0.f) return;
+  if (s.radius_squared < 0.f) return;
 
   // Integrate (kernels.cu:922-981).
-  const float weight = frcp(u2f(max(1u, a.z)));
-  if (SM_SU(SM_ROW_CREATION_STAMP, idx) < f.frame_index) {
-    const float confidence = SM_S(SM_ROW_CONFIDENCE, idx);
+  const float weight = frcp(u2f(max(1u, m.count)));
+  if (s.creation_stamp < f.frame_index) {
+    const float confidence = s.confidence;
     const float cw = fadd(weight, confidence);
-    SM_S(SM_ROW_CONFIDENCE, idx) = (cw < f.max_surfel_confidence) ? cw : f.max_surfel_confidence;
+    s.confidence = (cw < f.max_surfel_confidence) ? cw : f.max_surfel_confidence;
     const float normalization_factor = frcp(cw);
-    SM_S(SM_ROW_X, idx) = fmul(normalization_factor, ffma(SM_S(SM_ROW_X, idx), confidence, fmul(g.x, weight)));
-    SM_S(SM_ROW_Y, idx) = fmul(normalization_factor, ffma(confidence, SM_S(SM_ROW_Y, idx), fmul(g.y, weight)));
-    SM_S(SM_ROW_Z, idx) = fmul(normalization_factor, ffma(g.z, weight, fmul(confidence, SM_S(SM_ROW_Z, idx))));
-    const float nx = ffma(gn.x, weight, fmul(confidence, snx));
-    const float ny = ffma(gn.y, weight, fmul(confidence, sny));
-    const float nz = ffma(gn.z, weight, fmul(confidence, snz));
+    s.x = fmul(normalization_factor, ffma(s.x, confidence, fmul(g.x, weight)));
+    s.y = fmul(normalization_factor, ffma(confidence, s.y, fmul(g.y, weight)));
+    s.z = fmul(normalization_factor, ffma(g.z, weight, fmul(confidence, s.z)));
+    const float nx = ffma(gn.x, weight, fmul(confidence, s.nx));
+    const float ny = ffma(gn.y, weight, fmul(confidence, s.ny));
+    const float nz = ffma(gn.z, weight, fmul(confidence, s.nz));
     const float normal_normalization = frsqrt_approx(ffma(nz, nz, ffma(nx, nx, fmul(ny, ny))));
-    SM_S(SM_ROW_NORMAL_X, idx) = fmul(nx, normal_normalization);
-    SM_S(SM_ROW_NORMAL_Y, idx) = fmul(ny, normal_normalization);
-    SM_S(SM_ROW_NORMAL_Z, idx) = fmul(nz, normal_normalization);
-    SM_S(SM_ROW_RADIUS_SQUARED, idx) = fminf(surfel_radius_squared, row_ptr(f.radius, f.radius_pitch, y)[x]);
-    const u32 old_color = SM_SU(SM_ROW_COLOR, idx);
-    const u32 r = f2u_trunc(ffma(normalization_factor,
-                                 ffma(u2f(color.x), weight, fmul(confidence, u2f(old_color & 0xFFu))), 0.5f));
-    const u32 gr = f2u_trunc(ffma(normalization_factor,
-                                  ffma(u2f(color.y), weight, fmul(confidence, u2f((old_color >> 8) & 0xFFu))), 0.5f));
-    const u32 b = f2u_trunc(ffma(normalization_factor,
-                                 ffma(u2f(color.z), weight, fmul(confidence, u2f((old_color >> 16) & 0xFFu))), 0.5f));
-    SM_SU(SM_ROW_COLOR, idx) = (r & 0xFFu) | ((gr & 0xFFu) << 8) | ((b & 0xFFu) << 16);  // unsets the detach flag
-    SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
+    s.nx = fmul(nx, normal_normalization);
+    s.ny = fmul(ny, normal_normalization);
+    s.nz = fmul(nz, normal_normalization);
+    s.radius_squared = fminf(s.radius_squared, m.radius_squared);
+    const u32 old_color = s.color;
+    const u32 r = f2u_trunc(ffma(normalization_factor, ffma(u2f(m.r), weight, fmul(confidence, u2f(old_color & 0xFFu))), 0.5f));
+    const u32 gr = f2u_trunc(ffma(normalization_factor, ffma(u2f(m.g), weight, fmul(confidence, u2f((old_color >> 8) & 0xFFu))), 0.5f));
+    const u32 b = f2u_trunc(ffma(normalization_factor, ffma(u2f(m.b), weight, fmul(confidence, u2f((old_color >> 16) & 0xFFu))), 0.5f));
+    s.color = (r & 0xFFu) | ((gr & 0xFFu) << 8) | ((b & 0xFFu) << 16);  // unsets the detach flag
+    s.stamped = true;
+    s.dirty = true;
   }
 }
 
 __global__ void __launch_bounds__(kBlock) k_integrate(DeviceState d, FrameParams f) {
   const u32 n = d.counters->surfel_count[f.parity];
-  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
-    const u32 cnt = d.seg_count[seg];
-    const size_t list_base = static_cast<size_t>(seg) * kSegment;
-    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) {
-      const VisEntry e = d.vis[list_base + k];
-      const u32 idx = e.x & ~kActiveBit;
-      if (d.merge_flag[list_base + k]) {
-        // Apply the merge decided by k_merge (kernels.cu:1986-1989).
-        SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = 0;
-        SM_S(SM_ROW_RADIUS_SQUARED, idx) = -1.0f;
-        SM_SU(SM_ROW_COLOR, idx) = (SM_SU(SM_ROW_COLOR, idx) & 0x00FFFFFFu) | (1u << 24);
-        continue;
-      }
-      if (!(e.x & kActiveBit)) continue;
-      if (SM_S(SM_ROW_RADIUS_SQUARED, idx) < 0.f) continue;  // kernels.cu:1050
-      const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
-      const Projection p = project(f, d.width, d.height, x, y, z);
-      integrate_or_conflict(d, f, p.px, p.py, idx, x, y, z);
-      int ox, oy;
-      if (secondary_pixel(p, d.width, d.height, &ox, &oy)) integrate_or_conflict(d, f, ox, oy, idx, x, y, z);
+  for_each_visible(d, n, [&](size_t pos) {
+    const VisEntry e = d.vis[pos];
+    const u32 idx = e.x & ~kActiveBit;
+    if (d.merge_flag[pos]) {
+      // Apply the merge decided by k_merge (kernels.cu:1986-1989).
+      SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = 0;
+      SM_S(SM_ROW_RADIUS_SQUARED, idx) = -1.0f;
+      reinterpret_cast<u8*>(&SM_SU(SM_ROW_COLOR, idx))[3] = 1;
+      return;
     }
-  }
+    if (!(e.x & kActiveBit)) return;
+    const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
+    const Projection p = project(f, d.width, d.height, x, y, z);
+    int ox = p.px, oy = p.py;
+    const bool has2 = secondary_pixel(p, d.width, d.height, &ox, &oy);
+    // one batch of gathers: both pixels and the surfel
+    const PixelMeasurement m0 = load_pixel_measurement(d, f, p.px, p.py);
+    const PixelMeasurement m1 = load_pixel_measurement(d, f, ox, oy);
+    SurfelState s;
+    s.x = SM_S(SM_ROW_X, idx); s.y = SM_S(SM_ROW_Y, idx); s.z = SM_S(SM_ROW_Z, idx);
+    s.confidence = SM_S(SM_ROW_CONFIDENCE, idx);
+    s.radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+    s.nx = SM_S(SM_ROW_NORMAL_X, idx); s.ny = SM_S(SM_ROW_NORMAL_Y, idx); s.nz = SM_S(SM_ROW_NORMAL_Z, idx);
+    s.color = SM_SU(SM_ROW_COLOR, idx);
+    s.creation_stamp = SM_SU(SM_ROW_CREATION_STAMP, idx);
+    s.last_update_stamp = 0;
+    s.smooth_x = s.smooth_y = s.smooth_z = 0.f;
+    s.replaced = false; s.dirty = false; s.stamped = false;
+    if (s.radius_squared < 0.f) return;  // kernels.cu:1050
+    integrate_or_conflict(f, m0, p.px, p.py, idx, x, y, z, s);
+    if (has2) integrate_or_conflict(f, m1, ox, oy, idx, x, y, z, s);
+    if (!s.dirty) return;
+    SM_S(SM_ROW_X, idx) = s.x; SM_S(SM_ROW_Y, idx) = s.y; SM_S(SM_ROW_Z, idx) = s.z;
+    SM_S(SM_ROW_CONFIDENCE, idx) = s.confidence;
+    SM_S(SM_ROW_RADIUS_SQUARED, idx) = s.radius_squared;
+    SM_S(SM_ROW_NORMAL_X, idx) = s.nx; SM_S(SM_ROW_NORMAL_Y, idx) = s.ny; SM_S(SM_ROW_NORMAL_Z, idx) = s.nz;
+    SM_SU(SM_ROW_COLOR, idx) = s.color;
+    if (s.stamped) SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
+    if (s.replaced) {
+      SM_S(SM_ROW_SMOOTH_X, idx) = s.smooth_x; SM_S(SM_ROW_SMOOTH_Y, idx) = s.smooth_y; SM_S(SM_ROW_SMOOTH_Z, idx) = s.smooth_z;
+      SM_SU(SM_ROW_CREATION_STAMP, idx) = f.frame_index;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) SM_SU(SM_ROW_NEIGHBOR0 + i, idx) = kInvalidIndex;
+    }
+  });
 }
 
 // ---------------------------------------------------------------------------------------
@@ -571,87 +680,106 @@ __global__ void __launch_bounds__(kBlock) k_integrate(DeviceState d, FrameParams
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, FrameParams f) {
   const u32 n = d.counters->surfel_count[f.parity];
-  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
-    const u32 cnt = d.seg_count[seg];
-    const size_t list_base = static_cast<size_t>(seg) * kSegment;
-    for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) {
-      const u32 idx = d.vis[list_base + k].x & ~kActiveBit;
-      if (!is_active(SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx), f.frame_index, f.active_window)) continue;
-      // The position may have been changed by the integration: project again.
-      const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
-      const float cz_ = transform_row(f.local_T_global.r2, gx, gy, gz);
-      if (!(cz_ > 0.f)) continue;
-      const float cx_ = transform_row(f.local_T_global.r0, gx, gy, gz);
-      const float cy_ = transform_row(f.local_T_global.r1, gx, gy, gz);
-      const float inv_z = frcp(cz_);
-      const int x = f2i_trunc(ffma(fmul(cx_, inv_z), f.fx, f.cx));
-      const int y = f2i_trunc(ffma(fmul(cy_, inv_z), f.fy, f.cy));
-      constexpr int kBorder = 1;
-      if (x < kBorder || y < kBorder || x >= d.width - kBorder || y >= d.height - kBorder) continue;
+  for_each_visible(d, n, [&](size_t pos) {
+    const u32 idx = d.vis[pos].x & ~kActiveBit;
+    // batch 1: the surfel (its position may have been changed by the integration: project again)
+    const u32 stamp = SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx);
+    const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
+    const float nx = SM_S(SM_ROW_NORMAL_X, idx), ny = SM_S(SM_ROW_NORMAL_Y, idx), nz = SM_S(SM_ROW_NORMAL_Z, idx);
+    const float radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+    u32 neighbor_surfel_indices[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) neighbor_surfel_indices[m] = SM_SU(SM_ROW_NEIGHBOR0 + m, idx);
+    if (!is_active(stamp, f.frame_index, f.active_window)) return;
+    const float cz_ = transform_row(f.local_T_global.r2, gx, gy, gz);
+    if (!(cz_ > 0.f)) return;
+    const float cx_ = transform_row(f.local_T_global.r0, gx, gy, gz);
+    const float cy_ = transform_row(f.local_T_global.r1, gx, gy, gz);
+    const float inv_z = frcp(cz_);
+    const int x = f2i_trunc(ffma(fmul(cx_, inv_z), f.fx, f.cx));
+    const int y = f2i_trunc(ffma(fmul(cy_, inv_z), f.fy, f.cy));
+    constexpr int kBorder = 1;
+    if (x < kBorder || y < kBorder || x >= d.width - kBorder || y >= d.height - kBorder) return;
 
-      const float measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
-      if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) continue;
-      const float nx = SM_S(SM_ROW_NORMAL_X, idx), ny = SM_S(SM_ROW_NORMAL_Y, idx), nz = SM_S(SM_ROW_NORMAL_Z, idx);
-      float3 ln;
-      if (facing_dot(f, cx_, cy_, cz_, nx, ny, nz, &ln) > 0.f) continue;
-      const float radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
-      if (radius_squared < 0.f) continue;
-      // kCheckScaleCompatibilityForNeighborAssignment, factor 1.5^2.
-      if (fmul(row_ptr(f.radius, f.radius_pitch, y)[x], frcp(radius_squared)) > 2.25f) continue;
+    // batch 2: the pixel, the candidates of the 4-adjacent pixels, the current neighbours
+    const float measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
+    const float observation_radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
+    const int kDirectionsX[4] = {-1, 1, 0, 0};
+    const int kDirectionsY[4] = {0, 0, -1, 1};
+    u32 candidate[4];
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      candidate[direction] =
+          supporting_index(d.assoc[(y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction]].x);
+    }
+    float neighbor_distances_squared[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const u32 q = neighbor_surfel_indices[m];
+      if (q == kInvalidIndex) {
+        neighbor_distances_squared[m] = __int_as_float(0x7f800000);
+      } else {
+        neighbor_distances_squared[m] = squared_norm(fsub(gx, SM_S(SM_ROW_X, q)), fsub(gy, SM_S(SM_ROW_Y, q)),
+                                                     fsub(gz, SM_S(SM_ROW_Z, q)));
+      }
+    }
+    if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) return;  // occluded
+    float3 ln;
+    if (facing_dot(f, cx_, cy_, cz_, nx, ny, nz, &ln) > 0.f) return;
+    if (radius_squared < 0.f) return;
+    // kCheckScaleCompatibilityForNeighborAssignment, factor 1.5^2.
+    if (fmul(observation_radius_squared, frcp(radius_squared)) > 2.25f) return;
 
-      float neighbor_distances_squared[4];
-      u32 neighbor_surfel_indices[4];
+    // batch 3: positions and normals of the candidates
+    const float max_distance_squared = fmul(radius_squared, f.radius_factor_squared);
+    float cand_distance[4], cand_dot[4];
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      const u32 q = candidate[direction];
+      if (q == kInvalidIndex || q == idx) { candidate[direction] = kInvalidIndex; continue; }
+      cand_distance[direction] = squared_norm(fsub(SM_S(SM_ROW_X, q), gx), fsub(SM_S(SM_ROW_Y, q), gy),
+                                              fsub(SM_S(SM_ROW_Z, q), gz));
+      cand_dot[direction] = dot3(nx, ny, nz, SM_S(SM_ROW_NORMAL_X, q), SM_S(SM_ROW_NORMAL_Y, q), SM_S(SM_ROW_NORMAL_Z, q));
+    }
+    bool changed = false;
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      const u32 q = candidate[direction];
+      if (q == kInvalidIndex) continue;
+      const float distance_squared = cand_distance[direction];
+      if (distance_squared > max_distance_squared) continue;
+      if (cand_dot[direction] <= 0.f) continue;
+      // Already a neighbour, or best (farthest) slot to replace.
+      int best_n = -1;
+      float best_distance_squared = -1.f;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        neighbor_surfel_indices[m] = SM_SU(SM_ROW_NEIGHBOR0 + m, idx);
-        if (neighbor_surfel_indices[m] == kInvalidIndex) {
-          neighbor_distances_squared[m] = __int_as_float(0x7f800000);
-        } else {
-          const u32 q = neighbor_surfel_indices[m];
-          neighbor_distances_squared[m] = squared_norm(fsub(gx, SM_S(SM_ROW_X, q)), fsub(gy, SM_S(SM_ROW_Y, q)),
-                                                       fsub(gz, SM_S(SM_ROW_Z, q)));
+        if (q == neighbor_surfel_indices[m]) { best_n = -1; break; }
+        if (neighbor_distances_squared[m] > best_distance_squared) {
+          best_n = m;
+          best_distance_squared = neighbor_distances_squared[m];
         }
       }
-      const float max_distance_squared = fmul(radius_squared, f.radius_factor_squared);
-      const int kDirectionsX[4] = {-1, 1, 0, 0};
-      const int kDirectionsY[4] = {0, 0, -1, 1};
-#pragma unroll
-      for (int direction = 0; direction < 4; ++direction) {
-        const u32 q = supporting_index(d.assoc[(y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction]].x);
-        if (q == kInvalidIndex || q == idx) continue;
-        const float distance_squared = squared_norm(fsub(SM_S(SM_ROW_X, q), gx), fsub(SM_S(SM_ROW_Y, q), gy),
-                                                    fsub(SM_S(SM_ROW_Z, q), gz));
-        if (distance_squared > max_distance_squared) continue;
-        const float normal_dot = dot3(nx, ny, nz, SM_S(SM_ROW_NORMAL_X, q), SM_S(SM_ROW_NORMAL_Y, q),
-                                      SM_S(SM_ROW_NORMAL_Z, q));
-        if (normal_dot <= 0.f) continue;
-        // Already a neighbour, or best (farthest) slot to replace.
-        int best_n = -1;
-        float best_distance_squared = -1.f;
+      if (best_n >= 0 && distance_squared < best_distance_squared) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          if (q == neighbor_surfel_indices[m]) { best_n = -1; break; }
-          if (neighbor_distances_squared[m] > best_distance_squared) {
-            best_n = m;
-            best_distance_squared = neighbor_distances_squared[m];
-          }
+          if (m == best_n) { neighbor_surfel_indices[m] = q; neighbor_distances_squared[m] = distance_squared; }
         }
-        if (best_n >= 0 && distance_squared < best_distance_squared) {
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            if (m == best_n) { neighbor_surfel_indices[m] = q; neighbor_distances_squared[m] = distance_squared; }
-          }
-        }
+        changed = true;
       }
+    }
+    if (changed) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) SM_SU(SM_ROW_NEIGHBOR0 + m, idx) = neighbor_surfel_indices[m];
     }
-  }
+  });
 }
 
 // ---------------------------------------------------------------------------------------
 // a13: new-surfel flags + stable raster-order scan (single pass, decoupled look-back)
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long load_scan_state(unsigned long long* p) { return atomicAdd(p, 0ull); }
+
 __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, FrameParams f) {
   __shared__ u32 s_tile, s_prefix;
   __shared__ u32 warp_totals[kBlock / 32];
@@ -673,9 +801,8 @@ __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, Frame
       const int y = seq / d.width, x = seq - y * d.width;
       constexpr int kBorder = 1;
       if (x >= kBorder && y >= kBorder && x < d.width - kBorder && y < d.height - kBorder &&
-          row_ptr(f.depth, f.depth_pitch, y)[x] > 0) {
-        const PixelAssoc a = d.assoc[seq];
-        flag = (a.x == kInvalidIndex && a.y == kInvalidIndex) ? 1u : 0u;
+          row_ptr(f.depth, f.depth_pitch, y)[x] > 0 && !d.supported[seq]) {
+        flag = (d.assoc[seq].y == kInvalidIndex) ? 1u : 0u;
       }
     }
     flags[j] = flag;
@@ -697,33 +824,38 @@ __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, Frame
     if (w < warp) warp_base += t;
     block_total += t;
   }
-  if (threadIdx.x == 0) {
-    u32 prefix = 0;
-    if (tile == 0) {
-      atomicExch(&d.scan_state[0], (2ull << 32) | block_total);
-    } else {
-      atomicExch(&d.scan_state[tile], (1ull << 32) | block_total);
-      for (int t = static_cast<int>(tile) - 1; t >= 0; --t) {
-        unsigned long long v;
-        do {
-          v = atomicAdd(&d.scan_state[t], 0ull);
-        } while ((v >> 32) == 0ull);
-        prefix += static_cast<u32>(v);
-        if ((v >> 32) == 2ull) break;
+  if (warp == 0) {
+    // Publish this tile's aggregate, then look back 32 tiles at a time.
+    if (lane == 0) atomicExch(&d.scan_state[tile], ((tile == 0 ? 2ull : 1ull) << 32) | block_total);
+    u32 exclusive = 0;
+    int window_end = static_cast<int>(tile) - 1;  // nearest preceding tile
+    while (window_end >= 0) {
+      const int t = window_end - lane;
+      unsigned long long v = 2ull << 32;  // tiles before tile 0: inclusive prefix 0
+      if (t >= 0) {
+        do { v = load_scan_state(&d.scan_state[t]); } while ((v >> 32) == 0ull);
       }
-      atomicExch(&d.scan_state[tile], (2ull << 32) | (prefix + block_total));
+      const unsigned inclusive_mask = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
+      const int first_inclusive = __ffs(inclusive_mask) - 1;  // the closest tile that already has its prefix
+      const u32 contribution = (first_inclusive < 0 || lane <= first_inclusive) ? static_cast<u32>(v) : 0u;
+      exclusive += __reduce_add_sync(0xffffffffu, contribution);
+      if (first_inclusive >= 0) break;
+      window_end -= 32;
     }
-    s_prefix = prefix;
-    if (tile == static_cast<u32>(tiles) - 1) {
-      // new_surfel_count = indices[P-1] + flag[P-1] (kernels.cc:116-125, cuda_surfel_reconstruction.cc:291).
-      const u32 n_old = d.counters->surfel_count[f.parity];
-      u32 new_count = prefix + block_total;
-      if (static_cast<u64>(n_old) + new_count > d.capacity) {
-        d.counters->capacity_overflow = 1;  // the reference would write past the buffer here
-        new_count = 0;
+    if (lane == 0) {
+      if (tile != 0) atomicExch(&d.scan_state[tile], (2ull << 32) | (exclusive + block_total));
+      s_prefix = exclusive;
+      if (tile == static_cast<u32>(tiles) - 1) {
+        // new_surfel_count = indices[P-1] + flag[P-1] (kernels.cc:116-125, cuda_surfel_reconstruction.cc:291).
+        const u32 n_old = d.counters->surfel_count[f.parity];
+        u32 new_count = exclusive + block_total;
+        if (static_cast<u64>(n_old) + new_count > d.capacity) {
+          d.counters->capacity_overflow = 1;  // the reference would write past the buffer here
+          new_count = 0;
+        }
+        d.counters->new_surfel_count = new_count;
+        d.counters->surfel_count[f.parity ^ 1] = n_old + new_count;
       }
-      d.counters->new_surfel_count = new_count;
-      d.counters->surfel_count[f.parity ^ 1] = n_old + new_count;
     }
   }
   __syncthreads();
@@ -734,68 +866,86 @@ __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, Frame
     if (seq < total_pixels) {
       d.new_flag[seq] = static_cast<u8>(flags[j]);
       d.new_index[seq] = running;
+      if (flags[j]) d.new_list[running] = seq;  // compact list: the k-th new surfel comes from pixel new_list[k]
     }
     running += flags[j];
   }
 }
 
+// CreateNewSurfelsCUDACreationKernel (kernels.cu:133-231), one thread per NEW surfel.
 __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameParams f) {
-  if (d.counters->new_surfel_count == 0) return;
+  const u32 new_count = d.counters->new_surfel_count;
   const u32 surfel_count = d.counters->surfel_count[f.parity];
-  const int total_pixels = d.width * d.height;
-  for (int seq = blockIdx.x * blockDim.x + threadIdx.x; seq < total_pixels; seq += gridDim.x * blockDim.x) {
-    if (d.new_flag[seq] != 1) continue;
+  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < new_count; k += gridDim.x * blockDim.x) {
+    const int seq = d.new_list[k];
     const int y = seq / d.width, x = seq - y * d.width;
-    const u32 idx = surfel_count + d.new_index[seq];
+    const u32 idx = surfel_count + k;
+    // batch 1: the pixel and its four neighbours
     const float depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
+    const float2 nm = row_ptr(f.normals, f.normals_pitch, y)[x];
+    const uchar3 color = row_ptr(f.color, f.color_pitch, y)[x];
+    const float radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
+    const int kDirectionsX[4] = {-1, 1, 0, 0};
+    const int kDirectionsY[4] = {0, 0, -1, 1};
+    u32 neighbor_index[4], neighbor_new_index[4];
+    u8 neighbor_is_new[4];
+    u16 neighbor_depth[4];
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      const int nx_ = x + kDirectionsX[direction], ny_ = y + kDirectionsY[direction];
+      const int nseq = ny_ * d.width + nx_;
+      neighbor_index[direction] = supporting_index(d.assoc[nseq].x);
+      neighbor_is_new[direction] = d.new_flag[nseq];
+      neighbor_new_index[direction] = d.new_index[nseq];
+      neighbor_depth[direction] = row_ptr(f.depth, f.depth_pitch, ny_)[nx_];
+    }
     const float lx = fmul(depth, ffma(i2f(x), f.fx_inv, f.cx_inv));
     const float ly = fmul(depth, ffma(u2f(y), f.fy_inv, f.cy_inv));
     const float3 g = transform_point(f.global_T_local, lx, ly, depth);
-    SM_S(SM_ROW_X, idx) = g.x; SM_S(SM_ROW_Y, idx) = g.y; SM_S(SM_ROW_Z, idx) = g.z;
-    const float2 nm = row_ptr(f.normals, f.normals_pitch, y)[x];
     const float3 gn = rotate_vec(f.global_T_local, nm.x, nm.y, -normal_z_abs(nm.x, nm.y));
+    // batch 2: existing neighbours (kernels.cu:189-224)
+    const float max_distance_squared = fmul(radius_squared, f.radius_factor_squared);
+    float ndist[4], nsx[4], nsy[4], nsz[4];
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      const u32 q = neighbor_index[direction];
+      if (q == kInvalidIndex) continue;
+      ndist[direction] = squared_norm(fsub(SM_S(SM_ROW_X, q), g.x), fsub(SM_S(SM_ROW_Y, q), g.y), fsub(SM_S(SM_ROW_Z, q), g.z));
+      nsx[direction] = SM_S(SM_ROW_SMOOTH_X, q);
+      nsy[direction] = SM_S(SM_ROW_SMOOTH_Y, q);
+      nsz[direction] = SM_S(SM_ROW_SMOOTH_Z, q);
+    }
+    float sum_x = 0.f, sum_y = 0.f, sum_z = 0.f;
+    int existing_neighbor_count_plus_1 = 1;
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      u32 q = neighbor_index[direction];
+      if (q != kInvalidIndex) {
+        if (ndist[direction] > max_distance_squared) {
+          q = kInvalidIndex;
+        } else {
+          sum_x = fadd(sum_x, nsx[direction]);
+          sum_y = fadd(sum_y, nsy[direction]);
+          sum_z = fadd(sum_z, nsz[direction]);
+          ++existing_neighbor_count_plus_1;
+        }
+      } else if (neighbor_is_new[direction] == 1) {
+        const float diff = ffma(-u2f(neighbor_depth[direction]), f.inv_depth_scaling, depth);
+        if (!(fmul(diff, diff) > max_distance_squared)) q = surfel_count + neighbor_new_index[direction];
+      }
+      SM_SU(SM_ROW_NEIGHBOR0 + direction, idx) = q;
+    }
+    SM_S(SM_ROW_X, idx) = g.x; SM_S(SM_ROW_Y, idx) = g.y; SM_S(SM_ROW_Z, idx) = g.z;
     SM_S(SM_ROW_NORMAL_X, idx) = gn.x; SM_S(SM_ROW_NORMAL_Y, idx) = gn.y; SM_S(SM_ROW_NORMAL_Z, idx) = gn.z;
-    const uchar3 color = row_ptr(f.color, f.color_pitch, y)[x];
     SM_SU(SM_ROW_COLOR, idx) = color.x | (color.y << 8) | (color.z << 16);
     SM_S(SM_ROW_CONFIDENCE, idx) = 1.0f;
     SM_SU(SM_ROW_CREATION_STAMP, idx) = f.frame_index;
     SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
-    const float radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
     SM_S(SM_ROW_RADIUS_SQUARED, idx) = radius_squared;
     // The reference leaves rows 11-16 and 23 uninitialised; the regularisation of this
     // library relies on rows 11-13 and 23 being zero between calls (regularize.cu).
     SM_S(SM_ROW_GRADIENT_X, idx) = 0.f; SM_S(SM_ROW_GRADIENT_Y, idx) = 0.f; SM_S(SM_ROW_GRADIENT_Z, idx) = 0.f;
     SM_S(SM_ROW_GRADIENT_COUNT, idx) = 0.f;
-
-    // Initial neighbours (kernels.cu:189-224).
-    const float max_distance_squared = fmul(radius_squared, f.radius_factor_squared);
-    float sum_x = 0.f, sum_y = 0.f, sum_z = 0.f;
-    int existing_neighbor_count_plus_1 = 1;
-    const int kDirectionsX[4] = {-1, 1, 0, 0};
-    const int kDirectionsY[4] = {0, 0, -1, 1};
-#pragma unroll
-    for (int direction = 0; direction < 4; ++direction) {
-      const int nx_ = x + kDirectionsX[direction], ny_ = y + kDirectionsY[direction];
-      const int nseq = ny_ * d.width + nx_;
-      u32 neighbor_index = supporting_index(d.assoc[nseq].x);
-      if (neighbor_index != kInvalidIndex) {
-        const float distance_squared =
-            squared_norm(fsub(SM_S(SM_ROW_X, neighbor_index), g.x), fsub(SM_S(SM_ROW_Y, neighbor_index), g.y),
-                         fsub(SM_S(SM_ROW_Z, neighbor_index), g.z));
-        if (distance_squared > max_distance_squared) {
-          neighbor_index = kInvalidIndex;
-        } else {
-          sum_x = fadd(sum_x, SM_S(SM_ROW_SMOOTH_X, neighbor_index));
-          sum_y = fadd(sum_y, SM_S(SM_ROW_SMOOTH_Y, neighbor_index));
-          sum_z = fadd(sum_z, SM_S(SM_ROW_SMOOTH_Z, neighbor_index));
-          ++existing_neighbor_count_plus_1;
-        }
-      } else if (d.new_flag[nseq] == 1) {
-        const float diff = ffma(-u2f(row_ptr(f.depth, f.depth_pitch, ny_)[nx_]), f.inv_depth_scaling, depth);
-        if (!(fmul(diff, diff) > max_distance_squared)) neighbor_index = surfel_count + d.new_index[nseq];
-      }
-      SM_SU(SM_ROW_NEIGHBOR0 + direction, idx) = neighbor_index;
-    }
     const float rcp_count = frcp(i2f(existing_neighbor_count_plus_1));
     SM_S(SM_ROW_SMOOTH_X, idx) = fmul(fadd(g.x, sum_x), rcp_count);
     SM_S(SM_ROW_SMOOTH_Y, idx) = fmul(fadd(g.y, sum_y), rcp_count);
@@ -841,7 +991,7 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
     const int status = ClearAssociationRasters(stream, d);
     if (status != SM_OK) return status;
   }
-  { LaunchScope scope(stream, KID_PROJECT); k_project<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_PROJECT); k_project<<<sm_count * 4, kProjectBlock, 0, stream>>>(d, f); }
   { LaunchScope scope(stream, KID_ASSOCIATE); k_associate<<<list_grid, kBlock, 0, stream>>>(d, f); }
   record(1); record(2);
   { LaunchScope scope(stream, KID_MERGE); k_merge<<<list_grid, kBlock, 0, stream>>>(d, f); }
@@ -849,7 +999,7 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
   if (do_blending) {
     const int halo = f.blend_radius - 1 > 1 ? f.blend_radius - 1 : 1;
     const size_t rn = static_cast<size_t>(kBlendTileW + 2 * halo) * (kBlendTileH + 2 * halo);
-    const size_t smem = rn * (4 + 4 + 2 + 2 + 1 + 1 + 1) + 16;
+    const size_t smem = ((rn + 3) & ~static_cast<size_t>(3)) * 23 + 16;
     if (smem > 200 * 1024) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
     static size_t configured_smem = 0;
     if (smem > 48 * 1024 && smem > configured_smem) {
@@ -857,7 +1007,7 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
         return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend)");
       configured_smem = smem;
     }
-    { LaunchScope scope(stream, KID_BLEND); k_blend<<<pixel_tiles, 512, smem, stream>>>(d, f); }
+    { LaunchScope scope(stream, KID_BLEND); k_blend<<<pixel_tiles, kBlendBlock, smem, stream>>>(d, f); }
   }
   record(5); record(6);
   { LaunchScope scope(stream, KID_INTEGRATE); k_integrate<<<list_grid, kBlock, 0, stream>>>(d, f); }
@@ -865,7 +1015,7 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
   { LaunchScope scope(stream, KID_UPDATE_NEIGHBORS); k_update_neighbors<<<list_grid, kBlock, 0, stream>>>(d, f); }
   record(9); record(10);
   { LaunchScope scope(stream, KID_NEW_SURFEL_SCAN); k_new_surfel_scan<<<scan_tiles, kBlock, 0, stream>>>(d, f); }
-  { LaunchScope scope(stream, KID_CREATE_SURFELS); k_create_surfels<<<(d.width * d.height + kBlock - 1) / kBlock, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_CREATE_SURFELS); k_create_surfels<<<sm_count * 2, kBlock, 0, stream>>>(d, f); }
   record(11);
   return CheckLaunch("integrate");
 }

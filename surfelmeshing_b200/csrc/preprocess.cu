@@ -149,43 +149,45 @@ struct OutlierArgs {
   size_t other_pitches[kMaxOthers];
 };
 
-__device__ __forceinline__ bool outlier_check_one(const OutlierArgs& a, int k, float px, float py, float d) {
-  const Mat3x4& m = a.other_TR_reference[k];
-  const float oz = transform_row(m.r2, px, py, d);
-  if (oz <= 0.f) return false;
-  const float ox = transform_row(m.r0, px, py, d);
-  const float oy = transform_row(m.r1, px, py, d);
-  const float inv_z = frcp(oz);
-  const float u = ffma(fmul(ox, inv_z), a.fx, a.cx);
-  const float v = ffma(fmul(oy, inv_z), a.fy, a.cy);
-  const int ix = f2i_trunc(u);
-  const int iy = f2i_trunc(v);
-  if (ix < 0 || iy < 0 || ix >= a.width || iy >= a.height) return false;
-  const u16 od = row_ptr(a.other_depths[k], a.other_pitches[k], iy)[ix];
-  if (od == 0) return false;
-  const float odf = u2f(od);
-  if (fmul(a.max_tolerance_factor, oz) < odf) return false;
-  if (fmul(a.min_tolerance_factor, oz) > odf) return false;
-  return true;
-}
-
-// Returns the depth value to keep (depth_value or 0).
+// Returns the depth value to keep (depth_value or 0). The reference walks the other frames
+// one after the other and stops at the first failure; here the K projections are computed
+// first and the K depth gathers are issued together (same decisions, one memory round trip).
 __device__ __forceinline__ u16 outlier_pixel(const OutlierArgs& a, unsigned x, unsigned y, u16 depth_value) {
   if (depth_value == 0) return 0;
   const float d = u2f(depth_value);
   const float px = fmul(ffma(a.fx_inv, u2f(x), a.cx_inv), d);
   const float py = fmul(ffma(a.fy_inv, u2f(y), a.cy_inv), d);
-  if (a.required_count < 0) {
-    for (int k = 0; k < a.other_count; ++k) {
-      if (!outlier_check_one(a, k, px, py, d)) return 0;
-    }
-    return depth_value;
+  float oz[kMaxOthers];
+  const u16* sample[kMaxOthers];
+#pragma unroll
+  for (int k = 0; k < kMaxOthers; ++k) {
+    sample[k] = nullptr;
+    if (k >= a.other_count) continue;
+    const Mat3x4& m = a.other_TR_reference[k];
+    oz[k] = transform_row(m.r2, px, py, d);
+    if (oz[k] <= 0.f) continue;
+    const float ox = transform_row(m.r0, px, py, d);
+    const float oy = transform_row(m.r1, px, py, d);
+    const float inv_z = frcp(oz[k]);
+    const int ix = f2i_trunc(ffma(fmul(ox, inv_z), a.fx, a.cx));
+    const int iy = f2i_trunc(ffma(fmul(oy, inv_z), a.fy, a.cy));
+    if (ix < 0 || iy < 0 || ix >= a.width || iy >= a.height) continue;
+    sample[k] = row_ptr(a.other_depths[k], a.other_pitches[k], iy) + ix;
   }
+  u16 od[kMaxOthers];
+#pragma unroll
+  for (int k = 0; k < kMaxOthers; ++k) od[k] = sample[k] ? __ldg(sample[k]) : static_cast<u16>(0);
   int ok_count = 0;
-  for (int k = 0; k < a.other_count; ++k) {
-    ok_count += outlier_check_one(a, k, px, py, d) ? 1 : 0;
+#pragma unroll
+  for (int k = 0; k < kMaxOthers; ++k) {
+    if (k >= a.other_count || od[k] == 0) continue;
+    const float odf = u2f(od[k]);
+    if (fmul(a.max_tolerance_factor, oz[k]) < odf) continue;
+    if (fmul(a.min_tolerance_factor, oz[k]) > odf) continue;
+    ++ok_count;
   }
-  return ok_count >= a.required_count ? depth_value : 0;
+  const int required = a.required_count < 0 ? a.other_count : a.required_count;
+  return ok_count >= required ? depth_value : static_cast<u16>(0);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -413,7 +415,7 @@ struct TailArgs {
   float2* out_normals; size_t out_normals_pitch;
   float* out_radius; size_t out_radius_pitch;
   // Optional: association rasters to reset for the following Integrate().
-  uint4* assoc; float* first_depth;
+  uint4* assoc; float* first_depth; u8* supported;
 };
 
 constexpr int kMaxErode = 3;
@@ -502,6 +504,7 @@ k_erode_normals_radii(TailArgs a) {
         const size_t p = static_cast<size_t>(gy) * a.width + gx;
         a.assoc[p] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
         a.first_depth[p] = __int_as_float(0x7f800000);
+        a.supported[p] = 0;
       }
     }
   }
@@ -658,7 +661,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
                     const size_t* other_pitches, const float* others_TR_reference, u16* scratch_B,
                     size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch, float2* out_normals,
                     size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
-                    float* clear_first_depth) {
+                    float* clear_first_depth, u8* clear_supported) {
   if (p.depth_erosion_radius < 0 || p.depth_erosion_radius > kMaxErode) {
     return SetError(SM_ERR_INVALID_ARGUMENT, "depth_erosion_radius must be in [0, 3]");
   }
@@ -683,7 +686,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
   t.out_depth = out_depth; t.out_depth_pitch = out_depth_pitch;
   t.out_normals = out_normals; t.out_normals_pitch = out_normals_pitch;
   t.out_radius = out_radius; t.out_radius_pitch = out_radius_pitch;
-  t.assoc = clear_assoc; t.first_depth = clear_first_depth;
+  t.assoc = clear_assoc; t.first_depth = clear_first_depth; t.supported = clear_supported;
   { LaunchScope scope(stream, KID_ERODE_NORMALS_RADII); k_erode_normals_radii<<<TileGrid(width, height), 512, 0, stream>>>(t); }
   return CheckLaunch("erode/normals/radii");
 }

@@ -46,31 +46,45 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
     u32 nbr[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) nbr[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
+    if ((nbr[0] & nbr[1] & nbr[2] & nbr[3]) == kInvalidIndex) continue;  // no neighbours at all
 
-    if (i < n_remove) {
-      // UpdateNeighborsCUDARemoveReplacedNeighborsKernel (kernels.cu:1420-1437).
+    // batch 1: detach flags and stamps of the neighbours, and this surfel's own attributes
+    u32 flag_word[4], stamp[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (nbr[k] != kInvalidIndex && (SM_SU(SM_ROW_COLOR, nbr[k]) >> 24) == 1u) {
-          nbr[k] = kInvalidIndex;
-          SM_SU(SM_ROW_NEIGHBOR0 + k, i) = kInvalidIndex;
-        }
-      }
+    for (int k = 0; k < 4; ++k) {
+      const u32 q = nbr[k] != kInvalidIndex ? nbr[k] : i;
+      flag_word[k] = SM_SU(SM_ROW_COLOR, q);
+      stamp[k] = SM_SU(SM_ROW_LAST_UPDATE_STAMP, q);
     }
+    const float sx = SM_S(SM_ROW_SMOOTH_X, i), sy = SM_S(SM_ROW_SMOOTH_Y, i), sz = SM_S(SM_ROW_SMOOTH_Z, i);
+    const float nx = SM_S(SM_ROW_NORMAL_X, i), ny = SM_S(SM_ROW_NORMAL_Y, i), nz = SM_S(SM_ROW_NORMAL_Z, i);
+    const float radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, i);
 
-    // Count neighbours inside the window (kernels.cu:2125-2139).
+    // UpdateNeighborsCUDARemoveReplacedNeighborsKernel (kernels.cu:1420-1437) for the slots
+    // that existed before this frame, then the in-window count (kernels.cu:2125-2139).
     bool use[4];
     int neighbor_count = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      use[k] = nbr[k] != kInvalidIndex && !outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, nbr[k]), p);
+      if (i < n_remove && nbr[k] != kInvalidIndex && (flag_word[k] >> 24) == 1u) {
+        nbr[k] = kInvalidIndex;
+        SM_SU(SM_ROW_NEIGHBOR0 + k, i) = kInvalidIndex;
+      }
+      use[k] = nbr[k] != kInvalidIndex && !outside_window(stamp[k], p);
       neighbor_count += use[k] ? 1 : 0;
     }
     if (neighbor_count == 0) continue;
 
-    const float sx = SM_S(SM_ROW_SMOOTH_X, i), sy = SM_S(SM_ROW_SMOOTH_Y, i), sz = SM_S(SM_ROW_SMOOTH_Z, i);
-    const float nx = SM_S(SM_ROW_NORMAL_X, i), ny = SM_S(SM_ROW_NORMAL_Y, i), nz = SM_S(SM_ROW_NORMAL_Z, i);
-    const float max_distance_squared = fmul(SM_S(SM_ROW_RADIUS_SQUARED, i), p.radius_factor_squared);
+    // batch 2: smooth positions of the neighbours
+    float qx[4], qy[4], qz[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const u32 q = use[k] ? nbr[k] : i;
+      qx[k] = SM_S(SM_ROW_SMOOTH_X, q);
+      qy[k] = SM_S(SM_ROW_SMOOTH_Y, q);
+      qz[k] = SM_S(SM_ROW_SMOOTH_Z, q);
+    }
+    const float max_distance_squared = fmul(radius_squared, p.radius_factor_squared);
     const float rcp_count = frcp(i2f(neighbor_count));
     const float factor = fmul(fadd(p.regularizer_weight, p.regularizer_weight), rcp_count);  // 2 * w / count
     const float weight_term = fmul(rcp_count, p.regularizer_weight);                         // w / count
@@ -78,9 +92,9 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
     for (int k = 0; k < 4; ++k) {
       if (!use[k]) continue;
       const u32 q = nbr[k];
-      const float dx = fsub(SM_S(SM_ROW_SMOOTH_X, q), sx);
-      const float dy = fsub(SM_S(SM_ROW_SMOOTH_Y, q), sy);
-      const float dz = fsub(SM_S(SM_ROW_SMOOTH_Z, q), sz);
+      const float dx = fsub(qx[k], sx);
+      const float dy = fsub(qy[k], sy);
+      const float dz = fsub(qz[k], sz);
       const float f = fmul(factor, ffma(nz, dz, ffma(nx, dx, fmul(ny, dy))));
       atomicAdd(&SM_S(SM_ROW_GRADIENT_X, q), fmul(nx, f));
       atomicAdd(&SM_S(SM_ROW_GRADIENT_Y, q), fmul(ny, f));
@@ -104,14 +118,24 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
     float gz = ffma(fsub(sz, SM_S(SM_ROW_Z, i)), 2.0f, SM_S(SM_ROW_GRADIENT_Z, i));
     int neighbor_count = 0;
     float rx = 0.f, ry = 0.f, rz = 0.f;
+    u32 nbr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nbr[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
+    float qx[4], qy[4], qz[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const u32 q = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
-      if (q == kInvalidIndex) continue;
+      const u32 q = nbr[k] != kInvalidIndex ? nbr[k] : i;
+      qx[k] = SM_S(SM_ROW_SMOOTH_X, q);
+      qy[k] = SM_S(SM_ROW_SMOOTH_Y, q);
+      qz[k] = SM_S(SM_ROW_SMOOTH_Z, q);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (nbr[k] == kInvalidIndex) continue;
       ++neighbor_count;
-      const float dx = fsub(SM_S(SM_ROW_SMOOTH_X, q), sx);
-      const float dy = fsub(SM_S(SM_ROW_SMOOTH_Y, q), sy);
-      const float dz = fsub(SM_S(SM_ROW_SMOOTH_Z, q), sz);
+      const float dx = fsub(qx[k], sx);
+      const float dy = fsub(qy[k], sy);
+      const float dz = fsub(qz[k], sz);
       const float normal_dot_difference = ffma(nz, dz, ffma(nx, dx, fmul(ny, dy)));
       rx = ffma(-nx, normal_dot_difference, rx);
       ry = ffma(-ny, normal_dot_difference, ry);

@@ -85,11 +85,13 @@ struct DeviceState {
   int width, height;
   PixelAssoc* assoc;     // W*H
   float* first_depth;    // W*H
+  u8* supported;         // W*H: 1 iff the pixel has a supporting surfel (assoc.x != invalid)
   VisEntry* vis;         // capacity (rounded up to kSegment)
   u32* seg_count;        // capacity / kSegment
   u8* merge_flag;        // per list position
   u8* new_flag;          // W*H
   u32* new_index;        // W*H
+  u32* new_list;         // W*H: pixel (seq index) of the k-th new surfel
   unsigned long long* scan_state;  // per scan tile: status << 32 | value
   Counters* counters;
 };
@@ -122,7 +124,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
                     const size_t* other_pitches, const float* others_TR_reference, u16* scratch_B,
                     size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch, float2* out_normals,
                     size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
-                    float* clear_first_depth);
+                    float* clear_first_depth, u8* clear_supported);
 int StageBilateral(cudaStream_t stream, float sigma_xy, float sigma_value_factor, u16 value_to_ignore,
                    float radius_factor, u16 max_depth, float depth_valid_region_radius, int width, int height,
                    const u16* in, size_t in_pitch, u16* out, size_t out_pitch);

