@@ -1002,6 +1002,12 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
     const size_t smem = ((rn + 3) & ~static_cast<size_t>(3)) * 23 + 16;
     if (smem > 200 * 1024) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
     static size_t configured_smem = 0;
+    static bool carveout_set = false;
+    if (!carveout_set) {
+      // several 47 KB blocks per SM: ask for the maximum shared-memory carve-out
+      cudaFuncSetAttribute(k_blend, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      carveout_set = true;
+    }
     if (smem > 48 * 1024 && smem > configured_smem) {
       if (cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
         return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend)");
