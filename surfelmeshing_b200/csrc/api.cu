@@ -101,10 +101,17 @@ struct sm_reconstruction {
   Counters* host_counters = nullptr;
   // pre-processing scratch (APP/main.cc filtered_depth_buffer_B)
   u16* scratch_B = nullptr; size_t scratch_B_pitch = 0;
-  // stream-runner buffers
-  u16* run_depth = nullptr; size_t run_depth_pitch = 0;
-  float2* run_normals = nullptr; size_t run_normals_pitch = 0;
-  float* run_radius = nullptr; size_t run_radius_pitch = 0;
+  // Association rasters exist twice so that the fused pre-processing tail of frame f + 1 can
+  // reset one set while Integrate() of frame f still works on the other (sm_stream_run).
+  PixelAssoc* assoc_set[2] = {nullptr, nullptr};
+  float* first_depth_set[2] = {nullptr, nullptr};
+  u8* supported_set[2] = {nullptr, nullptr};
+  // stream-runner buffers (double-buffered pre-processing outputs)
+  u16* run_depth[2] = {nullptr, nullptr}; size_t run_depth_pitch = 0;
+  float2* run_normals[2] = {nullptr, nullptr}; size_t run_normals_pitch = 0;
+  float* run_radius[2] = {nullptr, nullptr}; size_t run_radius_pitch = 0;
+  cudaStream_t pre_stream = nullptr;
+  cudaEvent_t pre_done[2] = {nullptr, nullptr}, int_done[2] = {nullptr, nullptr}, entry_event = nullptr;
   std::vector<u16*> ring_depth; size_t ring_depth_pitch = 0;
   uchar3* ring_color[2] = {nullptr, nullptr}; size_t ring_color_pitch = 0;
   cudaStream_t upload_stream = nullptr;
@@ -189,11 +196,17 @@ int IntegrateImpl(sm_reconstruction* r, cudaStream_t stream, u32 frame_index, co
 
 int EnsureRunBuffers(sm_reconstruction* r, int ring, bool on_host) {
   const int W = r->d.width, H = r->d.height;
-  if (!r->run_depth) {
-    SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_depth), &r->run_depth_pitch, W * sizeof(u16), H));
-    SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_normals), &r->run_normals_pitch, W * sizeof(float2), H));
-    SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_radius), &r->run_radius_pitch, W * sizeof(float), H));
-    SM_CUDA(cudaMemset2D(r->run_radius, r->run_radius_pitch, 0, W * sizeof(float), H));
+  if (!r->run_depth[0]) {
+    for (int i = 0; i < 2; ++i) {
+      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_depth[i]), &r->run_depth_pitch, W * sizeof(u16), H));
+      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_normals[i]), &r->run_normals_pitch, W * sizeof(float2), H));
+      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_radius[i]), &r->run_radius_pitch, W * sizeof(float), H));
+      SM_CUDA(cudaMemset2D(r->run_radius[i], r->run_radius_pitch, 0, W * sizeof(float), H));
+      SM_CUDA(cudaEventCreateWithFlags(&r->pre_done[i], cudaEventDisableTiming));
+      SM_CUDA(cudaEventCreateWithFlags(&r->int_done[i], cudaEventDisableTiming));
+    }
+    SM_CUDA(cudaStreamCreateWithFlags(&r->pre_stream, cudaStreamNonBlocking));
+    SM_CUDA(cudaEventCreateWithFlags(&r->entry_event, cudaEventDisableTiming));
   }
   if (on_host && static_cast<int>(r->ring_depth.size()) != ring) {
     for (u16* b : r->ring_depth) cudaFree(b);
@@ -301,9 +314,12 @@ int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width,
   const size_t P = static_cast<size_t>(width) * height;
   const size_t scan_tiles = (P + kSegment - 1) / kSegment;
   SM_CUDA(cudaMalloc(&d.surfels, sizeof(float) * SM_ROW_COUNT * d.stride));
-  SM_CUDA(cudaMalloc(&d.assoc, sizeof(PixelAssoc) * P));
-  SM_CUDA(cudaMalloc(&d.first_depth, sizeof(float) * P));
-  SM_CUDA(cudaMalloc(&d.supported, P));
+  for (int i = 0; i < 2; ++i) {
+    SM_CUDA(cudaMalloc(&r->assoc_set[i], sizeof(PixelAssoc) * P));
+    SM_CUDA(cudaMalloc(&r->first_depth_set[i], sizeof(float) * P));
+    SM_CUDA(cudaMalloc(&r->supported_set[i], P));
+  }
+  d.assoc = r->assoc_set[0]; d.first_depth = r->first_depth_set[0]; d.supported = r->supported_set[0];
   SM_CUDA(cudaMalloc(&d.new_list, sizeof(u32) * P));
   SM_CUDA(cudaMalloc(&d.vis, sizeof(VisEntry) * padded));
   SM_CUDA(cudaMalloc(&d.seg_count, sizeof(u32) * (padded / kSegment)));
@@ -332,10 +348,19 @@ int sm_destroy(sm_reconstruction* r) {
   if (!r) return SM_OK;
   cudaDeviceSynchronize();
   DeviceState& d = r->d;
-  cudaFree(d.surfels); cudaFree(d.assoc); cudaFree(d.first_depth); cudaFree(d.supported); cudaFree(d.new_list); cudaFree(d.vis); cudaFree(d.seg_count);
+  cudaFree(d.surfels); cudaFree(d.new_list);
+  for (int i = 0; i < 2; ++i) { cudaFree(r->assoc_set[i]); cudaFree(r->first_depth_set[i]); cudaFree(r->supported_set[i]); }
+  cudaFree(d.vis); cudaFree(d.seg_count);
   cudaFree(d.merge_flag); cudaFree(d.new_flag); cudaFree(d.new_index); cudaFree(d.scan_state); cudaFree(d.counters);
   cudaFreeHost(r->host_counters);
-  cudaFree(r->scratch_B); cudaFree(r->run_depth); cudaFree(r->run_normals); cudaFree(r->run_radius);
+  cudaFree(r->scratch_B);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(r->run_depth[i]); cudaFree(r->run_normals[i]); cudaFree(r->run_radius[i]);
+    if (r->pre_done[i]) cudaEventDestroy(r->pre_done[i]);
+    if (r->int_done[i]) cudaEventDestroy(r->int_done[i]);
+  }
+  if (r->pre_stream) cudaStreamDestroy(r->pre_stream);
+  if (r->entry_event) cudaEventDestroy(r->entry_event);
   for (u16* b : r->ring_depth) cudaFree(b);
   cudaFree(r->ring_color[0]); cudaFree(r->ring_color[1]);
   if (r->upload_stream) {
@@ -585,29 +610,44 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
     *pitch = W * sizeof(u16);
     return s->depth + frame_elems * frame;
   };
+  // Two-deep software pipeline: the pre-processing of frame f + 1 (pre_stream) runs while frame f
+  // is integrated (caller's stream). Buffer set f & 1 holds frame f's pre-processing outputs and
+  // association rasters; it is reused by frame f + 2 once Integrate(f) has finished.
+  SM_CUDA(cudaEventRecord(r->entry_event, stream));
+  SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->entry_event, 0));
+  if (s->frames_on_host) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->entry_event, 0));
   int uploaded_until = first_frame - half - 1;
-  uint32_t integrated = 0;
-  for (int frame = first_frame; frame < last_frame; ++frame) {
-    const uint8_t* color = s->color + 3 * frame_elems * frame;
-    size_t color_pitch = static_cast<size_t>(W) * 3;
+  const uint8_t* frame_color[2] = {nullptr, nullptr};
+  size_t frame_color_pitch = static_cast<size_t>(W) * 3;
+
+  auto enqueue_preprocess = [&](int frame) -> int {
+    const int set = frame & 1;
+    const bool reuse = frame >= first_frame + 2;
+    frame_color[set] = s->color + 3 * frame_elems * frame;
     if (s->frames_on_host) {
       // Upload stream (main.cc:902-984): the new raw depth map(s) and this frame's colour image.
-      // Ring slots written for frame f were last read by frame f - 2.
-      if (frame >= first_frame + 2) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->frame_done[frame % 2], 0));
+      // The raw-depth ring slot written now was last read by the pre-processing of frame - 2,
+      // the colour slot by Integrate(frame - 2).
+      if (reuse) {
+        SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->pre_done[set], 0));
+        SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->int_done[set], 0));
+      }
       for (int f = uploaded_until + 1; f <= frame + half; ++f) {
         SM_CUDA(cudaMemcpy2DAsync(r->ring_depth[f % ring], r->ring_depth_pitch, s->depth + frame_elems * f,
                                   W * sizeof(u16), W * sizeof(u16), H, cudaMemcpyHostToDevice, r->upload_stream));
         h2d += frame_elems * sizeof(u16);
       }
       uploaded_until = frame + half;
-      SM_CUDA(cudaMemcpy2DAsync(r->ring_color[frame % 2], r->ring_color_pitch, color, static_cast<size_t>(W) * 3,
-                                static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice, r->upload_stream));
+      SM_CUDA(cudaMemcpy2DAsync(r->ring_color[set], r->ring_color_pitch, s->color + 3 * frame_elems * frame,
+                                static_cast<size_t>(W) * 3, static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice,
+                                r->upload_stream));
       h2d += frame_elems * 3;
       SM_CUDA(cudaEventRecord(r->upload_done, r->upload_stream));
-      SM_CUDA(cudaStreamWaitEvent(stream, r->upload_done, 0));  // main.cc:995
-      color = reinterpret_cast<const uint8_t*>(r->ring_color[frame % 2]);
-      color_pitch = r->ring_color_pitch;
+      SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->upload_done, 0));  // main.cc:995
+      frame_color[set] = reinterpret_cast<const uint8_t*>(r->ring_color[set]);
+      frame_color_pitch = r->ring_color_pitch;
     }
+    if (reuse) SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->int_done[set], 0));
     const u16* others[8];
     size_t other_pitches[8];
     for (int i = 0; i < half; ++i) {  // main.cc:1046-1059
@@ -616,17 +656,37 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
     }
     size_t raw_pitch;
     const u16* raw = raw_ptr(frame, &raw_pitch);
-    status = sm_preprocess(r, stream, pp, raw, raw_pitch, others, other_pitches,
-                           s->others_TR_reference + static_cast<size_t>(frame) * K * 12, r->run_depth,
-                           r->run_depth_pitch, reinterpret_cast<float*>(r->run_normals), r->run_normals_pitch,
-                           r->run_radius, r->run_radius_pitch);
+    const int st = PreprocessFused(r->pre_stream, *pp, W, H, r->fx, r->fy, r->cx, r->cy, raw, raw_pitch, others,
+                                   other_pitches, s->others_TR_reference + static_cast<size_t>(frame) * K * 12,
+                                   r->scratch_B, r->scratch_B_pitch, r->run_depth[set], r->run_depth_pitch,
+                                   r->run_normals[set], r->run_normals_pitch, r->run_radius[set], r->run_radius_pitch,
+                                   r->assoc_set[set], r->first_depth_set[set], r->supported_set[set]);
+    if (st != SM_OK) return st;
+    SM_CUDA(cudaEventRecord(r->pre_done[set], r->pre_stream));
+    return SM_OK;
+  };
+
+  uint32_t integrated = 0;
+  if (first_frame < last_frame) {
+    status = enqueue_preprocess(first_frame);
     if (status != SM_OK) return status;
-    status = IntegrateImpl(r, stream, static_cast<u32>(frame), *ip, r->run_depth, r->run_depth_pitch,
-                           reinterpret_cast<const float*>(r->run_normals), r->run_normals_pitch, r->run_radius,
-                           r->run_radius_pitch, color, color_pitch, s->global_T_frame + 12 * frame,
-                           s->frame_T_global + 12 * frame);
+  }
+  for (int frame = first_frame; frame < last_frame; ++frame) {
+    const int set = frame & 1;
+    if (frame + 1 < last_frame) {
+      status = enqueue_preprocess(frame + 1);
+      if (status != SM_OK) return status;
+    }
+    SM_CUDA(cudaStreamWaitEvent(stream, r->pre_done[set], 0));
+    r->d.assoc = r->assoc_set[set]; r->d.first_depth = r->first_depth_set[set]; r->d.supported = r->supported_set[set];
+    r->rasters_cleared = true;
+    status = IntegrateImpl(r, stream, static_cast<u32>(frame), *ip, r->run_depth[set], r->run_depth_pitch,
+                           reinterpret_cast<const float*>(r->run_normals[set]), r->run_normals_pitch,
+                           r->run_radius[set], r->run_radius_pitch, frame_color[set],
+                           s->frames_on_host ? r->ring_color_pitch : static_cast<size_t>(W) * 3,
+                           s->global_T_frame + 12 * frame, s->frame_T_global + 12 * frame);
     if (status != SM_OK) return status;
-    if (s->frames_on_host) SM_CUDA(cudaEventRecord(r->frame_done[frame % 2], stream));
+    SM_CUDA(cudaEventRecord(r->int_done[set], stream));
     ++integrated;
   }
   status = FetchCounters(r, stream);  // one 32-byte D2H + sync for the whole call

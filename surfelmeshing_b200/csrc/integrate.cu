@@ -350,7 +350,10 @@ __device__ __forceinline__ bool claim_byte(u8* map, int i, u32 expected) {
 
 __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParams f) {
   extern __shared__ __align__(16) unsigned char blend_smem[];
-  __shared__ int s_count[2][2];  // [ring][ping-pong] frontier sizes
+  // Frontier lists: ring 0 = measurement-border ring (distance_map), ring 1 = surfel-border
+  // ring (new_distance_map). Each list only grows (a pixel enters a ring once); the current
+  // frontier is the window [s_begin, s_end) and claims are appended at s_tail.
+  __shared__ int s_begin[2], s_end[2], s_tail[2];
   const int radius = f.blend_radius;
   const int halo = max(radius - 1, 1);          // (radius - 2) iterations + the 3x3 start stencil
   const int rw = kBlendTileW + 2 * halo, rh = kBlendTileH + 2 * halo;
@@ -360,17 +363,20 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   float* s_ndelta = s_delta + rn4;
   u16* s_depth0 = reinterpret_cast<u16*>(s_ndelta + rn4);  // depth as handed in (start stencil reads this)
   u16* s_depth = s_depth0 + rn4;                            // working depth
-  u16* s_front = s_depth + rn4;                             // frontier lists: [ring][ping-pong][rn4]
-  u8* s_sup = reinterpret_cast<u8*>(s_front + 4 * rn4);
+  u16* s_front = s_depth + rn4;                             // [ring][rn4], entries (ly << 8) | lx
+  u8* s_sup = reinterpret_cast<u8*>(s_front + 2 * rn4);
   u8* s_dist = s_sup + rn4;
   u8* s_ndist = s_dist + rn4;
 
   const int tile_x = blockIdx.x * kBlendTileW, tile_y = blockIdx.y * kBlendTileH;
   const int x0 = tile_x - halo, y0 = tile_y - halo;
+  // Region pixels (lx, ly) handled by this thread: i = threadIdx.x + k * kBlendBlock, walked
+  // incrementally (no division by the run-time region width).
+  const int step_y = kBlendBlock / rw, step_x = kBlendBlock - step_y * rw;
+  const int first_ly = threadIdx.x / rw, first_lx = threadIdx.x - first_ly * rw;
 
-  if (threadIdx.x < 4) (&s_count[0][0])[threadIdx.x] = 0;
-  for (int i = threadIdx.x; i < rn4; i += blockDim.x) {
-    const int ly = i / rw, lx = i - ly * rw;
+  if (threadIdx.x < 2) { s_begin[threadIdx.x] = 0; s_end[threadIdx.x] = 0; s_tail[threadIdx.x] = 0; }
+  for (int i = threadIdx.x, lx = first_lx, ly = first_ly; i < rn4; i += kBlendBlock) {
     const int gx = x0 + lx, gy = y0 + ly;
     u16 depth = 0;
     u8 sup = 0;
@@ -383,99 +389,102 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
     s_sup[i] = sup;
     s_dist[i] = 0;
     s_ndist[i] = 0;
+    lx += step_x; ly += step_y;
+    if (lx >= rw) { lx -= rw; ++ly; }
   }
   __syncthreads();
 
   const float depth_scaling = f.depth_scaling;  // the reference passes 1 / depth_correction_factor (kernels.cc:179)
   const float rcp_scaling = frcp(depth_scaling);
-  auto processed = [&](int lx, int ly) {
-    // pixels whose 3x3 stencil lies inside the region and that are interior image pixels
-    const int gx = x0 + lx, gy = y0 + ly;
-    return lx >= 1 && ly >= 1 && lx < rw - 1 && ly < rh - 1 && gx >= 1 && gy >= 1 && gx < d.width - 1 &&
-           gy < d.height - 1;
-  };
+  // pixels whose 3x3 stencil lies inside the region and that are interior image pixels
+  const int lx_min = max(1, 1 - x0), lx_max = min(rw - 2, d.width - 2 - x0);
+  const int ly_min = max(1, 1 - y0), ly_max = min(rh - 2, d.height - 2 - y0);
 
   // Start kernel (kernels.cu:563-615). The stencils read the depth as handed in (the
   // reference's in-place write, flagged TODO at :610, can only matter if a blended depth
   // rounds to 0). Ring pixels (distance 1) become the first frontiers.
-  for (int i = threadIdx.x; i < rn; i += blockDim.x) {
-    const int ly = i / rw, lx = i - ly * rw;
-    if (!processed(lx, ly)) continue;
-    if (s_depth0[i] == 0 || !s_sup[i]) continue;
-    bool measurement_border_pixel = false, surfel_border_pixel = false;
+  for (int i = threadIdx.x, lx = first_lx, ly = first_ly; i < rn; i += kBlendBlock) {
+    const bool consider = lx >= lx_min && lx <= lx_max && ly >= ly_min && ly <= ly_max && s_depth0[i] != 0 && s_sup[i];
+    if (consider) {
+      bool measurement_border_pixel = false, surfel_border_pixel = false;
 #pragma unroll
-    for (int wy = -1; wy <= 1; ++wy) {
+      for (int wy = -1; wy <= 1; ++wy) {
 #pragma unroll
-      for (int wx = -1; wx <= 1; ++wx) {
-        const int j = i + wy * rw + wx;
-        if (s_depth0[j] == 0) measurement_border_pixel = true;
-        else if (!s_sup[j]) surfel_border_pixel = true;
+        for (int wx = -1; wx <= 1; ++wx) {
+          const int j = i + wy * rw + wx;
+          if (s_depth0[j] == 0) measurement_border_pixel = true;
+          else if (!s_sup[j]) surfel_border_pixel = true;
+        }
+      }
+      if (!measurement_border_pixel && !surfel_border_pixel) {
+        s_dist[i] = 255;
+      } else {
+        const PixelAssoc a = d.assoc[(y0 + ly) * d.width + x0 + lx];
+        const float sum = __uint_as_float(a.w);
+        const float rcp_count = frcp(u2f(a.z));
+        const float depth_f = u2f(s_depth0[i]);
+        const u16 packed = static_cast<u16>((ly << 8) | lx);
+        if (surfel_border_pixel) {
+          s_ndist[i] = 1;
+          s_ndelta[i] = ffma(sum, rcp_count, -fmul(depth_f, rcp_scaling));
+          s_front[rn4 + atomicAdd(&s_tail[1], 1)] = packed;
+        }
+        if (measurement_border_pixel) {
+          s_dist[i] = 1;
+          const float surfel_depth_average = fmul(sum, rcp_count);
+          s_delta[i] = ffma(-depth_f, rcp_scaling, surfel_depth_average);
+          s_depth[i] = static_cast<u16>(f2u_trunc(ffma(surfel_depth_average, depth_scaling, 0.5f)));
+          s_front[atomicAdd(&s_tail[0], 1)] = packed;
+        } else {
+          s_dist[i] = 255;
+        }
       }
     }
-    if (!measurement_border_pixel && !surfel_border_pixel) { s_dist[i] = 255; continue; }
-    const PixelAssoc a = d.assoc[(y0 + ly) * d.width + x0 + lx];
-    const float sum = __uint_as_float(a.w);
-    const float rcp_count = frcp(u2f(a.z));
-    const float depth_f = u2f(s_depth0[i]);
-    if (surfel_border_pixel) {
-      s_ndist[i] = 1;
-      s_ndelta[i] = ffma(sum, rcp_count, -fmul(depth_f, rcp_scaling));
-      s_front[2 * rn4 + atomicAdd(&s_count[1][0], 1)] = static_cast<u16>(i);
-    }
-    if (measurement_border_pixel) {
-      s_dist[i] = 1;
-      const float surfel_depth_average = fmul(sum, rcp_count);
-      s_delta[i] = ffma(-depth_f, rcp_scaling, surfel_depth_average);
-      s_depth[i] = static_cast<u16>(f2u_trunc(ffma(surfel_depth_average, depth_scaling, 0.5f)));
-      s_front[atomicAdd(&s_count[0][0], 1)] = static_cast<u16>(i);
-    } else {
-      s_dist[i] = 255;
-    }
+    lx += step_x; ly += step_y;
+    if (lx >= rw) { lx -= rw; ++ly; }
   }
   __syncthreads();
-  if (s_count[0][0] == 0 && s_count[1][0] == 0) return;  // no border ring reaches this tile: depth unchanged
+  if (s_tail[0] == 0 && s_tail[1] == 0) return;  // no border ring reaches this tile: depth unchanged
 
   // Iteration kernels (kernels.cu:647-708), iteration = 2 .. radius - 1 (kernels.cc:190), as a
   // breadth-first wavefront: only the 8-neighbourhoods of the previous frontier are visited.
   const float interpolation_factor_term = 1.0f / (radius - 1.0f);   // host expression, kernels.cc:196
   for (int iteration = 2; iteration < radius; ++iteration) {
-    const int cur = iteration & 1, nxt = cur ^ 1;   // iteration 2 reads lists [0], writes [1]
-    const int src = cur, dst = nxt;
-    // (lists of the start phase are in slot 0; `cur` for iteration 2 is 0)
-    if (threadIdx.x < 2) s_count[threadIdx.x][dst] = 0;
+    if (threadIdx.x < 2) { s_begin[threadIdx.x] = s_end[threadIdx.x]; s_end[threadIdx.x] = s_tail[threadIdx.x]; }
     __syncthreads();
-    // claim phase
+    if (s_begin[0] == s_end[0] && s_begin[1] == s_end[1]) break;  // both wavefronts died out
+    // claim phase: neighbours of the previous frontier
 #pragma unroll
     for (int ring = 0; ring < 2; ++ring) {
-      const int len = s_count[ring][src];
-      const u16* list = s_front + (2 * ring + src) * rn4;
-      u16* out = s_front + (2 * ring + dst) * rn4;
-      for (int t = threadIdx.x; t < len * 8; t += blockDim.x) {
-        const int q = list[t >> 3];
+      const int begin = s_begin[ring], len = s_end[ring] - begin;
+      u16* list = s_front + ring * rn4;
+      for (int t = threadIdx.x; t < len * 8; t += kBlendBlock) {
+        const u32 q = list[begin + (t >> 3)];
         const int m = (t & 7) + ((t & 7) >= 4 ? 1 : 0);  // 0..8 without the centre
-        const int pidx = q + (m / 3 - 1) * rw + (m % 3 - 1);
-        const int ly = pidx / rw, lx = pidx - ly * rw;
-        if (!processed(lx, ly)) continue;
+        const int lx = static_cast<int>(q & 0xFFu) + (m % 3 - 1), ly = static_cast<int>(q >> 8) + (m / 3 - 1);
+        if (lx < lx_min || lx > lx_max || ly < ly_min || ly > ly_max) continue;
+        const int pidx = ly * rw + lx;
         bool claimed;
         if (ring == 0) {
           claimed = claim_byte(s_dist, pidx, 255u);
         } else {
           claimed = s_depth[pidx] != 0 && !s_sup[pidx] && claim_byte(s_ndist, pidx, 0u);
         }
-        if (claimed) out[atomicAdd(&s_count[ring][dst], 1)] = static_cast<u16>(pidx);
+        if (claimed) list[atomicAdd(&s_tail[ring], 1)] = static_cast<u16>((ly << 8) | lx);
       }
     }
     __syncthreads();
-    // update phase
+    // update phase: the pixels claimed in this iteration
     const float scaled = fmul(ffma(-i2f(iteration - 1), interpolation_factor_term, 1.0f), depth_scaling);
 #pragma unroll
     for (int ring = 0; ring < 2; ++ring) {
-      const int len = s_count[ring][dst];
-      const u16* list = s_front + (2 * ring + dst) * rn4;
-      u8* dist = ring == 0 ? s_dist : s_ndist;
+      const int begin = s_end[ring], len = s_tail[ring] - begin;
+      const u16* list = s_front + ring * rn4;
+      const u8* dist = ring == 0 ? s_dist : s_ndist;
       float* delta = ring == 0 ? s_delta : s_ndelta;
-      for (int t = threadIdx.x; t < len; t += blockDim.x) {
-        const int i = list[t];
+      for (int t = threadIdx.x; t < len; t += kBlendBlock) {
+        const u32 q = list[begin + t];
+        const int i = static_cast<int>(q >> 8) * rw + static_cast<int>(q & 0xFFu);
         float delta_sum = 0.f;
         int count = 0;
 #pragma unroll
@@ -496,13 +505,15 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
     // publish the new distances only after every update has read its stencil
 #pragma unroll
     for (int ring = 0; ring < 2; ++ring) {
-      const int len = s_count[ring][dst];
-      const u16* list = s_front + (2 * ring + dst) * rn4;
+      const int begin = s_end[ring], len = s_tail[ring] - begin;
+      const u16* list = s_front + ring * rn4;
       u8* dist = ring == 0 ? s_dist : s_ndist;
-      for (int t = threadIdx.x; t < len; t += blockDim.x) dist[list[t]] = static_cast<u8>(iteration);
+      for (int t = threadIdx.x; t < len; t += kBlendBlock) {
+        const u32 q = list[begin + t];
+        dist[static_cast<int>(q >> 8) * rw + static_cast<int>(q & 0xFFu)] = static_cast<u8>(iteration);
+      }
     }
     __syncthreads();
-    if (s_count[0][dst] == 0 && s_count[1][dst] == 0) break;  // both wavefronts died out
   }
 
   // Write back the tile interior.
@@ -999,7 +1010,7 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
   if (do_blending) {
     const int halo = f.blend_radius - 1 > 1 ? f.blend_radius - 1 : 1;
     const size_t rn = static_cast<size_t>(kBlendTileW + 2 * halo) * (kBlendTileH + 2 * halo);
-    const size_t smem = ((rn + 3) & ~static_cast<size_t>(3)) * 23 + 16;
+    const size_t smem = ((rn + 3) & ~static_cast<size_t>(3)) * 19 + 16;
     if (smem > 200 * 1024) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
     static size_t configured_smem = 0;
     static bool carveout_set = false;

@@ -24,8 +24,8 @@ namespace smb {
 
 namespace {
 
-constexpr int kTileW = 32;   // output tile
-constexpr int kTileH = 16;
+constexpr int kTileW = 32;   // output tile: 32 x 8 pixels, one pixel per thread
+constexpr int kTileH = 8;
 constexpr float kLog2e = 1.4426950216293334961f;  // 0x3FB8AA3B, the constant nvcc emits for exp()
 
 // ---------------------------------------------------------------------------------------
@@ -195,7 +195,7 @@ __device__ __forceinline__ u16 outlier_pixel(const OutlierArgs& a, unsigned x, u
 // ---------------------------------------------------------------------------------------
 
 template <int R, bool kWithOutlier>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 k_bilateral_outlier(BilateralArgs a, const __grid_constant__ OutlierArgs o, u16* out, size_t out_pitch) {
   constexpr int PADX = 8;
   constexpr int SW = kTileW + 2 * PADX;  // 48 floats per tile row
@@ -203,32 +203,25 @@ k_bilateral_outlier(BilateralArgs a, const __grid_constant__ OutlierArgs o, u16*
 
   const int tile_x = blockIdx.x * kTileW;
   const int tile_y = blockIdx.y * kTileH;
-
-  // Whole tile outside the valid circle? (cheap conservative test on the nearest tile point)
   load_depth_tile_f32<R, PADX, SW>(tile, a.in, a.in_pitch, a.width, a.height, tile_x, tile_y,
                                    u2f(a.value_to_ignore));
   __syncthreads();
 
-  const float rcp_xy = frcp(a.denom_xy);
   const int tx = threadIdx.x & 31;
-  const int ty = threadIdx.x >> 5;  // 0..7
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int ly = ty + half * 8;
-    const unsigned x = tile_x + tx;
-    const unsigned y = tile_y + ly;
-    if (x >= static_cast<unsigned>(a.width) || y >= static_cast<unsigned>(a.height)) continue;
-    u16 result = a.value_to_ignore;
-    if (!bilateral_pixel_masked(x, y, a)) {
-      const float c = tile[(ly + R) * SW + tx + PADX];
-      const unsigned ci = f2u_trunc(c);
-      if (ci != a.value_to_ignore && ci <= a.max_depth) {
-        result = bilateral_pixel<R, SW>(tile, tx + PADX, ly + R, c, a, rcp_xy);
-      }
+  const int ly = threadIdx.x >> 5;  // 0..7
+  const unsigned x = tile_x + tx;
+  const unsigned y = tile_y + ly;
+  if (x >= static_cast<unsigned>(a.width) || y >= static_cast<unsigned>(a.height)) return;
+  u16 result = a.value_to_ignore;
+  if (!bilateral_pixel_masked(x, y, a)) {
+    const float c = tile[(ly + R) * SW + tx + PADX];
+    const unsigned ci = f2u_trunc(c);
+    if (ci != a.value_to_ignore && ci <= a.max_depth) {
+      result = bilateral_pixel<R, SW>(tile, tx + PADX, ly + R, c, a, frcp(a.denom_xy));
     }
-    if (kWithOutlier) result = outlier_pixel(o, x, y, result);
-    row_ptr(out, out_pitch, y)[x] = result;
   }
+  if (kWithOutlier) result = outlier_pixel(o, x, y, result);
+  row_ptr(out, out_pitch, y)[x] = result;
 }
 
 // Generic-radius fallback (any radius): one thread per pixel, taps read through L1/L2.
@@ -420,69 +413,83 @@ struct TailArgs {
 
 constexpr int kMaxErode = 3;
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256, 8)
 k_erode_normals_radii(TailArgs a) {
-  // B tile: halo r+2, E tile (eroded): halo 2, N tile (normals stage): halo 1.
-  constexpr int BW = kTileW + 2 * (kMaxErode + 2), BH = kTileH + 2 * (kMaxErode + 2);
-  constexpr int EW = kTileW + 4, EH = kTileH + 4;
-  constexpr int NW = kTileW + 2, NH = kTileH + 2;
+  // Tiles (origin relative to the 32 x 8 output tile): B (outlier-filtered input) -5, HV
+  // (row-wise erosion validity) -2 / -(2 + r), E (eroded) -2, N (normals stage) -1.
+  constexpr int HB = kMaxErode + 2;
+  constexpr int BW = kTileW + 2 * HB, BH = kTileH + 2 * HB;   // 42 x 18
+  constexpr int EW = kTileW + 4, EH = kTileH + 4;             // 36 x 12
+  constexpr int HVH = EH + 2 * kMaxErode;                     // 18 rows
+  constexpr int NW = kTileW + 2, NH = kTileH + 2;             // 34 x 10
   __shared__ u16 sB[BH * BW];
+  __shared__ u8 sHV[HVH * EW];
   __shared__ u16 sE[EH * EW];
   __shared__ u16 sN[NH * NW];
 
   const int r = a.erosion_radius;
-  const int hb = r + 2;  // halo of the B tile actually used
   const int tile_x = blockIdx.x * kTileW;
   const int tile_y = blockIdx.y * kTileH;
-  const int bw = kTileW + 2 * hb, bh = kTileH + 2 * hb;
 
-  for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
-    const int ly = i / bw, lx = i - ly * bw;
-    const int gx = tile_x - hb + lx, gy = tile_y - hb + ly;
+  for (int i = threadIdx.x; i < BW * BH; i += 256) {
+    const int ly = i / BW, lx = i - ly * BW;
+    const int gx = tile_x - HB + lx, gy = tile_y - HB + ly;
     u16 v = 0;
     if (gx >= 0 && gy >= 0 && gx < a.width && gy < a.height) v = row_ptr(a.in, a.in_pitch, gy)[gx];
-    sB[ly * BW + lx] = v;
+    sB[i] = v;
   }
   __syncthreads();
 
-  // Erode into the E tile (image coordinates tile - 2 .. tile + 2).
-  for (int i = threadIdx.x; i < EW * EH; i += blockDim.x) {
-    const int ly = i / EW, lx = i - ly * EW;
-    const int gx = tile_x - 2 + lx, gy = tile_y - 2 + ly;
-    u16 v = 0;
-    if (gx >= 0 && gy >= 0 && gx < a.width && gy < a.height) {
-      auto get = [&](int yy, int xx) -> u16 { return sB[(yy - tile_y + hb) * BW + (xx - tile_x + hb)]; };
-      v = erode_pixel(r, gx, gy, a.width, a.height, get);
+  // Erosion (cuda_depth_processing.cu:514-538), separable: row-wise validity, then columns.
+  if (r > 0) {
+    for (int i = threadIdx.x; i < (EH + 2 * r) * EW; i += 256) {
+      const int hy = i / EW, ex = i - hy * EW;
+      const u16* row = &sB[(hy - r + HB - 2) * BW + ex + HB - 2];
+      bool valid = true;
+      for (int dx = -r; dx <= r; ++dx) valid &= row[dx] != 0;
+      sHV[i] = valid;
     }
-    sE[ly * EW + lx] = v;
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < EW * EH; i += 256) {
+    const int ey = i / EW, ex = i - ey * EW;
+    const u16 center = sB[(ey + HB - 2) * BW + ex + HB - 2];
+    u16 v = 0;
+    if (center != 0) {
+      if (r > 0) {
+        bool valid = true;
+        for (int dy = 0; dy <= 2 * r; ++dy) valid &= sHV[(ey + dy) * EW + ex] != 0;
+        v = valid ? center : static_cast<u16>(0);
+      } else {
+        // CopyWithoutBorderCUDAKernel (:589-607): 1-pixel border zeroed
+        const int gx = tile_x - 2 + ex, gy = tile_y - 2 + ey;
+        v = (gx < 1 || gy < 1 || gx >= a.width - 1 || gy >= a.height - 1) ? static_cast<u16>(0) : center;
+      }
+    }
+    sE[i] = v;
   }
   __syncthreads();
 
   // Normals stage on the N tile (image coordinates tile - 1 .. tile + 1).
-  for (int i = threadIdx.x; i < NW * NH; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NW * NH; i += 256) {
     const int ly = i / NW, lx = i - ly * NW;
     const int gx = tile_x - 1 + lx, gy = tile_y - 1 + ly;
+    const int e = (ly + 1) * EW + lx + 1;  // position in the E tile
+    const u16 center = sE[e];
     u16 v = 0;
-    if (gx >= 0 && gy >= 0 && gx < a.width && gy < a.height) {
-      const int ex = lx + 1, ey = ly + 1;  // position in the E tile
-      const u16 center = sE[ey * EW + ex];
-      float2 normal = make_float2(0.f, 0.f);
-      if (center != 0) {
-        // The reference reads the four neighbours without bounds checks and relies on the
-        // zero border left by the erosion (cuda_depth_processing.cuh:96-98); the E tile is
-        // zero outside the image, which is the same thing.
-        const u16 right = sE[ey * EW + ex + 1];
-        const u16 left = sE[ey * EW + ex - 1];
-        const u16 bottom = sE[(ey + 1) * EW + ex];
-        const u16 top = sE[(ey - 1) * EW + ex];
-        if (right != 0 && left != 0 && bottom != 0 && top != 0) {
-          v = normals_pixel(a.normals, gx, gy, center, left, right, top, bottom, &normal);
-        }
+    float2 normal = make_float2(0.f, 0.f);
+    if (center != 0) {
+      // The reference reads the four neighbours without bounds checks and relies on the
+      // zero border left by the erosion (cuda_depth_processing.cuh:96-98); the E tile is
+      // zero outside the image, which is the same thing.
+      const u16 right = sE[e + 1], left = sE[e - 1], bottom = sE[e + EW], top = sE[e - EW];
+      if (right != 0 && left != 0 && bottom != 0 && top != 0) {
+        v = normals_pixel(a.normals, gx, gy, center, left, right, top, bottom, &normal);
       }
-      const bool interior = lx >= 1 && lx <= kTileW && ly >= 1 && ly <= kTileH;
-      if (interior) row_ptr(a.out_normals, a.out_normals_pitch, gy)[gx] = normal;
     }
-    sN[ly * NW + lx] = v;
+    const bool interior = lx >= 1 && lx <= kTileW && ly >= 1 && ly <= kTileH;
+    if (interior && gx < a.width && gy < a.height) row_ptr(a.out_normals, a.out_normals_pitch, gy)[gx] = normal;
+    sN[i] = v;
   }
   __syncthreads();
 
@@ -687,7 +694,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
   t.out_normals = out_normals; t.out_normals_pitch = out_normals_pitch;
   t.out_radius = out_radius; t.out_radius_pitch = out_radius_pitch;
   t.assoc = clear_assoc; t.first_depth = clear_first_depth; t.supported = clear_supported;
-  { LaunchScope scope(stream, KID_ERODE_NORMALS_RADII); k_erode_normals_radii<<<TileGrid(width, height), 512, 0, stream>>>(t); }
+  { LaunchScope scope(stream, KID_ERODE_NORMALS_RADII); k_erode_normals_radii<<<TileGrid(width, height), 256, 0, stream>>>(t); }
   return CheckLaunch("erode/normals/radii");
 }
 
