@@ -49,6 +49,8 @@ cudaEvent_t TakeEvent() {
 }
 }  // namespace
 
+bool ProfilingEnabled() { return g_profile_enabled; }
+
 const char* KernelName(int id) {
   static const char* names[KID_COUNT] = {
       "k_clear", "k_bilateral_outlier", "k_bilateral_generic", "k_outlier", "k_erode_normals_radii", "k_erode",
@@ -110,6 +112,11 @@ struct sm_reconstruction {
   u16* run_depth[2] = {nullptr, nullptr}; size_t run_depth_pitch = 0;
   float2* run_normals[2] = {nullptr, nullptr}; size_t run_normals_pitch = 0;
   float* run_radius[2] = {nullptr, nullptr}; size_t run_radius_pitch = 0;
+  u16* run_depth_pre[2] = {nullptr, nullptr};   // pre-blend copy of run_depth (merge runs next to blend)
+  VisEntry* vis_set[2] = {nullptr, nullptr};
+  u32* seg_count_set[2] = {nullptr, nullptr};
+  u8* merge_flag_set[2] = {nullptr, nullptr};
+  PipelineCtx pipe{};
   cudaStream_t pre_stream = nullptr;
   cudaEvent_t pre_done[2] = {nullptr, nullptr}, int_done[2] = {nullptr, nullptr}, entry_event = nullptr;
   std::vector<u16*> ring_depth; size_t ring_depth_pitch = 0;
@@ -157,6 +164,7 @@ FrameParams MakeFrameParams(const sm_reconstruction* r, u32 frame_index, const s
   f.local_T_global = MakeMat3x4(local_T_global);
   f.global_T_local = MakeMat3x4(global_T_local);
   f.depth = depth; f.depth_pitch = depth_pitch;
+  f.depth_pre = depth; f.depth_pre_pitch = depth_pitch;
   f.normals = reinterpret_cast<const float2*>(normals); f.normals_pitch = normals_pitch;
   f.radius = radius; f.radius_pitch = radius_pitch;
   f.color = reinterpret_cast<const uchar3*>(color); f.color_pitch = color_pitch;
@@ -199,6 +207,9 @@ int EnsureRunBuffers(sm_reconstruction* r, int ring, bool on_host) {
   if (!r->run_depth[0]) {
     for (int i = 0; i < 2; ++i) {
       SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_depth[i]), &r->run_depth_pitch, W * sizeof(u16), H));
+      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_depth_pre[i]), &r->run_depth_pitch, W * sizeof(u16), H));
+      SM_CUDA(cudaEventCreateWithFlags(&r->pipe.ev_create[i], cudaEventDisableTiming));
+      SM_CUDA(cudaEventCreateWithFlags(&r->pipe.ev_update[i], cudaEventDisableTiming));
       SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_normals[i]), &r->run_normals_pitch, W * sizeof(float2), H));
       SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_radius[i]), &r->run_radius_pitch, W * sizeof(float), H));
       SM_CUDA(cudaMemset2D(r->run_radius[i], r->run_radius_pitch, 0, W * sizeof(float), H));
@@ -207,6 +218,11 @@ int EnsureRunBuffers(sm_reconstruction* r, int ring, bool on_host) {
     }
     SM_CUDA(cudaStreamCreateWithFlags(&r->pre_stream, cudaStreamNonBlocking));
     SM_CUDA(cudaEventCreateWithFlags(&r->entry_event, cudaEventDisableTiming));
+    SM_CUDA(cudaStreamCreateWithFlags(&r->pipe.aux, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&r->pipe.ev_assoc, &r->pipe.ev_merge, &r->pipe.ev_blend, &r->pipe.ev_scan,
+                           &r->pipe.ev_integrate, &r->pipe.ev_reg}) {
+      SM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
   }
   if (on_host && static_cast<int>(r->ring_depth.size()) != ring) {
     for (u16* b : r->ring_depth) cudaFree(b);
@@ -321,9 +337,12 @@ int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width,
   }
   d.assoc = r->assoc_set[0]; d.first_depth = r->first_depth_set[0]; d.supported = r->supported_set[0];
   SM_CUDA(cudaMalloc(&d.new_list, sizeof(u32) * P));
-  SM_CUDA(cudaMalloc(&d.vis, sizeof(VisEntry) * padded));
-  SM_CUDA(cudaMalloc(&d.seg_count, sizeof(u32) * (padded / kSegment)));
-  SM_CUDA(cudaMalloc(&d.merge_flag, padded));
+  for (int i = 0; i < 2; ++i) {
+    SM_CUDA(cudaMalloc(&r->vis_set[i], sizeof(VisEntry) * padded));
+    SM_CUDA(cudaMalloc(&r->seg_count_set[i], sizeof(u32) * (padded / kSegment)));
+    SM_CUDA(cudaMalloc(&r->merge_flag_set[i], padded));
+  }
+  d.vis = r->vis_set[0]; d.seg_count = r->seg_count_set[0]; d.merge_flag = r->merge_flag_set[0];
   SM_CUDA(cudaMalloc(&d.new_flag, P));
   SM_CUDA(cudaMalloc(&d.new_index, sizeof(u32) * P));
   SM_CUDA(cudaMalloc(&d.scan_state, sizeof(unsigned long long) * scan_tiles));
@@ -349,9 +368,12 @@ int sm_destroy(sm_reconstruction* r) {
   cudaDeviceSynchronize();
   DeviceState& d = r->d;
   cudaFree(d.surfels); cudaFree(d.new_list);
-  for (int i = 0; i < 2; ++i) { cudaFree(r->assoc_set[i]); cudaFree(r->first_depth_set[i]); cudaFree(r->supported_set[i]); }
-  cudaFree(d.vis); cudaFree(d.seg_count);
-  cudaFree(d.merge_flag); cudaFree(d.new_flag); cudaFree(d.new_index); cudaFree(d.scan_state); cudaFree(d.counters);
+  for (int i = 0; i < 2; ++i) { cudaFree(r->vis_set[i]); cudaFree(r->seg_count_set[i]); cudaFree(r->merge_flag_set[i]); cudaFree(r->run_depth_pre[i]);
+    if (r->pipe.ev_create[i]) cudaEventDestroy(r->pipe.ev_create[i]);
+    if (r->pipe.ev_update[i]) cudaEventDestroy(r->pipe.ev_update[i]);
+    cudaFree(r->assoc_set[i]); cudaFree(r->first_depth_set[i]); cudaFree(r->supported_set[i]); }
+  
+  cudaFree(d.new_flag); cudaFree(d.new_index); cudaFree(d.scan_state); cudaFree(d.counters);
   cudaFreeHost(r->host_counters);
   cudaFree(r->scratch_B);
   for (int i = 0; i < 2; ++i) {
@@ -360,6 +382,11 @@ int sm_destroy(sm_reconstruction* r) {
     if (r->int_done[i]) cudaEventDestroy(r->int_done[i]);
   }
   if (r->pre_stream) cudaStreamDestroy(r->pre_stream);
+  if (r->pipe.aux) {
+    cudaStreamDestroy(r->pipe.aux);
+    for (cudaEvent_t e : {r->pipe.ev_assoc, r->pipe.ev_merge, r->pipe.ev_blend, r->pipe.ev_scan, r->pipe.ev_integrate,
+                          r->pipe.ev_reg}) cudaEventDestroy(e);
+  }
   if (r->entry_event) cudaEventDestroy(r->entry_event);
   for (u16* b : r->ring_depth) cudaFree(b);
   cudaFree(r->ring_color[0]); cudaFree(r->ring_color[1]);
@@ -613,8 +640,12 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
   // Two-deep software pipeline: the pre-processing of frame f + 1 (pre_stream) runs while frame f
   // is integrated (caller's stream). Buffer set f & 1 holds frame f's pre-processing outputs and
   // association rasters; it is reused by frame f + 2 once Integrate(f) has finished.
+  // Per-kernel profiling and stage timings need the kernels one after the other on one stream.
+  const bool pipelined = !r->events.enabled && !ProfilingEnabled();
+  r->pipe.have_reg = false;
   SM_CUDA(cudaEventRecord(r->entry_event, stream));
   SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->entry_event, 0));
+  SM_CUDA(cudaStreamWaitEvent(r->pipe.aux, r->entry_event, 0));
   if (s->frames_on_host) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->entry_event, 0));
   int uploaded_until = first_frame - half - 1;
   const uint8_t* frame_color[2] = {nullptr, nullptr};
@@ -630,7 +661,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
       // the colour slot by Integrate(frame - 2).
       if (reuse) {
         SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->pre_done[set], 0));
-        SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->int_done[set], 0));
+        SM_CUDA(cudaStreamWaitEvent(r->upload_stream, pipelined ? r->pipe.ev_create[set] : r->int_done[set], 0));
       }
       for (int f = uploaded_until + 1; f <= frame + half; ++f) {
         SM_CUDA(cudaMemcpy2DAsync(r->ring_depth[f % ring], r->ring_depth_pitch, s->depth + frame_elems * f,
@@ -647,7 +678,14 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
       frame_color[set] = reinterpret_cast<const uint8_t*>(r->ring_color[set]);
       frame_color_pitch = r->ring_color_pitch;
     }
-    if (reuse) SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->int_done[set], 0));
+    if (reuse) {
+      if (pipelined) {
+        SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->pipe.ev_create[set], 0));
+        SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->pipe.ev_update[set], 0));
+      } else {
+        SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->int_done[set], 0));
+      }
+    }
     const u16* others[8];
     size_t other_pitches[8];
     for (int i = 0; i < half; ++i) {  // main.cc:1046-1059
@@ -660,7 +698,8 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
                                    other_pitches, s->others_TR_reference + static_cast<size_t>(frame) * K * 12,
                                    r->scratch_B, r->scratch_B_pitch, r->run_depth[set], r->run_depth_pitch,
                                    r->run_normals[set], r->run_normals_pitch, r->run_radius[set], r->run_radius_pitch,
-                                   r->assoc_set[set], r->first_depth_set[set], r->supported_set[set]);
+                                   r->assoc_set[set], r->first_depth_set[set], r->supported_set[set],
+                                   pipelined ? r->run_depth_pre[set] : nullptr, r->run_depth_pitch);
     if (st != SM_OK) return st;
     SM_CUDA(cudaEventRecord(r->pre_done[set], r->pre_stream));
     return SM_OK;
@@ -679,16 +718,36 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
     }
     SM_CUDA(cudaStreamWaitEvent(stream, r->pre_done[set], 0));
     r->d.assoc = r->assoc_set[set]; r->d.first_depth = r->first_depth_set[set]; r->d.supported = r->supported_set[set];
-    r->rasters_cleared = true;
-    status = IntegrateImpl(r, stream, static_cast<u32>(frame), *ip, r->run_depth[set], r->run_depth_pitch,
-                           reinterpret_cast<const float*>(r->run_normals[set]), r->run_normals_pitch,
-                           r->run_radius[set], r->run_radius_pitch, frame_color[set],
-                           s->frames_on_host ? r->ring_color_pitch : static_cast<size_t>(W) * 3,
-                           s->global_T_frame + 12 * frame, s->frame_T_global + 12 * frame);
-    if (status != SM_OK) return status;
-    SM_CUDA(cudaEventRecord(r->int_done[set], stream));
+    r->d.vis = r->vis_set[set]; r->d.seg_count = r->seg_count_set[set]; r->d.merge_flag = r->merge_flag_set[set];
+    const size_t color_pitch = s->frames_on_host ? r->ring_color_pitch : static_cast<size_t>(W) * 3;
+    if (pipelined) {
+      FrameParams f = MakeFrameParams(r, static_cast<u32>(frame), *ip, r->run_depth[set], r->run_depth_pitch,
+                                      reinterpret_cast<const float*>(r->run_normals[set]), r->run_normals_pitch,
+                                      r->run_radius[set], r->run_radius_pitch, frame_color[set], color_pitch,
+                                      s->global_T_frame + 12 * frame, s->frame_T_global + 12 * frame);
+      f.depth_pre = r->run_depth_pre[set];
+      f.depth_pre_pitch = r->run_depth_pitch;
+      RegularizeArgs reg;
+      reg.iterations = ip->regularization_iterations_per_integration_iteration;
+      reg.disable_denoising = reg.iterations == 0;
+      reg.radius_factor = ip->radius_factor_for_regularization_neighbors;
+      reg.regularizer_weight = ip->regularizer_weight;
+      reg.window = ip->regularization_frame_window_size;
+      status = IntegrateFramePipelined(stream, &r->pipe, set, r->d, f, ip->do_blending != 0, reg, r->sm_count);
+      if (status != SM_OK) return status;
+      r->parity ^= 1;
+    } else {
+      r->rasters_cleared = true;
+      status = IntegrateImpl(r, stream, static_cast<u32>(frame), *ip, r->run_depth[set], r->run_depth_pitch,
+                             reinterpret_cast<const float*>(r->run_normals[set]), r->run_normals_pitch,
+                             r->run_radius[set], r->run_radius_pitch, frame_color[set], color_pitch,
+                             s->global_T_frame + 12 * frame, s->frame_T_global + 12 * frame);
+      if (status != SM_OK) return status;
+      SM_CUDA(cudaEventRecord(r->int_done[set], stream));
+    }
     ++integrated;
   }
+  if (pipelined && r->pipe.have_reg) SM_CUDA(cudaStreamWaitEvent(stream, r->pipe.ev_reg, 0));  // join
   status = FetchCounters(r, stream);  // one 32-byte D2H + sync for the whole call
   if (stats) {
     stats->frames_integrated = integrated;

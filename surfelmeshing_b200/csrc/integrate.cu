@@ -214,7 +214,7 @@ struct PixelGate {
 
 __device__ __forceinline__ PixelGate load_pixel_gate(const DeviceState& d, const FrameParams& f, int x, int y) {
   PixelGate g;
-  g.measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
+  g.measurement_depth = fmul(u2f(row_ptr(f.depth_pre, f.depth_pre_pitch, y)[x]), f.inv_depth_scaling);
   g.first = d.first_depth[y * d.width + x];
   g.normal = row_ptr(f.normals, f.normals_pitch, y)[x];
   return g;
@@ -983,6 +983,30 @@ __global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int p
 
 }  // namespace
 
+namespace {
+int LaunchBlend(cudaStream_t stream, const DeviceState& d, const FrameParams& f) {
+  const dim3 pixel_tiles((d.width + kBlendTileW - 1) / kBlendTileW, (d.height + kBlendTileH - 1) / kBlendTileH);
+  const int halo = f.blend_radius - 1 > 1 ? f.blend_radius - 1 : 1;
+  const size_t rn = static_cast<size_t>(kBlendTileW + 2 * halo) * (kBlendTileH + 2 * halo);
+  const size_t smem = ((rn + 3) & ~static_cast<size_t>(3)) * 19 + 16;
+  if (smem > 200 * 1024) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
+  static size_t configured_smem = 0;
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    // several ~40 KB blocks per SM: ask for the maximum shared-memory carve-out
+    cudaFuncSetAttribute(k_blend, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
+  if (smem > 48 * 1024 && smem > configured_smem) {
+    if (cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend)");
+    configured_smem = smem;
+  }
+  { LaunchScope scope(stream, KID_BLEND); k_blend<<<pixel_tiles, kBlendBlock, smem, stream>>>(d, f); }
+  return SM_OK;
+}
+}  // namespace
+
 int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d) {
   const int blocks = (d.width * d.height + kBlock * 4 - 1) / (kBlock * 4);
   { LaunchScope scope(stream, KID_CLEAR); k_clear<<<blocks, kBlock, 0, stream>>>(d); }
@@ -994,7 +1018,6 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
   const bool timed = events && events->enabled;
   auto record = [&](int i) { if (timed) cudaEventRecord(events->ev[i], stream); };
   const int list_grid = sm_count * 8;  // persistent grid: 8 blocks of 256 threads per SM
-  const dim3 pixel_tiles((d.width + kBlendTileW - 1) / kBlendTileW, (d.height + kBlendTileH - 1) / kBlendTileH);
   const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
 
   record(0);
@@ -1008,23 +1031,8 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
   { LaunchScope scope(stream, KID_MERGE); k_merge<<<list_grid, kBlock, 0, stream>>>(d, f); }
   record(3); record(4);
   if (do_blending) {
-    const int halo = f.blend_radius - 1 > 1 ? f.blend_radius - 1 : 1;
-    const size_t rn = static_cast<size_t>(kBlendTileW + 2 * halo) * (kBlendTileH + 2 * halo);
-    const size_t smem = ((rn + 3) & ~static_cast<size_t>(3)) * 19 + 16;
-    if (smem > 200 * 1024) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
-    static size_t configured_smem = 0;
-    static bool carveout_set = false;
-    if (!carveout_set) {
-      // several 47 KB blocks per SM: ask for the maximum shared-memory carve-out
-      cudaFuncSetAttribute(k_blend, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      carveout_set = true;
-    }
-    if (smem > 48 * 1024 && smem > configured_smem) {
-      if (cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
-        return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend)");
-      configured_smem = smem;
-    }
-    { LaunchScope scope(stream, KID_BLEND); k_blend<<<pixel_tiles, kBlendBlock, smem, stream>>>(d, f); }
+    const int status = LaunchBlend(stream, d, f);
+    if (status != SM_OK) return status;
   }
   record(5); record(6);
   { LaunchScope scope(stream, KID_INTEGRATE); k_integrate<<<list_grid, kBlock, 0, stream>>>(d, f); }
@@ -1035,6 +1043,57 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
   { LaunchScope scope(stream, KID_CREATE_SURFELS); k_create_surfels<<<sm_count * 2, kBlock, 0, stream>>>(d, f); }
   record(11);
   return CheckLaunch("integrate");
+}
+
+int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const DeviceState& d, const FrameParams& f,
+                            bool do_blending, const RegularizeArgs& reg, int sm_count) {
+  const int list_grid = sm_count * 8;
+  const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
+  cudaStream_t aux = pc->aux;
+  // main: project -> associate -> blend -> [merge, previous regularisation] integrate -> [scan] create
+  { LaunchScope scope(stream, KID_PROJECT); k_project<<<sm_count * 4, kProjectBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_ASSOCIATE); k_associate<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  cudaEventRecord(pc->ev_assoc, stream);
+  // aux: merge (reads the pre-blend depth copy)
+  cudaStreamWaitEvent(aux, pc->ev_assoc, 0);
+  { LaunchScope scope(aux, KID_MERGE); k_merge<<<list_grid, kBlock, 0, aux>>>(d, f); }
+  cudaEventRecord(pc->ev_merge, aux);
+  if (do_blending) {
+    const int status = LaunchBlend(stream, d, f);
+    if (status != SM_OK) return status;
+  }
+  cudaEventRecord(pc->ev_blend, stream);
+  // aux: new-surfel flags + scan need the blended depth and the final association rasters
+  cudaStreamWaitEvent(aux, pc->ev_blend, 0);
+  { LaunchScope scope(aux, KID_NEW_SURFEL_SCAN); k_new_surfel_scan<<<scan_tiles, kBlock, 0, aux>>>(d, f); }
+  cudaEventRecord(pc->ev_scan, aux);
+  cudaStreamWaitEvent(stream, pc->ev_merge, 0);
+  if (pc->have_reg) cudaStreamWaitEvent(stream, pc->ev_reg, 0);  // the integration rewrites what regularisation reads
+  { LaunchScope scope(stream, KID_INTEGRATE); k_integrate<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  cudaEventRecord(pc->ev_integrate, stream);
+  cudaStreamWaitEvent(stream, pc->ev_scan, 0);
+  { LaunchScope scope(stream, KID_CREATE_SURFELS); k_create_surfels<<<sm_count * 2, kBlock, 0, stream>>>(d, f); }
+  cudaEventRecord(pc->ev_create[set], stream);
+  // aux: neighbour update, then the regularisation (needs the new surfels too)
+  cudaStreamWaitEvent(aux, pc->ev_integrate, 0);
+  { LaunchScope scope(aux, KID_UPDATE_NEIGHBORS); k_update_neighbors<<<list_grid, kBlock, 0, aux>>>(d, f); }
+  cudaEventRecord(pc->ev_update[set], aux);
+  cudaStreamWaitEvent(aux, pc->ev_create[set], 0);
+  int status = CheckLaunch("integrate (pipelined)");
+  if (status != SM_OK) return status;
+  const int old_slot = f.parity, new_slot = f.parity ^ 1;
+  if (reg.disable_denoising) {
+    status = RegularizeSurfels(aux, d, true, f.frame_index, reg.radius_factor, reg.regularizer_weight, reg.window,
+                               new_slot, old_slot, sm_count);
+  } else {
+    for (int i = 0; i < reg.iterations && status == SM_OK; ++i) {
+      status = RegularizeSurfels(aux, d, false, f.frame_index, reg.radius_factor, reg.regularizer_weight, reg.window,
+                                 new_slot, i == 0 ? old_slot : -1, sm_count);
+    }
+  }
+  cudaEventRecord(pc->ev_reg, aux);
+  pc->have_reg = true;
+  return status;
 }
 
 int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm_count, float* position_buffer,

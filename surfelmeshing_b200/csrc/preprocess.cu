@@ -405,6 +405,7 @@ struct TailArgs {
   RadiiArgs radii;
   const u16* in; size_t in_pitch;         // outlier-filtered depth (B)
   u16* out_depth; size_t out_depth_pitch;  // final depth (A)
+  u16* out_depth_copy; size_t out_depth_copy_pitch;  // optional second copy (pre-blend depth of the pipeline)
   float2* out_normals; size_t out_normals_pitch;
   float* out_radius; size_t out_radius_pitch;
   // Optional: association rasters to reset for the following Integrate().
@@ -507,6 +508,7 @@ k_erode_normals_radii(TailArgs a) {
         row_ptr(a.out_radius, a.out_radius_pitch, gy)[gx] = radius_squared;
       }
       row_ptr(a.out_depth, a.out_depth_pitch, gy)[gx] = kept;
+      if (a.out_depth_copy) row_ptr(a.out_depth_copy, a.out_depth_copy_pitch, gy)[gx] = kept;
       if (a.assoc) {
         const size_t p = static_cast<size_t>(gy) * a.width + gx;
         a.assoc[p] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
@@ -668,7 +670,8 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
                     const size_t* other_pitches, const float* others_TR_reference, u16* scratch_B,
                     size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch, float2* out_normals,
                     size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
-                    float* clear_first_depth, u8* clear_supported) {
+                    float* clear_first_depth, u8* clear_supported, u16* out_depth_copy,
+                    size_t out_depth_copy_pitch) {
   if (p.depth_erosion_radius < 0 || p.depth_erosion_radius > kMaxErode) {
     return SetError(SM_ERR_INVALID_ARGUMENT, "depth_erosion_radius must be in [0, 3]");
   }
@@ -691,6 +694,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
   t.radii = MakeRadiiArgs(p.point_radius_extension_factor, p.point_radius_clamp_factor, p.depth_scaling, fx, fy, cx, cy);
   t.in = scratch_B; t.in_pitch = scratch_B_pitch;
   t.out_depth = out_depth; t.out_depth_pitch = out_depth_pitch;
+  t.out_depth_copy = out_depth_copy; t.out_depth_copy_pitch = out_depth_copy_pitch;
   t.out_normals = out_normals; t.out_normals_pitch = out_normals_pitch;
   t.out_radius = out_radius; t.out_radius_pitch = out_radius_pitch;
   t.assoc = clear_assoc; t.first_depth = clear_first_depth; t.supported = clear_supported;

@@ -26,6 +26,7 @@ enum KernelId {
   KID_EXPORT_VERTICES, KID_COUNT
 };
 const char* KernelName(int id);
+bool ProfilingEnabled();
 class LaunchScope {
  public:
   LaunchScope(cudaStream_t stream, KernelId id);
@@ -113,6 +114,10 @@ struct FrameParams {
   Mat3x4 global_T_local;
   // input rasters
   u16* depth; size_t depth_pitch;
+  // The depth as it was before the measurement blending: read by the association and merge
+  // gates (the reference runs them before BlendMeasurements). Equal to `depth` unless the
+  // caller provides a separate copy so that merge and blend can run concurrently.
+  const u16* depth_pre; size_t depth_pre_pitch;
   const float2* normals; size_t normals_pitch;
   const float* radius; size_t radius_pitch;
   const uchar3* color; size_t color_pitch;
@@ -124,7 +129,8 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
                     const size_t* other_pitches, const float* others_TR_reference, u16* scratch_B,
                     size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch, float2* out_normals,
                     size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
-                    float* clear_first_depth, u8* clear_supported);
+                    float* clear_first_depth, u8* clear_supported, u16* out_depth_copy = nullptr,
+                    size_t out_depth_copy_pitch = 0);
 int StageBilateral(cudaStream_t stream, float sigma_xy, float sigma_value_factor, u16 value_to_ignore,
                    float radius_factor, u16 max_depth, float depth_valid_region_radius, int width, int height,
                    const u16* in, size_t in_pitch, u16* out, size_t out_pitch);
@@ -149,6 +155,28 @@ struct IntegrateEvents {
 int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams& f, bool do_blending,
                    bool rasters_already_cleared, int sm_count, const IntegrateEvents* events);
 int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d);
+
+// Streams / events of the frame pipeline used by sm_stream_run: the kernels of one frame form
+// a DAG (project -> associate -> {merge | blend} -> integrate -> {update_neighbors | create},
+// scan after blend, regularisation after update_neighbors + create) that is spread over the
+// caller's stream and one auxiliary stream; the regularisation of frame f overlaps with the
+// projection / association / blending of frame f + 1.
+struct PipelineCtx {
+  cudaStream_t aux;
+  cudaEvent_t ev_assoc, ev_merge, ev_blend, ev_scan, ev_integrate;  // transient, re-recorded every frame
+  cudaEvent_t ev_create[2], ev_update[2];                            // per buffer set (frame parity)
+  cudaEvent_t ev_reg;                                                // regularisation of the latest frame
+  bool have_reg;
+};
+struct RegularizeArgs {
+  bool disable_denoising;
+  int iterations;
+  float radius_factor, regularizer_weight;
+  int window;
+};
+// One frame through the DAG, including its regularisation. `set`: frame parity (buffer set).
+int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const DeviceState& d, const FrameParams& f,
+                            bool do_blending, const RegularizeArgs& reg, int sm_count);
 int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm_count, float* position_buffer,
                    u8* color_buffer);
 

@@ -433,3 +433,13 @@ def test_full_size_stream_properties(product, reference, sigma):
                           st.frame_T_global, st.others_TR_reference, pp, ip, first, last)
     assert sh.h2d_bytes > 0
     assert abs(int(sh.surfels_size) - int(sp.surfels_size)) <= 0.002 * sp.surfels_size + 5
+    # sm_stream_run spreads a frame's kernels over several streams (PipelineCtx); with stage timings
+    # enabled it runs them one after the other on the caller's stream. Same result either way
+    # (up to the float-atomic rounding that also separates two runs of the reference).
+    rec_s = R.CUDASurfelReconstruction(2_000_000, 640, 480, cam_.fx, cam_.fy, cam_.cx, cam_.cy)
+    rec_s.enable_timings(True)
+    ss = rec_s.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp, ip,
+                          first, last)
+    assert abs(int(ss.surfels_size) - int(sp.surfels_size)) <= 0.002 * sp.surfels_size + 5
+    assert abs(int(ss.surfel_count) - int(sp.surfel_count)) <= 0.002 * sp.surfel_count + 5
+    assert len(rec_s.GetTimings()) == 7
