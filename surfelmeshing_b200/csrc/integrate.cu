@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) 
 // a10: measurement blending, all iterations in one kernel
 // ---------------------------------------------------------------------------------------
 constexpr int kBlendTileW = 32, kBlendTileH = 16;
-constexpr int kBlendBlock = 512;
+constexpr int kBlendBlock = 256;  // 32 x 16 tile, ~40 KB of shared memory: 5 blocks per SM, one wave at VGA
 constexpr u32 kClaimed = 254;  // distance-map value of a pixel claimed in the running iteration
 
 // Claims byte `i` of a u8 map (4-byte CAS on the containing word) if it currently holds
@@ -517,8 +517,8 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   }
 
   // Write back the tile interior.
-  {
-    const int lx = (threadIdx.x & 31) + halo, ly = (threadIdx.x >> 5) + halo;
+  for (int row = threadIdx.x >> 5; row < kBlendTileH; row += kBlendBlock / 32) {
+    const int lx = (threadIdx.x & 31) + halo, ly = row + halo;
     const int gx = x0 + lx, gy = y0 + ly;
     const int i = ly * rw + lx;
     if (gx < d.width && gy < d.height && s_depth[i] != s_depth0[i]) row_ptr(f.depth, f.depth_pitch, gy)[gx] = s_depth[i];
