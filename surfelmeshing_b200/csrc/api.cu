@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -50,6 +51,11 @@ cudaEvent_t TakeEvent() {
 }  // namespace
 
 bool ProfilingEnabled() { return g_profile_enabled; }
+
+bool UsePdl() {
+  static const bool use = [] { const char* e = std::getenv("SM_B200_PDL"); return !(e && e[0] == '0'); }();
+  return use;
+}
 
 const char* KernelName(int id) {
   static const char* names[KID_COUNT] = {

@@ -113,6 +113,7 @@ __device__ __forceinline__ void for_each_visible(const DeviceState& d, u32 n, Bo
 // a6: clear
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_clear(DeviceState d) {
+  pdl_prologue();
   const int n = d.width * d.height;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     d.assoc[i] = make_uint4(kInvalidIndex, kInvalidIndex, 0u, 0u);
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(kBlock) k_clear(DeviceState d) {
 constexpr int kProjectBlock = 512;  // 2 slots per thread, kSegment slots per block-iteration
 
 __global__ void __launch_bounds__(kProjectBlock) k_project(DeviceState d, FrameParams f) {
+  pdl_prologue();
   __shared__ u32 warp_totals[kProjectBlock / 32];
   const u32 n = d.counters->surfel_count[f.parity];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,6 +244,7 @@ __device__ __forceinline__ bool supports_surfel(const DeviceState& d, const Fram
 }
 
 __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams f) {
+  pdl_prologue();
   const u32 n = d.counters->surfel_count[f.parity];
   for_each_visible(d, n, [&](size_t pos) {
     const VisEntry e = d.vis[pos];
@@ -279,6 +282,7 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
 
 // a9: merge decision (kernels.cu:1857-1992); applied by k_integrate.
 __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) {
+  pdl_prologue();
   const u32 n = d.counters->surfel_count[f.parity];
   u32 merged_by_thread = 0;
   for_each_visible(d, n, [&](size_t pos) {
@@ -331,6 +335,7 @@ __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) 
 // ---------------------------------------------------------------------------------------
 constexpr int kBlendTileW = 32, kBlendTileH = 16;
 constexpr int kBlendBlock = 256;  // 32 x 16 tile, ~40 KB of shared memory: 5 blocks per SM, one wave at VGA
+constexpr int kMaxBlendRadius = 64;
 constexpr u32 kClaimed = 254;  // distance-map value of a pixel claimed in the running iteration
 
 // Claims byte `i` of a u8 map (4-byte CAS on the containing word) if it currently holds
@@ -349,11 +354,13 @@ __device__ __forceinline__ bool claim_byte(u8* map, int i, u32 expected) {
 }
 
 __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParams f) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char blend_smem[];
   // Frontier lists: ring 0 = measurement-border ring (distance_map), ring 1 = surfel-border
   // ring (new_distance_map). Each list only grows (a pixel enters a ring once); the current
   // frontier is the window [s_begin, s_end) and claims are appended at s_tail.
-  __shared__ int s_begin[2], s_end[2], s_tail[2];
+  __shared__ int s_tail[2];
+  __shared__ int s_claims[kMaxBlendRadius][2];  // pixels claimed per iteration and ring
   const int radius = f.blend_radius;
   const int halo = max(radius - 1, 1);          // (radius - 2) iterations + the 3x3 start stencil
   const int rw = kBlendTileW + 2 * halo, rh = kBlendTileH + 2 * halo;
@@ -375,7 +382,8 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   const int step_y = kBlendBlock / rw, step_x = kBlendBlock - step_y * rw;
   const int first_ly = threadIdx.x / rw, first_lx = threadIdx.x - first_ly * rw;
 
-  if (threadIdx.x < 2) { s_begin[threadIdx.x] = 0; s_end[threadIdx.x] = 0; s_tail[threadIdx.x] = 0; }
+  if (threadIdx.x < 2) s_tail[threadIdx.x] = 0;
+  for (int t = threadIdx.x; t < kMaxBlendRadius * 2; t += kBlendBlock) (&s_claims[0][0])[t] = 0;
   for (int i = threadIdx.x, lx = first_lx, ly = first_ly; i < rn4; i += kBlendBlock) {
     const int gx = x0 + lx, gy = y0 + ly;
     u16 depth = 0;
@@ -447,44 +455,34 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   if (s_tail[0] == 0 && s_tail[1] == 0) return;  // no border ring reaches this tile: depth unchanged
 
   // Iteration kernels (kernels.cu:647-708), iteration = 2 .. radius - 1 (kernels.cc:190), as a
-  // breadth-first wavefront: only the 8-neighbourhoods of the previous frontier are visited.
+  // breadth-first wavefront with ONE barrier per iteration: a thread that claims a pixel (dist
+  // 255 -> kClaimed, or new-dist 0 -> kClaimed) updates it on the spot. That is safe because the
+  // update only reads neighbours at distance iteration - 1 (final since the previous barrier) and
+  // neither kClaimed nor `iteration` can be mistaken for iteration - 1.
   const float interpolation_factor_term = 1.0f / (radius - 1.0f);   // host expression, kernels.cc:196
+  int begin[2] = {0, 0}, end[2] = {s_tail[0], s_tail[1]};
   for (int iteration = 2; iteration < radius; ++iteration) {
-    if (threadIdx.x < 2) { s_begin[threadIdx.x] = s_end[threadIdx.x]; s_end[threadIdx.x] = s_tail[threadIdx.x]; }
-    __syncthreads();
-    if (s_begin[0] == s_end[0] && s_begin[1] == s_end[1]) break;  // both wavefronts died out
-    // claim phase: neighbours of the previous frontier
-#pragma unroll
-    for (int ring = 0; ring < 2; ++ring) {
-      const int begin = s_begin[ring], len = s_end[ring] - begin;
-      u16* list = s_front + ring * rn4;
-      for (int t = threadIdx.x; t < len * 8; t += kBlendBlock) {
-        const u32 q = list[begin + (t >> 3)];
-        const int m = (t & 7) + ((t & 7) >= 4 ? 1 : 0);  // 0..8 without the centre
-        const int lx = static_cast<int>(q & 0xFFu) + (m % 3 - 1), ly = static_cast<int>(q >> 8) + (m / 3 - 1);
-        if (lx < lx_min || lx > lx_max || ly < ly_min || ly > ly_max) continue;
-        const int pidx = ly * rw + lx;
-        bool claimed;
-        if (ring == 0) {
-          claimed = claim_byte(s_dist, pidx, 255u);
-        } else {
-          claimed = s_depth[pidx] != 0 && !s_sup[pidx] && claim_byte(s_ndist, pidx, 0u);
-        }
-        if (claimed) list[atomicAdd(&s_tail[ring], 1)] = static_cast<u16>((ly << 8) | lx);
-      }
-    }
-    __syncthreads();
-    // update phase: the pixels claimed in this iteration
+    if (begin[0] == end[0] && begin[1] == end[1]) break;  // both wavefronts died out
     const float scaled = fmul(ffma(-i2f(iteration - 1), interpolation_factor_term, 1.0f), depth_scaling);
 #pragma unroll
     for (int ring = 0; ring < 2; ++ring) {
-      const int begin = s_end[ring], len = s_tail[ring] - begin;
-      const u16* list = s_front + ring * rn4;
-      const u8* dist = ring == 0 ? s_dist : s_ndist;
+      const int len = end[ring] - begin[ring];
+      u16* list = s_front + ring * rn4;
+      u8* dist = ring == 0 ? s_dist : s_ndist;
       float* delta = ring == 0 ? s_delta : s_ndelta;
-      for (int t = threadIdx.x; t < len; t += kBlendBlock) {
-        const u32 q = list[begin + t];
-        const int i = static_cast<int>(q >> 8) * rw + static_cast<int>(q & 0xFFu);
+      for (int t = threadIdx.x; t < len * 8; t += kBlendBlock) {
+        const u32 q = list[begin[ring] + (t >> 3)];
+        const int m = (t & 7) + ((t & 7) >= 4 ? 1 : 0);  // 0..8 without the centre
+        const int lx = static_cast<int>(q & 0xFFu) + (m % 3 - 1), ly = static_cast<int>(q >> 8) + (m / 3 - 1);
+        if (lx < lx_min || lx > lx_max || ly < ly_min || ly > ly_max) continue;
+        const int i = ly * rw + lx;
+        bool claimed;
+        if (ring == 0) {
+          claimed = claim_byte(s_dist, i, 255u);
+        } else {
+          claimed = s_depth[i] != 0 && !s_sup[i] && claim_byte(s_ndist, i, 0u);
+        }
+        if (!claimed) continue;
         float delta_sum = 0.f;
         int count = 0;
 #pragma unroll
@@ -499,21 +497,16 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
         const float avg = fmul(frcp(i2f(count)), delta_sum);
         delta[i] = avg;
         s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
+        dist[i] = static_cast<u8>(iteration);
+        list[end[ring] + atomicAdd(&s_claims[iteration][ring], 1)] = static_cast<u16>((ly << 8) | lx);
       }
     }
     __syncthreads();
-    // publish the new distances only after every update has read its stencil
 #pragma unroll
     for (int ring = 0; ring < 2; ++ring) {
-      const int begin = s_end[ring], len = s_tail[ring] - begin;
-      const u16* list = s_front + ring * rn4;
-      u8* dist = ring == 0 ? s_dist : s_ndist;
-      for (int t = threadIdx.x; t < len; t += kBlendBlock) {
-        const u32 q = list[begin + t];
-        dist[static_cast<int>(q >> 8) * rw + static_cast<int>(q & 0xFFu)] = static_cast<u8>(iteration);
-      }
+      begin[ring] = end[ring];
+      end[ring] += s_claims[iteration][ring];
     }
-    __syncthreads();
   }
 
   // Write back the tile interior.
@@ -638,6 +631,7 @@ __device__ __forceinline__ void integrate_or_conflict(const FrameParams& f, cons
 }
 
 __global__ void __launch_bounds__(kBlock) k_integrate(DeviceState d, FrameParams f) {
+  pdl_prologue();
   const u32 n = d.counters->surfel_count[f.parity];
   for_each_visible(d, n, [&](size_t pos) {
     const VisEntry e = d.vis[pos];
@@ -690,6 +684,7 @@ __global__ void __launch_bounds__(kBlock) k_integrate(DeviceState d, FrameParams
 // a12: neighbour update (kernels.cu:1197-1380)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, FrameParams f) {
+  pdl_prologue();
   const u32 n = d.counters->surfel_count[f.parity];
   for_each_visible(d, n, [&](size_t pos) {
     const u32 idx = d.vis[pos].x & ~kActiveBit;
@@ -792,6 +787,7 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
 __device__ __forceinline__ unsigned long long load_scan_state(unsigned long long* p) { return atomicAdd(p, 0ull); }
 
 __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, FrameParams f) {
+  pdl_prologue();
   __shared__ u32 s_tile, s_prefix;
   __shared__ u32 warp_totals[kBlock / 32];
   const int total_pixels = d.width * d.height;
@@ -885,6 +881,7 @@ __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, Frame
 
 // CreateNewSurfelsCUDACreationKernel (kernels.cu:133-231), one thread per NEW surfel.
 __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameParams f) {
+  pdl_prologue();
   const u32 new_count = d.counters->new_surfel_count;
   const u32 surfel_count = d.counters->surfel_count[f.parity];
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < new_count; k += gridDim.x * blockDim.x) {
@@ -967,6 +964,7 @@ __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameP
 // ExportVerticesCUDAKernel (kernels.cu:2412-2433).
 __global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int parity, float* position_buffer,
                                                             u8* color_buffer) {
+  pdl_prologue();
   const u32 n = d.counters->surfel_count[parity];
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const bool merged = SM_S(SM_ROW_RADIUS_SQUARED, i) < 0.f;
@@ -989,7 +987,7 @@ int LaunchBlend(cudaStream_t stream, const DeviceState& d, const FrameParams& f)
   const int halo = f.blend_radius - 1 > 1 ? f.blend_radius - 1 : 1;
   const size_t rn = static_cast<size_t>(kBlendTileW + 2 * halo) * (kBlendTileH + 2 * halo);
   const size_t smem = ((rn + 3) & ~static_cast<size_t>(3)) * 19 + 16;
-  if (smem > 200 * 1024) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
+  if (smem > 200 * 1024 || f.blend_radius > kMaxBlendRadius) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
   static size_t configured_smem = 0;
   static bool carveout_set = false;
   if (!carveout_set) {
@@ -1002,14 +1000,14 @@ int LaunchBlend(cudaStream_t stream, const DeviceState& d, const FrameParams& f)
       return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend)");
     configured_smem = smem;
   }
-  { LaunchScope scope(stream, KID_BLEND); k_blend<<<pixel_tiles, kBlendBlock, smem, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_BLEND); LaunchKernel(k_blend, dim3(pixel_tiles), dim3(kBlendBlock), smem, stream, d, f); }
   return SM_OK;
 }
 }  // namespace
 
 int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d) {
   const int blocks = (d.width * d.height + kBlock * 4 - 1) / (kBlock * 4);
-  { LaunchScope scope(stream, KID_CLEAR); k_clear<<<blocks, kBlock, 0, stream>>>(d); }
+  { LaunchScope scope(stream, KID_CLEAR); LaunchKernel(k_clear, dim3(blocks), dim3(kBlock), 0, stream, d); }
   return CheckLaunch("clear");
 }
 
@@ -1025,22 +1023,22 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
     const int status = ClearAssociationRasters(stream, d);
     if (status != SM_OK) return status;
   }
-  { LaunchScope scope(stream, KID_PROJECT); k_project<<<sm_count * 4, kProjectBlock, 0, stream>>>(d, f); }
-  { LaunchScope scope(stream, KID_ASSOCIATE); k_associate<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_PROJECT); LaunchKernel(k_project, dim3(sm_count * 4), dim3(kProjectBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_ASSOCIATE); LaunchKernel(k_associate, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
   record(1); record(2);
-  { LaunchScope scope(stream, KID_MERGE); k_merge<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_MERGE); LaunchKernel(k_merge, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
   record(3); record(4);
   if (do_blending) {
     const int status = LaunchBlend(stream, d, f);
     if (status != SM_OK) return status;
   }
   record(5); record(6);
-  { LaunchScope scope(stream, KID_INTEGRATE); k_integrate<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
   record(7); record(8);
-  { LaunchScope scope(stream, KID_UPDATE_NEIGHBORS); k_update_neighbors<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_UPDATE_NEIGHBORS); LaunchKernel(k_update_neighbors, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
   record(9); record(10);
-  { LaunchScope scope(stream, KID_NEW_SURFEL_SCAN); k_new_surfel_scan<<<scan_tiles, kBlock, 0, stream>>>(d, f); }
-  { LaunchScope scope(stream, KID_CREATE_SURFELS); k_create_surfels<<<sm_count * 2, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_NEW_SURFEL_SCAN); LaunchKernel(k_new_surfel_scan, dim3(scan_tiles), dim3(kBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_CREATE_SURFELS); LaunchKernel(k_create_surfels, dim3(sm_count * 2), dim3(kBlock), 0, stream, d, f); }
   record(11);
   return CheckLaunch("integrate");
 }
@@ -1051,12 +1049,12 @@ int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const
   const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
   cudaStream_t aux = pc->aux;
   // main: project -> associate -> blend -> [merge, previous regularisation] integrate -> [scan] create
-  { LaunchScope scope(stream, KID_PROJECT); k_project<<<sm_count * 4, kProjectBlock, 0, stream>>>(d, f); }
-  { LaunchScope scope(stream, KID_ASSOCIATE); k_associate<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_PROJECT); LaunchKernel(k_project, dim3(sm_count * 4), dim3(kProjectBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_ASSOCIATE); LaunchKernel(k_associate, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
   cudaEventRecord(pc->ev_assoc, stream);
   // aux: merge (reads the pre-blend depth copy)
   cudaStreamWaitEvent(aux, pc->ev_assoc, 0);
-  { LaunchScope scope(aux, KID_MERGE); k_merge<<<list_grid, kBlock, 0, aux>>>(d, f); }
+  { LaunchScope scope(aux, KID_MERGE); LaunchKernel(k_merge, dim3(list_grid), dim3(kBlock), 0, aux, d, f); }
   cudaEventRecord(pc->ev_merge, aux);
   if (do_blending) {
     const int status = LaunchBlend(stream, d, f);
@@ -1065,18 +1063,18 @@ int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const
   cudaEventRecord(pc->ev_blend, stream);
   // aux: new-surfel flags + scan need the blended depth and the final association rasters
   cudaStreamWaitEvent(aux, pc->ev_blend, 0);
-  { LaunchScope scope(aux, KID_NEW_SURFEL_SCAN); k_new_surfel_scan<<<scan_tiles, kBlock, 0, aux>>>(d, f); }
+  { LaunchScope scope(aux, KID_NEW_SURFEL_SCAN); LaunchKernel(k_new_surfel_scan, dim3(scan_tiles), dim3(kBlock), 0, aux, d, f); }
   cudaEventRecord(pc->ev_scan, aux);
   cudaStreamWaitEvent(stream, pc->ev_merge, 0);
   if (pc->have_reg) cudaStreamWaitEvent(stream, pc->ev_reg, 0);  // the integration rewrites what regularisation reads
-  { LaunchScope scope(stream, KID_INTEGRATE); k_integrate<<<list_grid, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
   cudaEventRecord(pc->ev_integrate, stream);
   cudaStreamWaitEvent(stream, pc->ev_scan, 0);
-  { LaunchScope scope(stream, KID_CREATE_SURFELS); k_create_surfels<<<sm_count * 2, kBlock, 0, stream>>>(d, f); }
+  { LaunchScope scope(stream, KID_CREATE_SURFELS); LaunchKernel(k_create_surfels, dim3(sm_count * 2), dim3(kBlock), 0, stream, d, f); }
   cudaEventRecord(pc->ev_create[set], stream);
   // aux: neighbour update, then the regularisation (needs the new surfels too)
   cudaStreamWaitEvent(aux, pc->ev_integrate, 0);
-  { LaunchScope scope(aux, KID_UPDATE_NEIGHBORS); k_update_neighbors<<<list_grid, kBlock, 0, aux>>>(d, f); }
+  { LaunchScope scope(aux, KID_UPDATE_NEIGHBORS); LaunchKernel(k_update_neighbors, dim3(list_grid), dim3(kBlock), 0, aux, d, f); }
   cudaEventRecord(pc->ev_update[set], aux);
   cudaStreamWaitEvent(aux, pc->ev_create[set], 0);
   int status = CheckLaunch("integrate (pipelined)");
@@ -1098,7 +1096,7 @@ int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const
 
 int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm_count, float* position_buffer,
                    u8* color_buffer) {
-  { LaunchScope scope(stream, KID_EXPORT_VERTICES); k_export_vertices<<<sm_count * 8, kBlock, 0, stream>>>(d, parity, position_buffer, color_buffer); }
+  { LaunchScope scope(stream, KID_EXPORT_VERTICES); LaunchKernel(k_export_vertices, dim3(sm_count * 8), dim3(kBlock), 0, stream, d, parity, position_buffer, color_buffer); }
   return CheckLaunch("export vertices");
 }
 

@@ -197,6 +197,7 @@ __device__ __forceinline__ u16 outlier_pixel(const OutlierArgs& a, unsigned x, u
 template <int R, bool kWithOutlier>
 __global__ void __launch_bounds__(256, 8)
 k_bilateral_outlier(BilateralArgs a, const __grid_constant__ OutlierArgs o, u16* out, size_t out_pitch) {
+  pdl_prologue();
   constexpr int PADX = 8;
   constexpr int SW = kTileW + 2 * PADX;  // 48 floats per tile row
   __shared__ __align__(16) float tile[(kTileH + 2 * R) * SW];
@@ -227,6 +228,7 @@ k_bilateral_outlier(BilateralArgs a, const __grid_constant__ OutlierArgs o, u16*
 // Generic-radius fallback (any radius): one thread per pixel, taps read through L1/L2.
 __global__ void __launch_bounds__(256)
 k_bilateral_generic(BilateralArgs a, u16* out, size_t out_pitch) {
+  pdl_prologue();
   const unsigned x = blockIdx.x * 32 + (threadIdx.x & 31);
   const unsigned y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= static_cast<unsigned>(a.width) || y >= static_cast<unsigned>(a.height)) return;
@@ -262,6 +264,7 @@ k_bilateral_generic(BilateralArgs a, u16* out, size_t out_pitch) {
 
 __global__ void __launch_bounds__(256)
 k_outlier(const __grid_constant__ OutlierArgs o, const u16* in, size_t in_pitch, u16* out, size_t out_pitch) {
+  pdl_prologue();
   const unsigned x = blockIdx.x * 32 + (threadIdx.x & 31);
   const unsigned y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= static_cast<unsigned>(o.width) || y >= static_cast<unsigned>(o.height)) return;
@@ -416,6 +419,7 @@ constexpr int kMaxErode = 3;
 
 __global__ void __launch_bounds__(256, 8)
 k_erode_normals_radii(TailArgs a) {
+  pdl_prologue();
   // Tiles (origin relative to the 32 x 8 output tile): B (outlier-filtered input) -5, HV
   // (row-wise erosion validity) -2 / -(2 + r), E (eroded) -2, N (normals stage) -1.
   constexpr int HB = kMaxErode + 2;
@@ -523,6 +527,7 @@ k_erode_normals_radii(TailArgs a) {
 
 __global__ void __launch_bounds__(256)
 k_erode(int radius, int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch) {
+  pdl_prologue();
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= width || y >= height) return;
@@ -533,6 +538,7 @@ k_erode(int radius, int width, int height, const u16* in, size_t in_pitch, u16* 
 __global__ void __launch_bounds__(256)
 k_normals(NormalsArgs a, int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch,
           float2* normals, size_t normals_pitch) {
+  pdl_prologue();
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= width || y >= height) return;
@@ -556,6 +562,7 @@ k_normals(NormalsArgs a, int width, int height, const u16* in, size_t in_pitch, 
 __global__ void __launch_bounds__(256)
 k_radii(RadiiArgs a, int width, int height, const u16* in, size_t in_pitch, float* radius, size_t radius_pitch,
         u16* out, size_t out_pitch) {
+  pdl_prologue();
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= width || y >= height) return;
@@ -649,13 +656,13 @@ int LaunchBilateral(cudaStream_t stream, const BilateralArgs& a, const OutlierAr
   static const OutlierArgs kNoOutlier = {};
   if (a.radius == 6) {
     LaunchScope scope(stream, KID_BILATERAL_OUTLIER);
-    if (o) k_bilateral_outlier<6, true><<<TileGrid(a.width, a.height), 256, 0, stream>>>(a, *o, out, out_pitch);
-    else k_bilateral_outlier<6, false><<<TileGrid(a.width, a.height), 256, 0, stream>>>(a, kNoOutlier, out, out_pitch);
+    if (o) LaunchKernel(k_bilateral_outlier<6, true>, TileGrid(a.width, a.height), dim3(256), 0, stream, a, *o, out, out_pitch);
+    else LaunchKernel(k_bilateral_outlier<6, false>, TileGrid(a.width, a.height), dim3(256), 0, stream, a, kNoOutlier, out, out_pitch);
   } else {
     if (a.radius < 0) return SetError(SM_ERR_INVALID_ARGUMENT, "negative bilateral radius");
-    { LaunchScope scope(stream, KID_BILATERAL_GENERIC); k_bilateral_generic<<<PixelGrid(a.width, a.height), 256, 0, stream>>>(a, out, out_pitch); }
+    { LaunchScope scope(stream, KID_BILATERAL_GENERIC); LaunchKernel(k_bilateral_generic, PixelGrid(a.width, a.height), dim3(256), 0, stream, a, out, out_pitch); }
     if (o) {
-      { LaunchScope scope(stream, KID_OUTLIER); k_outlier<<<PixelGrid(a.width, a.height), 256, 0, stream>>>(*o, out, out_pitch, out, out_pitch); }
+      { LaunchScope scope(stream, KID_OUTLIER); LaunchKernel(k_outlier, PixelGrid(a.width, a.height), dim3(256), 0, stream, *o, out, out_pitch, out, out_pitch); }
     }
   }
   return CheckLaunch("bilateral/outlier");
@@ -698,7 +705,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
   t.out_normals = out_normals; t.out_normals_pitch = out_normals_pitch;
   t.out_radius = out_radius; t.out_radius_pitch = out_radius_pitch;
   t.assoc = clear_assoc; t.first_depth = clear_first_depth; t.supported = clear_supported;
-  { LaunchScope scope(stream, KID_ERODE_NORMALS_RADII); k_erode_normals_radii<<<TileGrid(width, height), 256, 0, stream>>>(t); }
+  { LaunchScope scope(stream, KID_ERODE_NORMALS_RADII); LaunchKernel(k_erode_normals_radii, TileGrid(width, height), dim3(256), 0, stream, t); }
   return CheckLaunch("erode/normals/radii");
 }
 
@@ -718,21 +725,21 @@ int StageOutlier(cudaStream_t stream, int other_count, int required_count, float
   const int status = MakeOutlierArgs(&o, other_count, required_count, tolerance, fx, fy, cx, cy, width, height,
                                      other_depths, other_pitches, others_TR_reference);
   if (status != SM_OK) return status;
-  { LaunchScope scope(stream, KID_OUTLIER); k_outlier<<<PixelGrid(width, height), 256, 0, stream>>>(o, in, in_pitch, out, out_pitch); }
+  { LaunchScope scope(stream, KID_OUTLIER); LaunchKernel(k_outlier, PixelGrid(width, height), dim3(256), 0, stream, o, in, in_pitch, out, out_pitch); }
   return CheckLaunch("outlier");
 }
 
 int StageErode(cudaStream_t stream, int radius, int width, int height, const u16* in, size_t in_pitch, u16* out,
                size_t out_pitch) {
   if (radius < 0 || radius > kMaxErode) return SetError(SM_ERR_INVALID_ARGUMENT, "radius value is not supported");
-  { LaunchScope scope(stream, KID_ERODE); k_erode<<<PixelGrid(width, height), 256, 0, stream>>>(radius, width, height, in, in_pitch, out, out_pitch); }
+  { LaunchScope scope(stream, KID_ERODE); LaunchKernel(k_erode, PixelGrid(width, height), dim3(256), 0, stream, radius, width, height, in, in_pitch, out, out_pitch); }
   return CheckLaunch("erode");
 }
 
 int StageNormals(cudaStream_t stream, float observation_angle_threshold_deg, float depth_scaling, float fx, float fy,
                  float cx, float cy, int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch,
                  float2* normals, size_t normals_pitch) {
-  { LaunchScope scope(stream, KID_NORMALS); k_normals<<<PixelGrid(width, height), 256, 0, stream>>>(
+  { LaunchScope scope(stream, KID_NORMALS); LaunchKernel(k_normals, PixelGrid(width, height), dim3(256), 0, stream, 
       MakeNormalsArgs(observation_angle_threshold_deg, depth_scaling, fx, fy, cx, cy), width, height, in, in_pitch, out,
       out_pitch, normals, normals_pitch); }
   return CheckLaunch("normals");
@@ -741,7 +748,7 @@ int StageNormals(cudaStream_t stream, float observation_angle_threshold_deg, flo
 int StageRadii(cudaStream_t stream, float point_radius_extension_factor, float point_radius_clamp_factor,
                float depth_scaling, float fx, float fy, float cx, float cy, int width, int height, const u16* in,
                size_t in_pitch, float* radius, size_t radius_pitch, u16* out, size_t out_pitch) {
-  { LaunchScope scope(stream, KID_RADII); k_radii<<<PixelGrid(width, height), 256, 0, stream>>>(
+  { LaunchScope scope(stream, KID_RADII); LaunchKernel(k_radii, PixelGrid(width, height), dim3(256), 0, stream, 
       MakeRadiiArgs(point_radius_extension_factor, point_radius_clamp_factor, depth_scaling, fx, fy, cx, cy), width,
       height, in, in_pitch, radius, radius_pitch, out, out_pitch); }
   return CheckLaunch("radii");

@@ -40,6 +40,7 @@ __device__ __forceinline__ bool outside_window(u32 stamp, const RegParams& p) {
 }
 
 __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegParams p) {
+  pdl_prologue();
   const u32 n = d.counters->surfel_count[p.count_slot];
   const u32 n_remove = p.remove_below_slot >= 0 ? d.counters->surfel_count[p.remove_below_slot] : 0u;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
 }
 
 __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p) {
+  pdl_prologue();
   const u32 n = d.counters->surfel_count[p.count_slot];
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
 }
 
 __global__ void __launch_bounds__(kBlock) k_reg_update(DeviceState d, RegParams p) {
+  pdl_prologue();
   const u32 n = d.counters->surfel_count[p.count_slot];
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
@@ -176,6 +179,7 @@ __global__ void __launch_bounds__(kBlock) k_reg_update(DeviceState d, RegParams 
 
 // RegularizeSurfelsCUDACopyOnlyKernel (kernels.cu:2310-2327) [+ detach-flag pass].
 __global__ void __launch_bounds__(kBlock) k_reg_copy_only(DeviceState d, RegParams p) {
+  pdl_prologue();
   const u32 n = d.counters->surfel_count[p.count_slot];
   const u32 n_remove = p.remove_below_slot >= 0 ? d.counters->surfel_count[p.remove_below_slot] : 0u;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -209,12 +213,12 @@ int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_de
   p.remove_below_slot = remove_replaced_below_slot;
   const int grid = sm_count * 8;
   if (disable_denoising) {
-    { LaunchScope scope(stream, KID_REG_COPY_ONLY); k_reg_copy_only<<<grid, kBlock, 0, stream>>>(d, p); }
+    { LaunchScope scope(stream, KID_REG_COPY_ONLY); LaunchKernel(k_reg_copy_only, dim3(grid), dim3(kBlock), 0, stream, d, p); }
     return CheckLaunch("regularize (copy only)");
   }
-  { LaunchScope scope(stream, KID_REG_ACCUMULATE); k_reg_accumulate<<<grid, kBlock, 0, stream>>>(d, p); }
-  { LaunchScope scope(stream, KID_REG_STEP); k_reg_step<<<grid, kBlock, 0, stream>>>(d, p); }
-  { LaunchScope scope(stream, KID_REG_UPDATE); k_reg_update<<<grid, kBlock, 0, stream>>>(d, p); }
+  { LaunchScope scope(stream, KID_REG_ACCUMULATE); LaunchKernel(k_reg_accumulate, dim3(grid), dim3(kBlock), 0, stream, d, p); }
+  { LaunchScope scope(stream, KID_REG_STEP); LaunchKernel(k_reg_step, dim3(grid), dim3(kBlock), 0, stream, d, p); }
+  { LaunchScope scope(stream, KID_REG_UPDATE); LaunchKernel(k_reg_update, dim3(grid), dim3(kBlock), 0, stream, d, p); }
   return CheckLaunch("regularize");
 }
 

@@ -123,6 +123,35 @@ struct FrameParams {
   const uchar3* color; size_t color_pitch;
 };
 
+// Programmatic dependent launch (sm_90+): every kernel starts with pdl_prologue(): it lets the NEXT
+// kernel of the stream be scheduled early (launch_dependents) and then waits until the PREVIOUS
+// kernel has completed and flushed its memory (wait). With the launch attribute set
+// (LaunchKernel below) this overlaps launch latency / block scheduling of dependent kernels with
+// the tail of their predecessor; without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+bool UsePdl();  // env SM_B200_PDL=0 disables (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+inline void LaunchKernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                         Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = UsePdl() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- preprocess.cu --------------------------------------------------------------------------
 int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int width, int height, float fx, float fy,
                     float cx, float cy, const u16* raw, size_t raw_pitch, const u16* const* other_depths,
