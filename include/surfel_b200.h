@@ -265,6 +265,7 @@ typedef struct sm_stream_stats {
   uint64_t kernel_launches;   /* kernels this library launched during the call */
   uint64_t h2d_bytes;         /* bytes uploaded inside the call */
   uint64_t d2h_bytes;         /* bytes downloaded inside the call */
+  double host_enqueue_ms;     /* host time spent enqueuing the frames (before the final synchronisation) */
 } sm_stream_stats;
 
 int sm_stream_run(sm_reconstruction* r, void* stream, const sm_stream_desc* s,
@@ -287,6 +288,15 @@ int sm_profile_report(double* total_ms, uint64_t* launches, int32_t n);
 /* Work counters of the last Integrate(): surfel slots swept (N), surfels that projected
  * into the image (V), sum of the supporting counts (S), new surfels (M). Synchronises. */
 int sm_frame_counters(sm_reconstruction* r, void* stream, uint64_t out[4]);
+
+/* Diagnostics: device timeline. After sm_timeline_enable(r, frames) every kernel of the frame
+ * pipeline stamps the start of its first block and the end of its last warp (%globaltimer,
+ * nanoseconds) into slot [frame_index % frames][kernel id]; this shows the pipeline as it runs on
+ * the GPU (events and profilers serialise it). sm_timeline_read copies frames x
+ * sm_profile_kernel_count() x {start, end} values (start = UINT64_MAX: not launched).
+ * frames = 0 disables and frees the buffer. No counterpart in the reference. */
+int sm_timeline_enable(sm_reconstruction* r, int32_t frames);
+int sm_timeline_read(sm_reconstruction* r, uint64_t* out, int32_t frames);
 
 #ifdef __cplusplus
 }

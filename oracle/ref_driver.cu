@@ -762,6 +762,7 @@ int smref_stream_run(smref_reconstruction* r, void* stream_v, const sm_stream_de
     stats->kernel_launches = r->launches - launches_before;
     stats->h2d_bytes = h2d;
     stats->d2h_bytes = d2h;
+    stats->host_enqueue_ms = 0;
   }
   return SM_OK;
 }

@@ -85,6 +85,7 @@ class StreamStats(C.Structure):
     _fields_ = [
         ("frames_integrated", C.c_uint32), ("surfels_size", C.c_uint32), ("surfel_count", C.c_uint32),
         ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("host_enqueue_ms", C.c_double),
     ]
 
 
@@ -135,6 +136,8 @@ _PRODUCT_ONLY = {
     "profile_kernel_name": (C.c_char_p, [_I]),
     "profile_report": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), _I]),
     "frame_counters": (C.c_int, [_P, _P, C.POINTER(C.c_uint64 * 4)]),
+    "timeline_enable": (C.c_int, [_P, _I]),
+    "timeline_read": (C.c_int, [_P, C.POINTER(C.c_uint64), _I]),
 }
 
 EXPORTED_SYMBOLS = sorted(["sm_" + n for n in list(_SIGNATURES) + list(_PRODUCT_ONLY)])

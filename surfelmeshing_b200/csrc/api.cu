@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,9 +53,28 @@ cudaEvent_t TakeEvent() {
 
 bool ProfilingEnabled() { return g_profile_enabled; }
 
-bool UsePdl() {
-  static const bool use = [] { const char* e = std::getenv("SM_B200_PDL"); return !(e && e[0] == '0'); }();
-  return use;
+// Device timeline (sm_timeline_enable): the buffer of the reconstruction that enabled it last.
+static unsigned long long* g_timeline = nullptr;
+static u32 g_timeline_frames = 0, g_timeline_frame = 0;
+void SetTimelineFrame(u32 frame) { g_timeline_frame = frame; }
+unsigned long long* TimelineSlot(int kernel_id) {
+  if (!g_timeline) return nullptr;
+  return g_timeline + (static_cast<size_t>(g_timeline_frame % g_timeline_frames) * KID_COUNT + kernel_id) * 2;
+}
+
+// SM_B200_GRID_PERCENT (measurement hook): percentage of the resident block count to launch.
+int ScaleGrid(int blocks) {
+  static const int percent = [] { const char* e = std::getenv("SM_B200_GRID_PERCENT"); return e ? std::atoi(e) : 100; }();
+  const int scaled = static_cast<int>(static_cast<long long>(blocks) * percent / 100);
+  return scaled > 0 ? scaled : 1;
+}
+
+int PdlMode() {
+  static const int mode = [] {
+    const char* e = std::getenv("SM_B200_PDL");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }();
+  return mode;
 }
 
 const char* KernelName(int id) {
@@ -225,6 +245,7 @@ int EnsureRunBuffers(sm_reconstruction* r, int ring, bool on_host) {
     SM_CUDA(cudaStreamCreateWithFlags(&r->pre_stream, cudaStreamNonBlocking));
     SM_CUDA(cudaEventCreateWithFlags(&r->entry_event, cudaEventDisableTiming));
     SM_CUDA(cudaStreamCreateWithFlags(&r->pipe.aux, cudaStreamNonBlocking));
+    SM_CUDA(cudaStreamCreateWithFlags(&r->pipe.side, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&r->pipe.ev_assoc, &r->pipe.ev_merge, &r->pipe.ev_blend, &r->pipe.ev_scan,
                            &r->pipe.ev_integrate, &r->pipe.ev_reg}) {
       SM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
@@ -324,6 +345,17 @@ int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width,
   }
   sm_reconstruction* r = new sm_reconstruction();
   SM_CUDA(cudaGetDevice(&r->device));
+  {
+    // Measurement hook: one shared-memory carve-out (percent of 228 KB) for all kernels. Off by
+    // default: the gather kernels want the L1 (a 100 % carve-out costs 25 % of the frame rate).
+    const char* e = std::getenv("SM_B200_CARVEOUT");
+    const int percent = e ? std::atoi(e) : -1;
+    if (percent >= 0) {
+      ConfigurePreprocessKernels(percent);
+      ConfigureIntegrateKernels(percent);
+      ConfigureRegularizeKernels(percent);
+    }
+  }
   cudaDeviceProp prop;
   SM_CUDA(cudaGetDeviceProperties(&prop, r->device));
   r->sm_count = prop.multiProcessorCount;
@@ -354,6 +386,8 @@ int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width,
   SM_CUDA(cudaMalloc(&d.scan_state, sizeof(unsigned long long) * scan_tiles));
   SM_CUDA(cudaMalloc(&d.counters, sizeof(Counters)));
   SM_CUDA(cudaMemset(d.counters, 0, sizeof(Counters)));
+  d.timeline = nullptr;
+  d.timeline_frames = 0;
   SM_CUDA(cudaMemset(d.new_flag, 0, P));
   SM_CUDA(cudaMemset(d.new_index, 0, sizeof(u32) * P));
   SM_CUDA(cudaMemset(d.scan_state, 0, sizeof(unsigned long long) * scan_tiles));
@@ -380,6 +414,7 @@ int sm_destroy(sm_reconstruction* r) {
     cudaFree(r->assoc_set[i]); cudaFree(r->first_depth_set[i]); cudaFree(r->supported_set[i]); }
   
   cudaFree(d.new_flag); cudaFree(d.new_index); cudaFree(d.scan_state); cudaFree(d.counters);
+  if (d.timeline) { if (g_timeline == d.timeline) g_timeline = nullptr; cudaFree(d.timeline); }
   cudaFreeHost(r->host_counters);
   cudaFree(r->scratch_B);
   for (int i = 0; i < 2; ++i) {
@@ -390,6 +425,7 @@ int sm_destroy(sm_reconstruction* r) {
   if (r->pre_stream) cudaStreamDestroy(r->pre_stream);
   if (r->pipe.aux) {
     cudaStreamDestroy(r->pipe.aux);
+    if (r->pipe.side) cudaStreamDestroy(r->pipe.side);
     for (cudaEvent_t e : {r->pipe.ev_assoc, r->pipe.ev_merge, r->pipe.ev_blend, r->pipe.ev_scan, r->pipe.ev_integrate,
                           r->pipe.ev_reg}) cudaEventDestroy(e);
   }
@@ -619,6 +655,36 @@ int sm_frame_counters(sm_reconstruction* r, void* stream_v, uint64_t out[4]) {
   return status;
 }
 
+int sm_timeline_enable(sm_reconstruction* r, int32_t frames) {
+  if (r == nullptr || frames < 0) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_timeline_enable: bad arguments");
+  SM_CUDA(cudaDeviceSynchronize());
+  if (r->d.timeline) {
+    if (g_timeline == r->d.timeline) g_timeline = nullptr;
+    cudaFree(r->d.timeline);
+    r->d.timeline = nullptr;
+    r->d.timeline_frames = 0;
+  }
+  if (frames == 0) return SM_OK;
+  const size_t slots = static_cast<size_t>(frames) * KID_COUNT;
+  SM_CUDA(cudaMalloc(&r->d.timeline, slots * 2 * sizeof(unsigned long long)));
+  std::vector<unsigned long long> init(slots * 2);
+  for (size_t i = 0; i < slots; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+  SM_CUDA(cudaMemcpy(r->d.timeline, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  r->d.timeline_frames = static_cast<u32>(frames);
+  g_timeline = r->d.timeline;
+  g_timeline_frames = r->d.timeline_frames;
+  return SM_OK;
+}
+
+int sm_timeline_read(sm_reconstruction* r, uint64_t* out, int32_t frames) {
+  if (r == nullptr || out == nullptr) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_timeline_read: bad arguments");
+  if (r->d.timeline == nullptr || frames != static_cast<int32_t>(r->d.timeline_frames))
+    return SetError(SM_ERR_INVALID_ARGUMENT, "sm_timeline_read: timeline not enabled with this frame count");
+  SM_CUDA(cudaDeviceSynchronize());
+  SM_CUDA(cudaMemcpy(out, r->d.timeline, static_cast<size_t>(frames) * KID_COUNT * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return SM_OK;
+}
+
 // The frame loop of APP/main.cc:885-1223 on a synthetic stream.
 int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s, const sm_preprocess_params* pp,
                   const sm_integrate_params* ip, int32_t first_frame, int32_t last_frame, sm_stream_stats* stats) {
@@ -636,6 +702,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
   int status = EnsureRunBuffers(r, ring, s->frames_on_host != 0);
   if (status != SM_OK) return status;
   const unsigned long long launches_before = g_launches.load();
+  const auto host_t0 = std::chrono::steady_clock::now();
   uint64_t h2d = 0;
 
   auto raw_ptr = [&](int frame, size_t* pitch) -> const u16* {
@@ -652,6 +719,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
   SM_CUDA(cudaEventRecord(r->entry_event, stream));
   SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->entry_event, 0));
   SM_CUDA(cudaStreamWaitEvent(r->pipe.aux, r->entry_event, 0));
+  SM_CUDA(cudaStreamWaitEvent(r->pipe.side, r->entry_event, 0));
   if (s->frames_on_host) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->entry_event, 0));
   int uploaded_until = first_frame - half - 1;
   const uint8_t* frame_color[2] = {nullptr, nullptr};
@@ -700,6 +768,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
     }
     size_t raw_pitch;
     const u16* raw = raw_ptr(frame, &raw_pitch);
+    SetTimelineFrame(static_cast<u32>(frame));
     const int st = PreprocessFused(r->pre_stream, *pp, W, H, r->fx, r->fy, r->cx, r->cy, raw, raw_pitch, others,
                                    other_pitches, s->others_TR_reference + static_cast<size_t>(frame) * K * 12,
                                    r->scratch_B, r->scratch_B_pitch, r->run_depth[set], r->run_depth_pitch,
@@ -754,6 +823,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
     ++integrated;
   }
   if (pipelined && r->pipe.have_reg) SM_CUDA(cudaStreamWaitEvent(stream, r->pipe.ev_reg, 0));  // join
+  const double host_enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   status = FetchCounters(r, stream);  // one 32-byte D2H + sync for the whole call
   if (stats) {
     stats->frames_integrated = integrated;
@@ -762,6 +832,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
     stats->kernel_launches = g_launches.load() - launches_before;
     stats->h2d_bytes = h2d;
     stats->d2h_bytes = sizeof(Counters);
+    stats->host_enqueue_ms = host_enqueue_ms;
   }
   return status;
 }

@@ -29,6 +29,9 @@
 // of a pixel is the MINIMUM supporting index (the reference: first atomicCAS wins), merge
 // decisions read the pre-merge state. Both are legal outcomes of the reference.
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "sm_kernels.cuh"
 
 namespace smb {
@@ -97,15 +100,37 @@ __device__ __forceinline__ float facing_dot(const FrameParams& f, float x, float
 }
 
 // Iterates the visible list with one entry per thread: a work item is one quarter (kBlock
-// positions) of a list segment; `body(pos)` runs for every occupied list position.
+// positions) of a list segment; `body(pos, entry)` runs for every occupied list position.
+// The kernels built on this are chains of dependent gathers, so the chain is kept short: the
+// first item's segment count and list entry are fetched before the surfel count has arrived
+// (any position below the list capacity is readable; the count check discards stale ones), and
+// the next item's are fetched before the current one is processed.
 template <typename Body>
-__device__ __forceinline__ void for_each_visible(const DeviceState& d, u32 n, Body&& body) {
+__device__ __forceinline__ void for_each_visible(const DeviceState& d, const u32* surfel_count, Body&& body) {
   constexpr u32 kItemsPerSegment = kSegment / kBlock;
+  const u32 max_items = ((d.capacity + kSegment - 1) / kSegment) * kItemsPerSegment;
+  const u32 n = *surfel_count;
+  u32 item = blockIdx.x;
+  u32 cnt = 0;
+  VisEntry e = make_uint4(0u, 0u, 0u, 0u);
+  if (item < max_items) {
+    cnt = d.seg_count[item / kItemsPerSegment];
+    e = d.vis[static_cast<size_t>(item) * kBlock + threadIdx.x];
+  }
   const u32 items = ((n + kSegment - 1) / kSegment) * kItemsPerSegment;
-  for (u32 item = blockIdx.x; item < items; item += gridDim.x) {
-    const u32 seg = item / kItemsPerSegment;
+  while (item < items) {
+    const u32 next = item + gridDim.x;
+    u32 cnt_next = 0;
+    VisEntry e_next = e;
+    if (next < items) {
+      cnt_next = d.seg_count[next / kItemsPerSegment];
+      e_next = d.vis[static_cast<size_t>(next) * kBlock + threadIdx.x];
+    }
     const u32 k = (item % kItemsPerSegment) * kBlock + threadIdx.x;
-    if (k < d.seg_count[seg]) body(static_cast<size_t>(seg) * kSegment + k);
+    if (k < cnt) body(static_cast<size_t>(item) * kBlock + threadIdx.x, e);
+    item = next;
+    cnt = cnt_next;
+    e = e_next;
   }
 }
 
@@ -129,6 +154,7 @@ constexpr int kProjectBlock = 512;  // 2 slots per thread, kSegment slots per bl
 
 __global__ void __launch_bounds__(kProjectBlock) k_project(DeviceState d, FrameParams f) {
   pdl_prologue();
+  const TimelineScope timeline_scope(d, f.frame_index, KID_PROJECT);
   __shared__ u32 warp_totals[kProjectBlock / 32];
   const u32 n = d.counters->surfel_count[f.parity];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -140,18 +166,31 @@ __global__ void __launch_bounds__(kProjectBlock) k_project(DeviceState d, FrameP
     if (threadIdx.x == 0) d.counters->scan_ticket = 0;
   }
 
+  // The rows of the first segment are requested before the surfel count has arrived (slots up to
+  // the row stride are readable; `i >= n` discards them), those of the next segment before the
+  // current one is processed.
+  struct SlotRows { float2 X, Y, Z; uint2 T; };
+  auto fetch = [&](u32 seg) {
+    SlotRows r;
+    const size_t base = static_cast<size_t>(seg) * kSegment + threadIdx.x * 2;
+    r.X = *reinterpret_cast<const float2*>(&SM_S(SM_ROW_X, base));
+    r.Y = *reinterpret_cast<const float2*>(&SM_S(SM_ROW_Y, base));
+    r.Z = *reinterpret_cast<const float2*>(&SM_S(SM_ROW_Z, base));
+    r.T = *reinterpret_cast<const uint2*>(&SM_SU(SM_ROW_LAST_UPDATE_STAMP, base));
+    return r;
+  };
+  SlotRows rows = {};
+  if ((static_cast<size_t>(blockIdx.x) + 1) * kSegment <= d.stride) rows = fetch(blockIdx.x);
   for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
     const u32 base = seg * kSegment + threadIdx.x * 2;
+    const SlotRows cur = rows;
+    if (static_cast<u64>(seg + gridDim.x) * kSegment < n) rows = fetch(seg + gridDim.x);
     VisEntry e[2];
     bool visible[2] = {false, false};
     u32 cnt = 0;
     if (base < n) {
-      const float2 X = *reinterpret_cast<const float2*>(&SM_S(SM_ROW_X, base));
-      const float2 Y = *reinterpret_cast<const float2*>(&SM_S(SM_ROW_Y, base));
-      const float2 Z = *reinterpret_cast<const float2*>(&SM_S(SM_ROW_Z, base));
-      const uint2 T = *reinterpret_cast<const uint2*>(&SM_SU(SM_ROW_LAST_UPDATE_STAMP, base));
-      const float xs[2] = {X.x, X.y}, ys[2] = {Y.x, Y.y}, zs[2] = {Z.x, Z.y};
-      const u32 ts[2] = {T.x, T.y};
+      const float xs[2] = {cur.X.x, cur.X.y}, ys[2] = {cur.Y.x, cur.Y.y}, zs[2] = {cur.Z.x, cur.Z.y};
+      const u32 ts[2] = {cur.T.x, cur.T.y};
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const u32 i = base + j;
@@ -245,9 +284,8 @@ __device__ __forceinline__ bool supports_surfel(const DeviceState& d, const Fram
 
 __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams f) {
   pdl_prologue();
-  const u32 n = d.counters->surfel_count[f.parity];
-  for_each_visible(d, n, [&](size_t pos) {
-    const VisEntry e = d.vis[pos];
+  const TimelineScope timeline_scope(d, f.frame_index, KID_ASSOCIATE);
+  for_each_visible(d, &d.counters->surfel_count[f.parity], [&](size_t, const VisEntry& e) {
     if (!(e.x & kActiveBit)) return;
     const u32 idx = e.x & ~kActiveBit;
     const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
@@ -283,10 +321,9 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
 // a9: merge decision (kernels.cu:1857-1992); applied by k_integrate.
 __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) {
   pdl_prologue();
-  const u32 n = d.counters->surfel_count[f.parity];
+  const TimelineScope timeline_scope(d, f.frame_index, KID_MERGE);
   u32 merged_by_thread = 0;
-  for_each_visible(d, n, [&](size_t pos) {
-    const VisEntry e = d.vis[pos];
+  for_each_visible(d, &d.counters->surfel_count[f.parity], [&](size_t pos, const VisEntry& e) {
     const u32 idx = e.x & ~kActiveBit;  // no active-window test here (kernels.cu:2016)
     const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
     const Projection p = project(f, d.width, d.height, x, y, z);
@@ -333,74 +370,94 @@ __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) 
 // ---------------------------------------------------------------------------------------
 // a10: measurement blending, all iterations in one kernel
 // ---------------------------------------------------------------------------------------
-constexpr int kBlendTileW = 32, kBlendTileH = 16;
-constexpr int kBlendBlock = 256;  // 32 x 16 tile, ~40 KB of shared memory: 5 blocks per SM, one wave at VGA
+constexpr int kBlendTileW = 80, kBlendTileH = 32;  // 8 x 15 = 120 tiles at VGA: one block per SM, one wave
+constexpr int kBlendBlock = 1024;
 constexpr int kMaxBlendRadius = 64;
-constexpr u32 kClaimed = 254;  // distance-map value of a pixel claimed in the running iteration
+// Pixel classes of the start stencil (kernels.cu:578-596): no measurement / measurement without a
+// supporting surfel / measurement with one.
+constexpr u32 kClsNoDepth = 0, kClsUnsupported = 1, kClsSupported = 2;
 
-// Claims byte `i` of a u8 map (4-byte CAS on the containing word) if it currently holds
-// `expected`; returns true for exactly one claimant.
-__device__ __forceinline__ bool claim_byte(u8* map, int i, u32 expected) {
-  u32* word = reinterpret_cast<u32*>(map) + (i >> 2);
-  const int shift = (i & 3) * 8;
-  u32 old = *reinterpret_cast<volatile u32*>(word);
-  while (((old >> shift) & 0xFFu) == expected) {
-    const u32 desired = (old & ~(0xFFu << shift)) | (kClaimed << shift);
-    const u32 seen = atomicCAS(word, old, desired);
-    if (seen == old) return true;
-    old = seen;
-  }
-  return false;
-}
+__host__ __device__ inline int blend_halo_y(int radius) { return radius - 1 > 1 ? radius - 1 : 1; }  // (radius - 2) iterations + the 3x3 start stencil
+__host__ __device__ inline int blend_halo_x(int radius) { return (blend_halo_y(radius) + 15) & ~15; }  // 16-pixel chunks stay aligned
+
+#ifdef SM_BLEND_CLOCKS
+#define SM_BLEND_CLOCK(i) blend_clock[i] = clock64()
+#else
+#define SM_BLEND_CLOCK(i)
+#endif
 
 __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParams f) {
+#ifdef SM_BLEND_CLOCKS
+  long long blend_clock[5] = {0, 0, 0, 0, 0};
+#endif
   pdl_prologue();
+  const TimelineScope timeline_scope(d, f.frame_index, KID_BLEND);
+  SM_BLEND_CLOCK(0);
   extern __shared__ __align__(16) unsigned char blend_smem[];
   // Frontier lists: ring 0 = measurement-border ring (distance_map), ring 1 = surfel-border
-  // ring (new_distance_map). Each list only grows (a pixel enters a ring once); the current
-  // frontier is the window [s_begin, s_end) and claims are appended at s_tail.
+  // ring (new_distance_map). Each list only grows (a pixel enters a ring once).
   __shared__ int s_tail[2];
   __shared__ int s_claims[kMaxBlendRadius][2];  // pixels claimed per iteration and ring
   const int radius = f.blend_radius;
-  const int halo = max(radius - 1, 1);          // (radius - 2) iterations + the 3x3 start stencil
-  const int rw = kBlendTileW + 2 * halo, rh = kBlendTileH + 2 * halo;
+  const int halo_x = blend_halo_x(radius), halo_y = blend_halo_y(radius);
+  const int rw = kBlendTileW + 2 * halo_x, rh = kBlendTileH + 2 * halo_y;  // rw is a multiple of 16
   const int rn = rw * rh;
-  const int rn4 = (rn + 3) & ~3;
+  const int rn16 = (rn + 15) & ~15;
   float* s_delta = reinterpret_cast<float*>(blend_smem);
-  float* s_ndelta = s_delta + rn4;
-  u16* s_depth0 = reinterpret_cast<u16*>(s_ndelta + rn4);  // depth as handed in (start stencil reads this)
-  u16* s_depth = s_depth0 + rn4;                            // working depth
-  u16* s_front = s_depth + rn4;                             // [ring][rn4], entries (ly << 8) | lx
-  u8* s_sup = reinterpret_cast<u8*>(s_front + 2 * rn4);
-  u8* s_dist = s_sup + rn4;
-  u8* s_ndist = s_dist + rn4;
+  float* s_ndelta = s_delta + rn16;
+  u16* s_depth0 = reinterpret_cast<u16*>(s_ndelta + rn16);  // depth as handed in (start stencil reads this)
+  u16* s_depth = s_depth0 + rn16;                            // working depth
+  u16* s_front = s_depth + rn16;                             // [ring][rn16], entries (ly << 8) | lx
+  u8* s_cls = reinterpret_cast<u8*>(s_front + 2 * rn16);
+  u8* s_dist = s_cls + rn16;
+  u8* s_ndist = s_dist + rn16;
+  u32* s_bits = reinterpret_cast<u32*>(s_ndist + rn16);      // one claim bit per pixel, rn16 / 32 + 1 words
 
   const int tile_x = blockIdx.x * kBlendTileW, tile_y = blockIdx.y * kBlendTileH;
-  const int x0 = tile_x - halo, y0 = tile_y - halo;
-  // Region pixels (lx, ly) handled by this thread: i = threadIdx.x + k * kBlendBlock, walked
-  // incrementally (no division by the run-time region width).
-  const int step_y = kBlendBlock / rw, step_x = kBlendBlock - step_y * rw;
-  const int first_ly = threadIdx.x / rw, first_lx = threadIdx.x - first_ly * rw;
+  const int x0 = tile_x - halo_x, y0 = tile_y - halo_y;  // x0 is a multiple of 16
+  const int lane = threadIdx.x & 31;
 
   if (threadIdx.x < 2) s_tail[threadIdx.x] = 0;
   for (int t = threadIdx.x; t < kMaxBlendRadius * 2; t += kBlendBlock) (&s_claims[0][0])[t] = 0;
-  for (int i = threadIdx.x, lx = first_lx, ly = first_ly; i < rn4; i += kBlendBlock) {
-    const int gx = x0 + lx, gy = y0 + ly;
-    u16 depth = 0;
-    u8 sup = 0;
-    if (i < rn && gx >= 0 && gy >= 0 && gx < d.width && gy < d.height) {
-      depth = row_ptr(f.depth, f.depth_pitch, gy)[gx];
-      sup = d.supported[gy * d.width + gx];
+  for (int t = threadIdx.x; t < rn16 / 32 + 1; t += kBlendBlock) s_bits[t] = 0;
+  // Region load in 16-pixel chunks (two 128-bit depth loads + one of the support raster per
+  // thread, all in flight together); rasters that are not 16-byte friendly take the scalar path.
+  const bool vector_ok = (d.width & 15) == 0 && (f.depth_pitch & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(f.depth) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(d.supported) & 15) == 0;
+  const int chunks_per_row = rw >> 4;
+  for (int t = threadIdx.x; t < rh * chunks_per_row; t += kBlendBlock) {
+    const int ly = t / chunks_per_row, chunk = t - ly * chunks_per_row;
+    const int gy = y0 + ly, gx = x0 + chunk * 16;
+    union { uint4 v[2]; u16 e[16]; } depth;
+    union { uint4 v; u8 e[16]; } sup, cls;
+    depth.v[0] = depth.v[1] = sup.v = make_uint4(0u, 0u, 0u, 0u);
+    if (gy >= 0 && gy < d.height) {
+      const u16* depth_row = row_ptr(f.depth, f.depth_pitch, gy);
+      const u8* sup_row = d.supported + static_cast<size_t>(gy) * d.width;
+      if (vector_ok && gx >= 0 && gx + 16 <= d.width) {
+        depth.v[0] = *reinterpret_cast<const uint4*>(depth_row + gx);
+        depth.v[1] = *reinterpret_cast<const uint4*>(depth_row + gx + 8);
+        sup.v = *reinterpret_cast<const uint4*>(sup_row + gx);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (gx + k >= 0 && gx + k < d.width) { depth.e[k] = depth_row[gx + k]; sup.e[k] = sup_row[gx + k]; }
+        }
+      }
     }
-    s_depth0[i] = depth;
-    s_depth[i] = depth;
-    s_sup[i] = sup;
-    s_dist[i] = 0;
-    s_ndist[i] = 0;
-    lx += step_x; ly += step_y;
-    if (lx >= rw) { lx -= rw; ++ly; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      cls.e[k] = static_cast<u8>(depth.e[k] == 0 ? kClsNoDepth : (sup.e[k] ? kClsSupported : kClsUnsupported));
+    const int i = ly * rw + chunk * 16;
+    *reinterpret_cast<uint4*>(s_depth0 + i) = depth.v[0];
+    *reinterpret_cast<uint4*>(s_depth0 + i + 8) = depth.v[1];
+    *reinterpret_cast<uint4*>(s_depth + i) = depth.v[0];
+    *reinterpret_cast<uint4*>(s_depth + i + 8) = depth.v[1];
+    *reinterpret_cast<uint4*>(s_cls + i) = cls.v;
   }
   __syncthreads();
+  SM_BLEND_CLOCK(1);
 
   const float depth_scaling = f.depth_scaling;  // the reference passes 1 / depth_correction_factor (kernels.cc:179)
   const float rcp_scaling = frcp(depth_scaling);
@@ -408,114 +465,226 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   const int lx_min = max(1, 1 - x0), lx_max = min(rw - 2, d.width - 2 - x0);
   const int ly_min = max(1, 1 - y0), ly_max = min(rh - 2, d.height - 2 - y0);
 
-  // Start kernel (kernels.cu:563-615). The stencils read the depth as handed in (the
-  // reference's in-place write, flagged TODO at :610, can only matter if a blended depth
-  // rounds to 0). Ring pixels (distance 1) become the first frontiers.
-  for (int i = threadIdx.x, lx = first_lx, ly = first_ly; i < rn; i += kBlendBlock) {
-    const bool consider = lx >= lx_min && lx <= lx_max && ly >= ly_min && ly <= ly_max && s_depth0[i] != 0 && s_sup[i];
-    if (consider) {
-      bool measurement_border_pixel = false, surfel_border_pixel = false;
+  // Start kernel (kernels.cu:563-615), pass A: classify the supported pixels, four per thread
+  // with byte-lane arithmetic on the class words (classes are 0/1/2: `nonzero` = bit0 | bit1,
+  // `unsupported` = bit0). Writes every word of both distance maps; ring pixels (distance 1)
+  // become the first frontiers.
+  {
+    const int groups_per_row = rw >> 2;
+    const u32* cls_words = reinterpret_cast<const u32*>(s_cls);
+    for (int base = 0; base < rh * groups_per_row; base += kBlendBlock) {
+      const int t = base + threadIdx.x;
+      u32 measurement_border = 0, surfel_border = 0;  // one byte (0/1) per pixel of the group
+      int ly = 0, lx0 = 0;
+      if (t < rh * groups_per_row) {
+        ly = t / groups_per_row;
+        const int group = t - ly * groups_per_row;
+        lx0 = group * 4;
+        u32 active = 0;
+        if (ly >= ly_min && ly <= ly_max) {
+          u32 all_nonzero = 0x01010101u, any_unsupported = 0;
 #pragma unroll
-      for (int wy = -1; wy <= 1; ++wy) {
+          for (int wy = -1; wy <= 1; ++wy) {
+            const int w = (ly + wy) * groups_per_row + group;
+            const u32 centre = cls_words[w];
+            const u32 previous = group > 0 ? cls_words[w - 1] : 0u;
+            const u32 next = group < groups_per_row - 1 ? cls_words[w + 1] : 0u;
+            const u32 left = __byte_perm(previous, centre, 0x6543);   // classes of the pixels at x - 1
+            const u32 right = __byte_perm(centre, next, 0x4321);      // classes of the pixels at x + 1
+            all_nonzero &= (left | (left >> 1)) & (centre | (centre >> 1)) & (right | (right >> 1));
+            any_unsupported |= left | centre | right;
+          }
+          const u32 centre = cls_words[ly * groups_per_row + group];
+          u32 in_range = 0;
 #pragma unroll
-        for (int wx = -1; wx <= 1; ++wx) {
-          const int j = i + wy * rw + wx;
-          if (s_depth0[j] == 0) measurement_border_pixel = true;
-          else if (!s_sup[j]) surfel_border_pixel = true;
+          for (int k = 0; k < 4; ++k) in_range |= (lx0 + k >= lx_min && lx0 + k <= lx_max) ? (1u << (8 * k)) : 0u;
+          active = (centre >> 1) & in_range & 0x01010101u;  // class kClsSupported
+          measurement_border = (all_nonzero ^ 0x01010101u) & active;
+          surfel_border = any_unsupported & active;
         }
+        // distance_map: 1 on the measurement-border ring, 255 for the other supported pixels
+        reinterpret_cast<u32*>(s_dist)[t] = measurement_border | ((active ^ measurement_border) * 255u);
+        reinterpret_cast<u32*>(s_ndist)[t] = surfel_border;
       }
-      if (!measurement_border_pixel && !surfel_border_pixel) {
-        s_dist[i] = 255;
-      } else {
-        const PixelAssoc a = d.assoc[(y0 + ly) * d.width + x0 + lx];
-        const float sum = __uint_as_float(a.w);
-        const float rcp_count = frcp(u2f(a.z));
-        const float depth_f = u2f(s_depth0[i]);
-        const u16 packed = static_cast<u16>((ly << 8) | lx);
-        if (surfel_border_pixel) {
-          s_ndist[i] = 1;
-          s_ndelta[i] = ffma(sum, rcp_count, -fmul(depth_f, rcp_scaling));
-          s_front[rn4 + atomicAdd(&s_tail[1], 1)] = packed;
-        }
-        if (measurement_border_pixel) {
-          s_dist[i] = 1;
-          const float surfel_depth_average = fmul(sum, rcp_count);
-          s_delta[i] = ffma(-depth_f, rcp_scaling, surfel_depth_average);
-          s_depth[i] = static_cast<u16>(f2u_trunc(ffma(surfel_depth_average, depth_scaling, 0.5f)));
-          s_front[atomicAdd(&s_tail[0], 1)] = packed;
-        } else {
-          s_dist[i] = 255;
-        }
+      // one list reservation per warp for both rings
+      const u32 counts = __popc(measurement_border) | (__popc(surfel_border) << 16);
+      u32 inclusive = counts;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(0xFFFFFFFFu, inclusive, o);
+        if (lane >= o) inclusive += v;
+      }
+      const u32 warp_total = __shfl_sync(0xFFFFFFFFu, inclusive, 31);
+      if (warp_total == 0) continue;
+      u32 warp_base = 0;
+      if (lane == 31) {
+        const u32 base0 = (warp_total & 0xFFFFu) ? atomicAdd(&s_tail[0], static_cast<int>(warp_total & 0xFFFFu)) : 0u;
+        const u32 base1 = (warp_total >> 16) ? atomicAdd(&s_tail[1], static_cast<int>(warp_total >> 16)) : 0u;
+        warp_base = base0 | (base1 << 16);
+      }
+      warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 31);
+      const u32 exclusive = inclusive - counts;
+      u32 out0 = (warp_base & 0xFFFFu) + (exclusive & 0xFFFFu), out1 = (warp_base >> 16) + (exclusive >> 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const u16 packed = static_cast<u16>((ly << 8) | (lx0 + k));
+        if ((measurement_border >> (8 * k)) & 1u) s_front[out0++] = packed;
+        if ((surfel_border >> (8 * k)) & 1u) s_front[rn16 + out1++] = packed;
       }
     }
-    lx += step_x; ly += step_y;
-    if (lx >= rw) { lx -= rw; ++ly; }
   }
   __syncthreads();
-  if (s_tail[0] == 0 && s_tail[1] == 0) return;  // no border ring reaches this tile: depth unchanged
+  SM_BLEND_CLOCK(2);
+  const int start_count[2] = {s_tail[0], s_tail[1]};
+  if (start_count[0] == 0 && start_count[1] == 0) return;  // no border ring reaches this tile: depth unchanged
+
+  // Pass B: the ring pixels fetch their association record (the only global reads of the start
+  // step, all issued together). The stencils read the depth as handed in (the reference's
+  // in-place write, flagged TODO at :610, can only matter if a blended depth rounds to 0).
+  for (int t = threadIdx.x; t < start_count[0] + start_count[1]; t += kBlendBlock) {
+    const bool surfel_ring = t >= start_count[0];
+    const u32 q = surfel_ring ? s_front[rn16 + t - start_count[0]] : s_front[t];
+    const int lx = static_cast<int>(q & 0xFFu), ly = static_cast<int>(q >> 8);
+    const int i = ly * rw + lx;
+    const PixelAssoc a = d.assoc[(y0 + ly) * d.width + x0 + lx];
+    const float sum = __uint_as_float(a.w);
+    const float rcp_count = frcp(u2f(a.z));
+    const float depth_f = u2f(s_depth0[i]);
+    if (surfel_ring) {
+      s_ndelta[i] = ffma(sum, rcp_count, -fmul(depth_f, rcp_scaling));
+    } else {
+      const float surfel_depth_average = fmul(sum, rcp_count);
+      s_delta[i] = ffma(-depth_f, rcp_scaling, surfel_depth_average);
+      s_depth[i] = static_cast<u16>(f2u_trunc(ffma(surfel_depth_average, depth_scaling, 0.5f)));
+    }
+  }
+  __syncthreads();
+  SM_BLEND_CLOCK(3);
 
   // Iteration kernels (kernels.cu:647-708), iteration = 2 .. radius - 1 (kernels.cc:190), as a
-  // breadth-first wavefront with ONE barrier per iteration: a thread that claims a pixel (dist
-  // 255 -> kClaimed, or new-dist 0 -> kClaimed) updates it on the spot. That is safe because the
-  // update only reads neighbours at distance iteration - 1 (final since the previous barrier) and
-  // neither kClaimed nor `iteration` can be mistaken for iteration - 1.
+  // breadth-first wavefront with ONE barrier per iteration: one thread per frontier pixel (both
+  // rings in the same sweep) looks at its 8 neighbours; the thread that wins the claim bit of an
+  // unassigned pixel updates it on the spot. That is safe because the update only reads
+  // neighbours at distance iteration - 1 (final since the previous barrier), and a pixel under
+  // update holds 255 / 0 / `iteration`, none of which can be mistaken for iteration - 1.
   const float interpolation_factor_term = 1.0f / (radius - 1.0f);   // host expression, kernels.cc:196
-  int begin[2] = {0, 0}, end[2] = {s_tail[0], s_tail[1]};
+  int begin0 = 0, begin1 = 0, end0 = start_count[0], end1 = start_count[1];
   for (int iteration = 2; iteration < radius; ++iteration) {
-    if (begin[0] == end[0] && begin[1] == end[1]) break;  // both wavefronts died out
+    const int len0 = end0 - begin0, len1 = end1 - begin1;
+    if (len0 + len1 == 0) break;  // both wavefronts died out
     const float scaled = fmul(ffma(-i2f(iteration - 1), interpolation_factor_term, 1.0f), depth_scaling);
-#pragma unroll
-    for (int ring = 0; ring < 2; ++ring) {
-      const int len = end[ring] - begin[ring];
-      u16* list = s_front + ring * rn4;
+    for (int base = 0; base < len0 + len1; base += kBlendBlock) {
+      const int t = base + threadIdx.x;
+      const bool has_item = t < len0 + len1;
+      const int ring = (has_item && t >= len0) ? 1 : 0;
+      u16* list = s_front + ring * rn16;
       u8* dist = ring == 0 ? s_dist : s_ndist;
       float* delta = ring == 0 ? s_delta : s_ndelta;
-      for (int t = threadIdx.x; t < len * 8; t += kBlendBlock) {
-        const u32 q = list[begin[ring] + (t >> 3)];
-        const int m = (t & 7) + ((t & 7) >= 4 ? 1 : 0);  // 0..8 without the centre
-        const int lx = static_cast<int>(q & 0xFFu) + (m % 3 - 1), ly = static_cast<int>(q >> 8) + (m / 3 - 1);
-        if (lx < lx_min || lx > lx_max || ly < ly_min || ly > ly_max) continue;
-        const int i = ly * rw + lx;
-        bool claimed;
-        if (ring == 0) {
-          claimed = claim_byte(s_dist, i, 255u);
-        } else {
-          claimed = s_depth[i] != 0 && !s_sup[i] && claim_byte(s_ndist, i, 0u);
+      u32 won = 0;  // bit m: this thread claimed neighbour m (0..8, centre unused)
+      int lx = 0, ly = 0;
+      if (has_item) {
+        const u32 q = list[ring == 0 ? begin0 + t : begin1 + t - len0];
+        lx = static_cast<int>(q & 0xFFu);
+        ly = static_cast<int>(q >> 8);
+        const int centre = ly * rw + lx;
+        // candidate neighbours: unassigned pixels the ring may grow into
+        u32 candidates = 0;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+          if (m == 4) continue;
+          const int j = centre + (m / 3 - 1) * rw + (m % 3 - 1);
+          const bool candidate = ring == 0 ? s_dist[j] == 255 : (s_cls[j] == kClsUnsupported && s_ndist[j] == 0);
+          candidates |= candidate ? (1u << m) : 0u;
         }
-        if (!claimed) continue;
-        float delta_sum = 0.f;
-        int count = 0;
+        while (candidates) {
+          const int m = __ffs(candidates) - 1;
+          candidates &= candidates - 1;
+          const int nx = lx + (m % 3 - 1), ny = ly + (m / 3 - 1);
+          if (nx < lx_min || nx > lx_max || ny < ly_min || ny > ly_max) continue;
+          const int i = ny * rw + nx;
+          const u32 bit = 1u << (i & 31);
+          if (atomicOr(&s_bits[i >> 5], bit) & bit) continue;  // another thread owns it
+          won |= 1u << m;
+          float delta_sum = 0.f;
+          int count = 0;
 #pragma unroll
-        for (int wy = -1; wy <= 1; ++wy) {
+          for (int wy = -1; wy <= 1; ++wy) {
 #pragma unroll
-          for (int wx = -1; wx <= 1; ++wx) {
-            const int j = i + wy * rw + wx;
-            if (dist[j] == iteration - 1) { delta_sum = fadd(delta_sum, delta[j]); ++count; }
+            for (int wx = -1; wx <= 1; ++wx) {
+              const int j = i + wy * rw + wx;
+              if (dist[j] == iteration - 1) { delta_sum = fadd(delta_sum, delta[j]); ++count; }
+            }
           }
+          // count > 0: the pixel was claimed through a neighbour at distance iteration - 1
+          const float avg = fmul(frcp(i2f(count)), delta_sum);
+          delta[i] = avg;
+          s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
+          dist[i] = static_cast<u8>(iteration);
         }
-        // count > 0: the pixel was claimed through a neighbour at distance iteration - 1
-        const float avg = fmul(frcp(i2f(count)), delta_sum);
-        delta[i] = avg;
-        s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
-        dist[i] = static_cast<u8>(iteration);
-        list[end[ring] + atomicAdd(&s_claims[iteration][ring], 1)] = static_cast<u16>((ly << 8) | lx);
+      }
+      // Append the claimed pixels to the ring's list: one reservation per warp and ring.
+      const u32 counts = ring == 0 ? __popc(won) : (__popc(won) << 16);
+      u32 inclusive = counts;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(0xFFFFFFFFu, inclusive, o);
+        if (lane >= o) inclusive += v;
+      }
+      const u32 warp_total = __shfl_sync(0xFFFFFFFFu, inclusive, 31);
+      if (warp_total == 0) continue;
+      u32 warp_base = 0;
+      if (lane == 31) {
+        const u32 base0 = (warp_total & 0xFFFFu) ? atomicAdd(&s_claims[iteration][0], static_cast<int>(warp_total & 0xFFFFu)) : 0u;
+        const u32 base1 = (warp_total >> 16) ? atomicAdd(&s_claims[iteration][1], static_cast<int>(warp_total >> 16)) : 0u;
+        warp_base = base0 | (base1 << 16);
+      }
+      warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 31);
+      const u32 exclusive = inclusive - counts;
+      int out = (ring == 0 ? end0 : end1) + static_cast<int>(ring == 0 ? (warp_base & 0xFFFFu) + (exclusive & 0xFFFFu)
+                                                        : (warp_base >> 16) + (exclusive >> 16));
+      while (won) {
+        const int m = __ffs(won) - 1;
+        won &= won - 1;
+        list[out++] = static_cast<u16>(((ly + m / 3 - 1) << 8) | (lx + m % 3 - 1));
       }
     }
     __syncthreads();
-#pragma unroll
-    for (int ring = 0; ring < 2; ++ring) {
-      begin[ring] = end[ring];
-      end[ring] += s_claims[iteration][ring];
-    }
+    begin0 = end0; end0 += s_claims[iteration][0];
+    begin1 = end1; end1 += s_claims[iteration][1];
   }
 
-  // Write back the tile interior.
-  for (int row = threadIdx.x >> 5; row < kBlendTileH; row += kBlendBlock / 32) {
-    const int lx = (threadIdx.x & 31) + halo, ly = row + halo;
-    const int gx = x0 + lx, gy = y0 + ly;
+  SM_BLEND_CLOCK(4);
+  // Write back the changed 8-pixel chunks of the tile interior.
+  constexpr int kChunksPerTileRow = kBlendTileW / 8;
+  for (int t = threadIdx.x; t < kBlendTileH * kChunksPerTileRow; t += kBlendBlock) {
+    const int row = t / kChunksPerTileRow, chunk = t - row * kChunksPerTileRow;
+    const int ly = row + halo_y, gy = y0 + ly;
+    const int lx = halo_x + chunk * 8, gx = x0 + lx;
+    if (gy >= d.height || gx >= d.width) continue;
     const int i = ly * rw + lx;
-    if (gx < d.width && gy < d.height && s_depth[i] != s_depth0[i]) row_ptr(f.depth, f.depth_pitch, gy)[gx] = s_depth[i];
+    union { uint4 v; u16 e[8]; } now, before;
+    now.v = *reinterpret_cast<const uint4*>(s_depth + i);
+    before.v = *reinterpret_cast<const uint4*>(s_depth0 + i);
+    if (now.v.x == before.v.x && now.v.y == before.v.y && now.v.z == before.v.z && now.v.w == before.v.w) continue;
+    u16* out_row = row_ptr(f.depth, f.depth_pitch, gy);
+    if (vector_ok && gx + 8 <= d.width) {
+      *reinterpret_cast<uint4*>(out_row + gx) = now.v;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (gx + k < d.width && now.e[k] != before.e[k]) out_row[gx + k] = now.e[k];
+    }
   }
+#ifdef SM_BLEND_CLOCKS
+  __syncthreads();
+  if (threadIdx.x == 0 && f.frame_index == 450u) {
+    const long long t5 = clock64();
+    printf("blend tile %d,%d load %lld startA %lld startB %lld iter %lld write %lld | start lists %d %d final %d %d\n", blockIdx.x, blockIdx.y,
+           blend_clock[1] - blend_clock[0], blend_clock[2] - blend_clock[1], blend_clock[3] - blend_clock[2],
+           blend_clock[4] - blend_clock[3], t5 - blend_clock[4], start_count[0], start_count[1], end0, end1);
+  }
+#endif
+
 }
 
 // ---------------------------------------------------------------------------------------
@@ -632,23 +801,15 @@ __device__ __forceinline__ void integrate_or_conflict(const FrameParams& f, cons
 
 __global__ void __launch_bounds__(kBlock) k_integrate(DeviceState d, FrameParams f) {
   pdl_prologue();
-  const u32 n = d.counters->surfel_count[f.parity];
-  for_each_visible(d, n, [&](size_t pos) {
-    const VisEntry e = d.vis[pos];
+  const TimelineScope timeline_scope(d, f.frame_index, KID_INTEGRATE);
+  for_each_visible(d, &d.counters->surfel_count[f.parity], [&](size_t pos, const VisEntry& e) {
     const u32 idx = e.x & ~kActiveBit;
-    if (d.merge_flag[pos]) {
-      // Apply the merge decided by k_merge (kernels.cu:1986-1989).
-      SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = 0;
-      SM_S(SM_ROW_RADIUS_SQUARED, idx) = -1.0f;
-      reinterpret_cast<u8*>(&SM_SU(SM_ROW_COLOR, idx))[3] = 1;
-      return;
-    }
-    if (!(e.x & kActiveBit)) return;
     const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
     const Projection p = project(f, d.width, d.height, x, y, z);
     int ox = p.px, oy = p.py;
     const bool has2 = secondary_pixel(p, d.width, d.height, &ox, &oy);
-    // one batch of gathers: both pixels and the surfel
+    // one batch of gathers: the merge decision, both pixels and the surfel
+    const u8 merged = d.merge_flag[pos];
     const PixelMeasurement m0 = load_pixel_measurement(d, f, p.px, p.py);
     const PixelMeasurement m1 = load_pixel_measurement(d, f, ox, oy);
     SurfelState s;
@@ -661,6 +822,14 @@ __global__ void __launch_bounds__(kBlock) k_integrate(DeviceState d, FrameParams
     s.last_update_stamp = 0;
     s.smooth_x = s.smooth_y = s.smooth_z = 0.f;
     s.replaced = false; s.dirty = false; s.stamped = false;
+    if (merged) {
+      // Apply the merge decided by k_merge (kernels.cu:1986-1989).
+      SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = 0;
+      SM_S(SM_ROW_RADIUS_SQUARED, idx) = -1.0f;
+      reinterpret_cast<u8*>(&SM_SU(SM_ROW_COLOR, idx))[3] = 1;
+      return;
+    }
+    if (!(e.x & kActiveBit)) return;
     if (s.radius_squared < 0.f) return;  // kernels.cu:1050
     integrate_or_conflict(f, m0, p.px, p.py, idx, x, y, z, s);
     if (has2) integrate_or_conflict(f, m1, ox, oy, idx, x, y, z, s);
@@ -685,9 +854,9 @@ __global__ void __launch_bounds__(kBlock) k_integrate(DeviceState d, FrameParams
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, FrameParams f) {
   pdl_prologue();
-  const u32 n = d.counters->surfel_count[f.parity];
-  for_each_visible(d, n, [&](size_t pos) {
-    const u32 idx = d.vis[pos].x & ~kActiveBit;
+  const TimelineScope timeline_scope(d, f.frame_index, KID_UPDATE_NEIGHBORS);
+  for_each_visible(d, &d.counters->surfel_count[f.parity], [&](size_t, const VisEntry& e) {
+    const u32 idx = e.x & ~kActiveBit;
     // batch 1: the surfel (its position may have been changed by the integration: project again)
     const u32 stamp = SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx);
     const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
@@ -788,6 +957,7 @@ __device__ __forceinline__ unsigned long long load_scan_state(unsigned long long
 
 __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, FrameParams f) {
   pdl_prologue();
+  const TimelineScope timeline_scope(d, f.frame_index, KID_NEW_SURFEL_SCAN);
   __shared__ u32 s_tile, s_prefix;
   __shared__ u32 warp_totals[kBlock / 32];
   const int total_pixels = d.width * d.height;
@@ -882,6 +1052,7 @@ __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, Frame
 // CreateNewSurfelsCUDACreationKernel (kernels.cu:133-231), one thread per NEW surfel.
 __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameParams f) {
   pdl_prologue();
+  const TimelineScope timeline_scope(d, f.frame_index, KID_CREATE_SURFELS);
   const u32 new_count = d.counters->new_surfel_count;
   const u32 surfel_count = d.counters->surfel_count[f.parity];
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < new_count; k += gridDim.x * blockDim.x) {
@@ -984,24 +1155,53 @@ __global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int p
 namespace {
 int LaunchBlend(cudaStream_t stream, const DeviceState& d, const FrameParams& f) {
   const dim3 pixel_tiles((d.width + kBlendTileW - 1) / kBlendTileW, (d.height + kBlendTileH - 1) / kBlendTileH);
-  const int halo = f.blend_radius - 1 > 1 ? f.blend_radius - 1 : 1;
-  const size_t rn = static_cast<size_t>(kBlendTileW + 2 * halo) * (kBlendTileH + 2 * halo);
-  const size_t smem = ((rn + 3) & ~static_cast<size_t>(3)) * 19 + 16;
-  if (smem > 200 * 1024 || f.blend_radius > kMaxBlendRadius) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
+  const size_t rn = static_cast<size_t>(kBlendTileW + 2 * blend_halo_x(f.blend_radius)) * (kBlendTileH + 2 * blend_halo_y(f.blend_radius));
+  const size_t rn16 = (rn + 15) & ~static_cast<size_t>(15);
+  const size_t smem = rn16 * 19 + (rn16 / 32 + 1) * 4 + 16;  // k_blend's carve-up: 19 B per region pixel + claim bits
+  // One region per block has to fit the 227 KB of an SM (radius <= 25 at the 80x32 tile).
+  if (smem > 224 * 1024 || f.blend_radius > kMaxBlendRadius) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
   static size_t configured_smem = 0;
-  static bool carveout_set = false;
-  if (!carveout_set) {
-    // several ~40 KB blocks per SM: ask for the maximum shared-memory carve-out
-    cudaFuncSetAttribute(k_blend, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    carveout_set = true;
-  }
   if (smem > 48 * 1024 && smem > configured_smem) {
     if (cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend)");
     configured_smem = smem;
   }
-  { LaunchScope scope(stream, KID_BLEND); LaunchKernel(k_blend, dim3(pixel_tiles), dim3(kBlendBlock), smem, stream, d, f); }
+  { LaunchScope scope(stream, KID_BLEND); LaunchDependent(k_blend, dim3(pixel_tiles), dim3(kBlendBlock), smem, stream, d, f); }
   return SM_OK;
+}
+
+// Grids of the list kernels: exactly the blocks that are resident at once (occupancy x SMs), so
+// that every block is scheduled in the first wave and the per-block loops (which fetch the next
+// item ahead) take care of longer lists. SM_B200_RESIDENT_GRIDS=0 restores fixed 8 blocks/SM.
+struct ListGrids { int project, associate, merge, integrate, update_neighbors; };
+
+template <typename Kernel>
+int ResidentBlocks(Kernel kernel, int block, int sm_count, int fallback_per_sm) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = fallback_per_sm;
+  }
+  return ScaleGrid(sm_count * per_sm);
+}
+
+const ListGrids& GetListGrids(int sm_count) {
+  static ListGrids grids = {0, 0, 0, 0, 0};
+  static int for_sm_count = -1;
+  if (for_sm_count != sm_count) {
+    const char* e = std::getenv("SM_B200_RESIDENT_GRIDS");
+    if (e && e[0] == '0') {
+      grids = {sm_count * 4, sm_count * 8, sm_count * 8, sm_count * 8, sm_count * 8};
+    } else {
+      grids.project = ResidentBlocks(k_project, kProjectBlock, sm_count, 2);
+      grids.associate = ResidentBlocks(k_associate, kBlock, sm_count, 8);
+      grids.merge = ResidentBlocks(k_merge, kBlock, sm_count, 4);
+      grids.integrate = ResidentBlocks(k_integrate, kBlock, sm_count, 3);
+      grids.update_neighbors = ResidentBlocks(k_update_neighbors, kBlock, sm_count, 3);
+    }
+    for_sm_count = sm_count;
+  }
+  return grids;
 }
 }  // namespace
 
@@ -1015,7 +1215,7 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
                    bool rasters_already_cleared, int sm_count, const IntegrateEvents* events) {
   const bool timed = events && events->enabled;
   auto record = [&](int i) { if (timed) cudaEventRecord(events->ev[i], stream); };
-  const int list_grid = sm_count * 8;  // persistent grid: 8 blocks of 256 threads per SM
+  const ListGrids& grids = GetListGrids(sm_count);
   const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
 
   record(0);
@@ -1023,19 +1223,19 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
     const int status = ClearAssociationRasters(stream, d);
     if (status != SM_OK) return status;
   }
-  { LaunchScope scope(stream, KID_PROJECT); LaunchKernel(k_project, dim3(sm_count * 4), dim3(kProjectBlock), 0, stream, d, f); }
-  { LaunchScope scope(stream, KID_ASSOCIATE); LaunchKernel(k_associate, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_PROJECT); LaunchKernel(k_project, dim3(grids.project), dim3(kProjectBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_ASSOCIATE); LaunchDependent(k_associate, dim3(grids.associate), dim3(kBlock), 0, stream, d, f); }
   record(1); record(2);
-  { LaunchScope scope(stream, KID_MERGE); LaunchKernel(k_merge, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_MERGE); LaunchKernel(k_merge, dim3(grids.merge), dim3(kBlock), 0, stream, d, f); }
   record(3); record(4);
   if (do_blending) {
     const int status = LaunchBlend(stream, d, f);
     if (status != SM_OK) return status;
   }
   record(5); record(6);
-  { LaunchScope scope(stream, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(grids.integrate), dim3(kBlock), 0, stream, d, f); }
   record(7); record(8);
-  { LaunchScope scope(stream, KID_UPDATE_NEIGHBORS); LaunchKernel(k_update_neighbors, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_UPDATE_NEIGHBORS); LaunchKernel(k_update_neighbors, dim3(grids.update_neighbors), dim3(kBlock), 0, stream, d, f); }
   record(9); record(10);
   { LaunchScope scope(stream, KID_NEW_SURFEL_SCAN); LaunchKernel(k_new_surfel_scan, dim3(scan_tiles), dim3(kBlock), 0, stream, d, f); }
   { LaunchScope scope(stream, KID_CREATE_SURFELS); LaunchKernel(k_create_surfels, dim3(sm_count * 2), dim3(kBlock), 0, stream, d, f); }
@@ -1045,36 +1245,36 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
 
 int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const DeviceState& d, const FrameParams& f,
                             bool do_blending, const RegularizeArgs& reg, int sm_count) {
-  const int list_grid = sm_count * 8;
+  const ListGrids& grids = GetListGrids(sm_count);
   const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
-  cudaStream_t aux = pc->aux;
+  cudaStream_t aux = pc->aux, side = pc->side;
   // main: project -> associate -> blend -> [merge, previous regularisation] integrate -> [scan] create
-  { LaunchScope scope(stream, KID_PROJECT); LaunchKernel(k_project, dim3(sm_count * 4), dim3(kProjectBlock), 0, stream, d, f); }
-  { LaunchScope scope(stream, KID_ASSOCIATE); LaunchKernel(k_associate, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_PROJECT); LaunchKernel(k_project, dim3(grids.project), dim3(kProjectBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_ASSOCIATE); LaunchDependent(k_associate, dim3(grids.associate), dim3(kBlock), 0, stream, d, f); }
   cudaEventRecord(pc->ev_assoc, stream);
-  // aux: merge (reads the pre-blend depth copy)
-  cudaStreamWaitEvent(aux, pc->ev_assoc, 0);
-  { LaunchScope scope(aux, KID_MERGE); LaunchKernel(k_merge, dim3(list_grid), dim3(kBlock), 0, aux, d, f); }
-  cudaEventRecord(pc->ev_merge, aux);
+  // side: merge decisions (read the pre-blend depth copy) beside the blending
+  cudaStreamWaitEvent(side, pc->ev_assoc, 0);
+  { LaunchScope scope(side, KID_MERGE); LaunchKernel(k_merge, dim3(grids.merge), dim3(kBlock), 0, side, d, f); }
+  cudaEventRecord(pc->ev_merge, side);
   if (do_blending) {
     const int status = LaunchBlend(stream, d, f);
     if (status != SM_OK) return status;
   }
   cudaEventRecord(pc->ev_blend, stream);
-  // aux: new-surfel flags + scan need the blended depth and the final association rasters
-  cudaStreamWaitEvent(aux, pc->ev_blend, 0);
-  { LaunchScope scope(aux, KID_NEW_SURFEL_SCAN); LaunchKernel(k_new_surfel_scan, dim3(scan_tiles), dim3(kBlock), 0, aux, d, f); }
-  cudaEventRecord(pc->ev_scan, aux);
+  // side: new-surfel flags + scan need the blended depth and the final association rasters
+  cudaStreamWaitEvent(side, pc->ev_blend, 0);
+  { LaunchScope scope(side, KID_NEW_SURFEL_SCAN); LaunchKernel(k_new_surfel_scan, dim3(scan_tiles), dim3(kBlock), 0, side, d, f); }
+  cudaEventRecord(pc->ev_scan, side);
   cudaStreamWaitEvent(stream, pc->ev_merge, 0);
   if (pc->have_reg) cudaStreamWaitEvent(stream, pc->ev_reg, 0);  // the integration rewrites what regularisation reads
-  { LaunchScope scope(stream, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(list_grid), dim3(kBlock), 0, stream, d, f); }
+  { LaunchScope scope(stream, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(grids.integrate), dim3(kBlock), 0, stream, d, f); }
   cudaEventRecord(pc->ev_integrate, stream);
   cudaStreamWaitEvent(stream, pc->ev_scan, 0);
   { LaunchScope scope(stream, KID_CREATE_SURFELS); LaunchKernel(k_create_surfels, dim3(sm_count * 2), dim3(kBlock), 0, stream, d, f); }
   cudaEventRecord(pc->ev_create[set], stream);
   // aux: neighbour update, then the regularisation (needs the new surfels too)
   cudaStreamWaitEvent(aux, pc->ev_integrate, 0);
-  { LaunchScope scope(aux, KID_UPDATE_NEIGHBORS); LaunchKernel(k_update_neighbors, dim3(list_grid), dim3(kBlock), 0, aux, d, f); }
+  { LaunchScope scope(aux, KID_UPDATE_NEIGHBORS); LaunchKernel(k_update_neighbors, dim3(grids.update_neighbors), dim3(kBlock), 0, aux, d, f); }
   cudaEventRecord(pc->ev_update[set], aux);
   cudaStreamWaitEvent(aux, pc->ev_create[set], 0);
   int status = CheckLaunch("integrate (pipelined)");
@@ -1098,6 +1298,22 @@ int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm
                    u8* color_buffer) {
   { LaunchScope scope(stream, KID_EXPORT_VERTICES); LaunchKernel(k_export_vertices, dim3(sm_count * 8), dim3(kBlock), 0, stream, d, parity, position_buffer, color_buffer); }
   return CheckLaunch("export vertices");
+}
+
+
+// Measurement hook (SM_B200_CARVEOUT): one shared-memory carve-out for every kernel of the file.
+void ConfigureIntegrateKernels(int carveout_percent) {
+  cudaFuncSetAttribute(k_clear, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_project, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_associate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_merge, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_blend, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_integrate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_update_neighbors, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_new_surfel_scan, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_create_surfels, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_export_vertices, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaGetLastError();
 }
 
 }  // namespace smb

@@ -43,6 +43,7 @@ struct BilateralArgs {
   int width, height;
   const u16* in;
   size_t in_pitch;
+  unsigned long long* timeline;  // device timeline slot of this launch or null (diagnostics)
 };
 
 // Cooperative fill of a (kTileH + 2R) x (tile_w_pad) fp32 tile from a pitched u16 raster.
@@ -198,6 +199,7 @@ template <int R, bool kWithOutlier>
 __global__ void __launch_bounds__(256, 8)
 k_bilateral_outlier(BilateralArgs a, const __grid_constant__ OutlierArgs o, u16* out, size_t out_pitch) {
   pdl_prologue();
+  const TimelineScope timeline_scope(a.timeline);
   constexpr int PADX = 8;
   constexpr int SW = kTileW + 2 * PADX;  // 48 floats per tile row
   __shared__ __align__(16) float tile[(kTileH + 2 * R) * SW];
@@ -413,6 +415,7 @@ struct TailArgs {
   float* out_radius; size_t out_radius_pitch;
   // Optional: association rasters to reset for the following Integrate().
   uint4* assoc; float* first_depth; u8* supported;
+  unsigned long long* timeline;  // device timeline slot of this launch or null (diagnostics)
 };
 
 constexpr int kMaxErode = 3;
@@ -420,6 +423,7 @@ constexpr int kMaxErode = 3;
 __global__ void __launch_bounds__(256, 8)
 k_erode_normals_radii(TailArgs a) {
   pdl_prologue();
+  const TimelineScope timeline_scope(a.timeline);
   // Tiles (origin relative to the 32 x 8 output tile): B (outlier-filtered input) -5, HV
   // (row-wise erosion validity) -2 / -(2 + r), E (eroded) -2, N (normals stage) -1.
   constexpr int HB = kMaxErode + 2;
@@ -595,6 +599,7 @@ BilateralArgs MakeBilateralArgs(float sigma_xy, float sigma_value_factor, u16 va
   a.valid_radius_squared = depth_valid_region_radius * depth_valid_region_radius;  // :151
   a.width = width; a.height = height;
   a.in = in; a.in_pitch = in_pitch;
+  a.timeline = nullptr;
   return a;
 }
 
@@ -656,8 +661,10 @@ int LaunchBilateral(cudaStream_t stream, const BilateralArgs& a, const OutlierAr
   static const OutlierArgs kNoOutlier = {};
   if (a.radius == 6) {
     LaunchScope scope(stream, KID_BILATERAL_OUTLIER);
-    if (o) LaunchKernel(k_bilateral_outlier<6, true>, TileGrid(a.width, a.height), dim3(256), 0, stream, a, *o, out, out_pitch);
-    else LaunchKernel(k_bilateral_outlier<6, false>, TileGrid(a.width, a.height), dim3(256), 0, stream, a, kNoOutlier, out, out_pitch);
+    BilateralArgs timed = a;
+    timed.timeline = TimelineSlot(KID_BILATERAL_OUTLIER);
+    if (o) LaunchKernel(k_bilateral_outlier<6, true>, TileGrid(a.width, a.height), dim3(256), 0, stream, timed, *o, out, out_pitch);
+    else LaunchKernel(k_bilateral_outlier<6, false>, TileGrid(a.width, a.height), dim3(256), 0, stream, timed, kNoOutlier, out, out_pitch);
   } else {
     if (a.radius < 0) return SetError(SM_ERR_INVALID_ARGUMENT, "negative bilateral radius");
     { LaunchScope scope(stream, KID_BILATERAL_GENERIC); LaunchKernel(k_bilateral_generic, PixelGrid(a.width, a.height), dim3(256), 0, stream, a, out, out_pitch); }
@@ -705,7 +712,8 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
   t.out_normals = out_normals; t.out_normals_pitch = out_normals_pitch;
   t.out_radius = out_radius; t.out_radius_pitch = out_radius_pitch;
   t.assoc = clear_assoc; t.first_depth = clear_first_depth; t.supported = clear_supported;
-  { LaunchScope scope(stream, KID_ERODE_NORMALS_RADII); LaunchKernel(k_erode_normals_radii, TileGrid(width, height), dim3(256), 0, stream, t); }
+  t.timeline = TimelineSlot(KID_ERODE_NORMALS_RADII);
+  { LaunchScope scope(stream, KID_ERODE_NORMALS_RADII); LaunchDependent(k_erode_normals_radii, TileGrid(width, height), dim3(256), 0, stream, t); }
   return CheckLaunch("erode/normals/radii");
 }
 
@@ -752,6 +760,20 @@ int StageRadii(cudaStream_t stream, float point_radius_extension_factor, float p
       MakeRadiiArgs(point_radius_extension_factor, point_radius_clamp_factor, depth_scaling, fx, fy, cx, cy), width,
       height, in, in_pitch, radius, radius_pitch, out, out_pitch); }
   return CheckLaunch("radii");
+}
+
+
+// Measurement hook (SM_B200_CARVEOUT): one shared-memory carve-out for every kernel of the file.
+void ConfigurePreprocessKernels(int carveout_percent) {
+  cudaFuncSetAttribute(k_bilateral_outlier<6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_bilateral_outlier<6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_bilateral_generic, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_outlier, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_erode_normals_radii, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_erode, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_normals, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_radii, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaGetLastError();
 }
 
 }  // namespace smb

@@ -13,6 +13,8 @@
 // regularisation window, and exactly those are reset by k_reg_update).
 // Float atomics make the accumulated gradients order-dependent, as in the reference.
 
+#include <cstdlib>
+
 #include "sm_kernels.cuh"
 
 namespace smb {
@@ -41,12 +43,26 @@ __device__ __forceinline__ bool outside_window(u32 stamp, const RegParams& p) {
 
 __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegParams p) {
   pdl_prologue();
+  const TimelineScope timeline_scope(d, p.frame_index, KID_REG_ACCUMULATE);
   const u32 n = d.counters->surfel_count[p.count_slot];
   const u32 n_remove = p.remove_below_slot >= 0 ? d.counters->surfel_count[p.remove_below_slot] : 0u;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  // The sweep is a chain of dependent gathers per surfel; the neighbour links (its first level)
+  // are requested one round ahead, the first round's before the counts have arrived.
+  const u32 step = gridDim.x * blockDim.x;
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 nbr_ahead[4] = {kInvalidIndex, kInvalidIndex, kInvalidIndex, kInvalidIndex};
+  if (i < d.stride) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nbr_ahead[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
+  }
+  for (; i < n; i += step) {
     u32 nbr[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) nbr[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
+    for (int k = 0; k < 4; ++k) nbr[k] = nbr_ahead[k];
+    if (i + step < n) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nbr_ahead[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i + step);
+    }
     if ((nbr[0] & nbr[1] & nbr[2] & nbr[3]) == kInvalidIndex) continue;  // no neighbours at all
 
     // batch 1: detach flags and stamps of the neighbours, and this surfel's own attributes
@@ -109,9 +125,28 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
 
 __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p) {
   pdl_prologue();
+  const TimelineScope timeline_scope(d, p.frame_index, KID_REG_STEP);
   const u32 n = d.counters->surfel_count[p.count_slot];
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
+  // Stamp and neighbour links (first level of the gather chain) are requested one round ahead.
+  const u32 step = gridDim.x * blockDim.x;
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 stamp_ahead = 0, nbr_ahead[4] = {kInvalidIndex, kInvalidIndex, kInvalidIndex, kInvalidIndex};
+  if (i < d.stride) {
+    stamp_ahead = SM_SU(SM_ROW_LAST_UPDATE_STAMP, i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nbr_ahead[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
+  }
+  for (; i < n; i += step) {
+    const u32 stamp = stamp_ahead;
+    u32 nbr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nbr[k] = nbr_ahead[k];
+    if (i + step < n) {
+      stamp_ahead = SM_SU(SM_ROW_LAST_UPDATE_STAMP, i + step);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nbr_ahead[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i + step);
+    }
+    if (outside_window(stamp, p)) continue;
     const float sx = SM_S(SM_ROW_SMOOTH_X, i), sy = SM_S(SM_ROW_SMOOTH_Y, i), sz = SM_S(SM_ROW_SMOOTH_Z, i);
     const float nx = SM_S(SM_ROW_NORMAL_X, i), ny = SM_S(SM_ROW_NORMAL_Y, i), nz = SM_S(SM_ROW_NORMAL_Z, i);
     // Data term (factor 2) + neighbour-induced terms.
@@ -120,9 +155,6 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
     float gz = ffma(fsub(sz, SM_S(SM_ROW_Z, i)), 2.0f, SM_S(SM_ROW_GRADIENT_Z, i));
     int neighbor_count = 0;
     float rx = 0.f, ry = 0.f, rz = 0.f;
-    u32 nbr[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) nbr[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i);
     float qx[4], qy[4], qz[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -164,6 +196,7 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
 
 __global__ void __launch_bounds__(kBlock) k_reg_update(DeviceState d, RegParams p) {
   pdl_prologue();
+  const TimelineScope timeline_scope(d, p.frame_index, KID_REG_UPDATE);
   const u32 n = d.counters->surfel_count[p.count_slot];
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
@@ -180,6 +213,7 @@ __global__ void __launch_bounds__(kBlock) k_reg_update(DeviceState d, RegParams 
 // RegularizeSurfelsCUDACopyOnlyKernel (kernels.cu:2310-2327) [+ detach-flag pass].
 __global__ void __launch_bounds__(kBlock) k_reg_copy_only(DeviceState d, RegParams p) {
   pdl_prologue();
+  const TimelineScope timeline_scope(d, p.frame_index, KID_REG_COPY_ONLY);
   const u32 n = d.counters->surfel_count[p.count_slot];
   const u32 n_remove = p.remove_below_slot >= 0 ? d.counters->surfel_count[p.remove_below_slot] : 0u;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -211,15 +245,42 @@ int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_de
   p.regularizer_weight = regularizer_weight;
   p.count_slot = count_slot;
   p.remove_below_slot = remove_replaced_below_slot;
-  const int grid = sm_count * 8;
+  // Grids = the blocks resident at once (see GetListGrids in integrate.cu).
+  static int grid_accumulate = 0, grid_step = 0, grid_update = 0, grid_copy = 0, grids_for = -1;
+  if (grids_for != sm_count) {
+    const char* e = std::getenv("SM_B200_RESIDENT_GRIDS");
+    auto resident = [&](auto kernel) {
+      int per_sm = 0;
+      if ((e && e[0] == '0') || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 8;
+      }
+      return ScaleGrid(sm_count * per_sm);
+    };
+    grid_accumulate = resident(k_reg_accumulate);
+    grid_step = resident(k_reg_step);
+    grid_update = resident(k_reg_update);
+    grid_copy = resident(k_reg_copy_only);
+    grids_for = sm_count;
+  }
   if (disable_denoising) {
-    { LaunchScope scope(stream, KID_REG_COPY_ONLY); LaunchKernel(k_reg_copy_only, dim3(grid), dim3(kBlock), 0, stream, d, p); }
+    { LaunchScope scope(stream, KID_REG_COPY_ONLY); LaunchKernel(k_reg_copy_only, dim3(grid_copy), dim3(kBlock), 0, stream, d, p); }
     return CheckLaunch("regularize (copy only)");
   }
-  { LaunchScope scope(stream, KID_REG_ACCUMULATE); LaunchKernel(k_reg_accumulate, dim3(grid), dim3(kBlock), 0, stream, d, p); }
-  { LaunchScope scope(stream, KID_REG_STEP); LaunchKernel(k_reg_step, dim3(grid), dim3(kBlock), 0, stream, d, p); }
-  { LaunchScope scope(stream, KID_REG_UPDATE); LaunchKernel(k_reg_update, dim3(grid), dim3(kBlock), 0, stream, d, p); }
+  { LaunchScope scope(stream, KID_REG_ACCUMULATE); LaunchKernel(k_reg_accumulate, dim3(grid_accumulate), dim3(kBlock), 0, stream, d, p); }
+  { LaunchScope scope(stream, KID_REG_STEP); LaunchDependent(k_reg_step, dim3(grid_step), dim3(kBlock), 0, stream, d, p); }
+  { LaunchScope scope(stream, KID_REG_UPDATE); LaunchDependent(k_reg_update, dim3(grid_update), dim3(kBlock), 0, stream, d, p); }
   return CheckLaunch("regularize");
+}
+
+
+// Measurement hook (SM_B200_CARVEOUT): one shared-memory carve-out for every kernel of the file.
+void ConfigureRegularizeKernels(int carveout_percent) {
+  cudaFuncSetAttribute(k_reg_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_reg_step, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_reg_update, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_reg_copy_only, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaGetLastError();
 }
 
 }  // namespace smb

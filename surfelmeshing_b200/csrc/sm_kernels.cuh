@@ -95,6 +95,10 @@ struct DeviceState {
   u32* new_list;         // W*H: pixel (seq index) of the k-th new surfel
   unsigned long long* scan_state;  // per scan tile: status << 32 | value
   Counters* counters;
+  // Device timeline (diagnostics, sm_timeline_enable): [frame % timeline_frames][kernel id]{first block start,
+  // last block end} in %globaltimer nanoseconds; null when disabled.
+  unsigned long long* timeline;
+  u32 timeline_frames;
 };
 
 struct FrameParams {
@@ -134,11 +138,41 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
 }
-bool UsePdl();  // env SM_B200_PDL=0 disables (A/B measurements)
+// Device timeline: the kernels stamp their own start / end (%globaltimer) so that the frame
+// pipeline can be read as it really ran on the GPU (events and the profiler serialise it).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+struct TimelineScope {
+  unsigned long long* slot;
+  __device__ __forceinline__ explicit TimelineScope(unsigned long long* s) : slot(s) { begin(); }
+  __device__ __forceinline__ TimelineScope(const DeviceState& d, u32 frame, int kernel_id)
+      : slot(d.timeline ? d.timeline + (static_cast<size_t>(frame % d.timeline_frames) * KID_COUNT + kernel_id) * 2 : nullptr) {
+    begin();
+  }
+  __device__ __forceinline__ void begin() {
+    if (slot && threadIdx.x == 0 && blockIdx.x < 8 && blockIdx.y == 0) atomicMin(slot, globaltimer_ns());
+  }
+  __device__ __forceinline__ ~TimelineScope() {
+    if (slot && threadIdx.x == 0) atomicMax(slot + 1, globaltimer_ns());
+  }
+};
+// Host side: slot of (frame announced by SetTimelineFrame, kernel id) for kernels without DeviceState.
+void SetTimelineFrame(u32 frame);
+unsigned long long* TimelineSlot(int kernel_id);
+
+// SM_B200_PDL: 0 = never, 1 (default) = only launches marked as dependents (LaunchDependent: the
+// kernel follows its producer on the same stream), 2 = every launch. Marking everything costs
+// ~3 % in the multi-stream frame pipeline (early-launched kernels take SM slots from the kernels
+// of the other streams).
+int PdlMode();
+int ScaleGrid(int blocks);  // SM_B200_GRID_PERCENT measurement hook (integrate.cu)
 
 template <typename... KArgs, typename... Args>
-inline void LaunchKernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                         Args&&... args) {
+inline void LaunchKernelImpl(bool dependent, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                             cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -148,9 +182,25 @@ inline void LaunchKernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = UsePdl() ? 1 : 0;
+  const int mode = PdlMode();
+  cfg.numAttrs = (mode == 2 || (mode == 1 && dependent)) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+template <typename... KArgs, typename... Args>
+inline void LaunchKernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                         Args&&... args) {
+  LaunchKernelImpl(false, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+// For a kernel whose producer is the previous kernel of the same stream.
+template <typename... KArgs, typename... Args>
+inline void LaunchDependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  LaunchKernelImpl(true, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+
+void ConfigurePreprocessKernels(int carveout_percent);
+void ConfigureIntegrateKernels(int carveout_percent);
+void ConfigureRegularizeKernels(int carveout_percent);
 
 // ---- preprocess.cu --------------------------------------------------------------------------
 int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int width, int height, float fx, float fy,
@@ -191,7 +241,8 @@ int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d);
 // caller's stream and one auxiliary stream; the regularisation of frame f overlaps with the
 // projection / association / blending of frame f + 1.
 struct PipelineCtx {
-  cudaStream_t aux;
+  cudaStream_t aux;    // neighbour update + regularisation
+  cudaStream_t side;   // merge decisions + new-surfel scan (short kernels beside blend / integrate)
   cudaEvent_t ev_assoc, ev_merge, ev_blend, ev_scan, ev_integrate;  // transient, re-recorded every frame
   cudaEvent_t ev_create[2], ev_update[2];                            // per buffer set (frame parity)
   cudaEvent_t ev_reg;                                                // regularisation of the latest frame

@@ -54,7 +54,7 @@ def test_default_params_match_reference_defaults(product):
 def test_struct_layouts():
     assert C.sizeof(_lib.IntegrateParams) == 44
     assert C.sizeof(_lib.PreprocessParams) == 52
-    assert C.sizeof(_lib.StreamStats) == 40
+    assert C.sizeof(_lib.StreamStats) == 48
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")

@@ -25,8 +25,12 @@ def main():
     ap.add_argument("--gen", default="cuda")
     ap.add_argument("--host", action="store_true", help="frames in pinned host memory (e2e path)")
     ap.add_argument("--timings", action="store_true")
+    ap.add_argument("--lib", default=None, help="path of a product library variant (A/B builds)")
     args = ap.parse_args()
-    lib = _lib.load_product() if args.impl == "product" else _lib.load_reference_oracle()
+    if args.lib:
+        lib = _lib.Library(Path(args.lib).resolve(), "sm_", product=True)
+    else:
+        lib = _lib.load_product() if args.impl == "product" else _lib.load_reference_oracle()
     cam = S.Camera.tum(args.width, args.height)
     t0 = time.time()
     st = S.make_stream(cam, args.frames, device=args.gen)
@@ -55,7 +59,7 @@ def main():
         ms = e0.elapsed_time(e1)
         print(f"{args.impl} rep {rep}: {stats.frames_integrated} frames, {ms:.2f} ms gpu / {wall:.2f} ms wall -> "
               f"{stats.frames_integrated / ms * 1e3:.1f} fps; surfels {stats.surfels_size} count {stats.surfel_count} "
-              f"launches {stats.kernel_launches} h2d {stats.h2d_bytes}", flush=True)
+              f"launches {stats.kernel_launches} h2d {stats.h2d_bytes} host_enqueue_ms {stats.host_enqueue_ms:.2f}", flush=True)
     if args.timings:
         rec.enable_timings(True)
         # time the last frames individually through the stream runner (1 frame per call)
