@@ -244,10 +244,17 @@ int EnsureRunBuffers(sm_reconstruction* r, int ring, bool on_host) {
     }
     SM_CUDA(cudaStreamCreateWithFlags(&r->pre_stream, cudaStreamNonBlocking));
     SM_CUDA(cudaEventCreateWithFlags(&r->entry_event, cudaEventDisableTiming));
-    SM_CUDA(cudaStreamCreateWithFlags(&r->pipe.aux, cudaStreamNonBlocking));
-    SM_CUDA(cudaStreamCreateWithFlags(&r->pipe.side, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&r->pipe.ev_assoc, &r->pipe.ev_merge, &r->pipe.ev_blend, &r->pipe.ev_scan,
-                           &r->pipe.ev_integrate, &r->pipe.ev_reg}) {
+    int least_priority = 0, greatest_priority = 0;
+    SM_CUDA(cudaDeviceGetStreamPriorityRange(&least_priority, &greatest_priority));
+    // SM_B200_PRIO (measurement hook): 0 (default) = no priorities, 1 = crit + side high, 2 = front too
+    // (everything of the integration above the pre-processing of the next frame).
+    const char* prio_env = std::getenv("SM_B200_PRIO");
+    const int prio_mode = (prio_env && prio_env[0] >= '0' && prio_env[0] <= '2') ? prio_env[0] - '0' : 0;
+    SM_CUDA(cudaStreamCreateWithPriority(&r->pipe.crit, cudaStreamNonBlocking, prio_mode >= 1 ? greatest_priority : least_priority));
+    SM_CUDA(cudaStreamCreateWithPriority(&r->pipe.side, cudaStreamNonBlocking, prio_mode >= 1 ? greatest_priority : least_priority));
+    SM_CUDA(cudaStreamCreateWithPriority(&r->pipe.front, cudaStreamNonBlocking, prio_mode >= 2 ? greatest_priority : least_priority));
+    for (cudaEvent_t* e : {&r->pipe.ev_assoc, &r->pipe.ev_merge, &r->pipe.ev_blend, &r->pipe.ev_integrate,
+                           &r->pipe.ev_reg}) {
       SM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
   }
@@ -368,6 +375,8 @@ int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width,
   const size_t P = static_cast<size_t>(width) * height;
   const size_t scan_tiles = (P + kSegment - 1) / kSegment;
   SM_CUDA(cudaMalloc(&d.surfels, sizeof(float) * SM_ROW_COUNT * d.stride));
+  SM_CUDA(cudaMalloc(&d.gradient, sizeof(float4) * d.stride));
+  SM_CUDA(cudaMemset(d.gradient, 0, sizeof(float4) * d.stride));
   for (int i = 0; i < 2; ++i) {
     SM_CUDA(cudaMalloc(&r->assoc_set[i], sizeof(PixelAssoc) * P));
     SM_CUDA(cudaMalloc(&r->first_depth_set[i], sizeof(float) * P));
@@ -407,7 +416,7 @@ int sm_destroy(sm_reconstruction* r) {
   if (!r) return SM_OK;
   cudaDeviceSynchronize();
   DeviceState& d = r->d;
-  cudaFree(d.surfels); cudaFree(d.new_list);
+  cudaFree(d.surfels); cudaFree(d.gradient); cudaFree(d.new_list);
   for (int i = 0; i < 2; ++i) { cudaFree(r->vis_set[i]); cudaFree(r->seg_count_set[i]); cudaFree(r->merge_flag_set[i]); cudaFree(r->run_depth_pre[i]);
     if (r->pipe.ev_create[i]) cudaEventDestroy(r->pipe.ev_create[i]);
     if (r->pipe.ev_update[i]) cudaEventDestroy(r->pipe.ev_update[i]);
@@ -423,11 +432,12 @@ int sm_destroy(sm_reconstruction* r) {
     if (r->int_done[i]) cudaEventDestroy(r->int_done[i]);
   }
   if (r->pre_stream) cudaStreamDestroy(r->pre_stream);
-  if (r->pipe.aux) {
-    cudaStreamDestroy(r->pipe.aux);
+  if (r->pipe.crit) {
+    cudaStreamDestroy(r->pipe.crit);
+    if (r->pipe.front) cudaStreamDestroy(r->pipe.front);
     if (r->pipe.side) cudaStreamDestroy(r->pipe.side);
-    for (cudaEvent_t e : {r->pipe.ev_assoc, r->pipe.ev_merge, r->pipe.ev_blend, r->pipe.ev_scan, r->pipe.ev_integrate,
-                          r->pipe.ev_reg}) cudaEventDestroy(e);
+    for (cudaEvent_t e : {r->pipe.ev_assoc, r->pipe.ev_merge, r->pipe.ev_blend, r->pipe.ev_integrate, r->pipe.ev_reg})
+      cudaEventDestroy(e);
   }
   if (r->entry_event) cudaEventDestroy(r->entry_event);
   for (u16* b : r->ring_depth) cudaFree(b);
@@ -595,7 +605,8 @@ int sm_load_state(sm_reconstruction* r, void* stream_v, const float* host_rows, 
     SM_CUDA(cudaMemcpy2DAsync(r->d.surfels, r->d.stride * sizeof(float), host_rows,
                               host_row_stride_elems * sizeof(float), surfels_size * sizeof(float), SM_ROW_COUNT,
                               cudaMemcpyHostToDevice, stream));
-    // Invariant of regularize.cu: gradient rows and the weight row are zero between calls.
+    // Invariant of regularize.cu: gradient accumulators (and the SoA rows they replace) are zero between calls.
+    SM_CUDA(cudaMemsetAsync(r->d.gradient, 0, surfels_size * sizeof(float4), stream));
     const int zero_rows[4] = {SM_ROW_GRADIENT_X, SM_ROW_GRADIENT_Y, SM_ROW_GRADIENT_Z, SM_ROW_GRADIENT_COUNT};
     for (int row : zero_rows) {
       SM_CUDA(cudaMemsetAsync(r->d.surfels + row * r->d.stride, 0, surfels_size * sizeof(float), stream));
@@ -715,10 +726,11 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
   // association rasters; it is reused by frame f + 2 once Integrate(f) has finished.
   // Per-kernel profiling and stage timings need the kernels one after the other on one stream.
   const bool pipelined = !r->events.enabled && !ProfilingEnabled();
-  r->pipe.have_reg = false;
+  r->pipe.have_frame = false;
   SM_CUDA(cudaEventRecord(r->entry_event, stream));
   SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->entry_event, 0));
-  SM_CUDA(cudaStreamWaitEvent(r->pipe.aux, r->entry_event, 0));
+  SM_CUDA(cudaStreamWaitEvent(r->pipe.crit, r->entry_event, 0));
+  SM_CUDA(cudaStreamWaitEvent(r->pipe.front, r->entry_event, 0));
   SM_CUDA(cudaStreamWaitEvent(r->pipe.side, r->entry_event, 0));
   if (s->frames_on_host) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->entry_event, 0));
   int uploaded_until = first_frame - half - 1;
@@ -791,7 +803,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
       status = enqueue_preprocess(frame + 1);
       if (status != SM_OK) return status;
     }
-    SM_CUDA(cudaStreamWaitEvent(stream, r->pre_done[set], 0));
+    SM_CUDA(cudaStreamWaitEvent(pipelined ? r->pipe.front : stream, r->pre_done[set], 0));
     r->d.assoc = r->assoc_set[set]; r->d.first_depth = r->first_depth_set[set]; r->d.supported = r->supported_set[set];
     r->d.vis = r->vis_set[set]; r->d.seg_count = r->seg_count_set[set]; r->d.merge_flag = r->merge_flag_set[set];
     const size_t color_pitch = s->frames_on_host ? r->ring_color_pitch : static_cast<size_t>(W) * 3;
@@ -808,7 +820,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
       reg.radius_factor = ip->radius_factor_for_regularization_neighbors;
       reg.regularizer_weight = ip->regularizer_weight;
       reg.window = ip->regularization_frame_window_size;
-      status = IntegrateFramePipelined(stream, &r->pipe, set, r->d, f, ip->do_blending != 0, reg, r->sm_count);
+      status = IntegrateFramePipelined(r->pipe.front, &r->pipe, set, r->d, f, ip->do_blending != 0, reg, r->sm_count);
       if (status != SM_OK) return status;
       r->parity ^= 1;
     } else {
@@ -822,7 +834,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
     }
     ++integrated;
   }
-  if (pipelined && r->pipe.have_reg) SM_CUDA(cudaStreamWaitEvent(stream, r->pipe.ev_reg, 0));  // join
+  if (pipelined && r->pipe.have_frame) SM_CUDA(cudaStreamWaitEvent(stream, r->pipe.ev_reg, 0));  // join
   const double host_enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   status = FetchCounters(r, stream);  // one 32-byte D2H + sync for the whole call
   if (stats) {

@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) 
 // a10: measurement blending, all iterations in one kernel
 // ---------------------------------------------------------------------------------------
 constexpr int kBlendTileW = 80, kBlendTileH = 32;  // 8 x 15 = 120 tiles at VGA: one block per SM, one wave
-constexpr int kBlendBlock = 1024;
+constexpr int kBlendBlock = 512;
 constexpr int kMaxBlendRadius = 64;
 // Pixel classes of the start stencil (kernels.cu:578-596): no measurement / measurement without a
 // supporting surfel / measurement with one.
@@ -1121,10 +1121,11 @@ __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameP
     SM_SU(SM_ROW_CREATION_STAMP, idx) = f.frame_index;
     SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
     SM_S(SM_ROW_RADIUS_SQUARED, idx) = radius_squared;
-    // The reference leaves rows 11-16 and 23 uninitialised; the regularisation of this
-    // library relies on rows 11-13 and 23 being zero between calls (regularize.cu).
+    // The reference leaves rows 11-16 and 23 uninitialised; here rows 11-13 and 23 are always
+    // zero and the regularisation accumulates in d.gradient, zero between calls (regularize.cu).
     SM_S(SM_ROW_GRADIENT_X, idx) = 0.f; SM_S(SM_ROW_GRADIENT_Y, idx) = 0.f; SM_S(SM_ROW_GRADIENT_Z, idx) = 0.f;
     SM_S(SM_ROW_GRADIENT_COUNT, idx) = 0.f;
+    d.gradient[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float rcp_count = frcp(i2f(existing_neighbor_count_plus_1));
     SM_S(SM_ROW_SMOOTH_X, idx) = fmul(fadd(g.x, sum_x), rcp_count);
     SM_S(SM_ROW_SMOOTH_Y, idx) = fmul(fadd(g.y, sum_y), rcp_count);
@@ -1247,8 +1248,10 @@ int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const
                             bool do_blending, const RegularizeArgs& reg, int sm_count) {
   const ListGrids& grids = GetListGrids(sm_count);
   const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
-  cudaStream_t aux = pc->aux, side = pc->side;
-  // main: project -> associate -> blend -> [merge, previous regularisation] integrate -> [scan] create
+  cudaStream_t crit = pc->crit, side = pc->side;
+  // front: project -> associate -> blend. Needs the surfels as the previous
+  // frame's integration and creation left them.
+  if (pc->have_frame) cudaStreamWaitEvent(stream, pc->ev_create[set ^ 1], 0);
   { LaunchScope scope(stream, KID_PROJECT); LaunchKernel(k_project, dim3(grids.project), dim3(kProjectBlock), 0, stream, d, f); }
   { LaunchScope scope(stream, KID_ASSOCIATE); LaunchDependent(k_associate, dim3(grids.associate), dim3(kBlock), 0, stream, d, f); }
   cudaEventRecord(pc->ev_assoc, stream);
@@ -1264,33 +1267,36 @@ int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const
   // side: new-surfel flags + scan need the blended depth and the final association rasters
   cudaStreamWaitEvent(side, pc->ev_blend, 0);
   { LaunchScope scope(side, KID_NEW_SURFEL_SCAN); LaunchKernel(k_new_surfel_scan, dim3(scan_tiles), dim3(kBlock), 0, side, d, f); }
-  cudaEventRecord(pc->ev_scan, side);
-  cudaStreamWaitEvent(stream, pc->ev_merge, 0);
-  if (pc->have_reg) cudaStreamWaitEvent(stream, pc->ev_reg, 0);  // the integration rewrites what regularisation reads
-  { LaunchScope scope(stream, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(grids.integrate), dim3(kBlock), 0, stream, d, f); }
-  cudaEventRecord(pc->ev_integrate, stream);
-  cudaStreamWaitEvent(stream, pc->ev_scan, 0);
-  { LaunchScope scope(stream, KID_CREATE_SURFELS); LaunchKernel(k_create_surfels, dim3(sm_count * 2), dim3(kBlock), 0, stream, d, f); }
-  cudaEventRecord(pc->ev_create[set], stream);
-  // aux: neighbour update, then the regularisation (needs the new surfels too)
-  cudaStreamWaitEvent(aux, pc->ev_integrate, 0);
-  { LaunchScope scope(aux, KID_UPDATE_NEIGHBORS); LaunchKernel(k_update_neighbors, dim3(grids.update_neighbors), dim3(kBlock), 0, aux, d, f); }
-  cudaEventRecord(pc->ev_update[set], aux);
-  cudaStreamWaitEvent(aux, pc->ev_create[set], 0);
+  // crit (high priority): the cycle that bounds the frame rate, one stream, back to back:
+  //   [regularisation of the previous frame] -> integrate -> update_neighbors -> regularisation
+  // (the integration rewrites what the previous regularisation reads, and this frame's
+  // regularisation needs the neighbour links and the new surfels).
+  cudaStreamWaitEvent(crit, pc->ev_blend, 0);
+  cudaStreamWaitEvent(crit, pc->ev_merge, 0);
+  { LaunchScope scope(crit, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(grids.integrate), dim3(kBlock), 0, crit, d, f); }
+  cudaEventRecord(pc->ev_integrate, crit);
+  { LaunchScope scope(crit, KID_UPDATE_NEIGHBORS); LaunchDependent(k_update_neighbors, dim3(grids.update_neighbors), dim3(kBlock), 0, crit, d, f); }
+  cudaEventRecord(pc->ev_update[set], crit);
+  // side: create the new surfels once the integration is through (kernels.cu order: after the
+  // neighbour update, which does not touch the new slots)
+  cudaStreamWaitEvent(side, pc->ev_integrate, 0);
+  { LaunchScope scope(side, KID_CREATE_SURFELS); LaunchKernel(k_create_surfels, dim3(sm_count * 2), dim3(kBlock), 0, side, d, f); }
+  cudaEventRecord(pc->ev_create[set], side);
+  cudaStreamWaitEvent(crit, pc->ev_create[set], 0);
   int status = CheckLaunch("integrate (pipelined)");
   if (status != SM_OK) return status;
   const int old_slot = f.parity, new_slot = f.parity ^ 1;
   if (reg.disable_denoising) {
-    status = RegularizeSurfels(aux, d, true, f.frame_index, reg.radius_factor, reg.regularizer_weight, reg.window,
+    status = RegularizeSurfels(crit, d, true, f.frame_index, reg.radius_factor, reg.regularizer_weight, reg.window,
                                new_slot, old_slot, sm_count);
   } else {
     for (int i = 0; i < reg.iterations && status == SM_OK; ++i) {
-      status = RegularizeSurfels(aux, d, false, f.frame_index, reg.radius_factor, reg.regularizer_weight, reg.window,
+      status = RegularizeSurfels(crit, d, false, f.frame_index, reg.radius_factor, reg.regularizer_weight, reg.window,
                                  new_slot, i == 0 ? old_slot : -1, sm_count);
     }
   }
-  cudaEventRecord(pc->ev_reg, aux);
-  pc->have_reg = true;
+  cudaEventRecord(pc->ev_reg, crit);
+  pc->have_frame = true;
   return status;
 }
 

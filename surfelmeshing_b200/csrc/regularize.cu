@@ -8,9 +8,11 @@
 //   k_reg_step       : gradient step, staged in the gradient rows (:2197-2290)
 //   k_reg_update     : smooth <- staged, and the gradient rows / weight row are reset to zero
 //
-// Invariant that makes the Clear sweep unnecessary: rows 11-13 and 23 are zero between calls
-// (new surfels are created with zeros, Accumulate only adds into surfels inside the
-// regularisation window, and exactly those are reset by k_reg_update).
+// The gradient / weight accumulators (the reference's rows 11-13 and 23) live in one float4 record
+// per slot (DeviceState::gradient) so that a neighbour contribution is one vector atomic.
+// Invariant that makes the Clear sweep unnecessary: the records are zero between calls (new
+// surfels are created with zeros, Accumulate only adds into surfels inside the regularisation
+// window, and exactly those are reset by k_reg_update). The SoA rows 11-13 / 23 stay zero.
 // Float atomics make the accumulated gradients order-dependent, as in the reference.
 
 #include <cstdlib>
@@ -113,10 +115,9 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
       const float dy = fsub(qy[k], sy);
       const float dz = fsub(qz[k], sz);
       const float f = fmul(factor, ffma(nz, dz, ffma(nx, dx, fmul(ny, dy))));
-      atomicAdd(&SM_S(SM_ROW_GRADIENT_X, q), fmul(nx, f));
-      atomicAdd(&SM_S(SM_ROW_GRADIENT_Y, q), fmul(ny, f));
-      atomicAdd(&SM_S(SM_ROW_GRADIENT_Z, q), fmul(nz, f));
-      atomicAdd(&SM_S(SM_ROW_GRADIENT_COUNT, q), weight_term);
+      // kernels.cu:2173-2176: four float atomicAdds; here one 16-byte vector atomic (sm_90+), the
+      // same four fp32 additions in the same (arbitrary) arrival order
+      atomicAdd(&d.gradient[q], make_float4(fmul(nx, f), fmul(ny, f), fmul(nz, f), weight_term));
       // If the neighbour is too far away, remove it (kernels.cu:2184-2192).
       if (squared_norm(dx, dy, dz) > max_distance_squared) SM_SU(SM_ROW_NEIGHBOR0 + k, i) = kInvalidIndex;
     }
@@ -150,9 +151,10 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
     const float sx = SM_S(SM_ROW_SMOOTH_X, i), sy = SM_S(SM_ROW_SMOOTH_Y, i), sz = SM_S(SM_ROW_SMOOTH_Z, i);
     const float nx = SM_S(SM_ROW_NORMAL_X, i), ny = SM_S(SM_ROW_NORMAL_Y, i), nz = SM_S(SM_ROW_NORMAL_Z, i);
     // Data term (factor 2) + neighbour-induced terms.
-    float gx = ffma(fsub(sx, SM_S(SM_ROW_X, i)), 2.0f, SM_S(SM_ROW_GRADIENT_X, i));
-    float gy = ffma(fsub(sy, SM_S(SM_ROW_Y, i)), 2.0f, SM_S(SM_ROW_GRADIENT_Y, i));
-    float gz = ffma(fsub(sz, SM_S(SM_ROW_Z, i)), 2.0f, SM_S(SM_ROW_GRADIENT_Z, i));
+    const float4 accumulated = d.gradient[i];
+    float gx = ffma(fsub(sx, SM_S(SM_ROW_X, i)), 2.0f, accumulated.x);
+    float gy = ffma(fsub(sy, SM_S(SM_ROW_Y, i)), 2.0f, accumulated.y);
+    float gz = ffma(fsub(sz, SM_S(SM_ROW_Z, i)), 2.0f, accumulated.z);
     int neighbor_count = 0;
     float rx = 0.f, ry = 0.f, rz = 0.f;
     float qx[4], qy[4], qz[4];
@@ -182,15 +184,13 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
       gz = ffma(factor, rz, gz);
     }
     const float gradient_length = fsqrt_approx(ffma(gz, gz, ffma(gx, gx, fmul(gy, gy))));
-    const float residual_terms_weight_sum = fadd(fadd(p.regularizer_weight, 1.0f), SM_S(SM_ROW_GRADIENT_COUNT, i));
+    const float residual_terms_weight_sum = fadd(fadd(p.regularizer_weight, 1.0f), accumulated.w);
     float step_factor = fmul(frcp(residual_terms_weight_sum), 0.5f);
     const float max_step_length = fsqrt_approx(SM_S(SM_ROW_RADIUS_SQUARED, i));
     const float step_length = fmul(step_factor, gradient_length);
     if (step_length > max_step_length) step_factor = fmul(step_factor, fmul(max_step_length, frcp(step_length)));
-    // Staged in the gradient rows; k_reg_update moves it to the smooth position.
-    SM_S(SM_ROW_GRADIENT_X, i) = ffma(step_factor, -gx, sx);
-    SM_S(SM_ROW_GRADIENT_Y, i) = ffma(step_factor, -gy, sy);
-    SM_S(SM_ROW_GRADIENT_Z, i) = ffma(step_factor, -gz, sz);
+    // Staged in the accumulator record; k_reg_update moves it to the smooth position.
+    d.gradient[i] = make_float4(ffma(step_factor, -gx, sx), ffma(step_factor, -gy, sy), ffma(step_factor, -gz, sz), 0.f);
   }
 }
 
@@ -200,13 +200,11 @@ __global__ void __launch_bounds__(kBlock) k_reg_update(DeviceState d, RegParams 
   const u32 n = d.counters->surfel_count[p.count_slot];
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
-    SM_S(SM_ROW_SMOOTH_X, i) = SM_S(SM_ROW_GRADIENT_X, i);
-    SM_S(SM_ROW_SMOOTH_Y, i) = SM_S(SM_ROW_GRADIENT_Y, i);
-    SM_S(SM_ROW_SMOOTH_Z, i) = SM_S(SM_ROW_GRADIENT_Z, i);
-    SM_S(SM_ROW_GRADIENT_X, i) = 0.f;
-    SM_S(SM_ROW_GRADIENT_Y, i) = 0.f;
-    SM_S(SM_ROW_GRADIENT_Z, i) = 0.f;
-    SM_S(SM_ROW_GRADIENT_COUNT, i) = 0.f;
+    const float4 staged = d.gradient[i];
+    SM_S(SM_ROW_SMOOTH_X, i) = staged.x;
+    SM_S(SM_ROW_SMOOTH_Y, i) = staged.y;
+    SM_S(SM_ROW_SMOOTH_Z, i) = staged.z;
+    d.gradient[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 

@@ -95,6 +95,10 @@ struct DeviceState {
   u32* new_list;         // W*H: pixel (seq index) of the k-th new surfel
   unsigned long long* scan_state;  // per scan tile: status << 32 | value
   Counters* counters;
+  // Regularisation gradient accumulators {gx, gy, gz, weight sum} per surfel slot: the reference's
+  // rows 11-13 and 23 as one 16-byte record, so that a neighbour contribution is ONE vector
+  // atomic instead of four. Zero between Regularize() calls (the SoA rows stay zero always).
+  float4* gradient;
   // Device timeline (diagnostics, sm_timeline_enable): [frame % timeline_frames][kernel id]{first block start,
   // last block end} in %globaltimer nanoseconds; null when disabled.
   unsigned long long* timeline;
@@ -235,18 +239,23 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
                    bool rasters_already_cleared, int sm_count, const IntegrateEvents* events);
 int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d);
 
-// Streams / events of the frame pipeline used by sm_stream_run: the kernels of one frame form
-// a DAG (project -> associate -> {merge | blend} -> integrate -> {update_neighbors | create},
-// scan after blend, regularisation after update_neighbors + create) that is spread over the
-// caller's stream and one auxiliary stream; the regularisation of frame f overlaps with the
-// projection / association / blending of frame f + 1.
+// Streams / events of the frame pipeline used by sm_stream_run. The kernels of one frame form a
+// DAG (project -> associate -> {merge | blend} -> integrate -> {update_neighbors | create}, scan
+// after blend, regularisation after update_neighbors + create) and consecutive frames are chained
+// by integrate(f + 1) after regularisation(f) and project(f + 1) after create(f). Three internal
+// streams (the caller's stream only brackets the run):
+//   front                : project, associate, blend of frame f + 1 while frame f regularises
+//   crit  (high priority): integrate, update_neighbors, regularisation - the cycle that bounds the
+//                          frame rate, kept back to back on one stream
+//   side  (high priority): merge, new-surfel scan, create - short kernels that gate the others
 struct PipelineCtx {
-  cudaStream_t aux;    // neighbour update + regularisation
-  cudaStream_t side;   // merge decisions + new-surfel scan (short kernels beside blend / integrate)
-  cudaEvent_t ev_assoc, ev_merge, ev_blend, ev_scan, ev_integrate;  // transient, re-recorded every frame
-  cudaEvent_t ev_create[2], ev_update[2];                            // per buffer set (frame parity)
-  cudaEvent_t ev_reg;                                                // regularisation of the latest frame
-  bool have_reg;
+  cudaStream_t front;
+  cudaStream_t crit;
+  cudaStream_t side;
+  cudaEvent_t ev_assoc, ev_merge, ev_blend, ev_integrate;  // transient, re-recorded every frame
+  cudaEvent_t ev_create[2], ev_update[2];                   // per buffer set (frame parity)
+  cudaEvent_t ev_reg;                                       // regularisation of the latest frame
+  bool have_frame;
 };
 struct RegularizeArgs {
   bool disable_denoising;

@@ -443,3 +443,53 @@ def test_full_size_stream_properties(product, reference, sigma):
     assert abs(int(ss.surfels_size) - int(sp.surfels_size)) <= 0.002 * sp.surfels_size + 5
     assert abs(int(ss.surfel_count) - int(sp.surfel_count)) <= 0.002 * sp.surfel_count + 5
     assert len(rec_s.GetTimings()) == 7
+
+
+def test_device_timeline_of_the_frame_pipeline(product):
+    """sm_timeline_enable: the kernels stamp their own start / end while sm_stream_run pipelines the
+    frames over its streams. The stamps must respect the data dependencies of the frame DAG
+    (DESIGN.md): associate after project, integrate after blend and merge, regularisation after
+    the neighbour update and the creation, the next frame's integration after this frame's
+    regularisation, the next frame's projection after this frame's creation."""
+    import ctypes as C
+    cam_ = S.Camera.tum(320, 240)
+    st = S.make_stream(cam_, 24, stream_id=1, device="cuda")
+    pp, ip = PreprocessParams.defaults(), IntegrateParams.defaults()
+    first, last = st.integrated_range()
+    rec = R.CUDASurfelReconstruction(500_000, 320, 240, cam_.fx, cam_.fy, cam_.cx, cam_.cy)
+    frames = 32
+    product.call("timeline_enable", rec._h, frames)
+    rec.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp, ip,
+                   first, last)
+    kernels = product.fn["profile_kernel_count"]()
+    names = [product.fn["profile_kernel_name"](i).decode() for i in range(kernels)]
+    buf = np.zeros((frames, kernels, 2), dtype=np.uint64)
+    product.call("timeline_read", rec._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), frames)
+    product.call("timeline_enable", rec._h, 0)
+    k = {n: i for i, n in enumerate(names)}
+    never = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+    def start(f, name):
+        return int(buf[f, k[name], 0])
+
+    def end(f, name):
+        return int(buf[f, k[name], 1])
+
+    chain = ["k_project", "k_associate", "k_blend", "k_integrate", "k_update_neighbors", "k_reg_accumulate",
+             "k_reg_step", "k_reg_update"]
+    for f in range(first + 2, last):
+        for name in chain + ["k_merge", "k_new_surfel_scan", "k_create_surfels", "k_bilateral_outlier",
+                             "k_erode_normals_radii"]:
+            assert buf[f, k[name], 0] != never, (f, name)
+            assert end(f, name) >= start(f, name)
+        for a, b in zip(chain[:-1], chain[1:]):
+            assert start(f, b) >= end(f, a), (f, a, b)
+        assert start(f, "k_merge") >= end(f, "k_associate")
+        assert start(f, "k_integrate") >= end(f, "k_merge")
+        assert start(f, "k_new_surfel_scan") >= end(f, "k_blend")
+        assert start(f, "k_create_surfels") >= max(end(f, "k_new_surfel_scan"), end(f, "k_integrate"))
+        assert start(f, "k_reg_accumulate") >= end(f, "k_create_surfels")
+        assert start(f, "k_project") >= end(f, "k_erode_normals_radii")
+        if f + 1 < last:
+            assert start(f + 1, "k_integrate") >= end(f, "k_reg_update")
+            assert start(f + 1, "k_project") >= end(f, "k_create_surfels")

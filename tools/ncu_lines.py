@@ -16,9 +16,9 @@ def lines_of_kernel(dis_path, kernel, source_name):
     out, inside, cur, locked = [], False, None, False
     for ln in open(dis_path):
         if ln.startswith("\t.section\t.text.") or ln.startswith("//-----"):
-            inside = (kernel + "EN") in ln or inside and not ln.startswith("\t.section")
+            inside = inside
             if ln.startswith("\t.section"):
-                inside = (kernel + "EN") in ln
+                inside = (kernel + "E") in ln
             continue
         if not inside:
             continue
