@@ -353,10 +353,14 @@ int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width,
   sm_reconstruction* r = new sm_reconstruction();
   SM_CUDA(cudaGetDevice(&r->device));
   {
-    // Measurement hook: one shared-memory carve-out (percent of 228 KB) for all kernels. Off by
-    // default: the gather kernels want the L1 (a 100 % carve-out costs 25 % of the frame rate).
+    // One shared-memory carve-out for every kernel of the library (SM_B200_CARVEOUT, percent of
+    // the 228 KB; -1 = leave it to the driver). k_blend needs ~100 KB per block and everything else
+    // a few KB; left to the driver, the SMs keep switching between configurations and the gather
+    // kernels (integrate, update_neighbors, regularisation) ran 1.5-2x slower after a blend
+    // (measured: 9.9k -> 11.7k frames/s with one configuration). 47 % selects the 132 KB
+    // configuration, the smallest that holds a blend block, and leaves 96 KB of L1 to the gathers.
     const char* e = std::getenv("SM_B200_CARVEOUT");
-    const int percent = e ? std::atoi(e) : -1;
+    const int percent = e ? std::atoi(e) : 47;
     if (percent >= 0) {
       ConfigurePreprocessKernels(percent);
       ConfigureIntegrateKernels(percent);

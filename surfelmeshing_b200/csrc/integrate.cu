@@ -370,12 +370,22 @@ __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) 
 // ---------------------------------------------------------------------------------------
 // a10: measurement blending, all iterations in one kernel
 // ---------------------------------------------------------------------------------------
-constexpr int kBlendTileW = 80, kBlendTileH = 32;  // 8 x 15 = 120 tiles at VGA: one block per SM, one wave
+// BlendMeasurementsCUDAStartKernel + (radius - 2) x IterationKernel (kernels.cu:563-708) grow two
+// rings of pixels, level by level, from (a) the supported pixels that touch a pixel without depth
+// ("measurement border", distance_map) and (b) the supported pixels that touch an unsupported
+// pixel ("surfel border", new_distance_map); a pixel reached at level k takes the average delta
+// of its 3x3 neighbours of level k - 1. Which pixel belongs to which level does not depend on the
+// blended values, so one block per tile
+//   1. loads the tile + halo and builds one bit per pixel for "no depth" / "unsupported" /
+//      "supported",
+//   2. finds the level sets with a bit-parallel breadth-first search (one thread per 32-pixel
+//      word: 3x3 dilation of the previous level AND the still unassigned eligible pixels) and
+//      compacts each level into a pixel list,
+//   3. walks the lists level by level (one thread per pixel, one barrier per level) doing the
+//      reference's float arithmetic; the search for level k + 1 runs beside the update of level k.
+constexpr int kBlendTileW = 80, kBlendTileH = 32;  // 8 x 15 = 120 tiles at VGA
 constexpr int kBlendBlock = 512;
 constexpr int kMaxBlendRadius = 64;
-// Pixel classes of the start stencil (kernels.cu:578-596): no measurement / measurement without a
-// supporting surfel / measurement with one.
-constexpr u32 kClsNoDepth = 0, kClsUnsupported = 1, kClsSupported = 2;
 
 __host__ __device__ inline int blend_halo_y(int radius) { return radius - 1 > 1 ? radius - 1 : 1; }  // (radius - 2) iterations + the 3x3 start stencil
 __host__ __device__ inline int blend_halo_x(int radius) { return (blend_halo_y(radius) + 15) & ~15; }  // 16-pixel chunks stay aligned
@@ -386,6 +396,46 @@ __host__ __device__ inline int blend_halo_x(int radius) { return (blend_halo_y(r
 #define SM_BLEND_CLOCK(i)
 #endif
 
+// 3x3 dilation of a bit raster (rows of `wpr` words, bit b of word w = pixel 32 w + b) at word
+// (y, w); rows / words outside the raster read as 0.
+__device__ __forceinline__ u32 dilate_word(const u32* mask, int y, int w, int rh, int wpr) {
+  u32 result = 0;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int r = y + dy;
+    if (r < 0 || r >= rh) continue;
+    const u32* row = mask + r * wpr;
+    const u32 centre = row[w];
+    const u32 left = w > 0 ? row[w - 1] : 0u;
+    const u32 right = w < wpr - 1 ? row[w + 1] : 0u;
+    result |= centre | (centre << 1) | (left >> 31) | (centre >> 1) | (right << 31);
+  }
+  return result;
+}
+
+// Appends the pixels of the set bits of `bits` (word w of row y) to a list; `take` lanes reserve
+// `__popc(bits)` slots with one atomic per warp. Must be called by all 32 lanes.
+__device__ __forceinline__ void append_word_pixels(u32 bits, int y, int w, u16* list, int list_base, int* counter, int lane) {
+  const u32 count = __popc(bits);
+  u32 inclusive = count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 v = __shfl_up_sync(0xFFFFFFFFu, inclusive, o);
+    if (lane >= o) inclusive += v;
+  }
+  const u32 warp_total = __shfl_sync(0xFFFFFFFFu, inclusive, 31);
+  if (warp_total == 0) return;
+  u32 warp_base = 0;
+  if (lane == 31) warp_base = atomicAdd(counter, static_cast<int>(warp_total));
+  warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 31);
+  int out = list_base + static_cast<int>(warp_base + inclusive - count);
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    list[out++] = static_cast<u16>((y << 8) | (w * 32 + b));
+  }
+}
+
 __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParams f) {
 #ifdef SM_BLEND_CLOCKS
   long long blend_clock[5] = {0, 0, 0, 0, 0};
@@ -394,45 +444,45 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   const TimelineScope timeline_scope(d, f.frame_index, KID_BLEND);
   SM_BLEND_CLOCK(0);
   extern __shared__ __align__(16) unsigned char blend_smem[];
-  // Frontier lists: ring 0 = measurement-border ring (distance_map), ring 1 = surfel-border
-  // ring (new_distance_map). Each list only grows (a pixel enters a ring once).
-  __shared__ int s_tail[2];
-  __shared__ int s_claims[kMaxBlendRadius][2];  // pixels claimed per iteration and ring
+  __shared__ int s_count[kMaxBlendRadius + 1][2];  // pixels per level and ring
   const int radius = f.blend_radius;
   const int halo_x = blend_halo_x(radius), halo_y = blend_halo_y(radius);
   const int rw = kBlendTileW + 2 * halo_x, rh = kBlendTileH + 2 * halo_y;  // rw is a multiple of 16
   const int rn = rw * rh;
   const int rn16 = (rn + 15) & ~15;
-  float* s_delta = reinterpret_cast<float*>(blend_smem);
-  float* s_ndelta = s_delta + rn16;
-  u16* s_depth0 = reinterpret_cast<u16*>(s_ndelta + rn16);  // depth as handed in (start stencil reads this)
+  const int wpr = (rw + 31) >> 5;   // mask words per region row
+  const int nw = rh * wpr;          // words per bit raster
+  float* s_delta = reinterpret_cast<float*>(blend_smem);    // ring 0 (distance_map) deltas
+  float* s_ndelta = s_delta + rn16;                          // ring 1 (new_distance_map) deltas
+  u16* s_depth0 = reinterpret_cast<u16*>(s_ndelta + rn16);  // depth as handed in
   u16* s_depth = s_depth0 + rn16;                            // working depth
-  u16* s_front = s_depth + rn16;                             // [ring][rn16], entries (ly << 8) | lx
-  u8* s_cls = reinterpret_cast<u8*>(s_front + 2 * rn16);
-  u8* s_dist = s_cls + rn16;
-  u8* s_ndist = s_dist + rn16;
-  u32* s_bits = reinterpret_cast<u32*>(s_ndist + rn16);      // one claim bit per pixel, rn16 / 32 + 1 words
+  u16* s_front = s_depth + rn16;                             // [ring][rn16] pixel lists, level after level, entries (ly << 8) | lx
+  u32* s_nodepth = reinterpret_cast<u32*>(s_front + 2 * rn16);  // bit rasters, nw words each
+  u32* s_unsupported = s_nodepth + nw;
+  u32* s_supported = s_unsupported + nw;
+  u32* s_eligible = s_supported + nw;                        // [ring][nw]: pixels the ring may still grow into
+  u32* s_level = s_eligible + 2 * nw;                        // [ring][3][nw]: level sets, plane = level % 3
 
   const int tile_x = blockIdx.x * kBlendTileW, tile_y = blockIdx.y * kBlendTileH;
   const int x0 = tile_x - halo_x, y0 = tile_y - halo_y;  // x0 is a multiple of 16
   const int lane = threadIdx.x & 31;
 
-  if (threadIdx.x < 2) s_tail[threadIdx.x] = 0;
-  for (int t = threadIdx.x; t < kMaxBlendRadius * 2; t += kBlendBlock) (&s_claims[0][0])[t] = 0;
-  for (int t = threadIdx.x; t < rn16 / 32 + 1; t += kBlendBlock) s_bits[t] = 0;
+  for (int t = threadIdx.x; t < (kMaxBlendRadius + 1) * 2; t += kBlendBlock) (&s_count[0][0])[t] = 0;
   // Region load in 16-pixel chunks (two 128-bit depth loads + one of the support raster per
   // thread, all in flight together); rasters that are not 16-byte friendly take the scalar path.
+  // Each chunk also yields 16 bits of the three class rasters.
   const bool vector_ok = (d.width & 15) == 0 && (f.depth_pitch & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(f.depth) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(d.supported) & 15) == 0;
-  const int chunks_per_row = rw >> 4;
+  const int chunks_per_row = wpr * 2;  // including the padding chunks right of the region
   for (int t = threadIdx.x; t < rh * chunks_per_row; t += kBlendBlock) {
     const int ly = t / chunks_per_row, chunk = t - ly * chunks_per_row;
     const int gy = y0 + ly, gx = x0 + chunk * 16;
     union { uint4 v[2]; u16 e[16]; } depth;
-    union { uint4 v; u8 e[16]; } sup, cls;
+    union { uint4 v; u8 e[16]; } sup;
     depth.v[0] = depth.v[1] = sup.v = make_uint4(0u, 0u, 0u, 0u);
-    if (gy >= 0 && gy < d.height) {
+    const bool in_region = chunk * 16 < rw;
+    if (in_region && gy >= 0 && gy < d.height) {
       const u16* depth_row = row_ptr(f.depth, f.depth_pitch, gy);
       const u8* sup_row = d.supported + static_cast<size_t>(gy) * d.width;
       if (vector_ok && gx >= 0 && gx + 16 <= d.width) {
@@ -446,15 +496,23 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
         }
       }
     }
+    u32 nodepth = 0, unsupported = 0, supported = 0;
+    if (in_region) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-      cls.e[k] = static_cast<u8>(depth.e[k] == 0 ? kClsNoDepth : (sup.e[k] ? kClsSupported : kClsUnsupported));
-    const int i = ly * rw + chunk * 16;
-    *reinterpret_cast<uint4*>(s_depth0 + i) = depth.v[0];
-    *reinterpret_cast<uint4*>(s_depth0 + i + 8) = depth.v[1];
-    *reinterpret_cast<uint4*>(s_depth + i) = depth.v[0];
-    *reinterpret_cast<uint4*>(s_depth + i + 8) = depth.v[1];
-    *reinterpret_cast<uint4*>(s_cls + i) = cls.v;
+      for (int k = 0; k < 16; ++k) {
+        if (depth.e[k] == 0) nodepth |= 1u << k;
+        else if (sup.e[k]) supported |= 1u << k;
+        else unsupported |= 1u << k;
+      }
+      const int i = ly * rw + chunk * 16;
+      *reinterpret_cast<uint4*>(s_depth0 + i) = depth.v[0];
+      *reinterpret_cast<uint4*>(s_depth0 + i + 8) = depth.v[1];
+      *reinterpret_cast<uint4*>(s_depth + i) = depth.v[0];
+      *reinterpret_cast<uint4*>(s_depth + i + 8) = depth.v[1];
+    }
+    reinterpret_cast<u16*>(s_nodepth)[t] = static_cast<u16>(nodepth);   // t = ly * 2 wpr + chunk: halfword index
+    reinterpret_cast<u16*>(s_unsupported)[t] = static_cast<u16>(unsupported);
+    reinterpret_cast<u16*>(s_supported)[t] = static_cast<u16>(supported);
   }
   __syncthreads();
   SM_BLEND_CLOCK(1);
@@ -465,85 +523,70 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   const int lx_min = max(1, 1 - x0), lx_max = min(rw - 2, d.width - 2 - x0);
   const int ly_min = max(1, 1 - y0), ly_max = min(rh - 2, d.height - 2 - y0);
 
-  // Start kernel (kernels.cu:563-615), pass A: classify the supported pixels, four per thread
-  // with byte-lane arithmetic on the class words (classes are 0/1/2: `nonzero` = bit0 | bit1,
-  // `unsupported` = bit0). Writes every word of both distance maps; ring pixels (distance 1)
-  // become the first frontiers.
-  {
-    const int groups_per_row = rw >> 2;
-    const u32* cls_words = reinterpret_cast<const u32*>(s_cls);
-    for (int base = 0; base < rh * groups_per_row; base += kBlendBlock) {
-      const int t = base + threadIdx.x;
-      u32 measurement_border = 0, surfel_border = 0;  // one byte (0/1) per pixel of the group
-      int ly = 0, lx0 = 0;
-      if (t < rh * groups_per_row) {
-        ly = t / groups_per_row;
-        const int group = t - ly * groups_per_row;
-        lx0 = group * 4;
-        u32 active = 0;
-        if (ly >= ly_min && ly <= ly_max) {
-          u32 all_nonzero = 0x01010101u, any_unsupported = 0;
-#pragma unroll
-          for (int wy = -1; wy <= 1; ++wy) {
-            const int w = (ly + wy) * groups_per_row + group;
-            const u32 centre = cls_words[w];
-            const u32 previous = group > 0 ? cls_words[w - 1] : 0u;
-            const u32 next = group < groups_per_row - 1 ? cls_words[w + 1] : 0u;
-            const u32 left = __byte_perm(previous, centre, 0x6543);   // classes of the pixels at x - 1
-            const u32 right = __byte_perm(centre, next, 0x4321);      // classes of the pixels at x + 1
-            all_nonzero &= (left | (left >> 1)) & (centre | (centre >> 1)) & (right | (right >> 1));
-            any_unsupported |= left | centre | right;
-          }
-          const u32 centre = cls_words[ly * groups_per_row + group];
-          u32 in_range = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) in_range |= (lx0 + k >= lx_min && lx0 + k <= lx_max) ? (1u << (8 * k)) : 0u;
-          active = (centre >> 1) & in_range & 0x01010101u;  // class kClsSupported
-          measurement_border = (all_nonzero ^ 0x01010101u) & active;
-          surfel_border = any_unsupported & active;
-        }
-        // distance_map: 1 on the measurement-border ring, 255 for the other supported pixels
-        reinterpret_cast<u32*>(s_dist)[t] = measurement_border | ((active ^ measurement_border) * 255u);
-        reinterpret_cast<u32*>(s_ndist)[t] = surfel_border;
+  // Start kernel (kernels.cu:563-615), classification: ring pixels (distance 1) are level 1.
+  int begin0 = 0, begin1 = 0, end0 = 0, end1 = 0;  // list segment of the newest level, per ring
+  for (int base = 0; base < nw; base += kBlendBlock) {
+    const int t = base + threadIdx.x;
+    u32 measurement_border = 0, surfel_border = 0;
+    int y = 0, w = 0;
+    if (t < nw) {
+      y = t / wpr;
+      w = t - y * wpr;
+      u32 valid = 0;
+      if (y >= ly_min && y <= ly_max) {
+        const int lo = min(max(lx_min - 32 * w, 0), 32), hi = min(max(lx_max + 1 - 32 * w, 0), 32);
+        const u32 below_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+        const u32 below_lo = lo >= 32 ? 0xFFFFFFFFu : ((1u << lo) - 1u);
+        valid = below_hi & ~below_lo;
       }
-      // one list reservation per warp for both rings
-      const u32 counts = __popc(measurement_border) | (__popc(surfel_border) << 16);
-      u32 inclusive = counts;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 v = __shfl_up_sync(0xFFFFFFFFu, inclusive, o);
-        if (lane >= o) inclusive += v;
-      }
-      const u32 warp_total = __shfl_sync(0xFFFFFFFFu, inclusive, 31);
-      if (warp_total == 0) continue;
-      u32 warp_base = 0;
-      if (lane == 31) {
-        const u32 base0 = (warp_total & 0xFFFFu) ? atomicAdd(&s_tail[0], static_cast<int>(warp_total & 0xFFFFu)) : 0u;
-        const u32 base1 = (warp_total >> 16) ? atomicAdd(&s_tail[1], static_cast<int>(warp_total >> 16)) : 0u;
-        warp_base = base0 | (base1 << 16);
-      }
-      warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 31);
-      const u32 exclusive = inclusive - counts;
-      u32 out0 = (warp_base & 0xFFFFu) + (exclusive & 0xFFFFu), out1 = (warp_base >> 16) + (exclusive >> 16);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const u16 packed = static_cast<u16>((ly << 8) | (lx0 + k));
-        if ((measurement_border >> (8 * k)) & 1u) s_front[out0++] = packed;
-        if ((surfel_border >> (8 * k)) & 1u) s_front[rn16 + out1++] = packed;
-      }
+      const u32 supported = s_supported[t] & valid;
+      measurement_border = supported & dilate_word(s_nodepth, y, w, rh, wpr);
+      surfel_border = supported & dilate_word(s_unsupported, y, w, rh, wpr);
+      s_level[(0 * 3 + 1) * nw + t] = measurement_border;
+      s_level[(1 * 3 + 1) * nw + t] = surfel_border;
+      s_eligible[t] = supported & ~measurement_border;  // distance_map == 255
+      s_eligible[nw + t] = s_unsupported[t] & valid;    // new_distance_map == 0, has depth, unsupported
     }
+    append_word_pixels(measurement_border, y, w, s_front, 0, &s_count[1][0], lane);
+    append_word_pixels(surfel_border, y, w, s_front + rn16, 0, &s_count[1][1], lane);
   }
   __syncthreads();
   SM_BLEND_CLOCK(2);
-  const int start_count[2] = {s_tail[0], s_tail[1]};
-  if (start_count[0] == 0 && start_count[1] == 0) return;  // no border ring reaches this tile: depth unchanged
+  end0 = s_count[1][0];
+  end1 = s_count[1][1];
+  if (end0 == 0 && end1 == 0) return;  // no border ring reaches this tile: depth unchanged
 
-  // Pass B: the ring pixels fetch their association record (the only global reads of the start
-  // step, all issued together). The stencils read the depth as handed in (the reference's
-  // in-place write, flagged TODO at :610, can only matter if a blended depth rounds to 0).
-  for (int t = threadIdx.x; t < start_count[0] + start_count[1]; t += kBlendBlock) {
-    const bool surfel_ring = t >= start_count[0];
-    const u32 q = surfel_ring ? s_front[rn16 + t - start_count[0]] : s_front[t];
+  // One level of the breadth-first search for both rings (threads 0 .. 2 nw - 1, one word each).
+  auto search_level = [&](int level) {
+    const int previous_plane = (level - 1) % 3, plane = level % 3;
+    for (int base = 0; base < 2 * nw; base += kBlendBlock) {
+      const int t = base + threadIdx.x;
+      u32 found = 0;
+      int y = 0, w = 0, ring = 0;
+      if (t < 2 * nw) {
+        ring = t >= nw ? 1 : 0;
+        const int word = t - ring * nw;
+        y = word / wpr;
+        w = word - y * wpr;
+        const u32 eligible = s_eligible[t];
+        found = eligible ? (eligible & dilate_word(s_level + (ring * 3 + previous_plane) * nw, y, w, rh, wpr)) : 0u;
+        s_level[(ring * 3 + plane) * nw + word] = found;
+        if (found) s_eligible[t] = eligible & ~found;
+      }
+      // (a warp never straddles the two rings unless nw is not a multiple of 32: append per ring)
+      append_word_pixels(ring == 0 ? found : 0u, y, w, s_front, end0, &s_count[level][0], lane);
+      append_word_pixels(ring == 1 ? found : 0u, y, w, s_front + rn16, end1, &s_count[level][1], lane);
+    }
+  };
+
+  // Start kernel, values: the ring pixels fetch their association record (the only global reads
+  // of the start step, all issued together). The stencils read the depth as handed in (the
+  // reference's in-place write, flagged TODO at :610, can only matter if a blended depth rounds
+  // to 0). The search for level 2 runs beside it.
+  if (radius > 2) search_level(2);
+  for (int t = threadIdx.x; t < end0 + end1; t += kBlendBlock) {
+    const bool surfel_ring = t >= end0;
+    const u32 q = surfel_ring ? s_front[rn16 + t - end0] : s_front[t];
     const int lx = static_cast<int>(q & 0xFFu), ly = static_cast<int>(q >> 8);
     const int i = ly * rw + lx;
     const PixelAssoc a = d.assoc[(y0 + ly) * d.width + x0 + lx];
@@ -560,97 +603,53 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   }
   __syncthreads();
   SM_BLEND_CLOCK(3);
+  begin0 = end0; end0 += s_count[2][0];
+  begin1 = end1; end1 += s_count[2][1];
 
-  // Iteration kernels (kernels.cu:647-708), iteration = 2 .. radius - 1 (kernels.cc:190), as a
-  // breadth-first wavefront with ONE barrier per iteration: one thread per frontier pixel (both
-  // rings in the same sweep) looks at its 8 neighbours; the thread that wins the claim bit of an
-  // unassigned pixel updates it on the spot. That is safe because the update only reads
-  // neighbours at distance iteration - 1 (final since the previous barrier), and a pixel under
-  // update holds 255 / 0 / `iteration`, none of which can be mistaken for iteration - 1.
+  // Iteration kernels (kernels.cu:647-708), iteration = 2 .. radius - 1 (kernels.cc:190): the
+  // pixels of level `iteration` take the average delta of their neighbours of level iteration - 1
+  // (final since the previous barrier), one thread per pixel; the search for the next level runs
+  // in the same barrier interval (it only touches the bit rasters).
   const float interpolation_factor_term = 1.0f / (radius - 1.0f);   // host expression, kernels.cc:196
-  int begin0 = 0, begin1 = 0, end0 = start_count[0], end1 = start_count[1];
   for (int iteration = 2; iteration < radius; ++iteration) {
     const int len0 = end0 - begin0, len1 = end1 - begin1;
     if (len0 + len1 == 0) break;  // both wavefronts died out
+    if (iteration + 1 < radius) search_level(iteration + 1);
     const float scaled = fmul(ffma(-i2f(iteration - 1), interpolation_factor_term, 1.0f), depth_scaling);
-    for (int base = 0; base < len0 + len1; base += kBlendBlock) {
-      const int t = base + threadIdx.x;
-      const bool has_item = t < len0 + len1;
-      const int ring = (has_item && t >= len0) ? 1 : 0;
-      u16* list = s_front + ring * rn16;
-      u8* dist = ring == 0 ? s_dist : s_ndist;
+    const int previous_plane = (iteration - 1) % 3;
+    for (int t = threadIdx.x; t < len0 + len1; t += kBlendBlock) {
+      const int ring = t >= len0 ? 1 : 0;
+      const u32 q = ring == 0 ? s_front[begin0 + t] : s_front[rn16 + begin1 + t - len0];
+      const int lx = static_cast<int>(q & 0xFFu), ly = static_cast<int>(q >> 8);
+      const int i = ly * rw + lx;
       float* delta = ring == 0 ? s_delta : s_ndelta;
-      u32 won = 0;  // bit m: this thread claimed neighbour m (0..8, centre unused)
-      int lx = 0, ly = 0;
-      if (has_item) {
-        const u32 q = list[ring == 0 ? begin0 + t : begin1 + t - len0];
-        lx = static_cast<int>(q & 0xFFu);
-        ly = static_cast<int>(q >> 8);
-        const int centre = ly * rw + lx;
-        // candidate neighbours: unassigned pixels the ring may grow into
-        u32 candidates = 0;
+      // 3x3 bits of the previous level around the pixel (bit 3 * (wy + 1) + wx + 1)
+      const u32* previous = s_level + (ring * 3 + previous_plane) * nw;
+      const int first_bit = lx - 1, word = first_bit >> 5, shift = first_bit & 31;
+      u32 taps = 0;
 #pragma unroll
-        for (int m = 0; m < 9; ++m) {
-          if (m == 4) continue;
-          const int j = centre + (m / 3 - 1) * rw + (m % 3 - 1);
-          const bool candidate = ring == 0 ? s_dist[j] == 255 : (s_cls[j] == kClsUnsupported && s_ndist[j] == 0);
-          candidates |= candidate ? (1u << m) : 0u;
-        }
-        while (candidates) {
-          const int m = __ffs(candidates) - 1;
-          candidates &= candidates - 1;
-          const int nx = lx + (m % 3 - 1), ny = ly + (m / 3 - 1);
-          if (nx < lx_min || nx > lx_max || ny < ly_min || ny > ly_max) continue;
-          const int i = ny * rw + nx;
-          const u32 bit = 1u << (i & 31);
-          if (atomicOr(&s_bits[i >> 5], bit) & bit) continue;  // another thread owns it
-          won |= 1u << m;
-          float delta_sum = 0.f;
-          int count = 0;
+      for (int wy = -1; wy <= 1; ++wy) {
+        const u32* row = previous + (ly + wy) * wpr;
+        const u32 lo = row[word];
+        const u32 hi = word + 1 < wpr ? row[word + 1] : 0u;
+        taps |= (__funnelshift_r(lo, hi, shift) & 7u) << (3 * (wy + 1));
+      }
+      float neighbour_delta[9];
 #pragma unroll
-          for (int wy = -1; wy <= 1; ++wy) {
+      for (int m = 0; m < 9; ++m) neighbour_delta[m] = ((taps >> m) & 1u) ? delta[i + (m / 3 - 1) * rw + (m % 3 - 1)] : 0.f;
+      float delta_sum = 0.f;
 #pragma unroll
-            for (int wx = -1; wx <= 1; ++wx) {
-              const int j = i + wy * rw + wx;
-              if (dist[j] == iteration - 1) { delta_sum = fadd(delta_sum, delta[j]); ++count; }
-            }
-          }
-          // count > 0: the pixel was claimed through a neighbour at distance iteration - 1
-          const float avg = fmul(frcp(i2f(count)), delta_sum);
-          delta[i] = avg;
-          s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
-          dist[i] = static_cast<u8>(iteration);
-        }
+      for (int m = 0; m < 9; ++m) {
+        if ((taps >> m) & 1u) delta_sum = fadd(delta_sum, neighbour_delta[m]);
       }
-      // Append the claimed pixels to the ring's list: one reservation per warp and ring.
-      const u32 counts = ring == 0 ? __popc(won) : (__popc(won) << 16);
-      u32 inclusive = counts;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 v = __shfl_up_sync(0xFFFFFFFFu, inclusive, o);
-        if (lane >= o) inclusive += v;
-      }
-      const u32 warp_total = __shfl_sync(0xFFFFFFFFu, inclusive, 31);
-      if (warp_total == 0) continue;
-      u32 warp_base = 0;
-      if (lane == 31) {
-        const u32 base0 = (warp_total & 0xFFFFu) ? atomicAdd(&s_claims[iteration][0], static_cast<int>(warp_total & 0xFFFFu)) : 0u;
-        const u32 base1 = (warp_total >> 16) ? atomicAdd(&s_claims[iteration][1], static_cast<int>(warp_total >> 16)) : 0u;
-        warp_base = base0 | (base1 << 16);
-      }
-      warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 31);
-      const u32 exclusive = inclusive - counts;
-      int out = (ring == 0 ? end0 : end1) + static_cast<int>(ring == 0 ? (warp_base & 0xFFFFu) + (exclusive & 0xFFFFu)
-                                                        : (warp_base >> 16) + (exclusive >> 16));
-      while (won) {
-        const int m = __ffs(won) - 1;
-        won &= won - 1;
-        list[out++] = static_cast<u16>(((ly + m / 3 - 1) << 8) | (lx + m % 3 - 1));
-      }
+      // taps != 0: the pixel was reached through a neighbour of the previous level
+      const float avg = fmul(frcp(i2f(__popc(taps))), delta_sum);
+      delta[i] = avg;
+      s_depth[i] = static_cast<u16>(f2u_trunc(fadd(ffma(avg, scaled, 0.5f), u2f(s_depth[i]))));
     }
     __syncthreads();
-    begin0 = end0; end0 += s_claims[iteration][0];
-    begin1 = end1; end1 += s_claims[iteration][1];
+    begin0 = end0; end0 += s_count[iteration + 1][0];
+    begin1 = end1; end1 += s_count[iteration + 1][1];
   }
 
   SM_BLEND_CLOCK(4);
@@ -679,12 +678,11 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   __syncthreads();
   if (threadIdx.x == 0 && f.frame_index == 450u) {
     const long long t5 = clock64();
-    printf("blend tile %d,%d load %lld startA %lld startB %lld iter %lld write %lld | start lists %d %d final %d %d\n", blockIdx.x, blockIdx.y,
+    printf("blend tile %d,%d load %lld startA %lld startB %lld iter %lld write %lld | final %d %d\n", blockIdx.x, blockIdx.y,
            blend_clock[1] - blend_clock[0], blend_clock[2] - blend_clock[1], blend_clock[3] - blend_clock[2],
-           blend_clock[4] - blend_clock[3], t5 - blend_clock[4], start_count[0], start_count[1], end0, end1);
+           blend_clock[4] - blend_clock[3], t5 - blend_clock[4], end0, end1);
   }
 #endif
-
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1158,7 +1156,9 @@ int LaunchBlend(cudaStream_t stream, const DeviceState& d, const FrameParams& f)
   const dim3 pixel_tiles((d.width + kBlendTileW - 1) / kBlendTileW, (d.height + kBlendTileH - 1) / kBlendTileH);
   const size_t rn = static_cast<size_t>(kBlendTileW + 2 * blend_halo_x(f.blend_radius)) * (kBlendTileH + 2 * blend_halo_y(f.blend_radius));
   const size_t rn16 = (rn + 15) & ~static_cast<size_t>(15);
-  const size_t smem = rn16 * 19 + (rn16 / 32 + 1) * 4 + 16;  // k_blend's carve-up: 19 B per region pixel + claim bits
+  const size_t rw = kBlendTileW + 2 * blend_halo_x(f.blend_radius), rh = kBlendTileH + 2 * blend_halo_y(f.blend_radius);
+  const size_t mask_words = rh * ((rw + 31) / 32);
+  const size_t smem = rn16 * 16 + mask_words * 11 * 4 + 16;  // k_blend's carve-up: 16 B per region pixel + 11 bit rasters
   // One region per block has to fit the 227 KB of an SM (radius <= 25 at the 80x32 tile).
   if (smem > 224 * 1024 || f.blend_radius > kMaxBlendRadius) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
   static size_t configured_smem = 0;
@@ -1307,7 +1307,7 @@ int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm
 }
 
 
-// Measurement hook (SM_B200_CARVEOUT): one shared-memory carve-out for every kernel of the file.
+// One shared-memory carve-out for every kernel of the file (see sm_create in api.cu).
 void ConfigureIntegrateKernels(int carveout_percent) {
   cudaFuncSetAttribute(k_clear, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_project, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);

@@ -771,7 +771,7 @@ int StageRadii(cudaStream_t stream, float point_radius_extension_factor, float p
 }
 
 
-// Measurement hook (SM_B200_CARVEOUT): one shared-memory carve-out for every kernel of the file.
+// One shared-memory carve-out for every kernel of the file (see sm_create in api.cu).
 void ConfigurePreprocessKernels(int carveout_percent) {
   cudaFuncSetAttribute(k_bilateral_outlier<6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_bilateral_outlier<6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);

@@ -272,7 +272,7 @@ int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_de
 }
 
 
-// Measurement hook (SM_B200_CARVEOUT): one shared-memory carve-out for every kernel of the file.
+// One shared-memory carve-out for every kernel of the file (see sm_create in api.cu).
 void ConfigureRegularizeKernels(int carveout_percent) {
   cudaFuncSetAttribute(k_reg_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_reg_step, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
