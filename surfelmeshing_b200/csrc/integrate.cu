@@ -797,7 +797,7 @@ __device__ __forceinline__ void integrate_or_conflict(const FrameParams& f, cons
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_integrate(DeviceState d, FrameParams f) {
+__global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FrameParams f) {
   pdl_prologue();
   const TimelineScope timeline_scope(d, f.frame_index, KID_INTEGRATE);
   for_each_visible(d, &d.counters->surfel_count[f.parity], [&](size_t pos, const VisEntry& e) {
@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
     constexpr int kBorder = 1;
     if (x < kBorder || y < kBorder || x >= d.width - kBorder || y >= d.height - kBorder) return;
 
-    // batch 2: the pixel, the candidates of the 4-adjacent pixels, the current neighbours
+    // batch 2: the pixel and the candidates of the 4-adjacent pixels
     const float measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
     const float observation_radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
     const int kDirectionsX[4] = {-1, 1, 0, 0};
@@ -885,6 +885,27 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
       candidate[direction] =
           supporting_index(d.assoc[(y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction]].x);
     }
+    if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) return;  // occluded
+    float3 ln;
+    if (facing_dot(f, cx_, cy_, cz_, nx, ny, nz, &ln) > 0.f) return;
+    if (radius_squared < 0.f) return;
+    // kCheckScaleCompatibilityForNeighborAssignment, factor 1.5^2.
+    if (fmul(observation_radius_squared, frcp(radius_squared)) > 2.25f) return;
+    // A candidate that already is a neighbour is skipped (kernels.cu:1340-1346) and the list only
+    // changes when some candidate is inserted: if every usable candidate is in the list as it
+    // stands, nothing can happen (the steady state for most surfels) and the gathers below are
+    // not needed.
+    bool any_new = false;
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      const u32 q = candidate[direction];
+      if (q == kInvalidIndex || q == idx) { candidate[direction] = kInvalidIndex; continue; }
+      any_new |= q != neighbor_surfel_indices[0] && q != neighbor_surfel_indices[1] &&
+                 q != neighbor_surfel_indices[2] && q != neighbor_surfel_indices[3];
+    }
+    if (!any_new) return;
+
+    // batch 3: the current neighbours' positions, positions and normals of the candidates
     float neighbor_distances_squared[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
@@ -896,20 +917,12 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
                                                      fsub(gz, SM_S(SM_ROW_Z, q)));
       }
     }
-    if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) return;  // occluded
-    float3 ln;
-    if (facing_dot(f, cx_, cy_, cz_, nx, ny, nz, &ln) > 0.f) return;
-    if (radius_squared < 0.f) return;
-    // kCheckScaleCompatibilityForNeighborAssignment, factor 1.5^2.
-    if (fmul(observation_radius_squared, frcp(radius_squared)) > 2.25f) return;
-
-    // batch 3: positions and normals of the candidates
     const float max_distance_squared = fmul(radius_squared, f.radius_factor_squared);
     float cand_distance[4], cand_dot[4];
 #pragma unroll
     for (int direction = 0; direction < 4; ++direction) {
       const u32 q = candidate[direction];
-      if (q == kInvalidIndex || q == idx) { candidate[direction] = kInvalidIndex; continue; }
+      if (q == kInvalidIndex) continue;
       cand_distance[direction] = squared_norm(fsub(SM_S(SM_ROW_X, q), gx), fsub(SM_S(SM_ROW_Y, q), gy),
                                               fsub(SM_S(SM_ROW_Z, q), gz));
       cand_dot[direction] = dot3(nx, ny, nz, SM_S(SM_ROW_NORMAL_X, q), SM_S(SM_ROW_NORMAL_Y, q), SM_S(SM_ROW_NORMAL_Z, q));
