@@ -138,8 +138,7 @@ def algorithmic_bytes(kernel, c):
         "k_new_surfel_scan": 2 * P + 8 * P + P + 4 * P,
         "k_create_surfels": 5 * P + 72 * M,
         "k_reg_accumulate": 16 * N + 16 * N + 32 * A,
-        "k_reg_step": 4 * N + (80 + 12 * 4) * A,
-        "k_reg_update": 4 * N + 28 * A,
+        "k_reg_step": (4 + 16 + 12 + 12) * N + (52 + 12 * 4 + 16) * A,
     }
     return float(table.get(kernel, 0.0))
 

@@ -81,7 +81,7 @@ const char* KernelName(int id) {
   static const char* names[KID_COUNT] = {
       "k_clear", "k_bilateral_outlier", "k_bilateral_generic", "k_outlier", "k_erode_normals_radii", "k_erode",
       "k_normals", "k_radii", "k_project", "k_associate", "k_merge", "k_blend", "k_integrate", "k_update_neighbors",
-      "k_new_surfel_scan", "k_create_surfels", "k_reg_accumulate", "k_reg_step", "k_reg_update", "k_reg_copy_only",
+      "k_new_surfel_scan", "k_create_surfels", "k_reg_accumulate", "k_reg_step", "k_reg_copy_only",
       "k_export_vertices"};
   return (id >= 0 && id < KID_COUNT) ? names[id] : "?";
 }
@@ -143,6 +143,7 @@ struct sm_reconstruction {
   u32* seg_count_set[2] = {nullptr, nullptr};
   u8* merge_flag_set[2] = {nullptr, nullptr};
   PipelineCtx pipe{};
+  float* smooth_alt = nullptr;    // second smooth-position buffer (DeviceState::smooth / smooth_next)
   cudaStream_t pre_stream = nullptr;
   cudaEvent_t pre_done[2] = {nullptr, nullptr}, int_done[2] = {nullptr, nullptr}, entry_event = nullptr;
   std::vector<u16*> ring_depth; size_t ring_depth_pitch = 0;
@@ -380,6 +381,9 @@ int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width,
   const size_t scan_tiles = (P + kSegment - 1) / kSegment;
   SM_CUDA(cudaMalloc(&d.surfels, sizeof(float) * SM_ROW_COUNT * d.stride));
   SM_CUDA(cudaMalloc(&d.gradient, sizeof(float4) * d.stride));
+  SM_CUDA(cudaMalloc(&r->smooth_alt, sizeof(float) * 3 * d.stride));
+  d.smooth = d.surfels + static_cast<size_t>(SM_ROW_SMOOTH_X) * d.stride;  // rows 3-5 are contiguous
+  d.smooth_next = r->smooth_alt;
   SM_CUDA(cudaMemset(d.gradient, 0, sizeof(float4) * d.stride));
   for (int i = 0; i < 2; ++i) {
     SM_CUDA(cudaMalloc(&r->assoc_set[i], sizeof(PixelAssoc) * P));
@@ -420,7 +424,7 @@ int sm_destroy(sm_reconstruction* r) {
   if (!r) return SM_OK;
   cudaDeviceSynchronize();
   DeviceState& d = r->d;
-  cudaFree(d.surfels); cudaFree(d.gradient); cudaFree(d.new_list);
+  cudaFree(d.surfels); cudaFree(d.gradient); cudaFree(r->smooth_alt); cudaFree(d.new_list);
   for (int i = 0; i < 2; ++i) { cudaFree(r->vis_set[i]); cudaFree(r->seg_count_set[i]); cudaFree(r->merge_flag_set[i]); cudaFree(r->run_depth_pre[i]);
     if (r->pipe.ev_create[i]) cudaEventDestroy(r->pipe.ev_create[i]);
     if (r->pipe.ev_update[i]) cudaEventDestroy(r->pipe.ev_update[i]);
@@ -557,9 +561,9 @@ int sm_transfer_all_to_cpu(sm_reconstruction* r, void* stream_v, uint32_t /*fram
   const size_t bytes = sizeof(float) * n;
   const float* s = r->d.surfels;
   const size_t st = r->d.stride;
-  SM_CUDA(cudaMemcpyAsync(x, s + SM_ROW_SMOOTH_X * st, bytes, cudaMemcpyDeviceToHost, stream));
-  SM_CUDA(cudaMemcpyAsync(y, s + SM_ROW_SMOOTH_Y * st, bytes, cudaMemcpyDeviceToHost, stream));
-  SM_CUDA(cudaMemcpyAsync(z, s + SM_ROW_SMOOTH_Z * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(x, r->d.smooth + 0 * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(y, r->d.smooth + 1 * st, bytes, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(z, r->d.smooth + 2 * st, bytes, cudaMemcpyDeviceToHost, stream));
   SM_CUDA(cudaMemcpyAsync(radius_squared, s + SM_ROW_RADIUS_SQUARED * st, bytes, cudaMemcpyDeviceToHost, stream));
   SM_CUDA(cudaMemcpyAsync(nx, s + SM_ROW_NORMAL_X * st, bytes, cudaMemcpyDeviceToHost, stream));
   SM_CUDA(cudaMemcpyAsync(ny, s + SM_ROW_NORMAL_Y * st, bytes, cudaMemcpyDeviceToHost, stream));
@@ -596,6 +600,10 @@ int sm_dump_state(sm_reconstruction* r, void* stream_v, float* host_rows, uint64
     SM_CUDA(cudaMemcpy2DAsync(host_rows, host_row_stride_elems * sizeof(float), r->d.surfels,
                               r->d.stride * sizeof(float), n * sizeof(float), SM_ROW_COUNT, cudaMemcpyDeviceToHost,
                               stream));
+    // rows 3-5: the current smooth-position buffer (may be the second one, DeviceState::smooth)
+    SM_CUDA(cudaMemcpy2DAsync(host_rows + SM_ROW_SMOOTH_X * host_row_stride_elems, host_row_stride_elems * sizeof(float),
+                              r->d.smooth, r->d.stride * sizeof(float), n * sizeof(float), 3, cudaMemcpyDeviceToHost,
+                              stream));
     SM_CUDA(cudaStreamSynchronize(stream));
   }
   return status;
@@ -605,6 +613,9 @@ int sm_load_state(sm_reconstruction* r, void* stream_v, const float* host_rows, 
                   uint32_t surfels_size, uint32_t merge_count) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (surfels_size > r->d.capacity) return SetError(SM_ERR_CAPACITY, "sm_load_state: state larger than the surfel cap");
+  // the loaded rows 3-5 are the current smooth-position buffer again
+  r->d.smooth = r->d.surfels + static_cast<size_t>(SM_ROW_SMOOTH_X) * r->d.stride;
+  r->d.smooth_next = r->smooth_alt;
   if (surfels_size > 0) {
     SM_CUDA(cudaMemcpy2DAsync(r->d.surfels, r->d.stride * sizeof(float), host_rows,
                               host_row_stride_elems * sizeof(float), surfels_size * sizeof(float), SM_ROW_COUNT,

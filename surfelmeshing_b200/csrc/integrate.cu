@@ -40,6 +40,7 @@ namespace {
 
 #define SM_S(row, i) d.surfels[static_cast<size_t>(row) * d.stride + (i)]
 #define SM_SU(row, i) reinterpret_cast<u32*>(d.surfels)[static_cast<size_t>(row) * d.stride + (i)]
+#define SM_SMOOTH(axis, i) d.smooth[static_cast<size_t>(axis) * d.stride + (i)]  // current smooth-position buffer
 
 constexpr int kBlock = 256;
 
@@ -839,7 +840,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
     SM_SU(SM_ROW_COLOR, idx) = s.color;
     if (s.stamped) SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
     if (s.replaced) {
-      SM_S(SM_ROW_SMOOTH_X, idx) = s.smooth_x; SM_S(SM_ROW_SMOOTH_Y, idx) = s.smooth_y; SM_S(SM_ROW_SMOOTH_Z, idx) = s.smooth_z;
+      SM_SMOOTH(0, idx) = s.smooth_x; SM_SMOOTH(1, idx) = s.smooth_y; SM_SMOOTH(2, idx) = s.smooth_z;
       SM_SU(SM_ROW_CREATION_STAMP, idx) = f.frame_index;
 #pragma unroll
       for (int i = 0; i < 4; ++i) SM_SU(SM_ROW_NEIGHBOR0 + i, idx) = kInvalidIndex;
@@ -1101,9 +1102,9 @@ __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameP
       const u32 q = neighbor_index[direction];
       if (q == kInvalidIndex) continue;
       ndist[direction] = squared_norm(fsub(SM_S(SM_ROW_X, q), g.x), fsub(SM_S(SM_ROW_Y, q), g.y), fsub(SM_S(SM_ROW_Z, q), g.z));
-      nsx[direction] = SM_S(SM_ROW_SMOOTH_X, q);
-      nsy[direction] = SM_S(SM_ROW_SMOOTH_Y, q);
-      nsz[direction] = SM_S(SM_ROW_SMOOTH_Z, q);
+      nsx[direction] = SM_SMOOTH(0, q);
+      nsy[direction] = SM_SMOOTH(1, q);
+      nsz[direction] = SM_SMOOTH(2, q);
     }
     float sum_x = 0.f, sum_y = 0.f, sum_z = 0.f;
     int existing_neighbor_count_plus_1 = 1;
@@ -1138,9 +1139,9 @@ __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameP
     SM_S(SM_ROW_GRADIENT_COUNT, idx) = 0.f;
     d.gradient[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float rcp_count = frcp(i2f(existing_neighbor_count_plus_1));
-    SM_S(SM_ROW_SMOOTH_X, idx) = fmul(fadd(g.x, sum_x), rcp_count);
-    SM_S(SM_ROW_SMOOTH_Y, idx) = fmul(fadd(g.y, sum_y), rcp_count);
-    SM_S(SM_ROW_SMOOTH_Z, idx) = fmul(fadd(g.z, sum_z), rcp_count);
+    SM_SMOOTH(0, idx) = fmul(fadd(g.x, sum_x), rcp_count);
+    SM_SMOOTH(1, idx) = fmul(fadd(g.y, sum_y), rcp_count);
+    SM_SMOOTH(2, idx) = fmul(fadd(g.z, sum_z), rcp_count);
   }
 }
 
@@ -1152,9 +1153,9 @@ __global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int p
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const bool merged = SM_S(SM_ROW_RADIUS_SQUARED, i) < 0.f;
     const float nan = __int_as_float(0x7fffffff);
-    position_buffer[3 * i + 0] = merged ? nan : SM_S(SM_ROW_SMOOTH_X, i);
-    position_buffer[3 * i + 1] = merged ? nan : SM_S(SM_ROW_SMOOTH_Y, i);
-    position_buffer[3 * i + 2] = merged ? nan : SM_S(SM_ROW_SMOOTH_Z, i);
+    position_buffer[3 * i + 0] = merged ? nan : SM_SMOOTH(0, i);
+    position_buffer[3 * i + 1] = merged ? nan : SM_SMOOTH(1, i);
+    position_buffer[3 * i + 2] = merged ? nan : SM_SMOOTH(2, i);
     const u32 c = SM_SU(SM_ROW_COLOR, i);
     color_buffer[3 * i + 0] = c & 0xFF;
     color_buffer[3 * i + 1] = (c >> 8) & 0xFF;
@@ -1257,7 +1258,7 @@ int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams&
   return CheckLaunch("integrate");
 }
 
-int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const DeviceState& d, const FrameParams& f,
+int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, DeviceState& d, const FrameParams& f,
                             bool do_blending, const RegularizeArgs& reg, int sm_count) {
   const ListGrids& grids = GetListGrids(sm_count);
   const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;

@@ -2,17 +2,17 @@
 //
 // Replaces RegularizeSurfelsCUDA (APP/cuda_surfel_reconstruction_kernels.cu:2099-2410: Clear,
 // Accumulate, Step, Update = 4 sweeps over all slots) and
-// UpdateNeighborsCUDARemoveReplacedNeighborsKernel (:1420-1437, a 5th sweep) by 3 sweeps:
+// UpdateNeighborsCUDARemoveReplacedNeighborsKernel (:1420-1437, a 5th sweep) by 2 sweeps:
 //
 //   k_reg_accumulate : [drop neighbour links to surfels with the detach flag] + Accumulate
-//   k_reg_step       : gradient step, staged in the gradient rows (:2197-2290)
-//   k_reg_update     : smooth <- staged, and the gradient rows / weight row are reset to zero
+//   k_reg_step       : gradient step (:2197-2290) from the current smooth buffer into the other one
+//                      (= the reference's Update sweep, :2292-2308), accumulators reset to zero
 //
 // The gradient / weight accumulators (the reference's rows 11-13 and 23) live in one float4 record
 // per slot (DeviceState::gradient) so that a neighbour contribution is one vector atomic.
 // Invariant that makes the Clear sweep unnecessary: the records are zero between calls (new
 // surfels are created with zeros, Accumulate only adds into surfels inside the regularisation
-// window, and exactly those are reset by k_reg_update). The SoA rows 11-13 / 23 stay zero.
+// window, and exactly those are reset by k_reg_step). The SoA rows 11-13 / 23 stay zero.
 // Float atomics make the accumulated gradients order-dependent, as in the reference.
 
 #include <cstdlib>
@@ -25,6 +25,8 @@ namespace {
 
 #define SM_S(row, i) d.surfels[static_cast<size_t>(row) * d.stride + (i)]
 #define SM_SU(row, i) reinterpret_cast<u32*>(d.surfels)[static_cast<size_t>(row) * d.stride + (i)]
+#define SM_SMOOTH(axis, i) d.smooth[static_cast<size_t>(axis) * d.stride + (i)]
+#define SM_SMOOTH_NEXT(axis, i) d.smooth_next[static_cast<size_t>(axis) * d.stride + (i)]
 
 constexpr int kBlock = 256;
 
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
       flag_word[k] = SM_SU(SM_ROW_COLOR, q);
       stamp[k] = SM_SU(SM_ROW_LAST_UPDATE_STAMP, q);
     }
-    const float sx = SM_S(SM_ROW_SMOOTH_X, i), sy = SM_S(SM_ROW_SMOOTH_Y, i), sz = SM_S(SM_ROW_SMOOTH_Z, i);
+    const float sx = SM_SMOOTH(0, i), sy = SM_SMOOTH(1, i), sz = SM_SMOOTH(2, i);
     const float nx = SM_S(SM_ROW_NORMAL_X, i), ny = SM_S(SM_ROW_NORMAL_Y, i), nz = SM_S(SM_ROW_NORMAL_Z, i);
     const float radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, i);
 
@@ -99,9 +101,9 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const u32 q = use[k] ? nbr[k] : i;
-      qx[k] = SM_S(SM_ROW_SMOOTH_X, q);
-      qy[k] = SM_S(SM_ROW_SMOOTH_Y, q);
-      qz[k] = SM_S(SM_ROW_SMOOTH_Z, q);
+      qx[k] = SM_SMOOTH(0, q);
+      qy[k] = SM_SMOOTH(1, q);
+      qz[k] = SM_SMOOTH(2, q);
     }
     const float max_distance_squared = fmul(radius_squared, p.radius_factor_squared);
     const float rcp_count = frcp(i2f(neighbor_count));
@@ -147,8 +149,12 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
 #pragma unroll
       for (int k = 0; k < 4; ++k) nbr_ahead[k] = SM_SU(SM_ROW_NEIGHBOR0 + k, i + step);
     }
-    if (outside_window(stamp, p)) continue;
-    const float sx = SM_S(SM_ROW_SMOOTH_X, i), sy = SM_S(SM_ROW_SMOOTH_Y, i), sz = SM_S(SM_ROW_SMOOTH_Z, i);
+    const float sx = SM_SMOOTH(0, i), sy = SM_SMOOTH(1, i), sz = SM_SMOOTH(2, i);
+    if (outside_window(stamp, p)) {
+      // not regularised (kernels.cu:2206): the smooth position carries over to the next buffer
+      SM_SMOOTH_NEXT(0, i) = sx; SM_SMOOTH_NEXT(1, i) = sy; SM_SMOOTH_NEXT(2, i) = sz;
+      continue;
+    }
     const float nx = SM_S(SM_ROW_NORMAL_X, i), ny = SM_S(SM_ROW_NORMAL_Y, i), nz = SM_S(SM_ROW_NORMAL_Z, i);
     // Data term (factor 2) + neighbour-induced terms.
     const float4 accumulated = d.gradient[i];
@@ -161,9 +167,9 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const u32 q = nbr[k] != kInvalidIndex ? nbr[k] : i;
-      qx[k] = SM_S(SM_ROW_SMOOTH_X, q);
-      qy[k] = SM_S(SM_ROW_SMOOTH_Y, q);
-      qz[k] = SM_S(SM_ROW_SMOOTH_Z, q);
+      qx[k] = SM_SMOOTH(0, q);
+      qy[k] = SM_SMOOTH(1, q);
+      qz[k] = SM_SMOOTH(2, q);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -189,21 +195,11 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
     const float max_step_length = fsqrt_approx(SM_S(SM_ROW_RADIUS_SQUARED, i));
     const float step_length = fmul(step_factor, gradient_length);
     if (step_length > max_step_length) step_factor = fmul(step_factor, fmul(max_step_length, frcp(step_length)));
-    // Staged in the accumulator record; k_reg_update moves it to the smooth position.
-    d.gradient[i] = make_float4(ffma(step_factor, -gx, sx), ffma(step_factor, -gy, sy), ffma(step_factor, -gz, sz), 0.f);
-  }
-}
-
-__global__ void __launch_bounds__(kBlock) k_reg_update(DeviceState d, RegParams p) {
-  pdl_prologue();
-  const TimelineScope timeline_scope(d, p.frame_index, KID_REG_UPDATE);
-  const u32 n = d.counters->surfel_count[p.count_slot];
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
-    const float4 staged = d.gradient[i];
-    SM_S(SM_ROW_SMOOTH_X, i) = staged.x;
-    SM_S(SM_ROW_SMOOTH_Y, i) = staged.y;
-    SM_S(SM_ROW_SMOOTH_Z, i) = staged.z;
+    // The new smooth position goes to the other buffer (the neighbours still read the old one);
+    // this surfel's accumulator, read by nobody else in this sweep, is reset for the next call.
+    SM_SMOOTH_NEXT(0, i) = ffma(step_factor, -gx, sx);
+    SM_SMOOTH_NEXT(1, i) = ffma(step_factor, -gy, sy);
+    SM_SMOOTH_NEXT(2, i) = ffma(step_factor, -gz, sz);
     d.gradient[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
@@ -223,15 +219,15 @@ __global__ void __launch_bounds__(kBlock) k_reg_copy_only(DeviceState d, RegPara
       }
     }
     if (outside_window(SM_SU(SM_ROW_LAST_UPDATE_STAMP, i), p)) continue;
-    SM_S(SM_ROW_SMOOTH_X, i) = SM_S(SM_ROW_X, i);
-    SM_S(SM_ROW_SMOOTH_Y, i) = SM_S(SM_ROW_Y, i);
-    SM_S(SM_ROW_SMOOTH_Z, i) = SM_S(SM_ROW_Z, i);
+    SM_SMOOTH(0, i) = SM_S(SM_ROW_X, i);
+    SM_SMOOTH(1, i) = SM_S(SM_ROW_Y, i);
+    SM_SMOOTH(2, i) = SM_S(SM_ROW_Z, i);
   }
 }
 
 }  // namespace
 
-int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_denoising, u32 frame_index,
+int RegularizeSurfels(cudaStream_t stream, DeviceState& d, bool disable_denoising, u32 frame_index,
                       float radius_factor_for_regularization_neighbors, float regularizer_weight,
                       int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot,
                       int sm_count) {
@@ -244,7 +240,7 @@ int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_de
   p.count_slot = count_slot;
   p.remove_below_slot = remove_replaced_below_slot;
   // Grids = the blocks resident at once (see GetListGrids in integrate.cu).
-  static int grid_accumulate = 0, grid_step = 0, grid_update = 0, grid_copy = 0, grids_for = -1;
+  static int grid_accumulate = 0, grid_step = 0, grid_copy = 0, grids_for = -1;
   if (grids_for != sm_count) {
     const char* e = std::getenv("SM_B200_RESIDENT_GRIDS");
     auto resident = [&](auto kernel) {
@@ -257,7 +253,6 @@ int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_de
     };
     grid_accumulate = resident(k_reg_accumulate);
     grid_step = resident(k_reg_step);
-    grid_update = resident(k_reg_update);
     grid_copy = resident(k_reg_copy_only);
     grids_for = sm_count;
   }
@@ -267,7 +262,10 @@ int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_de
   }
   { LaunchScope scope(stream, KID_REG_ACCUMULATE); LaunchKernel(k_reg_accumulate, dim3(grid_accumulate), dim3(kBlock), 0, stream, d, p); }
   { LaunchScope scope(stream, KID_REG_STEP); LaunchDependent(k_reg_step, dim3(grid_step), dim3(kBlock), 0, stream, d, p); }
-  { LaunchScope scope(stream, KID_REG_UPDATE); LaunchDependent(k_reg_update, dim3(grid_update), dim3(kBlock), 0, stream, d, p); }
+  // k_reg_step wrote every slot of the other smooth buffer: it is the current one from here on
+  float* const filled = d.smooth_next;
+  d.smooth_next = d.smooth;
+  d.smooth = filled;
   return CheckLaunch("regularize");
 }
 
@@ -276,7 +274,6 @@ int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_de
 void ConfigureRegularizeKernels(int carveout_percent) {
   cudaFuncSetAttribute(k_reg_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_reg_step, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_reg_update, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_reg_copy_only, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaGetLastError();
 }

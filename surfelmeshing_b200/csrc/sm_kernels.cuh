@@ -22,7 +22,7 @@ int CheckLaunch(const char* what);   // cudaGetLastError() -> SM_OK / SM_ERR_CUD
 enum KernelId {
   KID_CLEAR = 0, KID_BILATERAL_OUTLIER, KID_BILATERAL_GENERIC, KID_OUTLIER, KID_ERODE_NORMALS_RADII, KID_ERODE,
   KID_NORMALS, KID_RADII, KID_PROJECT, KID_ASSOCIATE, KID_MERGE, KID_BLEND, KID_INTEGRATE, KID_UPDATE_NEIGHBORS,
-  KID_NEW_SURFEL_SCAN, KID_CREATE_SURFELS, KID_REG_ACCUMULATE, KID_REG_STEP, KID_REG_UPDATE, KID_REG_COPY_ONLY,
+  KID_NEW_SURFEL_SCAN, KID_CREATE_SURFELS, KID_REG_ACCUMULATE, KID_REG_STEP, KID_REG_COPY_ONLY,
   KID_EXPORT_VERTICES, KID_COUNT
 };
 const char* KernelName(int id);
@@ -99,6 +99,11 @@ struct DeviceState {
   // rows 11-13 and 23 as one 16-byte record, so that a neighbour contribution is ONE vector
   // atomic instead of four. Zero between Regularize() calls (the SoA rows stay zero always).
   float4* gradient;
+  // Smooth positions (the reference's rows 3-5), double-buffered: [3][stride] each. `smooth` is the
+  // current buffer (initially the SoA rows themselves); the regularisation step reads it and writes
+  // every slot of `smooth_next`, then the two are swapped on the host (no separate update sweep).
+  float* smooth;
+  float* smooth_next;
   // Device timeline (diagnostics, sm_timeline_enable): [frame % timeline_frames][kernel id]{first block start,
   // last block end} in %globaltimer nanoseconds; null when disabled.
   unsigned long long* timeline;
@@ -264,7 +269,7 @@ struct RegularizeArgs {
   int window;
 };
 // One frame through the DAG, including its regularisation. `set`: frame parity (buffer set).
-int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, const DeviceState& d, const FrameParams& f,
+int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, DeviceState& d, const FrameParams& f,
                             bool do_blending, const RegularizeArgs& reg, int sm_count);
 int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm_count, float* position_buffer,
                    u8* color_buffer);
@@ -274,7 +279,7 @@ int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm
 // `remove_replaced_below`: if >= 0, slot of the surfel count below which neighbour links to
 // surfels with the detach flag are dropped first (UpdateNeighborsCUDARemoveReplacedNeighbors
 // fused into the first sweep); -1 = no removal.
-int RegularizeSurfels(cudaStream_t stream, const DeviceState& d, bool disable_denoising, u32 frame_index,
+int RegularizeSurfels(cudaStream_t stream, DeviceState& d, bool disable_denoising, u32 frame_index,
                       float radius_factor_for_regularization_neighbors, float regularizer_weight,
                       int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot,
                       int sm_count);

@@ -476,7 +476,7 @@ def test_device_timeline_of_the_frame_pipeline(product):
         return int(buf[f, k[name], 1])
 
     chain = ["k_project", "k_associate", "k_blend", "k_integrate", "k_update_neighbors", "k_reg_accumulate",
-             "k_reg_step", "k_reg_update"]
+             "k_reg_step"]
     for f in range(first + 2, last):
         for name in chain + ["k_merge", "k_new_surfel_scan", "k_create_surfels", "k_bilateral_outlier",
                              "k_erode_normals_radii"]:
@@ -491,5 +491,5 @@ def test_device_timeline_of_the_frame_pipeline(product):
         assert start(f, "k_reg_accumulate") >= end(f, "k_create_surfels")
         assert start(f, "k_project") >= end(f, "k_erode_normals_radii")
         if f + 1 < last:
-            assert start(f + 1, "k_integrate") >= end(f, "k_reg_update")
+            assert start(f + 1, "k_integrate") >= end(f, "k_reg_step")
             assert start(f + 1, "k_project") >= end(f, "k_create_surfels")
