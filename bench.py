@@ -123,6 +123,20 @@ def timed_steps(info, device, step_fn, warmup, steps):
     return e0.elapsed_time(e1), last
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/*_traffic.json, written by tools/ncu_summary.py), or None."""
+    best = None
+    for path in sorted((ROOT / "profiles").glob("*_traffic.json")):
+        try:
+            entry = json.loads(path.read_text())["kernels"].get(kernel)
+        except (OSError, ValueError, KeyError):
+            continue
+        if entry:
+            best = float(entry["dram_bytes_per_launch"])
+    return best
+
+
 def algorithmic_bytes(kernel, c):
     """algorithmic bytes of one launch. c: P, K, valid, N, V, S, M, A."""
     P, K, N, V, S_, M, A = c["P"], c["K"], c["N"], c["V"], c["S"], c["M"], c["A"]
@@ -186,6 +200,9 @@ def main():
     args = ap.parse_args()
     warmup = max(args.warmup, 3)
 
+    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) goes to stdout too
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     info = D.rank_info_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the surfel kernels have no CPU fallback")
@@ -277,9 +294,27 @@ def main():
         dur = kernel_table[dom]["mean_us"] * 1e-6
         achieved = b / dur / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b, "mean_launch_us": kernel_table[dom]["mean_us"],
                     "share_of_step": kernel_table[dom]["share"], "counters": counters}
+        # The same kernels as they run inside the multi-stream frame pipeline: start / end stamps written
+        # by the kernels themselves (sm_timeline_enable), mean over the step.
+        frames_pow2 = 1 << (args.frames - 1).bit_length()
+        lib.call("timeline_enable", rec._h, frames_pow2)
+        step_device()
+        stamps_buf = np.zeros((frames_pow2, nk, 2), dtype=np.uint64)
+        lib.call("timeline_read", rec._h, stamps_buf.ctypes.data_as(C.POINTER(C.c_uint64)), frames_pow2)
+        lib.call("timeline_enable", rec._h, 0)
+        launched = stamps_buf[:, :, 0] != np.uint64(0xFFFFFFFFFFFFFFFF)
+        for i in range(nk):
+            name = lib.fn["profile_kernel_name"](i).decode()
+            if name in kernel_table and launched[:, i].any():
+                dur = (stamps_buf[:, i, 1].astype(np.float64) - stamps_buf[:, i, 0].astype(np.float64))[launched[:, i]]
+                kernel_table[name]["pipelined_us"] = float(dur.mean() / 1e3)
+        project = [i for i in range(nk) if lib.fn["profile_kernel_name"](i).decode() == "k_project"][0]
+        starts = np.sort(stamps_buf[launched[:, project], project, 0].astype(np.float64))
+        if len(starts) > 2:
+            roofline["pipelined_frame_period_us"] = float(np.median(np.diff(starts)) / 1e3)
         for name in ("k_bilateral_outlier", "k_associate"):
             if name in kernel_table:
                 bb = algorithmic_bytes(name, counters)

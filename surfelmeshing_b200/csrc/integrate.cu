@@ -6,15 +6,16 @@
 //
 //   k_clear          a6   5 CUDABuffer::Clear launches -> one 128-bit store per pixel
 //   k_project        a7   RenderMinDepthCUDAKernel (kernels.cu:1466-1557): the only sweep over
-//                         ALL surfel slots (4 slots/thread, 128-bit SoA loads); splats min depth
+//                         ALL surfel slots (2 slots/thread, 64-bit SoA loads); splats min depth
 //                         and builds the segment-ordered list of surfels that project into the
 //                         image (block-local ballot/scan compaction, no global atomic)
 //   k_associate      a8   AssociateSurfelsCUDAKernel (:1586-1808) over the visible list
 //   k_merge          a9   MergeSurfelsCUDAKernel (:1857-2052) over the visible list; decisions
 //                         are taken on the pre-merge state and applied by k_integrate
 //   k_blend          a10  BlendMeasurements Start + (radius-2) Iteration kernels (:563-708) as
-//                         ONE kernel: every tile replays all wavefront iterations locally in
-//                         shared memory on a (radius-1)-pixel halo
+//                         ONE kernel: every tile finds the level sets of the two rings with a
+//                         bit-parallel breadth-first search in shared memory (halo radius - 1)
+//                         and then walks them level by level with the reference's arithmetic
 //   k_integrate      a11  IntegrateMeasurementsCUDAKernel (:741-1142) over the visible list
 //   k_update_neighbors a12 UpdateNeighborsCUDAKernel (:1197-1380) over the visible list
 //   k_new_surfel_scan  a13 CreateNewSurfelsCUDASerializingKernel (:90-111) + the CUB exclusive
@@ -26,8 +27,12 @@
 // regularisation sweep (regularize.cu). Arithmetic follows the reference SASS (sm_math.cuh).
 //
 // Deterministic where the reference is not (SURVEY §7 hard part 1): the supporting surfel
-// of a pixel is the MINIMUM supporting index (the reference: first atomicCAS wins), merge
-// decisions read the pre-merge state. Both are legal outcomes of the reference.
+// of a pixel is "primary-pixel association before secondary, then lowest index" (the
+// reference: first atomicCAS wins), merge decisions read the pre-merge state. Both are legal
+// outcomes of the reference.
+//
+// Host side at the end of the file: IntegrateFrame (one stream, stage events) and
+// IntegrateFramePipelined (the frame DAG over the streams of PipelineCtx, sm_kernels.cuh).
 
 #include <cstdio>
 #include <cstdlib>
