@@ -84,6 +84,13 @@ __device__ __forceinline__ void load_depth_tile_f32(float* tile, const u16* in, 
 
 // One tap (cuda_depth_processing.cu:98-112; SASS: FMUL d*-d, FMUL *rcp_v, FFMA(-gd2, rcp_xy, .),
 // FMUL *log2e, MUFU.EX2, FFMA sum, FADD weight). c - s is exact in fp32 (both < 2^16).
+//
+// kIgnoredTapsVanish: value_to_ignore is 0 and sigma_value_factor is small enough that an ignored
+// sample (s = 0) gets the weight exp(-c^2 / (2 (c sigma)^2) - ...) = exp(< -110), which
+// MUFU.EX2 with flush-to-zero returns as exactly +0: `sum += 0 * 0` and `weight += 0` are then
+// exact no-ops and the `s != ignore` test of the reference (:103) can be dropped (one
+// instruction per tap, 10 %). The host checks the precondition (LaunchBilateral).
+template <bool kIgnoredTapsVanish = false>
 __device__ __forceinline__ void bilateral_tap(float s, float c, float neg_gd2, float rcp_xy, float rcp_v, float ignore,
                                               float& sum, float& weight) {
   const float d = fsub(c, s);
@@ -91,7 +98,7 @@ __device__ __forceinline__ void bilateral_tap(float s, float c, float neg_gd2, f
   const float t = fmul(q, rcp_v);
   const float e = ffma(neg_gd2, rcp_xy, t);
   const float w = fex2_approx(fmul(e, kLog2e));
-  if (s != ignore) {
+  if (kIgnoredTapsVanish || s != ignore) {
     sum = ffma(w, s, sum);
     weight = fadd(weight, w);
   }
@@ -99,7 +106,7 @@ __device__ __forceinline__ void bilateral_tap(float s, float c, float neg_gd2, f
 
 // Bilateral value of the pixel whose tile coordinates are (lx, ly) (tile origin includes
 // the halo). Returns the u16 result. R > 0: compile-time disc, fully unrolled.
-template <int R, int SW>
+template <int R, int SW, bool kIgnoredTapsVanish>
 __device__ __forceinline__ u16 bilateral_pixel(const float* tile, int lx, int ly, float c, const BilateralArgs& a,
                                                float rcp_xy) {
   const float ignore = u2f(a.value_to_ignore);
@@ -112,7 +119,7 @@ __device__ __forceinline__ u16 bilateral_pixel(const float* tile, int lx, int ly
 #pragma unroll
     for (int dx = -R; dx <= R; ++dx) {
       if (dx * dx + dy * dy <= R * R) {
-        bilateral_tap(tile[(ly + dy) * SW + lx + dx], c, static_cast<float>(-(dx * dx + dy * dy)), rcp_xy, rcp_v,
+        bilateral_tap<kIgnoredTapsVanish>(tile[(ly + dy) * SW + lx + dx], c, static_cast<float>(-(dx * dx + dy * dy)), rcp_xy, rcp_v,
                       ignore, sum, weight);
       }
     }
@@ -201,7 +208,7 @@ __device__ __forceinline__ u16 outlier_pixel(const OutlierArgs& a, unsigned x, u
 // instead of doubling the kernel time (measured with 32 x 8 tiles: 18 us vs an issue bound of 9).
 constexpr int kBilateralTileH = 4;
 
-template <int R, bool kWithOutlier>
+template <int R, bool kWithOutlier, bool kIgnoredTapsVanish>
 __global__ void __launch_bounds__(32 * kBilateralTileH, 2048 / (32 * kBilateralTileH))
 k_bilateral_outlier(BilateralArgs a, const __grid_constant__ OutlierArgs o, u16* out, size_t out_pitch) {
   pdl_prologue();
@@ -226,7 +233,7 @@ k_bilateral_outlier(BilateralArgs a, const __grid_constant__ OutlierArgs o, u16*
     const float c = tile[(ly + R) * SW + tx + PADX];
     const unsigned ci = f2u_trunc(c);
     if (ci != a.value_to_ignore && ci <= a.max_depth) {
-      result = bilateral_pixel<R, SW>(tile, tx + PADX, ly + R, c, a, frcp(a.denom_xy));
+      result = bilateral_pixel<R, SW, kIgnoredTapsVanish>(tile, tx + PADX, ly + R, c, a, frcp(a.denom_xy));
     }
   }
   if (kWithOutlier) result = outlier_pixel(o, x, y, result);
@@ -671,8 +678,16 @@ int LaunchBilateral(cudaStream_t stream, const BilateralArgs& a, const OutlierAr
     timed.timeline = TimelineSlot(KID_BILATERAL_OUTLIER);
     const dim3 grid((a.width + kTileW - 1) / kTileW, (a.height + kBilateralTileH - 1) / kBilateralTileH);
     const dim3 block(32 * kBilateralTileH);
-    if (o) LaunchKernel(k_bilateral_outlier<6, true>, grid, block, 0, stream, timed, *o, out, out_pitch);
-    else LaunchKernel(k_bilateral_outlier<6, false>, grid, block, 0, stream, timed, kNoOutlier, out, out_pitch);
+    // ignored samples get weight exp(-1 / (2 sigma^2) - ...): exactly 0 under ftz once 1 / (2 sigma^2) > 110
+    const bool vanish = a.value_to_ignore == 0 && a.sigma_value_factor > 0.f &&
+                        1.0f / (2.0f * a.sigma_value_factor * a.sigma_value_factor) > 110.0f;
+    if (o) {
+      if (vanish) LaunchKernel(k_bilateral_outlier<6, true, true>, grid, block, 0, stream, timed, *o, out, out_pitch);
+      else LaunchKernel(k_bilateral_outlier<6, true, false>, grid, block, 0, stream, timed, *o, out, out_pitch);
+    } else {
+      if (vanish) LaunchKernel(k_bilateral_outlier<6, false, true>, grid, block, 0, stream, timed, kNoOutlier, out, out_pitch);
+      else LaunchKernel(k_bilateral_outlier<6, false, false>, grid, block, 0, stream, timed, kNoOutlier, out, out_pitch);
+    }
   } else {
     if (a.radius < 0) return SetError(SM_ERR_INVALID_ARGUMENT, "negative bilateral radius");
     { LaunchScope scope(stream, KID_BILATERAL_GENERIC); LaunchKernel(k_bilateral_generic, PixelGrid(a.width, a.height), dim3(256), 0, stream, a, out, out_pitch); }
@@ -773,8 +788,10 @@ int StageRadii(cudaStream_t stream, float point_radius_extension_factor, float p
 
 // One shared-memory carve-out for every kernel of the file (see sm_create in api.cu).
 void ConfigurePreprocessKernels(int carveout_percent) {
-  cudaFuncSetAttribute(k_bilateral_outlier<6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_bilateral_outlier<6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_bilateral_outlier<6, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_bilateral_outlier<6, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_bilateral_outlier<6, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_bilateral_outlier<6, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_bilateral_generic, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_outlier, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_erode_normals_radii, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
