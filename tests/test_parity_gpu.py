@@ -493,3 +493,42 @@ def test_device_timeline_of_the_frame_pipeline(product):
         if f + 1 < last:
             assert start(f + 1, "k_integrate") >= end(f, "k_reg_step")
             assert start(f + 1, "k_project") >= end(f, "k_create_surfels")
+
+
+def test_large_frame_stream_properties(product, reference):
+    """BASELINE config 2 shape (1280x960 frames, 20 M surfel cap), shortened to 16 frames: the
+    free-running product against the free-running oracle through size-independent properties, plus
+    the exact quantities that do not depend on the reference's races (first frame: no surfels yet,
+    so every pixel with a measurement creates exactly one surfel in both)."""
+    width, height = 1280, 960
+    cam_ = S.Camera(width, height, 1050.0, 1050.0, 640.0, 480.0)
+    st = S.make_stream(cam_, 16, stream_id=2, device="cuda")
+    pp, ip = PreprocessParams.defaults(), IntegrateParams.defaults()
+    pp.depth_valid_region_radius = cam_.valid_region_radius()
+    first, last = st.integrated_range()
+    cap = 20_000_000
+    rec_p = R.CUDASurfelReconstruction(cap, width, height, cam_.fx, cam_.fy, cam_.cx, cam_.cy)
+    rec_r = R.CUDASurfelReconstruction(cap, width, height, cam_.fx, cam_.fy, cam_.cx, cam_.cy, lib=reference)
+    # first integrated frame only: deterministic in the reference as well
+    sp1 = rec_p.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp, ip,
+                           first, first + 1)
+    sr1 = rec_r.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp, ip,
+                           first, first + 1)
+    assert sp1.surfels_size == sr1.surfels_size > 50_000
+    rows_p, n_p, _ = rec_p.dump_state()
+    rows_r, n_r, _ = rec_r.dump_state()
+    for row in (0, 1, 2, 7, 8, 9, 10, 17, 18, 24):
+        assert np.array_equal(rows_p[row, :n_p].view(np.uint32), rows_r[row, :n_r].view(np.uint32)), row
+    # whole stream
+    rec_p.reset()
+    rec_r.reset()
+    sp = rec_p.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp, ip,
+                          first, last)
+    sr = rec_r.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp, ip,
+                          first, last)
+    assert sp.frames_integrated == sr.frames_integrated == last - first
+    assert abs(int(sp.surfels_size) - int(sr.surfels_size)) <= 0.01 * sr.surfels_size
+    assert abs(int(sp.surfel_count) - int(sr.surfel_count)) <= 0.01 * sr.surfel_count
+    rows, n, merges = rec_p.dump_state()
+    assert n == sp.surfels_size and n - merges == sp.surfel_count
+    check_state_invariants(rows, n)
