@@ -247,7 +247,15 @@ int sm_download_rasters(sm_reconstruction* r, void* stream,
  * frames_on_host != 0 the depth/colour pointers are (pinned) host memory and
  * each raw depth map / colour image is uploaded once on an internal copy
  * stream, overlapped with compute, exactly like the reference's upload_stream
- * (APP/main.cc:902-995); otherwise they are device-resident. */
+ * (APP/main.cc:902-995); otherwise they are device-resident.
+ * The call never synchronises with the host inside the loop and spreads the
+ * kernels of consecutive frames over internal streams (frame pipeline,
+ * DESIGN.md section 5); `stream` only brackets the call: work enqueued on it
+ * before the call is complete before the first frame starts, work enqueued
+ * after the call sees all frames integrated. The call itself returns after
+ * one synchronisation at the end (to fetch the counters for `stats`). With
+ * sm_enable_timings(r, 1) or sm_profile_kernels(1) the frames run one kernel
+ * after the other on `stream`. */
 typedef struct sm_stream_desc {
   int32_t width, height, frame_count;
   int32_t frames_on_host;
