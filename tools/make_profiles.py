@@ -52,7 +52,13 @@ def main():
     if n2p.exists() and n2r.exists():
         a, b = load_line(n2p), load_line(n2r)
         lines.append(f"Two GPUs (torchrun, one independent stream per rank, max-over-ranks time): product {a['value']:.0f} "
-                     f"frames/s ({a['value'] / p1['value']:.2f}x of N = 1), reference {b['value']:.0f} frames/s.\n")
+                     f"frames/s ({a['value'] / p1['value']:.2f}x of N = 1), reference {b['value']:.0f} frames/s.")
+        n4 = src / "bench_product_n4.json"
+        if n4.exists():
+            c = load_line(n4)
+            lines.append(f"Four GPUs: product {c['value']:.0f} frames/s ({c['value'] / p1['value']:.2f}x of N = 1; "
+                         f"{c['ms_per_step']:.1f} ms per step on the slowest rank).")
+        lines.append("")
     rf = p1.get("roofline")
     if rf:
         lines.append(f"Roofline object of the product line: dominant kernel `{rf['kernel']}`, {rf['achieved']:.0f} GB/s on its "
