@@ -195,8 +195,9 @@ int sm_regularize(sm_reconstruction* r, void* stream, uint32_t frame_index,
                   int32_t regularization_frame_window_size);
 
 /* surfel_count() = entries - merged, surfels_size() = entries in use
- * (cuda_surfel_reconstruction.h:125-128). Both wait for the device-side
- * counters of the last submitted frame. */
+ * (cuda_surfel_reconstruction.h:125-128). Both synchronise with the stream of
+ * the most recently submitted call on this handle and return the counters of
+ * that call. */
 int sm_surfel_count(sm_reconstruction* r, uint32_t* out);
 int sm_surfels_size(sm_reconstruction* r, uint32_t* out);
 
@@ -248,9 +249,10 @@ int sm_download_rasters(sm_reconstruction* r, void* stream,
  * each raw depth map / colour image is uploaded once on an internal copy
  * stream, overlapped with compute, exactly like the reference's upload_stream
  * (APP/main.cc:902-995); otherwise they are device-resident.
- * The call never synchronises with the host inside the loop and spreads the
- * kernels of consecutive frames over internal streams (frame pipeline,
- * DESIGN.md section 5); `stream` only brackets the call: work enqueued on it
+ * The call never synchronises with the host inside the loop and overlaps the
+ * kernels of three consecutive frames (one instantiated CUDA graph per frame
+ * step on an internal stream; SM_B200_GRAPH=0 selects the
+ * multi-stream event pipeline instead); `stream` only brackets the call: work enqueued on it
  * before the call is complete before the first frame starts, work enqueued
  * after the call sees all frames integrated. The call itself returns after
  * one synchronisation at the end (to fetch the counters for `stats`). With
@@ -279,6 +281,13 @@ typedef struct sm_stream_stats {
 int sm_stream_run(sm_reconstruction* r, void* stream, const sm_stream_desc* s,
                   const sm_preprocess_params* pp, const sm_integrate_params* ip,
                   int32_t first_frame, int32_t last_frame, sm_stream_stats* stats);
+
+/* Named tuning knobs of a handle (no counterpart in the reference). Keys:
+ *   "tiebreak_wave", "tiebreak_early_fraction": the reproducible rule that picks the supporting
+ *   surfel of a pixel with several supporters, where the reference lets the first atomicCAS win
+ *   (APP/cuda_surfel_reconstruction_kernels.cu:1688); see DESIGN.md section 4. wave = 0 selects
+ *   "primary-pixel association before secondary, then lowest index". */
+int sm_configure(sm_reconstruction* r, const char* key, double value);
 
 /* Number of kernel launches issued by this library since load (all handles). */
 uint64_t sm_kernel_launch_count(void);

@@ -33,6 +33,7 @@
 
 typedef uint16_t u16;
 typedef uint32_t u32;
+typedef uint64_t u64;
 typedef uint8_t u8;
 
 #define CW_INVALID 0xFFFFFFFFu
@@ -273,11 +274,12 @@ static inline int cw_secondary(float u, float v, int px, int py, int W, int H, i
  * supporting_surfels receives the canonical winner (primary association before secondary,
  * then lowest index). The walk over surfels is sequential per thread; min-depth uses an
  * atomic min on the int-punned float exactly like the reference. */
-void cw_associate(const float* surfels, size_t stride, u32 surfel_count, u32 frame_index, int active_window, float fx,
+static void cw_associate_impl(const float* surfels, size_t stride, u32 surfel_count, u32 frame_index, int active_window, float fx,
                   float fy, float cx, float cy, const float* local_T_global, float sensor_noise_factor,
                   float normal_compatibility_threshold_deg, float depth_scaling, int W, int H, const u16* depth,
                   const float* normals, u32* supporting_surfels, u32* supporting_surfel_counts,
-                  float* supporting_surfel_depth_sums, u32* conflicting_surfels, float* first_surfel_depth) {
+                  float* supporting_surfel_depth_sums, u32* conflicting_surfels, float* first_surfel_depth,
+                  u32* event_pixel, u32* event_key, u64 max_events, u64* event_count) {
   const float cos_thr = cosf(M_PI / 180.0f * normal_compatibility_threshold_deg);
   const float corr = 1.0f / depth_scaling;
   const size_t P = (size_t)W * H;
@@ -334,6 +336,10 @@ void cw_associate(const float* surfels, size_t stride, u32 surfel_count, u32 fra
       }
       if (surfels[7 * stride + i] <= 0) continue;
       const u32 key = i | (k ? 0x80000000u : 0u);
+      if (event_count) { /* every association that reaches the atomicCAS of kernels.cu:1688 */
+        const u64 e = __atomic_fetch_add(event_count, 1ull, __ATOMIC_RELAXED);
+        if (e < max_events) { event_pixel[e] = (u32)p; event_key[e] = key; }
+      }
       u32 old = __atomic_load_n(&supporting_surfels[p], __ATOMIC_RELAXED);
       while (key < old && !__atomic_compare_exchange_n(&supporting_surfels[p], &old, key, 1, __ATOMIC_RELAXED,
                                                        __ATOMIC_RELAXED)) {}
@@ -344,4 +350,33 @@ void cw_associate(const float* surfels, size_t stride, u32 surfel_count, u32 fra
   }
   for (size_t i = 0; i < P; ++i)
     if (supporting_surfels[i] != CW_INVALID) supporting_surfels[i] &= 0x7FFFFFFFu;
+}
+
+void cw_associate(const float* surfels, size_t stride, u32 surfel_count, u32 frame_index, int active_window, float fx,
+                  float fy, float cx, float cy, const float* local_T_global, float sensor_noise_factor,
+                  float normal_compatibility_threshold_deg, float depth_scaling, int W, int H, const u16* depth,
+                  const float* normals, u32* supporting_surfels, u32* supporting_surfel_counts,
+                  float* supporting_surfel_depth_sums, u32* conflicting_surfels, float* first_surfel_depth) {
+  cw_associate_impl(surfels, stride, surfel_count, frame_index, active_window, fx, fy, cx, cy, local_T_global,
+                    sensor_noise_factor, normal_compatibility_threshold_deg, depth_scaling, W, H, depth, normals,
+                    supporting_surfels, supporting_surfel_counts, supporting_surfel_depth_sums, conflicting_surfels,
+                    first_surfel_depth, 0, 0, 0, 0);
+}
+
+/* The same walk, also listing every (pixel, surfel) association that reaches the reference's
+ * atomicCAS (kernels.cu:1688): event_key = surfel index | 0x80000000 for a secondary-pixel
+ * association. The supporter SET of a pixel = the events with that pixel; the reference's winner
+ * is whichever of them arrives first. *event_count receives the number of events (may exceed
+ * max_events: then only the first max_events were stored). Order of the events is arbitrary. */
+void cw_associate_events(const float* surfels, size_t stride, u32 surfel_count, u32 frame_index, int active_window,
+                         float fx, float fy, float cx, float cy, const float* local_T_global,
+                         float sensor_noise_factor, float normal_compatibility_threshold_deg, float depth_scaling, int W,
+                         int H, const u16* depth, const float* normals, u32* supporting_surfels,
+                         u32* supporting_surfel_counts, float* supporting_surfel_depth_sums, u32* conflicting_surfels,
+                         float* first_surfel_depth, u32* event_pixel, u32* event_key, u64 max_events, u64* event_count) {
+  *event_count = 0;
+  cw_associate_impl(surfels, stride, surfel_count, frame_index, active_window, fx, fy, cx, cy, local_T_global,
+                    sensor_noise_factor, normal_compatibility_threshold_deg, depth_scaling, W, H, depth, normals,
+                    supporting_surfels, supporting_surfel_counts, supporting_surfel_depth_sums, conflicting_surfels,
+                    first_surfel_depth, event_pixel, event_key, max_events, event_count);
 }

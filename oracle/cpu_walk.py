@@ -122,3 +122,31 @@ def associate(rows, frame_index, fx, fy, cx, cy, local_T_global, depth, nrm, sen
                         C.c_float(normal_threshold_deg), C.c_float(depth_scaling), W, H, _p(depth), _p(nrm),
                         *[_p(v) for v in out.values()])
     return {k: v.reshape(H, W) for k, v in out.items()}
+
+
+def associate_events(rows, frame_index, fx, fy, cx, cy, local_T_global, depth, nrm, sensor_noise_factor=0.05,
+                     normal_threshold_deg=40.0, depth_scaling=5000.0, active_window=2**31 - 1):
+    """Like `associate`, plus the supporter sets: returns (rasters, event_pixel, event_key) where every
+    event is one (pixel, surfel) association that reaches the reference's atomicCAS
+    (kernels.cu:1688); event_key = surfel index | 0x80000000 for a secondary-pixel association."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    n = rows.shape[1]
+    H, W = depth.shape
+    P = H * W
+    out = dict(supporting_surfels=np.empty(P, np.uint32), supporting_surfel_counts=np.empty(P, np.uint32),
+               supporting_surfel_depth_sums=np.empty(P, np.float32), conflicting_surfels=np.empty(P, np.uint32),
+               first_surfel_depth=np.empty(P, np.float32))
+    T = np.ascontiguousarray(local_T_global, dtype=np.float32).reshape(-1)
+    nrm = np.ascontiguousarray(nrm, dtype=np.float32)
+    depth = np.ascontiguousarray(depth)
+    max_events = 2 * n + 16
+    ev_pixel = np.empty(max_events, np.uint32)
+    ev_key = np.empty(max_events, np.uint32)
+    count = C.c_uint64(0)
+    load().cw_associate_events(_p(rows), C.c_size_t(rows.shape[1]), C.c_uint32(n), C.c_uint32(frame_index),
+                               C.c_int(active_window), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(T),
+                               C.c_float(sensor_noise_factor), C.c_float(normal_threshold_deg), C.c_float(depth_scaling),
+                               W, H, _p(depth), _p(nrm), *[_p(v) for v in out.values()], _p(ev_pixel), _p(ev_key),
+                               C.c_uint64(max_events), C.byref(count))
+    m = min(int(count.value), max_events)
+    return {k: v.reshape(H, W) for k, v in out.items()}, ev_pixel[:m], ev_key[:m]

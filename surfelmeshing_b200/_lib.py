@@ -136,6 +136,7 @@ _PRODUCT_ONLY = {
     "profile_kernel_name": (C.c_char_p, [_I]),
     "profile_report": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), _I]),
     "frame_counters": (C.c_int, [_P, _P, C.POINTER(C.c_uint64 * 4)]),
+    "configure": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "timeline_enable": (C.c_int, [_P, _I]),
     "timeline_read": (C.c_int, [_P, C.POINTER(C.c_uint64), _I]),
 }

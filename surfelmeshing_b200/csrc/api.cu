@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "sm_kernels.cuh"
+#include "sm_handle.cuh"
 
 namespace smb {
 
@@ -53,13 +53,66 @@ cudaEvent_t TakeEvent() {
 
 bool ProfilingEnabled() { return g_profile_enabled; }
 
-// Device timeline (sm_timeline_enable): the buffer of the reconstruction that enabled it last.
-static unsigned long long* g_timeline = nullptr;
-static u32 g_timeline_frames = 0, g_timeline_frame = 0;
-void SetTimelineFrame(u32 frame) { g_timeline_frame = frame; }
-unsigned long long* TimelineSlot(int kernel_id) {
-  if (!g_timeline) return nullptr;
-  return g_timeline + (static_cast<size_t>(g_timeline_frame % g_timeline_frames) * KID_COUNT + kernel_id) * 2;
+void CountLaunches(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+unsigned long long LaunchCount() { return g_launches.load(); }
+
+// Launch of a described kernel (KernelLaunch, sm_kernels.cuh) on a stream.
+void LaunchOnStream(cudaStream_t stream, const KernelLaunch& k, bool dependent) {
+  LaunchScope scope(stream, static_cast<KernelId>(k.kernel_id));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = k.grid;
+  cfg.blockDim = k.block;
+  cfg.dynamicSmemBytes = k.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const int mode = PdlMode();
+  cfg.numAttrs = (mode == 2 || (mode == 1 && dependent)) ? 1 : 0;
+  cudaLaunchKernelExC(&cfg, k.func, const_cast<void**>(k.args));
+}
+
+// ---- supporting-surfel tie-break (sm_kernels.cuh, kSecondaryBit) ---------------------------------
+namespace {
+// x^-1 mod m for gcd(x, m) = 1 (extended Euclid).
+u32 ModInverse(u32 x, u32 m) {
+  long long t = 0, new_t = 1, r = m, new_r = x % m;
+  while (new_r != 0) {
+    const long long q = r / new_r;
+    long long tmp = t - q * new_t; t = new_t; new_t = tmp;
+    tmp = r - q * new_r; r = new_r; new_r = tmp;
+  }
+  if (t < 0) t += m;
+  return static_cast<u32>(t);
+}
+}  // namespace
+
+int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity) {
+  if (wave != 0) {
+    // keys are (slot / W) * W + perm(slot % W) < 2^31 - 1
+    const unsigned long long top = (static_cast<unsigned long long>(capacity) / wave + 1) * wave;
+    if (wave < 2 || top >= 0x7FFFFFFFull) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range for this surfel cap");
+    const unsigned long long prime = 2654435761ull;  // > any wave, so gcd(prime % wave, wave) = 1
+    cfg->mul = static_cast<u32>(prime % wave);
+    if (cfg->mul == 0) cfg->mul = 1;
+    cfg->mul_inv = ModInverse(cfg->mul, wave);
+  }
+  cfg->wave = wave;
+  return SM_OK;
+}
+
+TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index) {
+  TieBreak t{};
+  t.wave = cfg.wave;
+  if (cfg.wave == 0) return t;
+  t.mul = cfg.mul;
+  t.mul_inv = cfg.mul_inv;
+  t.add = tb_hash(frame_index * 0x9E3779B9u + 0x7F4A7C15u) % cfg.wave;
+  t.salt = tb_hash(frame_index ^ 0x85EBCA6Bu);
+  const double scaled = cfg.early_fraction * 4294967296.0;
+  t.early_threshold = scaled <= 0 ? 0u : (scaled >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<u32>(scaled));
+  return t;
 }
 
 // SM_B200_GRID_PERCENT (measurement hook): percentage of the resident block count to launch.
@@ -117,42 +170,7 @@ using namespace smb;
     }                                                                                        \
   } while (0)
 
-struct sm_reconstruction {
-  DeviceState d{};
-  int device = 0;
-  int sm_count = 0;
-  float fx = 0, fy = 0, cx = 0, cy = 0;
-  int parity = 0;                 // Counters::surfel_count slot holding the current count
-  bool rasters_cleared = false;   // the fused pre-processing tail already reset the rasters
-  IntegrateEvents events{};
-  // host mirror of the counters (pinned) for on-demand queries
-  Counters* host_counters = nullptr;
-  // pre-processing scratch (APP/main.cc filtered_depth_buffer_B)
-  u16* scratch_B = nullptr; size_t scratch_B_pitch = 0;
-  // Association rasters exist twice so that the fused pre-processing tail of frame f + 1 can
-  // reset one set while Integrate() of frame f still works on the other (sm_stream_run).
-  PixelAssoc* assoc_set[2] = {nullptr, nullptr};
-  float* first_depth_set[2] = {nullptr, nullptr};
-  u8* supported_set[2] = {nullptr, nullptr};
-  // stream-runner buffers (double-buffered pre-processing outputs)
-  u16* run_depth[2] = {nullptr, nullptr}; size_t run_depth_pitch = 0;
-  float2* run_normals[2] = {nullptr, nullptr}; size_t run_normals_pitch = 0;
-  float* run_radius[2] = {nullptr, nullptr}; size_t run_radius_pitch = 0;
-  u16* run_depth_pre[2] = {nullptr, nullptr};   // pre-blend copy of run_depth (merge runs next to blend)
-  VisEntry* vis_set[2] = {nullptr, nullptr};
-  u32* seg_count_set[2] = {nullptr, nullptr};
-  u8* merge_flag_set[2] = {nullptr, nullptr};
-  PipelineCtx pipe{};
-  float* smooth_alt = nullptr;    // second smooth-position buffer (DeviceState::smooth / smooth_next)
-  cudaStream_t pre_stream = nullptr;
-  cudaEvent_t pre_done[2] = {nullptr, nullptr}, int_done[2] = {nullptr, nullptr}, entry_event = nullptr;
-  std::vector<u16*> ring_depth; size_t ring_depth_pitch = 0;
-  uchar3* ring_color[2] = {nullptr, nullptr}; size_t ring_color_pitch = 0;
-  cudaStream_t upload_stream = nullptr;
-  cudaEvent_t upload_done = nullptr, frame_done[2] = {nullptr, nullptr};
-};
-
-namespace {
+namespace smb {
 
 int FetchCounters(sm_reconstruction* r, cudaStream_t stream) {
   SM_CUDA(cudaMemcpyAsync(r->host_counters, r->d.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
@@ -164,13 +182,16 @@ int FetchCounters(sm_reconstruction* r, cudaStream_t stream) {
   return SM_OK;
 }
 
-FrameParams MakeFrameParams(const sm_reconstruction* r, u32 frame_index, const sm_integrate_params& p, u16* depth,
-                            size_t depth_pitch, const float* normals, size_t normals_pitch, const float* radius,
-                            size_t radius_pitch, const uint8_t* color, size_t color_pitch,
-                            const float* global_T_local, const float* local_T_global) {
+FrameParams MakeFrameParams(const sm_reconstruction* r, u32 frame_index, int count_slot, const sm_integrate_params& p,
+                            u16* depth, size_t depth_pitch, const u16* depth_pre, size_t depth_pre_pitch,
+                            const float* normals, size_t normals_pitch, const float* radius, size_t radius_pitch,
+                            const uint8_t* color, size_t color_pitch, const float* global_T_local,
+                            const float* local_T_global) {
   FrameParams f;
   f.frame_index = frame_index;
-  f.parity = r->parity;
+  f.count_slot = count_slot;
+  f.skip = 0;
+  f.tb = MakeTieBreak(r->tiebreak, frame_index);
   f.active_window = p.surfel_integration_active_window_size;
   f.fx = r->fx; f.fy = r->fy; f.cx = r->cx; f.cy = r->cy;
   // Unprojection intrinsics for pixel center convention (kernels.cc:68-74).
@@ -191,7 +212,7 @@ FrameParams MakeFrameParams(const sm_reconstruction* r, u32 frame_index, const s
   f.local_T_global = MakeMat3x4(local_T_global);
   f.global_T_local = MakeMat3x4(global_T_local);
   f.depth = depth; f.depth_pitch = depth_pitch;
-  f.depth_pre = depth; f.depth_pre_pitch = depth_pitch;
+  f.depth_pre = depth_pre; f.depth_pre_pitch = depth_pre_pitch;
   f.normals = reinterpret_cast<const float2*>(normals); f.normals_pitch = normals_pitch;
   f.radius = radius; f.radius_pitch = radius_pitch;
   f.color = reinterpret_cast<const uchar3*>(color); f.color_pitch = color_pitch;
@@ -203,13 +224,26 @@ int IntegrateImpl(sm_reconstruction* r, cudaStream_t stream, u32 frame_index, co
                   u16* depth, size_t depth_pitch, const float* normals, size_t normals_pitch, const float* radius,
                   size_t radius_pitch, const uint8_t* color, size_t color_pitch, const float* global_T_local,
                   const float* local_T_global) {
-  const FrameParams f = MakeFrameParams(r, frame_index, p, depth, depth_pitch, normals, normals_pitch, radius,
-                                        radius_pitch, color, color_pitch, global_T_local, local_T_global);
-  int status = IntegrateFrame(stream, r->d, f, p.do_blending != 0, r->rasters_cleared, r->sm_count, &r->events);
+  r->last_stream = stream;
+  // The association / merge gates read the depth as it is before the blending, and the blending
+  // reads that image while it writes the caller's buffer (k_blend): snapshot it first.
+  const u16* depth_pre = depth;
+  size_t depth_pre_pitch = depth_pitch;
+  if (p.do_blending) {
+    SM_CUDA(cudaMemcpy2DAsync(r->blend_src, r->blend_src_pitch, depth, depth_pitch, r->d.width * sizeof(u16),
+                              r->d.height, cudaMemcpyDeviceToDevice, stream));
+    depth_pre = r->blend_src;
+    depth_pre_pitch = r->blend_src_pitch;
+  }
+  const FrameParams f = MakeFrameParams(r, frame_index, r->count_slot, p, depth, depth_pitch, depth_pre, depth_pre_pitch,
+                                        normals, normals_pitch, radius, radius_pitch, color, color_pitch,
+                                        global_T_local, local_T_global);
+  r->last_tiebreak = f.tb;
+  int status = IntegrateFrame(stream, r->d, f, p.do_blending != 0, r->rasters_cleared, r->plan, &r->events);
   r->rasters_cleared = false;
   if (status != SM_OK) return status;
-  const int old_slot = r->parity;
-  r->parity ^= 1;  // k_new_surfel_scan wrote surfel_count[old ^ 1]
+  const int old_slot = r->count_slot;
+  r->count_slot = (r->count_slot + 1) % kCountSlots;  // k_new_surfel_scan wrote the next slot
   if (r->events.enabled) cudaEventRecord(r->events.ev[12], stream);
   // cuda_surfel_reconstruction.cc:295-317; the detach-flag pass of UpdateNeighborsCUDA
   // (kernels.cc:333-339) over the slots that existed before this frame rides on the first sweep.
@@ -217,66 +251,102 @@ int IntegrateImpl(sm_reconstruction* r, cudaStream_t stream, u32 frame_index, co
   if (iterations == 0) {
     status = RegularizeSurfels(stream, r->d, /*disable_denoising*/ true, frame_index,
                                p.radius_factor_for_regularization_neighbors, p.regularizer_weight,
-                               p.regularization_frame_window_size, r->parity, old_slot, r->sm_count);
+                               p.regularization_frame_window_size, r->count_slot, old_slot, r->plan);
   } else {
     for (int i = 0; i < iterations && status == SM_OK; ++i) {
       status = RegularizeSurfels(stream, r->d, /*disable_denoising*/ false, frame_index,
                                  p.radius_factor_for_regularization_neighbors, p.regularizer_weight,
-                                 p.regularization_frame_window_size, r->parity, i == 0 ? old_slot : -1, r->sm_count);
+                                 p.regularization_frame_window_size, r->count_slot, i == 0 ? old_slot : -1, r->plan);
     }
   }
   if (r->events.enabled) cudaEventRecord(r->events.ev[13], stream);
   return status;
 }
 
-int EnsureRunBuffers(sm_reconstruction* r, int ring, bool on_host) {
-  const int W = r->d.width, H = r->d.height;
-  if (!r->run_depth[0]) {
-    for (int i = 0; i < 2; ++i) {
-      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_depth[i]), &r->run_depth_pitch, W * sizeof(u16), H));
-      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_depth_pre[i]), &r->run_depth_pitch, W * sizeof(u16), H));
-      SM_CUDA(cudaEventCreateWithFlags(&r->pipe.ev_create[i], cudaEventDisableTiming));
-      SM_CUDA(cudaEventCreateWithFlags(&r->pipe.ev_update[i], cudaEventDisableTiming));
-      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_normals[i]), &r->run_normals_pitch, W * sizeof(float2), H));
-      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->run_radius[i]), &r->run_radius_pitch, W * sizeof(float), H));
-      SM_CUDA(cudaMemset2D(r->run_radius[i], r->run_radius_pitch, 0, W * sizeof(float), H));
-      SM_CUDA(cudaEventCreateWithFlags(&r->pre_done[i], cudaEventDisableTiming));
-      SM_CUDA(cudaEventCreateWithFlags(&r->int_done[i], cudaEventDisableTiming));
-    }
-    SM_CUDA(cudaStreamCreateWithFlags(&r->pre_stream, cudaStreamNonBlocking));
-    SM_CUDA(cudaEventCreateWithFlags(&r->entry_event, cudaEventDisableTiming));
-    int least_priority = 0, greatest_priority = 0;
-    SM_CUDA(cudaDeviceGetStreamPriorityRange(&least_priority, &greatest_priority));
-    // SM_B200_PRIO (measurement hook): 0 (default) = no priorities, 1 = crit + side high, 2 = front too
-    // (everything of the integration above the pre-processing of the next frame).
-    const char* prio_env = std::getenv("SM_B200_PRIO");
-    const int prio_mode = (prio_env && prio_env[0] >= '0' && prio_env[0] <= '2') ? prio_env[0] - '0' : 0;
-    SM_CUDA(cudaStreamCreateWithPriority(&r->pipe.crit, cudaStreamNonBlocking, prio_mode >= 1 ? greatest_priority : least_priority));
-    SM_CUDA(cudaStreamCreateWithPriority(&r->pipe.side, cudaStreamNonBlocking, prio_mode >= 1 ? greatest_priority : least_priority));
-    SM_CUDA(cudaStreamCreateWithPriority(&r->pipe.front, cudaStreamNonBlocking, prio_mode >= 2 ? greatest_priority : least_priority));
-    for (cudaEvent_t* e : {&r->pipe.ev_assoc, &r->pipe.ev_merge, &r->pipe.ev_blend, &r->pipe.ev_integrate,
-                           &r->pipe.ev_reg}) {
-      SM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    }
+}  // namespace smb
+
+namespace {
+
+// Everything sm_create allocates; on failure the caller destroys the partially built handle.
+int CreateImpl(sm_reconstruction* r, uint64_t max_surfel_count, int32_t width, int32_t height, float fx, float fy,
+               float cx, float cy) {
+  SM_CUDA(cudaGetDevice(&r->device));
+  cudaDeviceProp prop;
+  SM_CUDA(cudaGetDeviceProperties(&prop, r->device));
+  r->sm_count = prop.multiProcessorCount;
+  r->plan.sm_count = r->sm_count;
+  {
+    // One shared-memory carve-out for every kernel of the library (SM_B200_CARVEOUT, percent of
+    // the 228 KB; -1 = leave it to the driver). k_blend needs ~100 KB per block and everything else
+    // a few KB; left to the driver, the SMs keep switching between configurations and the gather
+    // kernels (integrate, update_neighbors, regularisation) ran 1.5-2x slower after a blend
+    // (measured: 9.9k -> 11.7k frames/s with one configuration). 47 % selects the 132 KB
+    // configuration, the smallest that holds a blend block, and leaves 96 KB of L1 to the gathers.
+    // Function attributes and occupancy are per device: configured for every handle.
+    const char* e = std::getenv("SM_B200_CARVEOUT");
+    const int percent = e ? std::atoi(e) : 47;
+    int status = ConfigurePreprocessKernels(percent);
+    if (status == SM_OK) status = ConfigureIntegrateKernels(percent, &r->plan);
+    if (status == SM_OK) status = ConfigureRegularizeKernels(percent, &r->plan);
+    if (status != SM_OK) return status;
   }
-  if (on_host && static_cast<int>(r->ring_depth.size()) != ring) {
-    for (u16* b : r->ring_depth) cudaFree(b);
-    r->ring_depth.assign(ring, nullptr);
-    for (auto& b : r->ring_depth) {
-      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&b), &r->ring_depth_pitch, W * sizeof(u16), H));
-    }
-    for (int i = 0; i < 2; ++i) {
-      if (!r->ring_color[i]) {
-        SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->ring_color[i]), &r->ring_color_pitch, W * 3, H));
-      }
-    }
-    if (!r->upload_stream) {
-      SM_CUDA(cudaStreamCreateWithFlags(&r->upload_stream, cudaStreamNonBlocking));
-      SM_CUDA(cudaEventCreateWithFlags(&r->upload_done, cudaEventDisableTiming));
-      SM_CUDA(cudaEventCreateWithFlags(&r->frame_done[0], cudaEventDisableTiming));
-      SM_CUDA(cudaEventCreateWithFlags(&r->frame_done[1], cudaEventDisableTiming));
-    }
+  r->fx = fx; r->fy = fy; r->cx = cx; r->cy = cy;
+  DeviceState& d = r->d;
+  d.width = width; d.height = height;
+  d.capacity = static_cast<u32>(max_surfel_count);
+  const size_t padded = (max_surfel_count + kSegment - 1) / kSegment * kSegment;
+  d.stride = padded;
+  const size_t P = static_cast<size_t>(width) * height;
+  const size_t scan_tiles = (P + kSegment - 1) / kSegment;
+  SM_CUDA(cudaMalloc(&d.surfels, sizeof(float) * SM_ROW_COUNT * d.stride));
+  SM_CUDA(cudaMalloc(&d.gradient, sizeof(float4) * d.stride));
+  SM_CUDA(cudaMalloc(&r->smooth_alt, sizeof(float) * 3 * d.stride));
+  d.smooth = d.surfels + static_cast<size_t>(SM_ROW_SMOOTH_X) * d.stride;  // rows 3-5 are contiguous
+  d.smooth_next = r->smooth_alt;
+  SM_CUDA(cudaMemset(d.gradient, 0, sizeof(float4) * d.stride));
+  for (int i = 0; i < kSets; ++i) {
+    SM_CUDA(cudaMalloc(&r->assoc_set[i], sizeof(PixelAssoc) * P));
+    SM_CUDA(cudaMalloc(&r->first_depth_set[i], sizeof(float) * P));
+    SM_CUDA(cudaMalloc(&r->supported_set[i], P));
+    SM_CUDA(cudaMalloc(&r->vis_set[i], sizeof(VisEntry) * padded));
+    SM_CUDA(cudaMalloc(&r->seg_count_set[i], sizeof(u32) * (padded / kSegment)));
+    SM_CUDA(cudaMalloc(&r->merge_flag_set[i], padded));
   }
+  d.assoc = r->assoc_set[0]; d.first_depth = r->first_depth_set[0]; d.supported = r->supported_set[0];
+  d.vis = r->vis_set[0]; d.seg_count = r->seg_count_set[0]; d.merge_flag = r->merge_flag_set[0];
+  SM_CUDA(cudaMalloc(&d.new_list, sizeof(u32) * P));
+  SM_CUDA(cudaMalloc(&d.new_flag, P));
+  SM_CUDA(cudaMalloc(&d.new_index, sizeof(u32) * P));
+  SM_CUDA(cudaMalloc(&d.scan_state, sizeof(unsigned long long) * scan_tiles));
+  SM_CUDA(cudaMalloc(&d.counters, sizeof(Counters)));
+  SM_CUDA(cudaMemset(d.counters, 0, sizeof(Counters)));
+  d.timeline = nullptr;
+  d.timeline_frames = 0;
+  SM_CUDA(cudaMemset(d.new_flag, 0, P));
+  SM_CUDA(cudaMemset(d.new_index, 0, sizeof(u32) * P));
+  SM_CUDA(cudaMemset(d.scan_state, 0, sizeof(unsigned long long) * scan_tiles));
+  SM_CUDA(cudaMallocHost(&r->host_counters, sizeof(Counters)));
+  std::memset(r->host_counters, 0, sizeof(Counters));
+  SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->scratch_B), &r->scratch_B_pitch, width * sizeof(u16), height));
+  SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->blend_src), &r->blend_src_pitch, width * sizeof(u16), height));
+  for (int i = 0; i < 14; ++i) SM_CUDA(cudaEventCreate(&r->events.ev[i]));
+  r->events.enabled = false;
+  // Supporting-surfel tie-break defaults; SM_B200_TIEBREAK="wave,early_fraction" overrides.
+  {
+    u32 wave = kDefaultTieBreakWave;
+    double early = kDefaultTieBreakEarlyFraction;
+    if (const char* e = std::getenv("SM_B200_TIEBREAK")) {
+      unsigned w = 0; double q = 0;
+      if (std::sscanf(e, "%u,%lf", &w, &q) == 2) { wave = w; early = q; }
+    }
+    if (wave != 0 && (static_cast<unsigned long long>(d.capacity) / wave + 1) * wave >= 0x7FFFFFFFull) wave = 0;
+    const int status = SetTieBreakWave(&r->tiebreak, wave, d.capacity);
+    if (status != SM_OK) return status;
+    r->tiebreak.early_fraction = early;
+  }
+  const int status = ClearAssociationRasters(nullptr, d);
+  if (status != SM_OK) return status;
+  SM_CUDA(cudaDeviceSynchronize());
   return SM_OK;
 }
 
@@ -348,74 +418,18 @@ int sm_profile_report(double* total_ms, uint64_t* launches, int32_t n) {
 
 int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width, int32_t height, float fx, float fy,
               float cx, float cy) {
+  if (out) *out = nullptr;
   if (!out || width <= 0 || height <= 0 || max_surfel_count == 0 || max_surfel_count > 0x7FFFFFFFull - kSegment) {
     return SetError(SM_ERR_INVALID_ARGUMENT, "sm_create: bad argument");
   }
   sm_reconstruction* r = new sm_reconstruction();
-  SM_CUDA(cudaGetDevice(&r->device));
-  {
-    // One shared-memory carve-out for every kernel of the library (SM_B200_CARVEOUT, percent of
-    // the 228 KB; -1 = leave it to the driver). k_blend needs ~100 KB per block and everything else
-    // a few KB; left to the driver, the SMs keep switching between configurations and the gather
-    // kernels (integrate, update_neighbors, regularisation) ran 1.5-2x slower after a blend
-    // (measured: 9.9k -> 11.7k frames/s with one configuration). 47 % selects the 132 KB
-    // configuration, the smallest that holds a blend block, and leaves 96 KB of L1 to the gathers.
-    const char* e = std::getenv("SM_B200_CARVEOUT");
-    const int percent = e ? std::atoi(e) : 47;
-    if (percent >= 0) {
-      ConfigurePreprocessKernels(percent);
-      ConfigureIntegrateKernels(percent);
-      ConfigureRegularizeKernels(percent);
-    }
+  const int status = CreateImpl(r, max_surfel_count, width, height, fx, fy, cx, cy);
+  if (status != SM_OK) {
+    const std::string message = g_last_error;  // sm_destroy must not overwrite the cause
+    sm_destroy(r);
+    g_last_error = message;
+    return status;
   }
-  cudaDeviceProp prop;
-  SM_CUDA(cudaGetDeviceProperties(&prop, r->device));
-  r->sm_count = prop.multiProcessorCount;
-  r->fx = fx; r->fy = fy; r->cx = cx; r->cy = cy;
-  DeviceState& d = r->d;
-  d.width = width; d.height = height;
-  d.capacity = static_cast<u32>(max_surfel_count);
-  const size_t padded = (max_surfel_count + kSegment - 1) / kSegment * kSegment;
-  d.stride = padded;
-  const size_t P = static_cast<size_t>(width) * height;
-  const size_t scan_tiles = (P + kSegment - 1) / kSegment;
-  SM_CUDA(cudaMalloc(&d.surfels, sizeof(float) * SM_ROW_COUNT * d.stride));
-  SM_CUDA(cudaMalloc(&d.gradient, sizeof(float4) * d.stride));
-  SM_CUDA(cudaMalloc(&r->smooth_alt, sizeof(float) * 3 * d.stride));
-  d.smooth = d.surfels + static_cast<size_t>(SM_ROW_SMOOTH_X) * d.stride;  // rows 3-5 are contiguous
-  d.smooth_next = r->smooth_alt;
-  SM_CUDA(cudaMemset(d.gradient, 0, sizeof(float4) * d.stride));
-  for (int i = 0; i < 2; ++i) {
-    SM_CUDA(cudaMalloc(&r->assoc_set[i], sizeof(PixelAssoc) * P));
-    SM_CUDA(cudaMalloc(&r->first_depth_set[i], sizeof(float) * P));
-    SM_CUDA(cudaMalloc(&r->supported_set[i], P));
-  }
-  d.assoc = r->assoc_set[0]; d.first_depth = r->first_depth_set[0]; d.supported = r->supported_set[0];
-  SM_CUDA(cudaMalloc(&d.new_list, sizeof(u32) * P));
-  for (int i = 0; i < 2; ++i) {
-    SM_CUDA(cudaMalloc(&r->vis_set[i], sizeof(VisEntry) * padded));
-    SM_CUDA(cudaMalloc(&r->seg_count_set[i], sizeof(u32) * (padded / kSegment)));
-    SM_CUDA(cudaMalloc(&r->merge_flag_set[i], padded));
-  }
-  d.vis = r->vis_set[0]; d.seg_count = r->seg_count_set[0]; d.merge_flag = r->merge_flag_set[0];
-  SM_CUDA(cudaMalloc(&d.new_flag, P));
-  SM_CUDA(cudaMalloc(&d.new_index, sizeof(u32) * P));
-  SM_CUDA(cudaMalloc(&d.scan_state, sizeof(unsigned long long) * scan_tiles));
-  SM_CUDA(cudaMalloc(&d.counters, sizeof(Counters)));
-  SM_CUDA(cudaMemset(d.counters, 0, sizeof(Counters)));
-  d.timeline = nullptr;
-  d.timeline_frames = 0;
-  SM_CUDA(cudaMemset(d.new_flag, 0, P));
-  SM_CUDA(cudaMemset(d.new_index, 0, sizeof(u32) * P));
-  SM_CUDA(cudaMemset(d.scan_state, 0, sizeof(unsigned long long) * scan_tiles));
-  SM_CUDA(cudaMallocHost(&r->host_counters, sizeof(Counters)));
-  std::memset(r->host_counters, 0, sizeof(Counters));
-  SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->scratch_B), &r->scratch_B_pitch, width * sizeof(u16), height));
-  for (int i = 0; i < 14; ++i) SM_CUDA(cudaEventCreate(&r->events.ev[i]));
-  r->events.enabled = false;
-  int status = ClearAssociationRasters(nullptr, d);
-  if (status != SM_OK) return status;
-  SM_CUDA(cudaDeviceSynchronize());
   *out = r;
   return SM_OK;
 }
@@ -423,46 +437,45 @@ int sm_create(sm_reconstruction** out, uint64_t max_surfel_count, int32_t width,
 int sm_destroy(sm_reconstruction* r) {
   if (!r) return SM_OK;
   cudaDeviceSynchronize();
+  cudaGetLastError();
+  DestroyFrameGraph(r->graph);
   DeviceState& d = r->d;
   cudaFree(d.surfels); cudaFree(d.gradient); cudaFree(r->smooth_alt); cudaFree(d.new_list);
-  for (int i = 0; i < 2; ++i) { cudaFree(r->vis_set[i]); cudaFree(r->seg_count_set[i]); cudaFree(r->merge_flag_set[i]); cudaFree(r->run_depth_pre[i]);
+  for (int i = 0; i < kSets; ++i) {
+    cudaFree(r->vis_set[i]); cudaFree(r->seg_count_set[i]); cudaFree(r->merge_flag_set[i]);
+    cudaFree(r->assoc_set[i]); cudaFree(r->first_depth_set[i]); cudaFree(r->supported_set[i]);
+    cudaFree(r->run_depth[i]); cudaFree(r->run_depth_pre[i]); cudaFree(r->run_normals[i]); cudaFree(r->run_radius[i]);
+  }
+  cudaFree(d.new_flag); cudaFree(d.new_index); cudaFree(d.scan_state); cudaFree(d.counters);
+  cudaFree(d.timeline);
+  if (r->host_counters) cudaFreeHost(r->host_counters);
+  cudaFree(r->scratch_B);
+  cudaFree(r->blend_src);
+  for (int i = 0; i < 2; ++i) {
     if (r->pipe.ev_create[i]) cudaEventDestroy(r->pipe.ev_create[i]);
     if (r->pipe.ev_update[i]) cudaEventDestroy(r->pipe.ev_update[i]);
-    cudaFree(r->assoc_set[i]); cudaFree(r->first_depth_set[i]); cudaFree(r->supported_set[i]); }
-  
-  cudaFree(d.new_flag); cudaFree(d.new_index); cudaFree(d.scan_state); cudaFree(d.counters);
-  if (d.timeline) { if (g_timeline == d.timeline) g_timeline = nullptr; cudaFree(d.timeline); }
-  cudaFreeHost(r->host_counters);
-  cudaFree(r->scratch_B);
-  for (int i = 0; i < 2; ++i) {
-    cudaFree(r->run_depth[i]); cudaFree(r->run_normals[i]); cudaFree(r->run_radius[i]);
     if (r->pre_done[i]) cudaEventDestroy(r->pre_done[i]);
     if (r->int_done[i]) cudaEventDestroy(r->int_done[i]);
   }
-  if (r->pre_stream) cudaStreamDestroy(r->pre_stream);
-  if (r->pipe.crit) {
-    cudaStreamDestroy(r->pipe.crit);
-    if (r->pipe.front) cudaStreamDestroy(r->pipe.front);
-    if (r->pipe.side) cudaStreamDestroy(r->pipe.side);
-    for (cudaEvent_t e : {r->pipe.ev_assoc, r->pipe.ev_merge, r->pipe.ev_blend, r->pipe.ev_integrate, r->pipe.ev_reg})
-      cudaEventDestroy(e);
-  }
-  if (r->entry_event) cudaEventDestroy(r->entry_event);
+  for (cudaStream_t st : {r->pre_stream, r->pipe.crit, r->pipe.front, r->pipe.side, r->upload_stream, r->graph_stream})
+    if (st) cudaStreamDestroy(st);
+  for (cudaEvent_t e : {r->pipe.ev_assoc, r->pipe.ev_merge, r->pipe.ev_blend, r->pipe.ev_integrate, r->pipe.ev_reg,
+                        r->entry_event, r->upload_done, r->graph_exit})
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : r->iteration_done) if (e) cudaEventDestroy(e);
   for (u16* b : r->ring_depth) cudaFree(b);
-  cudaFree(r->ring_color[0]); cudaFree(r->ring_color[1]);
-  if (r->upload_stream) {
-    cudaStreamDestroy(r->upload_stream);
-    cudaEventDestroy(r->upload_done); cudaEventDestroy(r->frame_done[0]); cudaEventDestroy(r->frame_done[1]);
-  }
-  for (int i = 0; i < 14; ++i) cudaEventDestroy(r->events.ev[i]);
+  for (uchar3* b : r->ring_color) cudaFree(b);
+  for (int i = 0; i < 14; ++i) if (r->events.ev[i]) cudaEventDestroy(r->events.ev[i]);
   delete r;
+  cudaGetLastError();
   return SM_OK;
 }
 
 int sm_reset(sm_reconstruction* r, void* stream) {
   SM_CUDA(cudaMemsetAsync(r->d.counters, 0, sizeof(Counters), static_cast<cudaStream_t>(stream)));
-  r->parity = 0;
+  r->count_slot = 0;
   r->rasters_cleared = false;
+  r->last_stream = static_cast<cudaStream_t>(stream);
   return SM_OK;
 }
 
@@ -533,20 +546,23 @@ int sm_integrate(sm_reconstruction* r, void* stream, uint32_t frame_index, const
 
 int sm_regularize(sm_reconstruction* r, void* stream, uint32_t frame_index, float regularizer_weight,
                   float radius_factor_for_regularization_neighbors, int32_t regularization_frame_window_size) {
+  r->last_stream = static_cast<cudaStream_t>(stream);
   return RegularizeSurfels(static_cast<cudaStream_t>(stream), r->d, /*disable_denoising*/ false, frame_index,
                            radius_factor_for_regularization_neighbors, regularizer_weight,
-                           regularization_frame_window_size, r->parity, -1, r->sm_count);
+                           regularization_frame_window_size, r->count_slot, -1, r->plan);
 }
 
+// The two count queries have no stream argument (cuda_surfel_reconstruction.h:125-128): they
+// synchronise with the stream of the most recently submitted work.
 int sm_surfel_count(sm_reconstruction* r, uint32_t* out) {
-  const int status = FetchCounters(r, nullptr);
-  *out = r->host_counters->surfel_count[r->parity] - r->host_counters->merge_count;
+  const int status = FetchCounters(r, r->last_stream);
+  *out = r->host_counters->surfel_count[r->count_slot] - r->host_counters->merge_count;
   return status;
 }
 
 int sm_surfels_size(sm_reconstruction* r, uint32_t* out) {
-  const int status = FetchCounters(r, nullptr);
-  *out = r->host_counters->surfel_count[r->parity];
+  const int status = FetchCounters(r, r->last_stream);
+  *out = r->host_counters->surfel_count[r->count_slot];
   return status;
 }
 
@@ -555,7 +571,7 @@ int sm_transfer_all_to_cpu(sm_reconstruction* r, void* stream_v, uint32_t /*fram
                            uint32_t* last_update_stamp, uint64_t* out_count) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int status = FetchCounters(r, stream);
-  const u32 n = r->host_counters->surfel_count[r->parity];
+  const u32 n = r->host_counters->surfel_count[r->count_slot];
   if (out_count) *out_count = n;
   if (n == 0) return status;
   const size_t bytes = sizeof(float) * n;
@@ -573,7 +589,7 @@ int sm_transfer_all_to_cpu(sm_reconstruction* r, void* stream_v, uint32_t /*fram
 }
 
 int sm_export_vertices(sm_reconstruction* r, void* stream, float* position_buffer, uint8_t* color_buffer) {
-  return ExportVertices(static_cast<cudaStream_t>(stream), r->d, r->parity, r->sm_count, position_buffer,
+  return ExportVertices(static_cast<cudaStream_t>(stream), r->d, r->count_slot, r->sm_count, position_buffer,
                         color_buffer);
 }
 
@@ -593,9 +609,10 @@ int sm_dump_state(sm_reconstruction* r, void* stream_v, float* host_rows, uint64
                   uint32_t* surfels_size, uint32_t* merge_count) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int status = FetchCounters(r, stream);
-  const u32 n = r->host_counters->surfel_count[r->parity];
+  const u32 n = r->host_counters->surfel_count[r->count_slot];
   if (surfels_size) *surfels_size = n;
   if (merge_count) *merge_count = r->host_counters->merge_count;
+  if (host_rows && n > host_row_stride_elems) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_dump_state: host rows shorter than surfels_size()");
   if (host_rows && n > 0) {
     SM_CUDA(cudaMemcpy2DAsync(host_rows, host_row_stride_elems * sizeof(float), r->d.surfels,
                               r->d.stride * sizeof(float), n * sizeof(float), SM_ROW_COUNT, cudaMemcpyDeviceToHost,
@@ -628,12 +645,13 @@ int sm_load_state(sm_reconstruction* r, void* stream_v, const float* host_rows, 
     }
   }
   Counters c{};
-  c.surfel_count[0] = c.surfel_count[1] = surfels_size;
+  for (int i = 0; i < kCountSlots; ++i) c.surfel_count[i] = surfels_size;
   c.merge_count = merge_count;
   *r->host_counters = c;
   SM_CUDA(cudaMemcpyAsync(r->d.counters, r->host_counters, sizeof(Counters), cudaMemcpyHostToDevice, stream));
   SM_CUDA(cudaStreamSynchronize(stream));
-  r->parity = 0;
+  r->count_slot = 0;
+  r->last_stream = stream;
   return SM_OK;
 }
 
@@ -653,7 +671,7 @@ int sm_download_rasters(sm_reconstruction* r, void* stream_v, uint32_t* supporti
     SM_CUDA(cudaMemcpyAsync(new_surfel_indices, r->d.new_index, sizeof(u32) * P, cudaMemcpyDeviceToHost, stream));
   SM_CUDA(cudaStreamSynchronize(stream));
   for (size_t i = 0; i < P; ++i) {
-    if (supporting_surfels) supporting_surfels[i] = supporting_index(assoc[i].x);
+    if (supporting_surfels) supporting_surfels[i] = supporting_index(r->last_tiebreak, assoc[i].x);
     if (conflicting_surfels) conflicting_surfels[i] = assoc[i].y;
     if (supporting_surfel_counts) supporting_surfel_counts[i] = assoc[i].z;
     if (supporting_surfel_depth_sums) std::memcpy(&supporting_surfel_depth_sums[i], &assoc[i].w, sizeof(float));
@@ -665,7 +683,7 @@ int sm_frame_counters(sm_reconstruction* r, void* stream_v, uint64_t out[4]) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int status = FetchCounters(r, stream);
   // The last Integrate() swept the slots that existed before its new surfels were appended.
-  const u32 n_after = r->host_counters->surfel_count[r->parity];
+  const u32 n_after = r->host_counters->surfel_count[r->count_slot];
   const u32 n_swept = n_after - r->host_counters->new_surfel_count;
   const size_t segments = (static_cast<size_t>(n_swept) + kSegment - 1) / kSegment;
   std::vector<u32> seg(segments);
@@ -685,7 +703,6 @@ int sm_timeline_enable(sm_reconstruction* r, int32_t frames) {
   if (r == nullptr || frames < 0) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_timeline_enable: bad arguments");
   SM_CUDA(cudaDeviceSynchronize());
   if (r->d.timeline) {
-    if (g_timeline == r->d.timeline) g_timeline = nullptr;
     cudaFree(r->d.timeline);
     r->d.timeline = nullptr;
     r->d.timeline_frames = 0;
@@ -697,8 +714,6 @@ int sm_timeline_enable(sm_reconstruction* r, int32_t frames) {
   for (size_t i = 0; i < slots; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
   SM_CUDA(cudaMemcpy(r->d.timeline, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
   r->d.timeline_frames = static_cast<u32>(frames);
-  g_timeline = r->d.timeline;
-  g_timeline_frames = r->d.timeline_frames;
   return SM_OK;
 }
 
@@ -711,157 +726,29 @@ int sm_timeline_read(sm_reconstruction* r, uint64_t* out, int32_t frames) {
   return SM_OK;
 }
 
-// The frame loop of APP/main.cc:885-1223 on a synthetic stream.
+// The frame loop of APP/main.cc:885-1223 on a synthetic stream (pipeline.cu).
 int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s, const sm_preprocess_params* pp,
                   const sm_integrate_params* ip, int32_t first_frame, int32_t last_frame, sm_stream_stats* stats) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const int W = r->d.width, H = r->d.height;
-  if (s->width != W || s->height != H) return SetError(SM_ERR_INVALID_ARGUMENT, "stream size mismatch");
-  const int K = pp->outlier_filtering_frame_count;
-  const int half = K / 2;
-  if (K < 2 || K > 8 || first_frame < half || last_frame > s->frame_count - half || first_frame > last_frame) {
-    return SetError(SM_ERR_INVALID_ARGUMENT,
-                    "frame range needs outlier_filtering_frame_count/2 frames on both sides (main.cc:987-992)");
+  if (!r || !s || !pp || !ip) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_stream_run: null argument");
+  return StreamRun(r, static_cast<cudaStream_t>(stream_v), s, pp, ip, first_frame, last_frame, stats);
+}
+
+// Named tuning / experiment knobs of a handle (no counterpart in the reference):
+//   "tiebreak_wave"            slots per launch wave of the modelled association race (0 = plain rule)
+//   "tiebreak_early_fraction"  fraction of secondary-pixel associations that compete like primary ones
+int sm_configure(sm_reconstruction* r, const char* key, double value) {
+  if (!r || !key) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_configure: null argument");
+  const std::string k(key);
+  if (k == "tiebreak_wave") {
+    if (value < 0 || value > 2147483647.0) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range");
+    return SetTieBreakWave(&r->tiebreak, static_cast<u32>(value), r->d.capacity);
   }
-  const size_t frame_elems = static_cast<size_t>(W) * H;
-  const int ring = K + 2;
-  int status = EnsureRunBuffers(r, ring, s->frames_on_host != 0);
-  if (status != SM_OK) return status;
-  const unsigned long long launches_before = g_launches.load();
-  const auto host_t0 = std::chrono::steady_clock::now();
-  uint64_t h2d = 0;
-
-  auto raw_ptr = [&](int frame, size_t* pitch) -> const u16* {
-    if (s->frames_on_host) { *pitch = r->ring_depth_pitch; return r->ring_depth[frame % ring]; }
-    *pitch = W * sizeof(u16);
-    return s->depth + frame_elems * frame;
-  };
-  // Two-deep software pipeline: the pre-processing of frame f + 1 (pre_stream) runs while frame f
-  // is integrated (caller's stream). Buffer set f & 1 holds frame f's pre-processing outputs and
-  // association rasters; it is reused by frame f + 2 once Integrate(f) has finished.
-  // Per-kernel profiling and stage timings need the kernels one after the other on one stream.
-  const bool pipelined = !r->events.enabled && !ProfilingEnabled();
-  r->pipe.have_frame = false;
-  SM_CUDA(cudaEventRecord(r->entry_event, stream));
-  SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->entry_event, 0));
-  SM_CUDA(cudaStreamWaitEvent(r->pipe.crit, r->entry_event, 0));
-  SM_CUDA(cudaStreamWaitEvent(r->pipe.front, r->entry_event, 0));
-  SM_CUDA(cudaStreamWaitEvent(r->pipe.side, r->entry_event, 0));
-  if (s->frames_on_host) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->entry_event, 0));
-  int uploaded_until = first_frame - half - 1;
-  const uint8_t* frame_color[2] = {nullptr, nullptr};
-  size_t frame_color_pitch = static_cast<size_t>(W) * 3;
-
-  auto enqueue_preprocess = [&](int frame) -> int {
-    const int set = frame & 1;
-    const bool reuse = frame >= first_frame + 2;
-    frame_color[set] = s->color + 3 * frame_elems * frame;
-    if (s->frames_on_host) {
-      // Upload stream (main.cc:902-984): the new raw depth map(s) and this frame's colour image.
-      // The raw-depth ring slot written now was last read by the pre-processing of frame - 2,
-      // the colour slot by Integrate(frame - 2).
-      if (reuse) {
-        SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->pre_done[set], 0));
-        SM_CUDA(cudaStreamWaitEvent(r->upload_stream, pipelined ? r->pipe.ev_create[set] : r->int_done[set], 0));
-      }
-      for (int f = uploaded_until + 1; f <= frame + half; ++f) {
-        SM_CUDA(cudaMemcpy2DAsync(r->ring_depth[f % ring], r->ring_depth_pitch, s->depth + frame_elems * f,
-                                  W * sizeof(u16), W * sizeof(u16), H, cudaMemcpyHostToDevice, r->upload_stream));
-        h2d += frame_elems * sizeof(u16);
-      }
-      uploaded_until = frame + half;
-      SM_CUDA(cudaMemcpy2DAsync(r->ring_color[set], r->ring_color_pitch, s->color + 3 * frame_elems * frame,
-                                static_cast<size_t>(W) * 3, static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice,
-                                r->upload_stream));
-      h2d += frame_elems * 3;
-      SM_CUDA(cudaEventRecord(r->upload_done, r->upload_stream));
-      SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->upload_done, 0));  // main.cc:995
-      frame_color[set] = reinterpret_cast<const uint8_t*>(r->ring_color[set]);
-      frame_color_pitch = r->ring_color_pitch;
-    }
-    if (reuse) {
-      if (pipelined) {
-        SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->pipe.ev_create[set], 0));
-        SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->pipe.ev_update[set], 0));
-      } else {
-        SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->int_done[set], 0));
-      }
-    }
-    const u16* others[8];
-    size_t other_pitches[8];
-    for (int i = 0; i < half; ++i) {  // main.cc:1046-1059
-      others[i] = raw_ptr(frame - (i + 1), &other_pitches[i]);
-      others[half + i] = raw_ptr(frame + (i + 1), &other_pitches[half + i]);
-    }
-    size_t raw_pitch;
-    const u16* raw = raw_ptr(frame, &raw_pitch);
-    SetTimelineFrame(static_cast<u32>(frame));
-    const int st = PreprocessFused(r->pre_stream, *pp, W, H, r->fx, r->fy, r->cx, r->cy, raw, raw_pitch, others,
-                                   other_pitches, s->others_TR_reference + static_cast<size_t>(frame) * K * 12,
-                                   r->scratch_B, r->scratch_B_pitch, r->run_depth[set], r->run_depth_pitch,
-                                   r->run_normals[set], r->run_normals_pitch, r->run_radius[set], r->run_radius_pitch,
-                                   r->assoc_set[set], r->first_depth_set[set], r->supported_set[set],
-                                   pipelined ? r->run_depth_pre[set] : nullptr, r->run_depth_pitch);
-    if (st != SM_OK) return st;
-    SM_CUDA(cudaEventRecord(r->pre_done[set], r->pre_stream));
+  if (k == "tiebreak_early_fraction") {
+    if (!(value >= 0.0 && value <= 1.0)) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_early_fraction must be in [0, 1]");
+    r->tiebreak.early_fraction = value;
     return SM_OK;
-  };
-
-  uint32_t integrated = 0;
-  if (first_frame < last_frame) {
-    status = enqueue_preprocess(first_frame);
-    if (status != SM_OK) return status;
   }
-  for (int frame = first_frame; frame < last_frame; ++frame) {
-    const int set = frame & 1;
-    if (frame + 1 < last_frame) {
-      status = enqueue_preprocess(frame + 1);
-      if (status != SM_OK) return status;
-    }
-    SM_CUDA(cudaStreamWaitEvent(pipelined ? r->pipe.front : stream, r->pre_done[set], 0));
-    r->d.assoc = r->assoc_set[set]; r->d.first_depth = r->first_depth_set[set]; r->d.supported = r->supported_set[set];
-    r->d.vis = r->vis_set[set]; r->d.seg_count = r->seg_count_set[set]; r->d.merge_flag = r->merge_flag_set[set];
-    const size_t color_pitch = s->frames_on_host ? r->ring_color_pitch : static_cast<size_t>(W) * 3;
-    if (pipelined) {
-      FrameParams f = MakeFrameParams(r, static_cast<u32>(frame), *ip, r->run_depth[set], r->run_depth_pitch,
-                                      reinterpret_cast<const float*>(r->run_normals[set]), r->run_normals_pitch,
-                                      r->run_radius[set], r->run_radius_pitch, frame_color[set], color_pitch,
-                                      s->global_T_frame + 12 * frame, s->frame_T_global + 12 * frame);
-      f.depth_pre = r->run_depth_pre[set];
-      f.depth_pre_pitch = r->run_depth_pitch;
-      RegularizeArgs reg;
-      reg.iterations = ip->regularization_iterations_per_integration_iteration;
-      reg.disable_denoising = reg.iterations == 0;
-      reg.radius_factor = ip->radius_factor_for_regularization_neighbors;
-      reg.regularizer_weight = ip->regularizer_weight;
-      reg.window = ip->regularization_frame_window_size;
-      status = IntegrateFramePipelined(r->pipe.front, &r->pipe, set, r->d, f, ip->do_blending != 0, reg, r->sm_count);
-      if (status != SM_OK) return status;
-      r->parity ^= 1;
-    } else {
-      r->rasters_cleared = true;
-      status = IntegrateImpl(r, stream, static_cast<u32>(frame), *ip, r->run_depth[set], r->run_depth_pitch,
-                             reinterpret_cast<const float*>(r->run_normals[set]), r->run_normals_pitch,
-                             r->run_radius[set], r->run_radius_pitch, frame_color[set], color_pitch,
-                             s->global_T_frame + 12 * frame, s->frame_T_global + 12 * frame);
-      if (status != SM_OK) return status;
-      SM_CUDA(cudaEventRecord(r->int_done[set], stream));
-    }
-    ++integrated;
-  }
-  if (pipelined && r->pipe.have_frame) SM_CUDA(cudaStreamWaitEvent(stream, r->pipe.ev_reg, 0));  // join
-  const double host_enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
-  status = FetchCounters(r, stream);  // one 32-byte D2H + sync for the whole call
-  if (stats) {
-    stats->frames_integrated = integrated;
-    stats->surfels_size = r->host_counters->surfel_count[r->parity];
-    stats->surfel_count = stats->surfels_size - r->host_counters->merge_count;
-    stats->kernel_launches = g_launches.load() - launches_before;
-    stats->h2d_bytes = h2d;
-    stats->d2h_bytes = sizeof(Counters);
-    stats->host_enqueue_ms = host_enqueue_ms;
-  }
-  return status;
+  return SetError(SM_ERR_INVALID_ARGUMENT, "sm_configure: unknown key");
 }
 
 }  // extern "C"

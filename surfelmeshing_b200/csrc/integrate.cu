@@ -160,9 +160,10 @@ constexpr int kProjectBlock = 512;  // 2 slots per thread, kSegment slots per bl
 
 __global__ void __launch_bounds__(kProjectBlock) k_project(DeviceState d, FrameParams f) {
   pdl_prologue();
+  if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_PROJECT);
   __shared__ u32 warp_totals[kProjectBlock / 32];
-  const u32 n = d.counters->surfel_count[f.parity];
+  const u32 n = d.counters->surfel_count[f.count_slot];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   if (blockIdx.x == 0) {
@@ -290,8 +291,9 @@ __device__ __forceinline__ bool supports_surfel(const DeviceState& d, const Fram
 
 __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams f) {
   pdl_prologue();
+  if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_ASSOCIATE);
-  for_each_visible(d, &d.counters->surfel_count[f.parity], [&](size_t, const VisEntry& e) {
+  for_each_visible(d, &d.counters->surfel_count[f.count_slot], [&](size_t, const VisEntry& e) {
     if (!(e.x & kActiveBit)) return;
     const u32 idx = e.x & ~kActiveBit;
     const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
@@ -312,11 +314,9 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
       if (!supports_surfel(d, f, k == 0 ? g0 : g1, pp, idx, z, dot_angle, ln)) continue;
       if (!(surfel_radius_squared > 0.f)) continue;
       PixelAssoc* a = &d.assoc[pp];
-      // Reference: atomicCAS(INV -> idx), first come wins. Every thread of the reference kernel
-      // handles its primary pixel before its secondary pixel, so primary associations typically
-      // arrive first; the deterministic rule here is "primary before secondary, then lowest
-      // index" (kSecondaryBit orders the keys), which is one of the reference's legal outcomes.
-      atomicMin(&a->x, idx | (k == 1 ? kSecondaryBit : 0u));
+      // Reference: atomicCAS(INV -> idx), first come wins. Here: the minimum of a reproducible
+      // arrival key (sm_kernels.cuh, kSecondaryBit) - one of the reference's legal outcomes.
+      atomicMin(&a->x, tb_encode(f.tb, idx, k == 1));
       atomicAdd(&a->z, 1u);
       atomicAdd(reinterpret_cast<float*>(&a->w), z);
       d.supported[pp] = 1;
@@ -327,16 +327,17 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
 // a9: merge decision (kernels.cu:1857-1992); applied by k_integrate.
 __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) {
   pdl_prologue();
+  if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_MERGE);
   u32 merged_by_thread = 0;
-  for_each_visible(d, &d.counters->surfel_count[f.parity], [&](size_t pos, const VisEntry& e) {
+  for_each_visible(d, &d.counters->surfel_count[f.count_slot], [&](size_t pos, const VisEntry& e) {
     const u32 idx = e.x & ~kActiveBit;  // no active-window test here (kernels.cu:2016)
     const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
     const Projection p = project(f, d.width, d.height, x, y, z);
     const int pp = p.py * d.width + p.px;
     // batch 1
     const PixelGate g = load_pixel_gate(d, f, p.px, p.py);
-    const u32 supported_surfel = supporting_index(d.assoc[pp].x);
+    const u32 supported_surfel = supporting_index(f.tb, d.assoc[pp].x);
     const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
     const float snx = SM_S(SM_ROW_NORMAL_X, idx), sny = SM_S(SM_ROW_NORMAL_Y, idx), snz = SM_S(SM_ROW_NORMAL_Z, idx);
     const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   long long blend_clock[5] = {0, 0, 0, 0, 0};
 #endif
   pdl_prologue();
+  if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_BLEND);
   SM_BLEND_CLOCK(0);
   extern __shared__ __align__(16) unsigned char blend_smem[];
@@ -477,8 +479,11 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   // Region load in 16-pixel chunks (two 128-bit depth loads + one of the support raster per
   // thread, all in flight together); rasters that are not 16-byte friendly take the scalar path.
   // Each chunk also yields 16 bits of the three class rasters.
-  const bool vector_ok = (d.width & 15) == 0 && (f.depth_pitch & 15) == 0 &&
-                         (reinterpret_cast<uintptr_t>(f.depth) & 15) == 0 &&
+  // The region (tile + halo) is read from the PRE-blend image f.depth_pre and only the tile interior
+  // is written, to f.depth: a neighbouring tile's halo overlaps this interior, so reading and
+  // writing the same raster would let a later-scheduled block see already blended depths.
+  const bool vector_ok = (d.width & 15) == 0 && ((f.depth_pitch | f.depth_pre_pitch) & 15) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(f.depth) | reinterpret_cast<uintptr_t>(f.depth_pre)) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(d.supported) & 15) == 0;
   const int chunks_per_row = wpr * 2;  // including the padding chunks right of the region
   for (int t = threadIdx.x; t < rh * chunks_per_row; t += kBlendBlock) {
@@ -489,7 +494,7 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
     depth.v[0] = depth.v[1] = sup.v = make_uint4(0u, 0u, 0u, 0u);
     const bool in_region = chunk * 16 < rw;
     if (in_region && gy >= 0 && gy < d.height) {
-      const u16* depth_row = row_ptr(f.depth, f.depth_pitch, gy);
+      const u16* depth_row = row_ptr(f.depth_pre, f.depth_pre_pitch, gy);
       const u8* sup_row = d.supported + static_cast<size_t>(gy) * d.width;
       if (vector_ok && gx >= 0 && gx + 16 <= d.width) {
         depth.v[0] = *reinterpret_cast<const uint4*>(depth_row + gx);
@@ -805,8 +810,9 @@ __device__ __forceinline__ void integrate_or_conflict(const FrameParams& f, cons
 
 __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FrameParams f) {
   pdl_prologue();
+  if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_INTEGRATE);
-  for_each_visible(d, &d.counters->surfel_count[f.parity], [&](size_t pos, const VisEntry& e) {
+  for_each_visible(d, &d.counters->surfel_count[f.count_slot], [&](size_t pos, const VisEntry& e) {
     const u32 idx = e.x & ~kActiveBit;
     const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
     const Projection p = project(f, d.width, d.height, x, y, z);
@@ -858,8 +864,9 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, FrameParams f) {
   pdl_prologue();
+  if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_UPDATE_NEIGHBORS);
-  for_each_visible(d, &d.counters->surfel_count[f.parity], [&](size_t, const VisEntry& e) {
+  for_each_visible(d, &d.counters->surfel_count[f.count_slot], [&](size_t, const VisEntry& e) {
     const u32 idx = e.x & ~kActiveBit;
     // batch 1: the surfel (its position may have been changed by the integration: project again)
     const u32 stamp = SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx);
@@ -889,7 +896,7 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
 #pragma unroll
     for (int direction = 0; direction < 4; ++direction) {
       candidate[direction] =
-          supporting_index(d.assoc[(y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction]].x);
+          supporting_index(f.tb, d.assoc[(y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction]].x);
     }
     if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) return;  // occluded
     float3 ln;
@@ -974,6 +981,7 @@ __device__ __forceinline__ unsigned long long load_scan_state(unsigned long long
 
 __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, FrameParams f) {
   pdl_prologue();
+  if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_NEW_SURFEL_SCAN);
   __shared__ u32 s_tile, s_prefix;
   __shared__ u32 warp_totals[kBlock / 32];
@@ -1041,14 +1049,14 @@ __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, Frame
       s_prefix = exclusive;
       if (tile == static_cast<u32>(tiles) - 1) {
         // new_surfel_count = indices[P-1] + flag[P-1] (kernels.cc:116-125, cuda_surfel_reconstruction.cc:291).
-        const u32 n_old = d.counters->surfel_count[f.parity];
+        const u32 n_old = d.counters->surfel_count[f.count_slot];
         u32 new_count = exclusive + block_total;
         if (static_cast<u64>(n_old) + new_count > d.capacity) {
           d.counters->capacity_overflow = 1;  // the reference would write past the buffer here
           new_count = 0;
         }
         d.counters->new_surfel_count = new_count;
-        d.counters->surfel_count[f.parity ^ 1] = n_old + new_count;
+        d.counters->surfel_count[(f.count_slot + 1) % kCountSlots] = n_old + new_count;
       }
     }
   }
@@ -1069,9 +1077,10 @@ __global__ void __launch_bounds__(kBlock) k_new_surfel_scan(DeviceState d, Frame
 // CreateNewSurfelsCUDACreationKernel (kernels.cu:133-231), one thread per NEW surfel.
 __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameParams f) {
   pdl_prologue();
+  if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_CREATE_SURFELS);
   const u32 new_count = d.counters->new_surfel_count;
-  const u32 surfel_count = d.counters->surfel_count[f.parity];
+  const u32 surfel_count = d.counters->surfel_count[f.count_slot];
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < new_count; k += gridDim.x * blockDim.x) {
     const int seq = d.new_list[k];
     const int y = seq / d.width, x = seq - y * d.width;
@@ -1090,7 +1099,7 @@ __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameP
     for (int direction = 0; direction < 4; ++direction) {
       const int nx_ = x + kDirectionsX[direction], ny_ = y + kDirectionsY[direction];
       const int nseq = ny_ * d.width + nx_;
-      neighbor_index[direction] = supporting_index(d.assoc[nseq].x);
+      neighbor_index[direction] = supporting_index(f.tb, d.assoc[nseq].x);
       neighbor_is_new[direction] = d.new_flag[nseq];
       neighbor_new_index[direction] = d.new_index[nseq];
       neighbor_depth[direction] = row_ptr(f.depth, f.depth_pitch, ny_)[nx_];
@@ -1151,10 +1160,10 @@ __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameP
 }
 
 // ExportVerticesCUDAKernel (kernels.cu:2412-2433).
-__global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int parity, float* position_buffer,
+__global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int count_slot, float* position_buffer,
                                                             u8* color_buffer) {
   pdl_prologue();
-  const u32 n = d.counters->surfel_count[parity];
+  const u32 n = d.counters->surfel_count[count_slot];
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const bool merged = SM_S(SM_ROW_RADIUS_SQUARED, i) < 0.f;
     const float nan = __int_as_float(0x7fffffff);
@@ -1171,57 +1180,73 @@ __global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int p
 }  // namespace
 
 namespace {
-int LaunchBlend(cudaStream_t stream, const DeviceState& d, const FrameParams& f) {
-  const dim3 pixel_tiles((d.width + kBlendTileW - 1) / kBlendTileW, (d.height + kBlendTileH - 1) / kBlendTileH);
-  const size_t rn = static_cast<size_t>(kBlendTileW + 2 * blend_halo_x(f.blend_radius)) * (kBlendTileH + 2 * blend_halo_y(f.blend_radius));
-  const size_t rn16 = (rn + 15) & ~static_cast<size_t>(15);
-  const size_t rw = kBlendTileW + 2 * blend_halo_x(f.blend_radius), rh = kBlendTileH + 2 * blend_halo_y(f.blend_radius);
+// Dynamic shared memory of k_blend: 16 B per region pixel + 11 bit rasters (see the kernel's carve-up).
+size_t BlendSmemBytes(int radius) {
+  const size_t rw = kBlendTileW + 2 * blend_halo_x(radius), rh = kBlendTileH + 2 * blend_halo_y(radius);
+  const size_t rn16 = (rw * rh + 15) & ~static_cast<size_t>(15);
   const size_t mask_words = rh * ((rw + 31) / 32);
-  const size_t smem = rn16 * 16 + mask_words * 11 * 4 + 16;  // k_blend's carve-up: 16 B per region pixel + 11 bit rasters
-  // One region per block has to fit the 227 KB of an SM (radius <= 25 at the 80x32 tile).
-  if (smem > 224 * 1024 || f.blend_radius > kMaxBlendRadius) return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large");
-  static size_t configured_smem = 0;
-  if (smem > 48 * 1024 && smem > configured_smem) {
-    if (cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
-      return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend)");
-    configured_smem = smem;
+  return rn16 * 16 + mask_words * 11 * 4 + 16;
+}
+constexpr size_t kBlendSmemLimit = 224 * 1024;  // one region per block has to fit an SM (radius <= 25 at the 80x32 tile)
+
+#define SM_EV(call)                                                              \
+  do {                                                                           \
+    const cudaError_t e_ = (call);                                               \
+    if (e_ != cudaSuccess) return SetError(SM_ERR_CUDA, cudaGetErrorString(e_)); \
+  } while (0)
+}  // namespace
+
+int DescribeFrameKernel(FrameKernel which, const LaunchPlan& plan, const DeviceState& d, const FrameParams& f,
+                        KernelLaunch* out) {
+  static_assert(sizeof(DeviceState) + sizeof(FrameParams) + 32 <= sizeof(out->storage), "KernelLaunch::storage too small");
+  const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
+  switch (which) {
+    case FK_PROJECT:
+      out->Reset(reinterpret_cast<const void*>(k_project), dim3(plan.project), dim3(kProjectBlock), 0, KID_PROJECT);
+      break;
+    case FK_ASSOCIATE:
+      out->Reset(reinterpret_cast<const void*>(k_associate), dim3(plan.associate), dim3(kBlock), 0, KID_ASSOCIATE);
+      break;
+    case FK_MERGE:
+      out->Reset(reinterpret_cast<const void*>(k_merge), dim3(plan.merge), dim3(kBlock), 0, KID_MERGE);
+      break;
+    case FK_BLEND: {
+      const size_t smem = BlendSmemBytes(f.blend_radius);
+      if (f.blend_radius < 1 || f.blend_radius > kMaxBlendRadius || smem > kBlendSmemLimit)
+        return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius out of range (1 .. 25)");
+      const dim3 pixel_tiles((d.width + kBlendTileW - 1) / kBlendTileW, (d.height + kBlendTileH - 1) / kBlendTileH);
+      out->Reset(reinterpret_cast<const void*>(k_blend), pixel_tiles, dim3(kBlendBlock), smem, KID_BLEND);
+      break;
+    }
+    case FK_INTEGRATE:
+      out->Reset(reinterpret_cast<const void*>(k_integrate), dim3(plan.integrate), dim3(kBlock), 0, KID_INTEGRATE);
+      break;
+    case FK_UPDATE_NEIGHBORS:
+      out->Reset(reinterpret_cast<const void*>(k_update_neighbors), dim3(plan.update_neighbors), dim3(kBlock), 0,
+                 KID_UPDATE_NEIGHBORS);
+      break;
+    case FK_SCAN:
+      out->Reset(reinterpret_cast<const void*>(k_new_surfel_scan), dim3(scan_tiles), dim3(kBlock), 0, KID_NEW_SURFEL_SCAN);
+      break;
+    case FK_CREATE:
+      out->Reset(reinterpret_cast<const void*>(k_create_surfels), dim3(plan.sm_count * 2), dim3(kBlock), 0, KID_CREATE_SURFELS);
+      break;
+    default:
+      return SetError(SM_ERR_INVALID_ARGUMENT, "DescribeFrameKernel");
   }
-  { LaunchScope scope(stream, KID_BLEND); LaunchDependent(k_blend, dim3(pixel_tiles), dim3(kBlendBlock), smem, stream, d, f); }
+  out->Arg(d);
+  out->Arg(f);
   return SM_OK;
 }
 
-// Grids of the list kernels: exactly the blocks that are resident at once (occupancy x SMs), so
-// that every block is scheduled in the first wave and the per-block loops (which fetch the next
-// item ahead) take care of longer lists. SM_B200_RESIDENT_GRIDS=0 restores fixed 8 blocks/SM.
-struct ListGrids { int project, associate, merge, integrate, update_neighbors; };
-
-template <typename Kernel>
-int ResidentBlocks(Kernel kernel, int block, int sm_count, int fallback_per_sm) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) {
-    cudaGetLastError();
-    per_sm = fallback_per_sm;
-  }
-  return ScaleGrid(sm_count * per_sm);
-}
-
-const ListGrids& GetListGrids(int sm_count) {
-  static ListGrids grids = {0, 0, 0, 0, 0};
-  static int for_sm_count = -1;
-  if (for_sm_count != sm_count) {
-    const char* e = std::getenv("SM_B200_RESIDENT_GRIDS");
-    if (e && e[0] == '0') {
-      grids = {sm_count * 4, sm_count * 8, sm_count * 8, sm_count * 8, sm_count * 8};
-    } else {
-      grids.project = ResidentBlocks(k_project, kProjectBlock, sm_count, 2);
-      grids.associate = ResidentBlocks(k_associate, kBlock, sm_count, 8);
-      grids.merge = ResidentBlocks(k_merge, kBlock, sm_count, 4);
-      grids.integrate = ResidentBlocks(k_integrate, kBlock, sm_count, 3);
-      grids.update_neighbors = ResidentBlocks(k_update_neighbors, kBlock, sm_count, 3);
-    }
-    for_sm_count = sm_count;
-  }
-  return grids;
+namespace {
+int LaunchFrameKernel(cudaStream_t stream, FrameKernel which, const LaunchPlan& plan, const DeviceState& d,
+                      const FrameParams& f, bool dependent) {
+  KernelLaunch k;
+  const int status = DescribeFrameKernel(which, plan, d, f, &k);
+  if (status != SM_OK) return status;
+  LaunchOnStream(stream, k, dependent);
+  return SM_OK;
 }
 }  // namespace
 
@@ -1232,113 +1257,145 @@ int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d) {
 }
 
 int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams& f, bool do_blending,
-                   bool rasters_already_cleared, int sm_count, const IntegrateEvents* events) {
+                   bool rasters_already_cleared, const LaunchPlan& plan, const IntegrateEvents* events) {
   const bool timed = events && events->enabled;
   auto record = [&](int i) { if (timed) cudaEventRecord(events->ev[i], stream); };
-  const ListGrids& grids = GetListGrids(sm_count);
-  const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
-
+  int status = SM_OK;
+  auto launch = [&](FrameKernel which, bool dependent) {
+    if (status == SM_OK) status = LaunchFrameKernel(stream, which, plan, d, f, dependent);
+  };
   record(0);
   if (!rasters_already_cleared) {
-    const int status = ClearAssociationRasters(stream, d);
+    status = ClearAssociationRasters(stream, d);
     if (status != SM_OK) return status;
   }
-  { LaunchScope scope(stream, KID_PROJECT); LaunchKernel(k_project, dim3(grids.project), dim3(kProjectBlock), 0, stream, d, f); }
-  { LaunchScope scope(stream, KID_ASSOCIATE); LaunchDependent(k_associate, dim3(grids.associate), dim3(kBlock), 0, stream, d, f); }
+  launch(FK_PROJECT, false);
+  launch(FK_ASSOCIATE, true);
   record(1); record(2);
-  { LaunchScope scope(stream, KID_MERGE); LaunchKernel(k_merge, dim3(grids.merge), dim3(kBlock), 0, stream, d, f); }
+  launch(FK_MERGE, false);
   record(3); record(4);
-  if (do_blending) {
-    const int status = LaunchBlend(stream, d, f);
-    if (status != SM_OK) return status;
-  }
+  if (do_blending) launch(FK_BLEND, true);
   record(5); record(6);
-  { LaunchScope scope(stream, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(grids.integrate), dim3(kBlock), 0, stream, d, f); }
+  launch(FK_INTEGRATE, false);
   record(7); record(8);
-  { LaunchScope scope(stream, KID_UPDATE_NEIGHBORS); LaunchKernel(k_update_neighbors, dim3(grids.update_neighbors), dim3(kBlock), 0, stream, d, f); }
+  launch(FK_UPDATE_NEIGHBORS, false);
   record(9); record(10);
-  { LaunchScope scope(stream, KID_NEW_SURFEL_SCAN); LaunchKernel(k_new_surfel_scan, dim3(scan_tiles), dim3(kBlock), 0, stream, d, f); }
-  { LaunchScope scope(stream, KID_CREATE_SURFELS); LaunchKernel(k_create_surfels, dim3(sm_count * 2), dim3(kBlock), 0, stream, d, f); }
+  launch(FK_SCAN, false);
+  launch(FK_CREATE, false);
   record(11);
+  if (status != SM_OK) return status;
   return CheckLaunch("integrate");
 }
 
+// The multi-stream frame pipeline of round 1 (SM_B200_GRAPH=0; the frame graph of pipeline.cu
+// replaces it by default): every hand-over between streams is an event record + wait.
 int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, DeviceState& d, const FrameParams& f,
-                            bool do_blending, const RegularizeArgs& reg, int sm_count) {
-  const ListGrids& grids = GetListGrids(sm_count);
-  const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
+                            bool do_blending, const RegularizeArgs& reg, const LaunchPlan& plan) {
   cudaStream_t crit = pc->crit, side = pc->side;
+  int status = SM_OK;
+  auto launch = [&](cudaStream_t s, FrameKernel which, bool dependent) {
+    if (status == SM_OK) status = LaunchFrameKernel(s, which, plan, d, f, dependent);
+  };
   // front: project -> associate -> blend. Needs the surfels as the previous
   // frame's integration and creation left them.
-  if (pc->have_frame) cudaStreamWaitEvent(stream, pc->ev_create[set ^ 1], 0);
-  { LaunchScope scope(stream, KID_PROJECT); LaunchKernel(k_project, dim3(grids.project), dim3(kProjectBlock), 0, stream, d, f); }
-  { LaunchScope scope(stream, KID_ASSOCIATE); LaunchDependent(k_associate, dim3(grids.associate), dim3(kBlock), 0, stream, d, f); }
-  cudaEventRecord(pc->ev_assoc, stream);
+  if (pc->have_frame) SM_EV(cudaStreamWaitEvent(stream, pc->ev_create[set ^ 1], 0));
+  launch(stream, FK_PROJECT, false);
+  launch(stream, FK_ASSOCIATE, true);
+  SM_EV(cudaEventRecord(pc->ev_assoc, stream));
   // side: merge decisions (read the pre-blend depth copy) beside the blending
-  cudaStreamWaitEvent(side, pc->ev_assoc, 0);
-  { LaunchScope scope(side, KID_MERGE); LaunchKernel(k_merge, dim3(grids.merge), dim3(kBlock), 0, side, d, f); }
-  cudaEventRecord(pc->ev_merge, side);
-  if (do_blending) {
-    const int status = LaunchBlend(stream, d, f);
-    if (status != SM_OK) return status;
-  }
-  cudaEventRecord(pc->ev_blend, stream);
+  SM_EV(cudaStreamWaitEvent(side, pc->ev_assoc, 0));
+  launch(side, FK_MERGE, false);
+  SM_EV(cudaEventRecord(pc->ev_merge, side));
+  if (do_blending) launch(stream, FK_BLEND, true);
+  SM_EV(cudaEventRecord(pc->ev_blend, stream));
   // side: new-surfel flags + scan need the blended depth and the final association rasters
-  cudaStreamWaitEvent(side, pc->ev_blend, 0);
-  { LaunchScope scope(side, KID_NEW_SURFEL_SCAN); LaunchKernel(k_new_surfel_scan, dim3(scan_tiles), dim3(kBlock), 0, side, d, f); }
-  // crit (high priority): the cycle that bounds the frame rate, one stream, back to back:
+  SM_EV(cudaStreamWaitEvent(side, pc->ev_blend, 0));
+  launch(side, FK_SCAN, false);
+  // crit: the cycle that bounds the frame rate, one stream, back to back:
   //   [regularisation of the previous frame] -> integrate -> update_neighbors -> regularisation
   // (the integration rewrites what the previous regularisation reads, and this frame's
   // regularisation needs the neighbour links and the new surfels).
-  cudaStreamWaitEvent(crit, pc->ev_blend, 0);
-  cudaStreamWaitEvent(crit, pc->ev_merge, 0);
-  { LaunchScope scope(crit, KID_INTEGRATE); LaunchKernel(k_integrate, dim3(grids.integrate), dim3(kBlock), 0, crit, d, f); }
-  cudaEventRecord(pc->ev_integrate, crit);
-  { LaunchScope scope(crit, KID_UPDATE_NEIGHBORS); LaunchDependent(k_update_neighbors, dim3(grids.update_neighbors), dim3(kBlock), 0, crit, d, f); }
-  cudaEventRecord(pc->ev_update[set], crit);
+  SM_EV(cudaStreamWaitEvent(crit, pc->ev_blend, 0));
+  SM_EV(cudaStreamWaitEvent(crit, pc->ev_merge, 0));
+  launch(crit, FK_INTEGRATE, false);
+  SM_EV(cudaEventRecord(pc->ev_integrate, crit));
+  launch(crit, FK_UPDATE_NEIGHBORS, true);
+  SM_EV(cudaEventRecord(pc->ev_update[set], crit));
   // side: create the new surfels once the integration is through (kernels.cu order: after the
   // neighbour update, which does not touch the new slots)
-  cudaStreamWaitEvent(side, pc->ev_integrate, 0);
-  { LaunchScope scope(side, KID_CREATE_SURFELS); LaunchKernel(k_create_surfels, dim3(sm_count * 2), dim3(kBlock), 0, side, d, f); }
-  cudaEventRecord(pc->ev_create[set], side);
-  cudaStreamWaitEvent(crit, pc->ev_create[set], 0);
-  int status = CheckLaunch("integrate (pipelined)");
+  SM_EV(cudaStreamWaitEvent(side, pc->ev_integrate, 0));
+  launch(side, FK_CREATE, false);
+  SM_EV(cudaEventRecord(pc->ev_create[set], side));
+  SM_EV(cudaStreamWaitEvent(crit, pc->ev_create[set], 0));
   if (status != SM_OK) return status;
-  const int old_slot = f.parity, new_slot = f.parity ^ 1;
+  status = CheckLaunch("integrate (pipelined)");
+  if (status != SM_OK) return status;
+  const int old_slot = f.count_slot, new_slot = (f.count_slot + 1) % kCountSlots;
   if (reg.disable_denoising) {
     status = RegularizeSurfels(crit, d, true, f.frame_index, reg.radius_factor, reg.regularizer_weight, reg.window,
-                               new_slot, old_slot, sm_count);
+                               new_slot, old_slot, plan);
   } else {
     for (int i = 0; i < reg.iterations && status == SM_OK; ++i) {
       status = RegularizeSurfels(crit, d, false, f.frame_index, reg.radius_factor, reg.regularizer_weight, reg.window,
-                                 new_slot, i == 0 ? old_slot : -1, sm_count);
+                                 new_slot, i == 0 ? old_slot : -1, plan);
     }
   }
-  cudaEventRecord(pc->ev_reg, crit);
+  SM_EV(cudaEventRecord(pc->ev_reg, crit));
   pc->have_frame = true;
   return status;
 }
 
-int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm_count, float* position_buffer,
+int ExportVertices(cudaStream_t stream, const DeviceState& d, int count_slot, int sm_count, float* position_buffer,
                    u8* color_buffer) {
-  { LaunchScope scope(stream, KID_EXPORT_VERTICES); LaunchKernel(k_export_vertices, dim3(sm_count * 8), dim3(kBlock), 0, stream, d, parity, position_buffer, color_buffer); }
+  { LaunchScope scope(stream, KID_EXPORT_VERTICES); LaunchKernel(k_export_vertices, dim3(sm_count * 8), dim3(kBlock), 0, stream, d, count_slot, position_buffer, color_buffer); }
   return CheckLaunch("export vertices");
 }
 
-
-// One shared-memory carve-out for every kernel of the file (see sm_create in api.cu).
-void ConfigureIntegrateKernels(int carveout_percent) {
-  cudaFuncSetAttribute(k_clear, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_project, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_associate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_merge, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_blend, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_integrate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_update_neighbors, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_new_surfel_scan, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_create_surfels, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_export_vertices, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaGetLastError();
+// Per-device configuration of the kernels of this file for the CURRENT device (called by
+// sm_create for every handle: function attributes and occupancy are per device):
+//  - one shared-memory carve-out for all kernels (see sm_create in api.cu),
+//  - k_blend's dynamic shared memory limit,
+//  - grids of the list kernels = exactly the blocks that are resident at once (occupancy x SMs), so
+//    that every block is scheduled in the first wave and the per-block loops (which fetch the next
+//    item ahead) take care of longer lists. SM_B200_RESIDENT_GRIDS=0 restores fixed 8 blocks/SM.
+int ConfigureIntegrateKernels(int carveout_percent, LaunchPlan* plan) {
+  if (carveout_percent >= 0) {
+    cudaFuncSetAttribute(k_clear, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_project, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_associate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_merge, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_blend, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_integrate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_update_neighbors, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_new_surfel_scan, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_create_surfels, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_export_vertices, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaGetLastError();
+  }
+  if (cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBlendSmemLimit)) != cudaSuccess) {
+    return SetError(SM_ERR_CUDA, "cudaFuncSetAttribute(k_blend, MaxDynamicSharedMemorySize)");
+  }
+  const int sm_count = plan->sm_count;
+  const char* e = std::getenv("SM_B200_RESIDENT_GRIDS");
+  if (e && e[0] == '0') {
+    plan->project = sm_count * 4;
+    plan->associate = plan->merge = plan->integrate = plan->update_neighbors = sm_count * 8;
+    return SM_OK;
+  }
+  auto resident = [&](auto kernel, int block, int fallback_per_sm) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = fallback_per_sm;
+    }
+    return ScaleGrid(sm_count * per_sm);
+  };
+  plan->project = resident(k_project, kProjectBlock, 2);
+  plan->associate = resident(k_associate, kBlock, 8);
+  plan->merge = resident(k_merge, kBlock, 4);
+  plan->integrate = resident(k_integrate, kBlock, 3);
+  plan->update_neighbors = resident(k_update_neighbors, kBlock, 3);
+  return SM_OK;
 }
 
 }  // namespace smb

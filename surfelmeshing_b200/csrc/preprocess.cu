@@ -44,6 +44,7 @@ struct BilateralArgs {
   const u16* in;
   size_t in_pitch;
   unsigned long long* timeline;  // device timeline slot of this launch or null (diagnostics)
+  int skip;                      // placeholder launch of the frame graph: return at once
 };
 
 // Cooperative fill of a (TH + 2R) x (tile_w_pad) fp32 tile from a pitched u16 raster.
@@ -212,6 +213,7 @@ template <int R, bool kWithOutlier, bool kIgnoredTapsVanish>
 __global__ void __launch_bounds__(32 * kBilateralTileH, 2048 / (32 * kBilateralTileH))
 k_bilateral_outlier(BilateralArgs a, const __grid_constant__ OutlierArgs o, u16* out, size_t out_pitch) {
   pdl_prologue();
+  if (a.skip) return;
   const TimelineScope timeline_scope(a.timeline);
   constexpr int PADX = 8;
   constexpr int SW = kTileW + 2 * PADX;  // 48 floats per tile row
@@ -429,6 +431,7 @@ struct TailArgs {
   // Optional: association rasters to reset for the following Integrate().
   uint4* assoc; float* first_depth; u8* supported;
   unsigned long long* timeline;  // device timeline slot of this launch or null (diagnostics)
+  int skip;                      // placeholder launch of the frame graph: return at once
 };
 
 constexpr int kMaxErode = 3;
@@ -436,6 +439,7 @@ constexpr int kMaxErode = 3;
 __global__ void __launch_bounds__(256, 8)
 k_erode_normals_radii(TailArgs a) {
   pdl_prologue();
+  if (a.skip) return;
   const TimelineScope timeline_scope(a.timeline);
   // Tiles (origin relative to the 32 x 8 output tile): B (outlier-filtered input) -5, HV
   // (row-wise erosion validity) -2 / -(2 + r), E (eroded) -2, N (normals stage) -1.
@@ -613,6 +617,7 @@ BilateralArgs MakeBilateralArgs(float sigma_xy, float sigma_value_factor, u16 va
   a.width = width; a.height = height;
   a.in = in; a.in_pitch = in_pitch;
   a.timeline = nullptr;
+  a.skip = 0;
   return a;
 }
 
@@ -670,24 +675,32 @@ RadiiArgs MakeRadiiArgs(float point_radius_extension_factor, float point_radius_
 dim3 TileGrid(int width, int height) { return dim3((width + kTileW - 1) / kTileW, (height + kTileH - 1) / kTileH); }
 dim3 PixelGrid(int width, int height) { return dim3((width + 31) / 32, (height + 7) / 8); }
 
-int LaunchBilateral(cudaStream_t stream, const BilateralArgs& a, const OutlierArgs* o, u16* out, size_t out_pitch) {
+// The fused a1 + a2 launch (radius 6) as a descriptor.
+void DescribeBilateralOutlier(KernelLaunch* k, const BilateralArgs& a, const OutlierArgs* o, u16* out, size_t out_pitch) {
   static const OutlierArgs kNoOutlier = {};
+  const dim3 grid((a.width + kTileW - 1) / kTileW, (a.height + kBilateralTileH - 1) / kBilateralTileH);
+  const dim3 block(32 * kBilateralTileH);
+  // ignored samples get weight exp(-1 / (2 sigma^2) - ...): exactly 0 under ftz once 1 / (2 sigma^2) > 110
+  const bool vanish = a.value_to_ignore == 0 && a.sigma_value_factor > 0.f &&
+                      1.0f / (2.0f * a.sigma_value_factor * a.sigma_value_factor) > 110.0f;
+  const void* func;
+  if (o) func = vanish ? reinterpret_cast<const void*>(k_bilateral_outlier<6, true, true>)
+                       : reinterpret_cast<const void*>(k_bilateral_outlier<6, true, false>);
+  else func = vanish ? reinterpret_cast<const void*>(k_bilateral_outlier<6, false, true>)
+                     : reinterpret_cast<const void*>(k_bilateral_outlier<6, false, false>);
+  static_assert(sizeof(BilateralArgs) + sizeof(OutlierArgs) + 64 <= sizeof(k->storage), "KernelLaunch::storage too small");
+  k->Reset(func, grid, block, 0, KID_BILATERAL_OUTLIER);
+  k->Arg(a);
+  k->Arg(o ? *o : kNoOutlier);
+  k->Arg(out);
+  k->Arg(out_pitch);
+}
+
+int LaunchBilateral(cudaStream_t stream, const BilateralArgs& a, const OutlierArgs* o, u16* out, size_t out_pitch) {
   if (a.radius == 6) {
-    LaunchScope scope(stream, KID_BILATERAL_OUTLIER);
-    BilateralArgs timed = a;
-    timed.timeline = TimelineSlot(KID_BILATERAL_OUTLIER);
-    const dim3 grid((a.width + kTileW - 1) / kTileW, (a.height + kBilateralTileH - 1) / kBilateralTileH);
-    const dim3 block(32 * kBilateralTileH);
-    // ignored samples get weight exp(-1 / (2 sigma^2) - ...): exactly 0 under ftz once 1 / (2 sigma^2) > 110
-    const bool vanish = a.value_to_ignore == 0 && a.sigma_value_factor > 0.f &&
-                        1.0f / (2.0f * a.sigma_value_factor * a.sigma_value_factor) > 110.0f;
-    if (o) {
-      if (vanish) LaunchKernel(k_bilateral_outlier<6, true, true>, grid, block, 0, stream, timed, *o, out, out_pitch);
-      else LaunchKernel(k_bilateral_outlier<6, true, false>, grid, block, 0, stream, timed, *o, out, out_pitch);
-    } else {
-      if (vanish) LaunchKernel(k_bilateral_outlier<6, false, true>, grid, block, 0, stream, timed, kNoOutlier, out, out_pitch);
-      else LaunchKernel(k_bilateral_outlier<6, false, false>, grid, block, 0, stream, timed, kNoOutlier, out, out_pitch);
-    }
+    KernelLaunch k;
+    DescribeBilateralOutlier(&k, a, o, out, out_pitch);
+    LaunchOnStream(stream, k, false);
   } else {
     if (a.radius < 0) return SetError(SM_ERR_INVALID_ARGUMENT, "negative bilateral radius");
     { LaunchScope scope(stream, KID_BILATERAL_GENERIC); LaunchKernel(k_bilateral_generic, PixelGrid(a.width, a.height), dim3(256), 0, stream, a, out, out_pitch); }
@@ -702,42 +715,99 @@ int LaunchBilateral(cudaStream_t stream, const BilateralArgs& a, const OutlierAr
 
 // ---- entry points used by api.cu ----------------------------------------------------------
 
+namespace {
+// Arguments of the two fused launches for one frame (APP/main.cc:1015-1191).
+int MakePreprocessArgs(const sm_preprocess_params& p, int width, int height, float fx, float fy, float cx, float cy,
+                       const u16* raw, size_t raw_pitch, const u16* const* other_depths, const size_t* other_pitches,
+                       const float* others_TR_reference, u16* scratch_B, size_t scratch_B_pitch, u16* out_depth,
+                       size_t out_depth_pitch, float2* out_normals, size_t out_normals_pitch, float* out_radius,
+                       size_t out_radius_pitch, uint4* clear_assoc, float* clear_first_depth, u8* clear_supported,
+                       u16* out_depth_copy, size_t out_depth_copy_pitch, BilateralArgs* b, OutlierArgs* o, TailArgs* t) {
+  if (p.depth_erosion_radius < 0 || p.depth_erosion_radius > kMaxErode) {
+    return SetError(SM_ERR_INVALID_ARGUMENT, "depth_erosion_radius must be in [0, 3]");
+  }
+  *b = MakeBilateralArgs(p.bilateral_filter_sigma_xy, p.bilateral_filter_sigma_depth_factor, 0,
+                         p.bilateral_filter_radius_factor,
+                         static_cast<u16>(p.depth_scaling * p.max_depth),  // main.cc:1021
+                         p.depth_valid_region_radius, width, height, raw, raw_pitch);
+  const int status = MakeOutlierArgs(o, p.outlier_filtering_frame_count, p.outlier_filtering_required_inliers,
+                                     p.outlier_filtering_depth_tolerance_factor, fx, fy, cx, cy, width, height,
+                                     other_depths, other_pitches, others_TR_reference);
+  if (status != SM_OK) return status;
+  t->width = width; t->height = height;
+  t->erosion_radius = p.depth_erosion_radius;
+  t->normals = MakeNormalsArgs(p.observation_angle_threshold_deg, p.depth_scaling, fx, fy, cx, cy);
+  t->radii = MakeRadiiArgs(p.point_radius_extension_factor, p.point_radius_clamp_factor, p.depth_scaling, fx, fy, cx, cy);
+  t->in = scratch_B; t->in_pitch = scratch_B_pitch;
+  t->out_depth = out_depth; t->out_depth_pitch = out_depth_pitch;
+  t->out_depth_copy = out_depth_copy; t->out_depth_copy_pitch = out_depth_copy_pitch;
+  t->out_normals = out_normals; t->out_normals_pitch = out_normals_pitch;
+  t->out_radius = out_radius; t->out_radius_pitch = out_radius_pitch;
+  t->assoc = clear_assoc; t->first_depth = clear_first_depth; t->supported = clear_supported;
+  t->timeline = nullptr;
+  t->skip = 0;
+  return SM_OK;
+}
+
+void DescribeTail(KernelLaunch* k, const TailArgs& t) {
+  static_assert(sizeof(TailArgs) + 16 <= sizeof(k->storage), "KernelLaunch::storage too small");
+  k->Reset(reinterpret_cast<const void*>(k_erode_normals_radii), TileGrid(t.width, t.height), dim3(256), 0,
+           KID_ERODE_NORMALS_RADII);
+  k->Arg(t);
+}
+}  // namespace
+
 int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int width, int height, float fx, float fy,
                     float cx, float cy, const u16* raw, size_t raw_pitch, const u16* const* other_depths,
                     const size_t* other_pitches, const float* others_TR_reference, u16* scratch_B,
                     size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch, float2* out_normals,
                     size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
                     float* clear_first_depth, u8* clear_supported, u16* out_depth_copy,
-                    size_t out_depth_copy_pitch) {
-  if (p.depth_erosion_radius < 0 || p.depth_erosion_radius > kMaxErode) {
-    return SetError(SM_ERR_INVALID_ARGUMENT, "depth_erosion_radius must be in [0, 3]");
-  }
-  const BilateralArgs b = MakeBilateralArgs(p.bilateral_filter_sigma_xy, p.bilateral_filter_sigma_depth_factor, 0,
-                                            p.bilateral_filter_radius_factor,
-                                            static_cast<u16>(p.depth_scaling * p.max_depth),  // main.cc:1021
-                                            p.depth_valid_region_radius, width, height, raw, raw_pitch);
+                    size_t out_depth_copy_pitch, unsigned long long* timeline_bilateral,
+                    unsigned long long* timeline_tail) {
+  BilateralArgs b;
   OutlierArgs o;
-  int status = MakeOutlierArgs(&o, p.outlier_filtering_frame_count, p.outlier_filtering_required_inliers,
-                               p.outlier_filtering_depth_tolerance_factor, fx, fy, cx, cy, width, height,
-                               other_depths, other_pitches, others_TR_reference);
+  TailArgs t;
+  int status = MakePreprocessArgs(p, width, height, fx, fy, cx, cy, raw, raw_pitch, other_depths, other_pitches,
+                                  others_TR_reference, scratch_B, scratch_B_pitch, out_depth, out_depth_pitch,
+                                  out_normals, out_normals_pitch, out_radius, out_radius_pitch, clear_assoc,
+                                  clear_first_depth, clear_supported, out_depth_copy, out_depth_copy_pitch, &b, &o, &t);
   if (status != SM_OK) return status;
+  b.timeline = timeline_bilateral;
+  t.timeline = timeline_tail;
   status = LaunchBilateral(stream, b, &o, scratch_B, scratch_B_pitch);
   if (status != SM_OK) return status;
-
-  TailArgs t;
-  t.width = width; t.height = height;
-  t.erosion_radius = p.depth_erosion_radius;
-  t.normals = MakeNormalsArgs(p.observation_angle_threshold_deg, p.depth_scaling, fx, fy, cx, cy);
-  t.radii = MakeRadiiArgs(p.point_radius_extension_factor, p.point_radius_clamp_factor, p.depth_scaling, fx, fy, cx, cy);
-  t.in = scratch_B; t.in_pitch = scratch_B_pitch;
-  t.out_depth = out_depth; t.out_depth_pitch = out_depth_pitch;
-  t.out_depth_copy = out_depth_copy; t.out_depth_copy_pitch = out_depth_copy_pitch;
-  t.out_normals = out_normals; t.out_normals_pitch = out_normals_pitch;
-  t.out_radius = out_radius; t.out_radius_pitch = out_radius_pitch;
-  t.assoc = clear_assoc; t.first_depth = clear_first_depth; t.supported = clear_supported;
-  t.timeline = TimelineSlot(KID_ERODE_NORMALS_RADII);
-  { LaunchScope scope(stream, KID_ERODE_NORMALS_RADII); LaunchDependent(k_erode_normals_radii, TileGrid(width, height), dim3(256), 0, stream, t); }
+  KernelLaunch k;
+  DescribeTail(&k, t);
+  LaunchOnStream(stream, k, true);
   return CheckLaunch("erode/normals/radii");
+}
+
+int DescribePreprocess(KernelLaunch* bilateral, KernelLaunch* tail, bool skip, const sm_preprocess_params& p, int width,
+                       int height, float fx, float fy, float cx, float cy, const u16* raw, size_t raw_pitch,
+                       const u16* const* other_depths, const size_t* other_pitches, const float* others_TR_reference,
+                       u16* scratch_B, size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch,
+                       float2* out_normals, size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch,
+                       uint4* clear_assoc, float* clear_first_depth, u8* clear_supported, u16* out_depth_copy,
+                       size_t out_depth_copy_pitch, unsigned long long* timeline_bilateral,
+                       unsigned long long* timeline_tail) {
+  BilateralArgs b;
+  OutlierArgs o;
+  TailArgs t;
+  const int status = MakePreprocessArgs(p, width, height, fx, fy, cx, cy, raw, raw_pitch, other_depths, other_pitches,
+                                        others_TR_reference, scratch_B, scratch_B_pitch, out_depth, out_depth_pitch,
+                                        out_normals, out_normals_pitch, out_radius, out_radius_pitch, clear_assoc,
+                                        clear_first_depth, clear_supported, out_depth_copy, out_depth_copy_pitch, &b,
+                                        &o, &t);
+  if (status != SM_OK) return status;
+  if (b.radius != 6) return SetError(SM_ERR_INVALID_ARGUMENT, "the frame graph needs the fused bilateral kernel (radius 6)");
+  b.timeline = timeline_bilateral;
+  t.timeline = timeline_tail;
+  b.skip = skip ? 1 : 0;
+  t.skip = skip ? 1 : 0;
+  DescribeBilateralOutlier(bilateral, b, &o, scratch_B, scratch_B_pitch);
+  DescribeTail(tail, t);
+  return SM_OK;
 }
 
 int StageBilateral(cudaStream_t stream, float sigma_xy, float sigma_value_factor, u16 value_to_ignore,
@@ -787,7 +857,8 @@ int StageRadii(cudaStream_t stream, float point_radius_extension_factor, float p
 
 
 // One shared-memory carve-out for every kernel of the file (see sm_create in api.cu).
-void ConfigurePreprocessKernels(int carveout_percent) {
+int ConfigurePreprocessKernels(int carveout_percent) {
+  if (carveout_percent < 0) return SM_OK;
   cudaFuncSetAttribute(k_bilateral_outlier<6, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_bilateral_outlier<6, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_bilateral_outlier<6, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
@@ -799,6 +870,7 @@ void ConfigurePreprocessKernels(int carveout_percent) {
   cudaFuncSetAttribute(k_normals, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_radii, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaGetLastError();
+  return SM_OK;
 }
 
 }  // namespace smb

@@ -37,6 +37,7 @@ struct RegParams {
   float regularizer_weight;
   int count_slot;
   int remove_below_slot;      // -1: no detach-flag pass
+  int skip;                   // placeholder launch of the frame graph: return at once
 };
 
 // `stamp < frame_index - window` evaluated like the reference: the subtraction in u32, the
@@ -47,6 +48,7 @@ __device__ __forceinline__ bool outside_window(u32 stamp, const RegParams& p) {
 
 __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegParams p) {
   pdl_prologue();
+  if (p.skip) return;
   const TimelineScope timeline_scope(d, p.frame_index, KID_REG_ACCUMULATE);
   const u32 n = d.counters->surfel_count[p.count_slot];
   const u32 n_remove = p.remove_below_slot >= 0 ? d.counters->surfel_count[p.remove_below_slot] : 0u;
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
 
 __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p) {
   pdl_prologue();
+  if (p.skip) return;
   const TimelineScope timeline_scope(d, p.frame_index, KID_REG_STEP);
   const u32 n = d.counters->surfel_count[p.count_slot];
   // Stamp and neighbour links (first level of the gather chain) are requested one round ahead.
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p)
 // RegularizeSurfelsCUDACopyOnlyKernel (kernels.cu:2310-2327) [+ detach-flag pass].
 __global__ void __launch_bounds__(kBlock) k_reg_copy_only(DeviceState d, RegParams p) {
   pdl_prologue();
+  if (p.skip) return;
   const TimelineScope timeline_scope(d, p.frame_index, KID_REG_COPY_ONLY);
   const u32 n = d.counters->surfel_count[p.count_slot];
   const u32 n_remove = p.remove_below_slot >= 0 ? d.counters->surfel_count[p.remove_below_slot] : 0u;
@@ -227,10 +231,10 @@ __global__ void __launch_bounds__(kBlock) k_reg_copy_only(DeviceState d, RegPara
 
 }  // namespace
 
-int RegularizeSurfels(cudaStream_t stream, DeviceState& d, bool disable_denoising, u32 frame_index,
-                      float radius_factor_for_regularization_neighbors, float regularizer_weight,
-                      int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot,
-                      int sm_count) {
+int DescribeRegularize(KernelLaunch* first, KernelLaunch* second, bool skip, const LaunchPlan& plan,
+                       const DeviceState& d, bool disable_denoising, u32 frame_index,
+                       float radius_factor_for_regularization_neighbors, float regularizer_weight,
+                       int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot) {
   RegParams p;
   p.frame_index = frame_index;
   p.window = regularization_frame_window_size;
@@ -239,29 +243,34 @@ int RegularizeSurfels(cudaStream_t stream, DeviceState& d, bool disable_denoisin
   p.regularizer_weight = regularizer_weight;
   p.count_slot = count_slot;
   p.remove_below_slot = remove_replaced_below_slot;
-  // Grids = the blocks resident at once (see GetListGrids in integrate.cu).
-  static int grid_accumulate = 0, grid_step = 0, grid_copy = 0, grids_for = -1;
-  if (grids_for != sm_count) {
-    const char* e = std::getenv("SM_B200_RESIDENT_GRIDS");
-    auto resident = [&](auto kernel) {
-      int per_sm = 0;
-      if ((e && e[0] == '0') || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm < 1) {
-        cudaGetLastError();
-        per_sm = 8;
-      }
-      return ScaleGrid(sm_count * per_sm);
-    };
-    grid_accumulate = resident(k_reg_accumulate);
-    grid_step = resident(k_reg_step);
-    grid_copy = resident(k_reg_copy_only);
-    grids_for = sm_count;
-  }
+  p.skip = skip ? 1 : 0;
+  static_assert(sizeof(DeviceState) + sizeof(RegParams) + 32 <= sizeof(first->storage), "KernelLaunch::storage too small");
   if (disable_denoising) {
-    { LaunchScope scope(stream, KID_REG_COPY_ONLY); LaunchKernel(k_reg_copy_only, dim3(grid_copy), dim3(kBlock), 0, stream, d, p); }
-    return CheckLaunch("regularize (copy only)");
+    first->Reset(reinterpret_cast<const void*>(k_reg_copy_only), dim3(plan.reg_copy), dim3(kBlock), 0, KID_REG_COPY_ONLY);
+    first->Arg(d);
+    first->Arg(p);
+    return 1;
   }
-  { LaunchScope scope(stream, KID_REG_ACCUMULATE); LaunchKernel(k_reg_accumulate, dim3(grid_accumulate), dim3(kBlock), 0, stream, d, p); }
-  { LaunchScope scope(stream, KID_REG_STEP); LaunchDependent(k_reg_step, dim3(grid_step), dim3(kBlock), 0, stream, d, p); }
+  first->Reset(reinterpret_cast<const void*>(k_reg_accumulate), dim3(plan.reg_accumulate), dim3(kBlock), 0, KID_REG_ACCUMULATE);
+  first->Arg(d);
+  first->Arg(p);
+  second->Reset(reinterpret_cast<const void*>(k_reg_step), dim3(plan.reg_step), dim3(kBlock), 0, KID_REG_STEP);
+  second->Arg(d);
+  second->Arg(p);
+  return 2;
+}
+
+int RegularizeSurfels(cudaStream_t stream, DeviceState& d, bool disable_denoising, u32 frame_index,
+                      float radius_factor_for_regularization_neighbors, float regularizer_weight,
+                      int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot,
+                      const LaunchPlan& plan) {
+  KernelLaunch first, second;
+  const int n = DescribeRegularize(&first, &second, false, plan, d, disable_denoising, frame_index,
+                                   radius_factor_for_regularization_neighbors, regularizer_weight,
+                                   regularization_frame_window_size, count_slot, remove_replaced_below_slot);
+  LaunchOnStream(stream, first, false);
+  if (n == 1) return CheckLaunch("regularize (copy only)");
+  LaunchOnStream(stream, second, true);
   // k_reg_step wrote every slot of the other smooth buffer: it is the current one from here on
   float* const filled = d.smooth_next;
   d.smooth_next = d.smooth;
@@ -269,13 +278,28 @@ int RegularizeSurfels(cudaStream_t stream, DeviceState& d, bool disable_denoisin
   return CheckLaunch("regularize");
 }
 
-
-// One shared-memory carve-out for every kernel of the file (see sm_create in api.cu).
-void ConfigureRegularizeKernels(int carveout_percent) {
-  cudaFuncSetAttribute(k_reg_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_reg_step, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_reg_copy_only, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaGetLastError();
+// Per-device configuration: one shared-memory carve-out for every kernel of the file (see
+// sm_create in api.cu) and grids = the blocks resident at once (see ConfigureIntegrateKernels).
+int ConfigureRegularizeKernels(int carveout_percent, LaunchPlan* plan) {
+  if (carveout_percent >= 0) {
+    cudaFuncSetAttribute(k_reg_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_reg_step, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaFuncSetAttribute(k_reg_copy_only, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    cudaGetLastError();
+  }
+  const char* e = std::getenv("SM_B200_RESIDENT_GRIDS");
+  auto resident = [&](auto kernel) {
+    int per_sm = 0;
+    if ((e && e[0] == '0') || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 8;
+    }
+    return ScaleGrid(plan->sm_count * per_sm);
+  };
+  plan->reg_accumulate = resident(k_reg_accumulate);
+  plan->reg_step = resident(k_reg_step);
+  plan->reg_copy = resident(k_reg_copy_only);
+  return SM_OK;
 }
 
 }  // namespace smb

@@ -1,0 +1,99 @@
+// sm_handle.cuh — the handle behind the C ABI (struct sm_reconstruction), shared by api.cu
+// (entry points) and pipeline.cu (the RGB-D stream runner and its frame graph).
+#pragma once
+
+#include <vector>
+
+#include "sm_kernels.cuh"
+
+namespace smb {
+
+constexpr int kSets = 3;  // buffer sets of the frame pipeline: frames f, f + 1, f + 2 are in flight
+
+// Supporting-surfel tie-break configuration (sm_configure "tiebreak_*"; TieBreak in sm_kernels.cuh
+// holds the per-frame values derived from it).
+struct TieBreakConfig {
+  u32 wave;              // slots per launch wave of the modelled race (0: plain "primary, then lowest index")
+  double early_fraction; // fraction of secondary associations that compete like primary ones
+  u32 mul, mul_inv;      // derived from wave
+};
+// Defaults (DESIGN.md section 4 has the measurements that picked them).
+constexpr u32 kDefaultTieBreakWave = 0;
+constexpr double kDefaultTieBreakEarlyFraction = 0.0;
+TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index);
+int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity);
+
+struct FrameGraph;  // pipeline.cu
+void DestroyFrameGraph(FrameGraph* g);
+
+}  // namespace smb
+
+struct sm_reconstruction {
+  smb::DeviceState d{};
+  int device = 0;
+  int sm_count = 0;
+  smb::LaunchPlan plan{};
+  float fx = 0, fy = 0, cx = 0, cy = 0;
+  int count_slot = 0;             // Counters::surfel_count slot holding the current count
+  bool rasters_cleared = false;   // the fused pre-processing tail already reset the rasters
+  smb::IntegrateEvents events{};
+  smb::TieBreakConfig tiebreak{};
+  smb::TieBreak last_tiebreak{};  // of the most recent frame (decodes the supporting raster, sm_download_rasters)
+  // host mirror of the counters (pinned) for on-demand queries
+  smb::Counters* host_counters = nullptr;
+  // Stream of the most recently submitted work: the count queries, which have no stream argument,
+  // synchronise with it (work on a non-blocking stream is not ordered with the NULL stream).
+  cudaStream_t last_stream = nullptr;
+  // pre-processing scratch (APP/main.cc filtered_depth_buffer_B)
+  smb::u16* scratch_B = nullptr; size_t scratch_B_pitch = 0;
+  // sm_integrate: snapshot of the depth before the measurement blending (k_blend reads the snapshot and
+  // writes the caller's buffer: see the kernel)
+  smb::u16* blend_src = nullptr; size_t blend_src_pitch = 0;
+  // Association rasters / lists per buffer set: the pre-processing tail of a later frame resets one set
+  // while Integrate() of an earlier frame still works on another (sm_stream_run).
+  smb::PixelAssoc* assoc_set[smb::kSets] = {};
+  float* first_depth_set[smb::kSets] = {};
+  smb::u8* supported_set[smb::kSets] = {};
+  smb::VisEntry* vis_set[smb::kSets] = {};
+  smb::u32* seg_count_set[smb::kSets] = {};
+  smb::u8* merge_flag_set[smb::kSets] = {};
+  // stream-runner buffers (pre-processing outputs per buffer set)
+  smb::u16* run_depth[smb::kSets] = {}; size_t run_depth_pitch = 0;
+  float2* run_normals[smb::kSets] = {}; size_t run_normals_pitch = 0;
+  float* run_radius[smb::kSets] = {}; size_t run_radius_pitch = 0;
+  smb::u16* run_depth_pre[smb::kSets] = {};   // pre-blend copy of run_depth (merge runs next to blend)
+  float* smooth_alt = nullptr;    // second smooth-position buffer (DeviceState::smooth / smooth_next)
+  // multi-stream pipeline of round 1 (SM_B200_GRAPH=0)
+  smb::PipelineCtx pipe{};
+  cudaStream_t pre_stream = nullptr;
+  cudaEvent_t pre_done[2] = {nullptr, nullptr}, int_done[2] = {nullptr, nullptr}, entry_event = nullptr;
+  // host-resident streams: raw-depth / colour rings filled by the upload stream
+  std::vector<smb::u16*> ring_depth; size_t ring_depth_pitch = 0;
+  std::vector<uchar3*> ring_color; size_t ring_color_pitch = 0;
+  cudaStream_t upload_stream = nullptr;
+  cudaEvent_t upload_done = nullptr;
+  std::vector<cudaEvent_t> iteration_done;   // frame graph: one event per iteration slot (ring reuse)
+  // frame graph (pipeline.cu)
+  cudaStream_t graph_stream = nullptr;
+  cudaEvent_t graph_exit = nullptr;
+  smb::FrameGraph* graph = nullptr;
+};
+
+namespace smb {
+// api.cu
+int FetchCounters(sm_reconstruction* r, cudaStream_t stream);
+FrameParams MakeFrameParams(const sm_reconstruction* r, u32 frame_index, int count_slot, const sm_integrate_params& p,
+                            u16* depth, size_t depth_pitch, const u16* depth_pre, size_t depth_pre_pitch,
+                            const float* normals, size_t normals_pitch, const float* radius, size_t radius_pitch,
+                            const uint8_t* color, size_t color_pitch, const float* global_T_local,
+                            const float* local_T_global);
+int IntegrateImpl(sm_reconstruction* r, cudaStream_t stream, u32 frame_index, const sm_integrate_params& p, u16* depth,
+                  size_t depth_pitch, const float* normals, size_t normals_pitch, const float* radius,
+                  size_t radius_pitch, const uint8_t* color, size_t color_pitch, const float* global_T_local,
+                  const float* local_T_global);
+void CountLaunches(unsigned long long n);
+unsigned long long LaunchCount();
+// pipeline.cu
+int StreamRun(sm_reconstruction* r, cudaStream_t stream, const sm_stream_desc* s, const sm_preprocess_params* pp,
+              const sm_integrate_params* ip, int first_frame, int last_frame, sm_stream_stats* stats);
+}  // namespace smb

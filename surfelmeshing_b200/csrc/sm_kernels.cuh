@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/surfel_b200.h"
 #include "sm_math.cuh"
@@ -50,11 +51,44 @@ constexpr u32 kInvalidIndex = 0xFFFFFFFFu;   // APP/surfel.h:63, kernels.cu:74
 constexpr int kSegment = 1024;               // surfel slots per list segment (one block-iteration)
 constexpr u32 kActiveBit = 0x80000000u;      // VisEntry.idx: surfel was active at projection time
 
-// PixelAssoc.x while a frame is processed: supporting surfel index, with this bit set when the
-// association came through the surfel's secondary pixel (orders primary before secondary).
+// PixelAssoc.x while a frame is processed: the arrival key of the winning association. The
+// reference lets the first atomicCAS win (kernels.cu:1688): which of several supporters of a
+// pixel becomes its supporting surfel is a race. The product takes the minimum of a key that
+// orders the associations the way the reference's race does ON AVERAGE and is reproducible:
+//   bit 31      "late": set for most secondary-pixel associations (a reference thread handles its
+//               primary pixel first, so primaries usually arrive first) - all but a pseudo-random
+//               fraction tb.early_fraction of them, which compete like primaries;
+//   bits 0..30  wave * W + perm(slot mod W): slots are grouped into launch waves of W slots (the
+//               reference's 1024-thread blocks are scheduled in slot order, a later wave always
+//               arrives later); inside a wave the order is a per-frame pseudo-random permutation.
+// W = 0 selects the plain rule of round 1 (late = secondary, then lowest slot index).
+// DESIGN.md section 4 has the measurements behind the parameters.
 constexpr u32 kSecondaryBit = 0x80000000u;
-__host__ __device__ __forceinline__ u32 supporting_index(u32 key) {
-  return key == kInvalidIndex ? kInvalidIndex : (key & ~kSecondaryBit);
+struct TieBreak {
+  u32 wave;            // W: slots per wave (0: plain rule)
+  u32 mul, mul_inv;    // perm(r) = (r * mul + add) mod W, mul * mul_inv = 1 (mod W)
+  u32 add;             // per frame
+  u32 salt;            // per frame, for the "late" draw
+  u32 early_threshold; // secondary association is NOT late iff hash(slot, salt) < early_threshold
+};
+__host__ __device__ __forceinline__ u32 tb_hash(u32 x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ u32 tb_encode(const TieBreak& t, u32 idx, bool secondary) {
+  if (t.wave == 0) return idx | (secondary ? kSecondaryBit : 0u);
+  const u32 w = idx / t.wave, r = idx - w * t.wave;
+  const u32 rp = static_cast<u32>((static_cast<u64>(r) * t.mul + t.add) % t.wave);
+  const bool late = secondary && !(tb_hash(idx ^ t.salt) < t.early_threshold);
+  return (w * t.wave + rp) | (late ? kSecondaryBit : 0u);
+}
+__host__ __device__ __forceinline__ u32 supporting_index(const TieBreak& t, u32 key) {
+  if (key == kInvalidIndex) return kInvalidIndex;
+  const u32 v = key & ~kSecondaryBit;
+  if (t.wave == 0) return v;
+  const u32 w = v / t.wave, rp = v - w * t.wave;
+  const u32 r = static_cast<u32>((static_cast<u64>(rp + t.wave - t.add) % t.wave) * t.mul_inv % t.wave);
+  return w * t.wave + r;
 }
 
 // Per-pixel association record (the reference keeps four separate rasters,
@@ -69,13 +103,18 @@ typedef uint4 PixelAssoc;
 // is deterministic.
 typedef uint4 VisEntry;
 
+// surfel_count is a 3-slot history: frame f reads slot s (count before the frame), its scan
+// writes slot (s + 1) % 3 (count after the frame) and its regularisation reads both. In the frame
+// pipeline the scan of frame f + 1 (slot (s + 2) % 3) may run while the regularisation of frame f
+// is still reading, which is why two slots are not enough.
+constexpr int kCountSlots = 3;
 struct Counters {
-  u32 surfel_count[2];   // entries in use; [parity] is current, the scan of frame f writes [parity ^ 1]
+  u32 surfel_count[kCountSlots];
   u32 merge_count;
   u32 new_surfel_count;  // of the last frame
   u32 capacity_overflow; // sticky: a frame wanted more surfels than the cap (creation skipped)
   u32 scan_ticket;       // dynamic tile ids of the new-surfel scan
-  u32 pad[2];
+  u32 pad;
 };
 
 struct DeviceState {
@@ -112,7 +151,9 @@ struct DeviceState {
 
 struct FrameParams {
   u32 frame_index;
-  int parity;            // which Counters::surfel_count slot is current
+  int count_slot;        // Counters::surfel_count slot holding the count before this frame
+  int skip;              // != 0: the launch is a placeholder of the frame graph, the kernel returns at once
+  TieBreak tb;           // supporting-surfel tie-break (see kSecondaryBit)
   int active_window;     // surfel_integration_active_window_size
   float fx, fy, cx, cy;
   float fx_inv, fy_inv, cx_inv, cy_inv;  // pixel-centre unprojection, kernels.cc:68-74
@@ -168,9 +209,10 @@ struct TimelineScope {
     if (slot && threadIdx.x == 0) atomicMax(slot + 1, globaltimer_ns());
   }
 };
-// Host side: slot of (frame announced by SetTimelineFrame, kernel id) for kernels without DeviceState.
-void SetTimelineFrame(u32 frame);
-unsigned long long* TimelineSlot(int kernel_id);
+// Host side: slot of (frame, kernel id) for kernels that do not take a DeviceState.
+inline unsigned long long* TimelineSlot(const DeviceState& d, u32 frame, int kernel_id) {
+  return d.timeline ? d.timeline + (static_cast<size_t>(frame % d.timeline_frames) * KID_COUNT + kernel_id) * 2 : nullptr;
+}
 
 // SM_B200_PDL: 0 = never, 1 (default) = only launches marked as dependents (LaunchDependent: the
 // kernel follows its producer on the same stream), 2 = every launch. Marking everything costs
@@ -207,9 +249,47 @@ inline void LaunchDependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   LaunchKernelImpl(true, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
-void ConfigurePreprocessKernels(int carveout_percent);
-void ConfigureIntegrateKernels(int carveout_percent);
-void ConfigureRegularizeKernels(int carveout_percent);
+// One kernel launch with its by-value arguments packed into `storage`: what a stream launch and
+// a kernel node of the frame graph (pipeline.cu) are both made from. The translation unit that
+// owns a kernel fills the descriptor (Describe* functions below), so kernels and their argument
+// structs stay file-local.
+struct KernelLaunch {
+  const void* func;
+  dim3 grid, block;
+  size_t smem;
+  int kernel_id;                 // KernelId
+  int arg_count;
+  void* args[4];                 // point into storage
+  alignas(16) unsigned char storage[2304];
+  size_t used;
+  void Reset(const void* f, dim3 g, dim3 b, size_t shared, int id) {
+    func = f; grid = g; block = b; smem = shared; kernel_id = id; arg_count = 0; used = 0;
+  }
+  template <typename T>
+  void Arg(const T& v) {
+    used = (used + alignof(T) - 1) / alignof(T) * alignof(T);
+    static_assert(alignof(T) <= 16, "argument alignment");
+    memcpy(storage + used, &v, sizeof(T));   // used + sizeof(T) <= sizeof(storage): checked by the static_asserts at the call sites
+    args[arg_count++] = storage + used;
+    used += sizeof(T);
+  }
+};
+// Launches a described kernel on a stream (counts it, profiles it like LaunchKernel).
+void LaunchOnStream(cudaStream_t stream, const KernelLaunch& k, bool dependent);
+
+// Grid sizes of the list / sweep kernels: exactly the blocks that are resident at once
+// (occupancy x SMs) so that every block is scheduled in the first wave. Occupancy and function
+// attributes are per device, so the plan lives in the handle (sm_create), not in statics.
+struct LaunchPlan {
+  int sm_count;
+  int project, associate, merge, integrate, update_neighbors;
+  int reg_accumulate, reg_step, reg_copy;
+};
+// Per-device kernel configuration of the current device: shared-memory carve-out (percent, < 0:
+// driver default), k_blend's dynamic shared memory limit, the resident grids.
+int ConfigurePreprocessKernels(int carveout_percent);
+int ConfigureIntegrateKernels(int carveout_percent, LaunchPlan* plan);
+int ConfigureRegularizeKernels(int carveout_percent, LaunchPlan* plan);
 
 // ---- preprocess.cu --------------------------------------------------------------------------
 int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int width, int height, float fx, float fy,
@@ -218,7 +298,17 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
                     size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch, float2* out_normals,
                     size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
                     float* clear_first_depth, u8* clear_supported, u16* out_depth_copy = nullptr,
-                    size_t out_depth_copy_pitch = 0);
+                    size_t out_depth_copy_pitch = 0, unsigned long long* timeline_bilateral = nullptr,
+                    unsigned long long* timeline_tail = nullptr);
+// The same two launches as descriptors (frame graph). `skip`: placeholder launches.
+int DescribePreprocess(KernelLaunch* bilateral, KernelLaunch* tail, bool skip, const sm_preprocess_params& p, int width,
+                       int height, float fx, float fy, float cx, float cy, const u16* raw, size_t raw_pitch,
+                       const u16* const* other_depths, const size_t* other_pitches, const float* others_TR_reference,
+                       u16* scratch_B, size_t scratch_B_pitch, u16* out_depth, size_t out_depth_pitch,
+                       float2* out_normals, size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch,
+                       uint4* clear_assoc, float* clear_first_depth, u8* clear_supported, u16* out_depth_copy,
+                       size_t out_depth_copy_pitch, unsigned long long* timeline_bilateral,
+                       unsigned long long* timeline_tail);
 int StageBilateral(cudaStream_t stream, float sigma_xy, float sigma_value_factor, u16 value_to_ignore,
                    float radius_factor, u16 max_depth, float depth_valid_region_radius, int width, int height,
                    const u16* in, size_t in_pitch, u16* out, size_t out_pitch);
@@ -241,7 +331,11 @@ struct IntegrateEvents {
   bool enabled;
 };
 int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams& f, bool do_blending,
-                   bool rasters_already_cleared, int sm_count, const IntegrateEvents* events);
+                   bool rasters_already_cleared, const LaunchPlan& plan, const IntegrateEvents* events);
+// Kernels of one Integrate() as descriptors (stream launches and frame-graph nodes).
+enum FrameKernel { FK_PROJECT = 0, FK_ASSOCIATE, FK_MERGE, FK_BLEND, FK_INTEGRATE, FK_UPDATE_NEIGHBORS, FK_SCAN, FK_CREATE, FK_COUNT };
+int DescribeFrameKernel(FrameKernel which, const LaunchPlan& plan, const DeviceState& d, const FrameParams& f,
+                        KernelLaunch* out);
 int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d);
 
 // Streams / events of the frame pipeline used by sm_stream_run. The kernels of one frame form a
@@ -270,8 +364,8 @@ struct RegularizeArgs {
 };
 // One frame through the DAG, including its regularisation. `set`: frame parity (buffer set).
 int IntegrateFramePipelined(cudaStream_t stream, PipelineCtx* pc, int set, DeviceState& d, const FrameParams& f,
-                            bool do_blending, const RegularizeArgs& reg, int sm_count);
-int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm_count, float* position_buffer,
+                            bool do_blending, const RegularizeArgs& reg, const LaunchPlan& plan);
+int ExportVertices(cudaStream_t stream, const DeviceState& d, int count_slot, int sm_count, float* position_buffer,
                    u8* color_buffer);
 
 // ---- regularize.cu --------------------------------------------------------------------------
@@ -282,6 +376,14 @@ int ExportVertices(cudaStream_t stream, const DeviceState& d, int parity, int sm
 int RegularizeSurfels(cudaStream_t stream, DeviceState& d, bool disable_denoising, u32 frame_index,
                       float radius_factor_for_regularization_neighbors, float regularizer_weight,
                       int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot,
-                      int sm_count);
+                      const LaunchPlan& plan);
+// One regularisation iteration as descriptors: `first` = k_reg_accumulate (or k_reg_copy_only when
+// denoising is disabled, then *second is unused and the function returns 1), `second` = k_reg_step;
+// returns the number of launches. Does NOT swap d.smooth / d.smooth_next (the caller does after a
+// denoising iteration).
+int DescribeRegularize(KernelLaunch* first, KernelLaunch* second, bool skip, const LaunchPlan& plan,
+                       const DeviceState& d, bool disable_denoising, u32 frame_index,
+                       float radius_factor_for_regularization_neighbors, float regularizer_weight,
+                       int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot);
 
 }  // namespace smb

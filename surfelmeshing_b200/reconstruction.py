@@ -254,6 +254,10 @@ class CUDASurfelReconstruction:
         return v.value
 
     # -- extras: fused pre-processing, state access, stream runner --------------------------
+    def configure(self, key: str, value: float):
+        """sm_configure: named tuning knobs (product only), e.g. "tiebreak_wave"."""
+        self.lib.call("configure", self._h, key.encode(), float(value))
+
     def reset(self, stream=None):
         self.lib.call("reset", self._h, _stream_handle(stream))
 
