@@ -153,6 +153,15 @@ int sm_outlier_depth_map_fusion(
     const uint16_t* const* other_depths, const size_t* other_pitches,
     const float* others_TR_reference,
     uint16_t* out_depth, size_t out_pitch);
+/* MedianFilterAndDensifyDepthMap(), APP/main.cc:207-252, which the reference runs on the CPU
+ * inside its upload loop (main.cc:927-939): `iterations` passes (main.cc:435,
+ * --median_filter_and_densify_iterations) of the 3x3 zero-excluding median that also fills
+ * holes with >= 2 valid neighbours. Device buffers; `scratch` (same size) is needed for more
+ * than one pass; the result is in out_depth. iterations == 0 copies. */
+int sm_median_filter_and_densify_depth_map(
+    void* stream, int32_t iterations, int32_t width, int32_t height,
+    const uint16_t* in_depth, size_t in_pitch, uint16_t* out_depth, size_t out_pitch,
+    uint16_t* scratch, size_t scratch_pitch);
 int sm_erode_depth_map(void* stream, int32_t radius /* 0 = copy w/o border */,
                        int32_t width, int32_t height,
                        const uint16_t* in_depth, size_t in_pitch,
@@ -212,11 +221,67 @@ int sm_transfer_all_to_cpu(sm_reconstruction* r, void* stream, uint32_t frame_in
                            float* nx, float* ny, float* nz, uint32_t* last_update_stamp,
                            uint64_t* out_count);
 
+/* Delta form of TransferAllToCPU. The reference copies all eight rows on
+ * every transfer (cuda_surfel_reconstruction.cc:339-359; 160 MB at 5 M surfels, into pageable
+ * memory) and its consumer then compares every CPU surfel with the arrays
+ * (SurfelMeshing::IntegrateCUDABuffers, APP/surfel_meshing.cc:189-288). This call brings arrays
+ * that hold an EARLIER transfer up to date: the slots whose transferred attributes can have
+ * changed since then (new, integrated, regularised, merged) are compacted on the GPU, moved with
+ * one copy through pinned staging and scattered into the untouched CUDASurfelBuffersCPU layout;
+ * afterwards the arrays are identical to what sm_transfer_all_to_cpu would have produced.
+ * `token` identifies the transfer that last filled THESE arrays (zero-initialise it for arrays
+ * that were never filled: the call then does a full transfer) and is updated; with the
+ * reference's write/read double buffer (cuda_surfels_cpu.h:83-124) keep one token per buffer.
+ * After sm_reset / sm_load_state, or when most of the cloud changed, the call falls back to the
+ * full transfer. Synchronises `stream`. */
+typedef struct sm_transfer_token {
+  uint64_t generation;    /* 0 = never */
+  uint64_t epoch;
+  uint64_t surfel_count;
+} sm_transfer_token;
+typedef struct sm_transfer_stats {
+  uint64_t surfel_count;   /* surfels_size() */
+  uint64_t changed_count;  /* records moved (= surfel_count for a full transfer) */
+  uint64_t d2h_bytes;
+  int32_t full_transfer;
+  int32_t reserved;
+} sm_transfer_stats;
+int sm_transfer_delta_to_cpu(sm_reconstruction* r, void* stream, uint32_t frame_index,
+                             sm_transfer_token* token,
+                             float* x, float* y, float* z, float* radius_squared,
+                             float* nx, float* ny, float* nz, uint32_t* last_update_stamp,
+                             sm_transfer_stats* stats /* may be NULL */);
+
 /* Replaces ExportVertices(), cuda_surfel_reconstruction.cc:405-410 /
  * kernels.cu:2412-2464: packed xyz (NaN for merged) and rgb, device buffers of
  * 3*surfels_size() elements each. */
 int sm_export_vertices(sm_reconstruction* r, void* stream,
                        float* position_buffer, uint8_t* color_buffer);
+
+/* Replaces UpdateVisualizationBuffers(), cuda_surfel_reconstruction.cc:361-403, and the three
+ * kernels behind it (UpdateSurfelVertexBufferCUDA, UpdateNeighborIndexBufferCUDA,
+ * UpdateNormalVertexBufferCUDA, kernels.cu:274-560) with one sweep. The reference writes CUDA-mapped
+ * OpenGL buffers (cudaGraphicsResource_t); here the caller passes the mapped device pointers
+ * (cudaGraphicsResourceGetMappedPointer) or any plain device buffers; a NULL pointer skips that
+ * buffer, as the reference skips a null resource:
+ *   vertex_buffer          surfels_size() x point_size_in_floats floats: x (NaN hides a surfel that
+ *                          was replaced after the last triangulation), y, z, rgba bits
+ *   neighbor_index_buffer  surfels_size() x 4 x {surfel, neighbour-or-surfel} u32 (16-byte aligned)
+ *   normal_vertex_buffer   surfels_size() x {p, p + radius * normal} floats */
+typedef struct sm_visualization_params {
+  uint32_t frame_index;
+  uint32_t latest_triangulated_frame_index;
+  uint32_t latest_mesh_surfel_count;
+  int32_t surfel_integration_active_window_size;
+  uint32_t point_size_in_floats;               /* sizeof(Point3fC3u8) / sizeof(float) = 4 */
+  int32_t visualize_last_update_timestamp;
+  int32_t visualize_creation_timestamp;
+  int32_t visualize_radii;
+  int32_t visualize_normals;
+} sm_visualization_params;
+int sm_update_visualization_buffers(sm_reconstruction* r, void* stream, const sm_visualization_params* p,
+                                    float* vertex_buffer, uint32_t* neighbor_index_buffer,
+                                    float* normal_vertex_buffer);
 
 /* Replaces GetTimings(), cuda_surfel_reconstruction.cc:412-429 (milliseconds of
  * the last Integrate: data association, merging, blending, integration,
@@ -286,7 +351,10 @@ int sm_stream_run(sm_reconstruction* r, void* stream, const sm_stream_desc* s,
  *   "tiebreak_wave", "tiebreak_early_fraction": the reproducible rule that picks the supporting
  *   surfel of a pixel with several supporters, where the reference lets the first atomicCAS win
  *   (APP/cuda_surfel_reconstruction_kernels.cu:1688); see DESIGN.md section 4. wave = 0 selects
- *   "primary-pixel association before secondary, then lowest index". */
+ *   "primary-pixel association before secondary, then lowest index".
+ *   "median_filter_and_densify_iterations": sm_stream_run applies that many
+ *   MedianFilterAndDensifyDepthMap passes (APP/main.cc:207-252, 927-939) to every raw depth map
+ *   as it enters the device-side frame ring (default 0, as in the reference). */
 int sm_configure(sm_reconstruction* r, const char* key, double value);
 
 /* Number of kernel launches issued by this library since load (all handles). */

@@ -218,6 +218,47 @@ void cw_radii(float point_radius_extension_factor, float point_radius_clamp_fact
   }
 }
 
+/* ---- f2: MedianFilterAndDensifyDepthMap (APP/main.cc:207-252), one iteration ---------------
+ * 3x3 window clipped to the image, zeros excluded; with >= 2 valid values the output is their
+ * median (even count: the middle element closer to the float average, the upper one on a tie),
+ * otherwise the input pixel. Fills holes that have >= 2 valid neighbours. */
+void cw_median_filter_and_densify(int W, int H, const u16* in, u16* out) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; ++y) {
+    for (int x = 0; x < W; ++x) {
+      u16 values[9];
+      int n = 0;
+      const int dy_end = (H - 1 < y + 1) ? H - 1 : y + 1;
+      for (int dy = (y - 1 > 0) ? y - 1 : 0; dy <= dy_end; ++dy) {
+        const int dx_end = (W - 1 < x + 1) ? W - 1 : x + 1;
+        for (int dx = (x - 1 > 0) ? x - 1 : 0; dx <= dx_end; ++dx) {
+          if (in[dy * W + dx] != 0) values[n++] = in[dy * W + dx];
+        }
+      }
+      if (n >= 2) {
+        for (int i = 1; i < n; ++i) { /* insertion sort = std::sort on <= 9 keys */
+          const u16 v = values[i];
+          int j = i - 1;
+          while (j >= 0 && values[j] > v) { values[j + 1] = values[j]; --j; }
+          values[j + 1] = v;
+        }
+        if (n % 2 == 0) {
+          float sum = 0;
+          for (int i = 0; i < n; ++i) sum += values[i];
+          const float average = sum / n;
+          const float prev_diff = fabsf(values[n / 2 - 1] - average);
+          const float next_diff = fabsf(values[n / 2] - average);
+          out[y * W + x] = (prev_diff < next_diff) ? values[n / 2 - 1] : values[n / 2];
+        } else {
+          out[y * W + x] = values[n / 2];
+        }
+      } else {
+        out[y * W + x] = in[y * W + x];
+      }
+    }
+  }
+}
+
 /* ---- a16: the five stages of APP/main.cc:1015-1191 ------------------------------------- */
 typedef struct cw_preprocess_params {
   float depth_scaling, max_depth, depth_valid_region_radius, bilateral_filter_sigma_xy, bilateral_filter_radius_factor,

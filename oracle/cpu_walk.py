@@ -150,3 +150,12 @@ def associate_events(rows, frame_index, fx, fy, cx, cy, local_T_global, depth, n
                                C.c_uint64(max_events), C.byref(count))
     m = min(int(count.value), max_events)
     return {k: v.reshape(H, W) for k, v in out.items()}, ev_pixel[:m], ev_key[:m]
+
+
+def median_filter_and_densify(depth):
+    """One pass of MedianFilterAndDensifyDepthMap (APP/main.cc:207-252) on a [H, W] uint16 array."""
+    depth = np.ascontiguousarray(depth, dtype=np.uint16)
+    H, W = depth.shape
+    out = np.empty_like(depth)
+    load().cw_median_filter_and_densify(W, H, _p(depth), _p(out))
+    return out

@@ -599,6 +599,42 @@ int smref_export_vertices(smref_reconstruction* r, void* stream, float* position
   return SM_OK;
 }
 
+// cuda_surfel_reconstruction.cc:361-403: the reference writes CUDA-mapped OpenGL buffers. No GL here:
+// oracle/Makefile redirects the three interop calls of the reference's object file
+// (cudaGraphicsMapResources / ...GetMappedPointer / ...UnmapResources) to the stand-ins below, which
+// treat the "resource" handle as a plain device pointer, so the reference's own wrappers and kernels
+// (kernels.cu:274-560) run unmodified into device buffers.
+extern "C" cudaError_t smref_gl_map_resources(int, cudaGraphicsResource_t*, cudaStream_t) { return cudaSuccess; }
+extern "C" cudaError_t smref_gl_unmap_resources(int, cudaGraphicsResource_t*, cudaStream_t) { return cudaSuccess; }
+extern "C" cudaError_t smref_gl_get_mapped_pointer(void** pointer, size_t* size, cudaGraphicsResource_t resource) {
+  *pointer = reinterpret_cast<void*>(resource);
+  if (size) *size = 0;
+  return cudaSuccess;
+}
+
+int smref_update_visualization_buffers(smref_reconstruction* r, void* stream, const sm_visualization_params* p,
+                                       float* vertex_buffer, uint32_t* neighbor_index_buffer,
+                                       float* normal_vertex_buffer) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (vertex_buffer) {
+    UpdateSurfelVertexBufferCUDA(s, p->frame_index, p->surfel_integration_active_window_size, r->surfel_count,
+                                 r->surfels.b, p->latest_triangulated_frame_index, p->latest_mesh_surfel_count,
+                                 reinterpret_cast<cudaGraphicsResource_t>(vertex_buffer), p->point_size_in_floats,
+                                 p->visualize_last_update_timestamp != 0, p->visualize_creation_timestamp != 0,
+                                 p->visualize_radii != 0, p->visualize_normals != 0);
+  }
+  if (neighbor_index_buffer) {
+    UpdateNeighborIndexBufferCUDA(s, r->surfel_count, r->surfels.b,
+                                  reinterpret_cast<cudaGraphicsResource_t>(neighbor_index_buffer));
+  }
+  if (normal_vertex_buffer) {
+    UpdateNormalVertexBufferCUDA(s, r->surfel_count, r->surfels.b,
+                                 reinterpret_cast<cudaGraphicsResource_t>(normal_vertex_buffer));
+  }
+  REF_CUDA(cudaGetLastError());
+  return SM_OK;
+}
+
 // cuda_surfel_reconstruction.cc:412-429.
 int smref_get_timings(smref_reconstruction* r, float out_ms[7]) {
   if (!r->timings) return Fail(SM_ERR_INVALID_ARGUMENT, "timings not enabled");

@@ -18,6 +18,9 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 LIB_PATH = PKG_DIR / "libsurfel_b200.so"
 REF_LIB_PATH = REPO_ROOT / "oracle" / "_ref" / "libsurfel_ref.so"
+# TEST INFRASTRUCTURE: the reference's restated host glue linked against the vis:: link shims
+# (include/vis_shims/) instead of the reference's cuda_depth_processing.cu object.
+SHIM_LIB_PATH = REPO_ROOT / "oracle" / "_ref" / "libsurfel_shimref.so"
 
 SM_OK = 0
 SM_ERR_CUDA = -1
@@ -81,6 +84,25 @@ class StreamDesc(C.Structure):
     ]
 
 
+class TransferToken(C.Structure):
+    """sm_transfer_token: identifies the transfer that last filled a set of CUDASurfelBuffersCPU arrays."""
+    _fields_ = [("generation", C.c_uint64), ("epoch", C.c_uint64), ("surfel_count", C.c_uint64)]
+
+
+class TransferStats(C.Structure):
+    _fields_ = [("surfel_count", C.c_uint64), ("changed_count", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("full_transfer", C.c_int32), ("reserved", C.c_int32)]
+
+
+class VisualizationParams(C.Structure):
+    """sm_visualization_params (arguments of UpdateVisualizationBuffers, cuda_surfel_reconstruction.cc:361-403)."""
+    _fields_ = [("frame_index", C.c_uint32), ("latest_triangulated_frame_index", C.c_uint32),
+                ("latest_mesh_surfel_count", C.c_uint32), ("surfel_integration_active_window_size", C.c_int32),
+                ("point_size_in_floats", C.c_uint32), ("visualize_last_update_timestamp", C.c_int32),
+                ("visualize_creation_timestamp", C.c_int32), ("visualize_radii", C.c_int32),
+                ("visualize_normals", C.c_int32)]
+
+
 class StreamStats(C.Structure):
     _fields_ = [
         ("frames_integrated", C.c_uint32), ("surfels_size", C.c_uint32), ("surfel_count", C.c_uint32),
@@ -118,6 +140,7 @@ _SIGNATURES = {
     "surfels_size": (C.c_int, [_P, C.POINTER(_U32)]),
     "transfer_all_to_cpu": (C.c_int, [_P, _P, _U32, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_uint64)]),
     "export_vertices": (C.c_int, [_P, _P, _P, _P]),
+    "update_visualization_buffers": (C.c_int, [_P, _P, C.POINTER(VisualizationParams), _P, _P, _P]),
     "get_timings": (C.c_int, [_P, C.POINTER(_F * 7)]),
     "enable_timings": (C.c_int, [_P, _I]),
     "dump_state": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(_U32), C.POINTER(_U32)]),
@@ -137,6 +160,9 @@ _PRODUCT_ONLY = {
     "profile_report": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), _I]),
     "frame_counters": (C.c_int, [_P, _P, C.POINTER(C.c_uint64 * 4)]),
     "configure": (C.c_int, [_P, C.c_char_p, C.c_double]),
+    "median_filter_and_densify_depth_map": (C.c_int, [_P, _I, _I, _I, _P, _SZ, _P, _SZ, _P, _SZ]),
+    "transfer_delta_to_cpu": (C.c_int, [_P, _P, _U32, C.POINTER(TransferToken), _P, _P, _P, _P, _P, _P, _P, _P,
+                                        C.POINTER(TransferStats)]),
     "timeline_enable": (C.c_int, [_P, _I]),
     "timeline_read": (C.c_int, [_P, C.POINTER(C.c_uint64), _I]),
 }
@@ -184,6 +210,7 @@ class Library:
 
 _product: Library | None = None
 _reference: Library | None = None
+_shimref: Library | None = None
 
 
 def load_product() -> Library:
@@ -199,3 +226,13 @@ def load_reference_oracle() -> Library:
     if _reference is None:
         _reference = Library(REF_LIB_PATH, "smref_", product=False)
     return _reference
+
+
+def load_shim_oracle() -> Library:
+    """TEST INFRASTRUCTURE ONLY: reference host glue + vis:: link shims -> the product's kernels."""
+    global _shimref
+    if _shimref is None:
+        load_product()  # the shim library links against libsurfel_b200.so
+        C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+        _shimref = Library(SHIM_LIB_PATH, "smref_", product=False)
+    return _shimref

@@ -135,7 +135,7 @@ const char* KernelName(int id) {
       "k_clear", "k_bilateral_outlier", "k_bilateral_generic", "k_outlier", "k_erode_normals_radii", "k_erode",
       "k_normals", "k_radii", "k_project", "k_associate", "k_merge", "k_blend", "k_integrate", "k_update_neighbors",
       "k_new_surfel_scan", "k_create_surfels", "k_reg_accumulate", "k_reg_step", "k_reg_copy_only",
-      "k_export_vertices"};
+      "k_export_vertices", "k_median_densify", "k_delta_select", "k_viz_buffers", "k_project_tail"};
   return (id >= 0 && id < KID_COUNT) ? names[id] : "?";
 }
 
@@ -191,6 +191,7 @@ FrameParams MakeFrameParams(const sm_reconstruction* r, u32 frame_index, int cou
   f.frame_index = frame_index;
   f.count_slot = count_slot;
   f.skip = 0;
+  f.op_epoch = r->op_epoch;
   f.tb = MakeTieBreak(r->tiebreak, frame_index);
   f.active_window = p.surfel_integration_active_window_size;
   f.fx = r->fx; f.fy = r->fy; f.cx = r->cx; f.cy = r->cy;
@@ -225,6 +226,7 @@ int IntegrateImpl(sm_reconstruction* r, cudaStream_t stream, u32 frame_index, co
                   size_t radius_pitch, const uint8_t* color, size_t color_pitch, const float* global_T_local,
                   const float* local_T_global) {
   r->last_stream = stream;
+  RecordOperation(r, static_cast<int>(frame_index - static_cast<u32>(p.regularization_frame_window_size)));
   // The association / merge gates read the depth as it is before the blending, and the blending
   // reads that image while it writes the caller's buffer (k_blend): snapshot it first.
   const u16* depth_pre = depth;
@@ -451,6 +453,8 @@ int sm_destroy(sm_reconstruction* r) {
   if (r->host_counters) cudaFreeHost(r->host_counters);
   cudaFree(r->scratch_B);
   cudaFree(r->blend_src);
+  cudaFree(r->median_stage[0]); cudaFree(r->median_stage[1]);
+  FreeTransferBuffers(r);
   for (int i = 0; i < 2; ++i) {
     if (r->pipe.ev_create[i]) cudaEventDestroy(r->pipe.ev_create[i]);
     if (r->pipe.ev_update[i]) cudaEventDestroy(r->pipe.ev_update[i]);
@@ -476,6 +480,8 @@ int sm_reset(sm_reconstruction* r, void* stream) {
   r->count_slot = 0;
   r->rasters_cleared = false;
   r->last_stream = static_cast<cudaStream_t>(stream);
+  ++r->state_generation;  // tokens of earlier transfers no longer apply
+  r->op_history.clear();
   return SM_OK;
 }
 
@@ -509,6 +515,13 @@ int sm_outlier_depth_map_fusion(void* stream, int32_t other_count, int32_t requi
   return StageOutlier(static_cast<cudaStream_t>(stream), other_count, required_count, tolerance, fx, fy, cx, cy,
                       width, height, in_depth, in_pitch, other_depths, other_pitches, others_TR_reference, out_depth,
                       out_pitch);
+}
+
+int sm_median_filter_and_densify_depth_map(void* stream, int32_t iterations, int32_t width, int32_t height,
+                                           const uint16_t* in_depth, size_t in_pitch, uint16_t* out_depth,
+                                           size_t out_pitch, uint16_t* scratch, size_t scratch_pitch) {
+  return StageMedianDensify(static_cast<cudaStream_t>(stream), iterations, width, height, in_depth, in_pitch, out_depth,
+                            out_pitch, scratch, scratch_pitch);
 }
 
 int sm_erode_depth_map(void* stream, int32_t radius, int32_t width, int32_t height, const uint16_t* in_depth,
@@ -547,6 +560,7 @@ int sm_integrate(sm_reconstruction* r, void* stream, uint32_t frame_index, const
 int sm_regularize(sm_reconstruction* r, void* stream, uint32_t frame_index, float regularizer_weight,
                   float radius_factor_for_regularization_neighbors, int32_t regularization_frame_window_size) {
   r->last_stream = static_cast<cudaStream_t>(stream);
+  RecordOperation(r, static_cast<int>(frame_index - static_cast<u32>(regularization_frame_window_size)));
   return RegularizeSurfels(static_cast<cudaStream_t>(stream), r->d, /*disable_denoising*/ false, frame_index,
                            radius_factor_for_regularization_neighbors, regularizer_weight,
                            regularization_frame_window_size, r->count_slot, -1, r->plan);
@@ -586,6 +600,21 @@ int sm_transfer_all_to_cpu(sm_reconstruction* r, void* stream_v, uint32_t /*fram
   SM_CUDA(cudaMemcpyAsync(nz, s + SM_ROW_NORMAL_Z * st, bytes, cudaMemcpyDeviceToHost, stream));
   SM_CUDA(cudaMemcpyAsync(last_update_stamp, s + SM_ROW_LAST_UPDATE_STAMP * st, bytes, cudaMemcpyDeviceToHost, stream));
   return status;
+}
+
+int sm_transfer_delta_to_cpu(sm_reconstruction* r, void* stream, uint32_t frame_index, sm_transfer_token* token,
+                             float* x, float* y, float* z, float* radius_squared, float* nx, float* ny, float* nz,
+                             uint32_t* last_update_stamp, sm_transfer_stats* stats) {
+  if (!r || !token) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_transfer_delta_to_cpu: null argument");
+  return TransferDelta(r, static_cast<cudaStream_t>(stream), frame_index, token, x, y, z, radius_squared, nx, ny, nz,
+                       last_update_stamp, stats);
+}
+
+int sm_update_visualization_buffers(sm_reconstruction* r, void* stream, const sm_visualization_params* p,
+                                    float* vertex_buffer, uint32_t* neighbor_index_buffer, float* normal_vertex_buffer) {
+  if (!r || !p) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_update_visualization_buffers: null argument");
+  return UpdateVisualizationBuffers(r, static_cast<cudaStream_t>(stream), *p, vertex_buffer, neighbor_index_buffer,
+                                    normal_vertex_buffer);
 }
 
 int sm_export_vertices(sm_reconstruction* r, void* stream, float* position_buffer, uint8_t* color_buffer) {
@@ -652,6 +681,8 @@ int sm_load_state(sm_reconstruction* r, void* stream_v, const float* host_rows, 
   SM_CUDA(cudaStreamSynchronize(stream));
   r->count_slot = 0;
   r->last_stream = stream;
+  ++r->state_generation;  // tokens of earlier transfers no longer apply
+  r->op_history.clear();
   return SM_OK;
 }
 
@@ -736,6 +767,8 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
 // Named tuning / experiment knobs of a handle (no counterpart in the reference):
 //   "tiebreak_wave"            slots per launch wave of the modelled association race (0 = plain rule)
 //   "tiebreak_early_fraction"  fraction of secondary-pixel associations that compete like primary ones
+//   "median_filter_and_densify_iterations"  sm_stream_run: MedianFilterAndDensifyDepthMap passes over every raw
+//                              depth map on its way into the frame ring (APP/main.cc:435, 927-939; default 0)
 int sm_configure(sm_reconstruction* r, const char* key, double value) {
   if (!r || !key) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_configure: null argument");
   const std::string k(key);
@@ -746,6 +779,11 @@ int sm_configure(sm_reconstruction* r, const char* key, double value) {
   if (k == "tiebreak_early_fraction") {
     if (!(value >= 0.0 && value <= 1.0)) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_early_fraction must be in [0, 1]");
     r->tiebreak.early_fraction = value;
+    return SM_OK;
+  }
+  if (k == "median_filter_and_densify_iterations") {
+    if (value < 0 || value > 16 || value != static_cast<int>(value)) return SetError(SM_ERR_INVALID_ARGUMENT, "median_filter_and_densify_iterations must be an integer in [0, 16]");
+    r->median_iterations = static_cast<int>(value);
     return SM_OK;
   }
   return SetError(SM_ERR_INVALID_ARGUMENT, "sm_configure: unknown key");

@@ -158,15 +158,21 @@ __global__ void __launch_bounds__(kBlock) k_clear(DeviceState d) {
 // ---------------------------------------------------------------------------------------
 constexpr int kProjectBlock = 512;  // 2 slots per thread, kSegment slots per block-iteration
 
-__global__ void __launch_bounds__(kProjectBlock) k_project(DeviceState d, FrameParams f) {
+// `part`: which list segments the launch covers. The surfels created by the previous frame occupy the
+// slots [count before the previous frame, count before this frame): every segment entirely below them
+// only needs the previous frame's INTEGRATION, so the frame graph projects those (kProjectMain) beside
+// the previous frame's creation kernel and the remaining tail (kProjectTail) after it.
+enum { kProjectAll = 0, kProjectMain = 1, kProjectTail = 2 };
+
+__global__ void __launch_bounds__(kProjectBlock) k_project(DeviceState d, FrameParams f, int part) {
   pdl_prologue();
   if (f.skip) return;
-  const TimelineScope timeline_scope(d, f.frame_index, KID_PROJECT);
+  const TimelineScope timeline_scope(d, f.frame_index, part == kProjectTail ? KID_PROJECT_TAIL : KID_PROJECT);
   __shared__ u32 warp_totals[kProjectBlock / 32];
-  const u32 n = d.counters->surfel_count[f.count_slot];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 first_seg_if_all = blockIdx.x;
 
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && part != kProjectMain) {
     // Reset the state of this frame's new-surfel scan (runs after several kernel boundaries).
     const int tiles = (d.width * d.height + kSegment - 1) / kSegment;
     for (int t = threadIdx.x; t < tiles; t += blockDim.x) d.scan_state[t] = 0ull;
@@ -187,8 +193,15 @@ __global__ void __launch_bounds__(kProjectBlock) k_project(DeviceState d, FrameP
     return r;
   };
   SlotRows rows = {};
-  if ((static_cast<size_t>(blockIdx.x) + 1) * kSegment <= d.stride) rows = fetch(blockIdx.x);
-  for (u32 seg = blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
+  if (part != kProjectTail && (static_cast<size_t>(first_seg_if_all) + 1) * kSegment <= d.stride) rows = fetch(first_seg_if_all);
+  // Count before the previous frame (3-slot history, sm_kernels.cuh). kProjectMain must not read the
+  // current count: the previous frame's scan, which writes it, may still be running.
+  const u32 n_before = part == kProjectAll ? 0u : d.counters->surfel_count[(f.count_slot + kCountSlots - 1) % kCountSlots];
+  const u32 seg_begin = part == kProjectTail ? n_before / kSegment : 0u;
+  const u32 n = part == kProjectMain ? (n_before / kSegment) * kSegment
+                                     : d.counters->surfel_count[f.count_slot];   // slots [seg_begin * kSegment, n)
+  if (part == kProjectTail && static_cast<u64>(seg_begin + blockIdx.x) * kSegment < n) rows = fetch(seg_begin + blockIdx.x);
+  for (u32 seg = seg_begin + blockIdx.x; static_cast<u64>(seg) * kSegment < n; seg += gridDim.x) {
     const u32 base = seg * kSegment + threadIdx.x * 2;
     const SlotRows cur = rows;
     if (static_cast<u64>(seg + gridDim.x) * kSegment < n) rows = fetch(seg + gridDim.x);
@@ -837,6 +850,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
       SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = 0;
       SM_S(SM_ROW_RADIUS_SQUARED, idx) = -1.0f;
       reinterpret_cast<u8*>(&SM_SU(SM_ROW_COLOR, idx))[3] = 1;
+      SM_SU(SM_ROW_ACCUM_X, idx) = f.op_epoch;  // row 14 is unused by the reference: when it was merged (delta transfer)
       return;
     }
     if (!(e.x & kActiveBit)) return;
@@ -1202,7 +1216,11 @@ int DescribeFrameKernel(FrameKernel which, const LaunchPlan& plan, const DeviceS
   const int scan_tiles = (d.width * d.height + kSegment - 1) / kSegment;
   switch (which) {
     case FK_PROJECT:
+    case FK_PROJECT_MAIN:
       out->Reset(reinterpret_cast<const void*>(k_project), dim3(plan.project), dim3(kProjectBlock), 0, KID_PROJECT);
+      break;
+    case FK_PROJECT_TAIL:  // the segments that hold the previous frame's new surfels: a handful
+      out->Reset(reinterpret_cast<const void*>(k_project), dim3(plan.sm_count), dim3(kProjectBlock), 0, KID_PROJECT_TAIL);
       break;
     case FK_ASSOCIATE:
       out->Reset(reinterpret_cast<const void*>(k_associate), dim3(plan.associate), dim3(kBlock), 0, KID_ASSOCIATE);
@@ -1236,6 +1254,9 @@ int DescribeFrameKernel(FrameKernel which, const LaunchPlan& plan, const DeviceS
   }
   out->Arg(d);
   out->Arg(f);
+  if (which == FK_PROJECT) out->Arg(static_cast<int>(kProjectAll));
+  if (which == FK_PROJECT_MAIN) out->Arg(static_cast<int>(kProjectMain));
+  if (which == FK_PROJECT_TAIL) out->Arg(static_cast<int>(kProjectTail));
   return SM_OK;
 }
 

@@ -49,7 +49,7 @@ int EnvInt(const char* name, int fallback) {
   return (e && e[0]) ? std::atoi(e) : fallback;
 }
 
-int EnsureRunBuffers(sm_reconstruction* r, bool on_host) {
+int EnsureRunBuffers(sm_reconstruction* r, bool on_host, bool depth_ring) {
   const int W = r->d.width, H = r->d.height;
   if (!r->run_depth[0]) {
     for (int i = 0; i < kSets; ++i) {
@@ -82,19 +82,28 @@ int EnsureRunBuffers(sm_reconstruction* r, bool on_host) {
       SM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
   }
-  if (on_host && r->ring_depth.empty()) {
-    r->ring_depth.assign(kDepthRing, nullptr);
-    for (auto& b : r->ring_depth) {
-      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&b), &r->ring_depth_pitch, W * sizeof(u16), H));
-    }
-    r->ring_color.assign(kColorRing, nullptr);
-    for (auto& b : r->ring_color) {
-      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&b), &r->ring_color_pitch, W * 3, H));
-    }
+  if ((on_host || depth_ring) && !r->upload_stream) {
     SM_CUDA(cudaStreamCreateWithFlags(&r->upload_stream, cudaStreamNonBlocking));
     SM_CUDA(cudaEventCreateWithFlags(&r->upload_done, cudaEventDisableTiming));
     r->iteration_done.assign(kIterationEvents, nullptr);
     for (auto& e : r->iteration_done) SM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  if (depth_ring && r->ring_depth.empty()) {
+    r->ring_depth.assign(kDepthRing, nullptr);
+    for (auto& b : r->ring_depth) {
+      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&b), &r->ring_depth_pitch, W * sizeof(u16), H));
+    }
+  }
+  if (on_host && r->ring_color.empty()) {
+    r->ring_color.assign(kColorRing, nullptr);
+    for (auto& b : r->ring_color) {
+      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&b), &r->ring_color_pitch, W * 3, H));
+    }
+  }
+  if (r->median_iterations > 0 && !r->median_stage[0]) {
+    for (int i = 0; i < 2; ++i) {
+      SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->median_stage[i]), &r->median_stage_pitch, W * sizeof(u16), H));
+    }
   }
   return SM_OK;
 }
@@ -107,13 +116,14 @@ struct RunContext {
   const sm_integrate_params* ip;
   int W, H, K, half, first, last;
   size_t frame_elems;
-  bool on_host;
+  bool on_host;           // depth / colour frames are in (pinned) host memory
+  bool depth_ring;        // raw depth maps pass through the device-side ring (host frames, or median densify on)
   int base_slot;          // Counters::surfel_count slot before the first frame
   uint64_t h2d = 0;
 
   int CountSlot(int frame) const { return (base_slot + (frame - first)) % kCountSlots; }
   const u16* Raw(int frame, size_t* pitch) const {
-    if (on_host) { *pitch = r->ring_depth_pitch; return r->ring_depth[frame % kDepthRing]; }
+    if (depth_ring) { *pitch = r->ring_depth_pitch; return r->ring_depth[frame % kDepthRing]; }
     *pitch = W * sizeof(u16);
     return s->depth + frame_elems * frame;
   }
@@ -137,6 +147,29 @@ struct RunContext {
                            r->run_radius[set], r->run_radius_pitch, color, color_pitch, s->global_T_frame + 12 * frame,
                            s->frame_T_global + 12 * frame);
   }
+  // Upload stream: raw depth map `frame` into its ring slot (main.cc:902-965), through the
+  // MedianFilterAndDensifyDepthMap passes when configured (main.cc:927-939, there on the CPU).
+  int EnqueueRawFrame(int frame) {
+    u16* const slot = r->ring_depth[frame % kDepthRing];
+    const u16* const src = s->depth + frame_elems * frame;
+    const int n = r->median_iterations;
+    u16* const target = n > 0 ? r->median_stage[0] : slot;
+    const size_t target_pitch = n > 0 ? r->median_stage_pitch : r->ring_depth_pitch;
+    SM_CUDA(cudaMemcpy2DAsync(target, target_pitch, src, W * sizeof(u16), W * sizeof(u16), H, cudaMemcpyDefault, r->upload_stream));
+    if (on_host) h2d += frame_elems * sizeof(u16);
+    if (n > 0) {
+      return StageMedianDensify(r->upload_stream, n, W, H, r->median_stage[0], r->median_stage_pitch, slot,
+                                r->ring_depth_pitch, r->median_stage[1], r->median_stage_pitch);
+    }
+    return SM_OK;
+  }
+  int EnqueueColorFrame(int frame) {
+    SM_CUDA(cudaMemcpy2DAsync(r->ring_color[frame % kColorRing], r->ring_color_pitch, s->color + 3 * frame_elems * frame,
+                              static_cast<size_t>(W) * 3, static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice,
+                              r->upload_stream));
+    h2d += frame_elems * 3;
+    return SM_OK;
+  }
   void Others(int frame, const u16** others, size_t* pitches) const {  // main.cc:1046-1059
     for (int i = 0; i < half; ++i) {
       others[i] = Raw(frame - (i + 1), &pitches[i]);
@@ -156,7 +189,7 @@ int RunStreams(RunContext& c, cudaStream_t stream, bool pipelined, uint32_t* int
   for (cudaStream_t st : {r->pre_stream, r->pipe.crit, r->pipe.front, r->pipe.side}) {
     SM_CUDA(cudaStreamWaitEvent(st, r->entry_event, 0));
   }
-  if (c.on_host) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->entry_event, 0));
+  if (c.depth_ring) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->entry_event, 0));
   int uploaded_until = c.first - half - 1;
 
   // Two-deep software pipeline: the pre-processing of frame f + 1 (pre_stream) runs while frame f
@@ -165,7 +198,7 @@ int RunStreams(RunContext& c, cudaStream_t stream, bool pipelined, uint32_t* int
   auto enqueue_preprocess = [&](int frame) -> int {
     const int set = frame & 1;
     const bool reuse = frame >= c.first + 2;
-    if (c.on_host) {
+    if (c.depth_ring) {
       // Upload stream (main.cc:902-984): the new raw depth map(s) and this frame's colour image. The
       // rings are deep enough that the slots written now were last read two or more frames ago.
       if (reuse) {
@@ -173,15 +206,14 @@ int RunStreams(RunContext& c, cudaStream_t stream, bool pipelined, uint32_t* int
         SM_CUDA(cudaStreamWaitEvent(r->upload_stream, pipelined ? r->pipe.ev_create[set] : r->int_done[set], 0));
       }
       for (int f = uploaded_until + 1; f <= frame + half; ++f) {
-        SM_CUDA(cudaMemcpy2DAsync(r->ring_depth[f % kDepthRing], r->ring_depth_pitch, c.s->depth + c.frame_elems * f,
-                                  W * sizeof(u16), W * sizeof(u16), H, cudaMemcpyHostToDevice, r->upload_stream));
-        c.h2d += c.frame_elems * sizeof(u16);
+        const int st = c.EnqueueRawFrame(f);
+        if (st != SM_OK) return st;
       }
       uploaded_until = frame + half;
-      SM_CUDA(cudaMemcpy2DAsync(r->ring_color[frame % kColorRing], r->ring_color_pitch, c.s->color + 3 * c.frame_elems * frame,
-                                static_cast<size_t>(W) * 3, static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice,
-                                r->upload_stream));
-      c.h2d += c.frame_elems * 3;
+      if (c.on_host) {
+        const int st = c.EnqueueColorFrame(frame);
+        if (st != SM_OK) return st;
+      }
       SM_CUDA(cudaEventRecord(r->upload_done, r->upload_stream));
       SM_CUDA(cudaStreamWaitEvent(r->pre_stream, r->upload_done, 0));  // main.cc:995
     }
@@ -226,6 +258,7 @@ int RunStreams(RunContext& c, cudaStream_t stream, bool pipelined, uint32_t* int
     r->d.assoc = r->assoc_set[set]; r->d.first_depth = r->first_depth_set[set]; r->d.supported = r->supported_set[set];
     r->d.vis = r->vis_set[set]; r->d.seg_count = r->seg_count_set[set]; r->d.merge_flag = r->merge_flag_set[set];
     if (pipelined) {
+      RecordOperation(r, static_cast<int>(static_cast<u32>(frame) - static_cast<u32>(c.ip->regularization_frame_window_size)));
       const FrameParams f = c.Params(frame, set);
       r->last_tiebreak = f.tb;
       RegularizeArgs reg;
@@ -281,15 +314,18 @@ namespace {
 
 // Positions in the launch list of one step.
 struct StepLayout {
-  int integrate, scan, update, create, reg0, reg_count, project, associate, merge, blend /* -1: none */, bilateral, tail, count;
+  int integrate, scan, update, create, reg0, reg_count, project, project_tail /* -1: one projection kernel */, associate,
+      merge, blend /* -1: none */, bilateral, tail, count;
 };
 
-StepLayout MakeLayout(bool blending, int reg_launches) {
+StepLayout MakeLayout(bool blending, int reg_launches, bool split_project) {
   StepLayout l;
   int n = 0;
   l.integrate = n++; l.scan = n++; l.update = n++; l.create = n++;
   l.reg0 = n; l.reg_count = reg_launches; n += reg_launches;
-  l.project = n++; l.associate = n++; l.merge = n++;
+  l.project = n++;
+  l.project_tail = split_project ? n++ : -1;
+  l.associate = n++; l.merge = n++;
   l.blend = blending ? n++ : -1;
   l.bilateral = n++; l.tail = n++;
   l.count = n;
@@ -340,9 +376,17 @@ int BuildFrameGraph(FrameGraph* g, const StepLayout& l, const std::vector<Kernel
     edge(l.create, l.reg0, false);
     for (int i = 1; i < l.reg_count; ++i) edge(l.reg0 + i - 1, l.reg0 + i, true);
   }
-  // front (frame f + 1): needs this step's new surfels
-  edge(l.create, l.project, false);
-  edge(l.project, l.associate, true);
+  // front (frame f + 1): the projection needs this step's integration and, for the segments that hold
+  // this step's new surfels, its creation kernel
+  if (l.project_tail >= 0) {
+    edge(l.integrate, l.project, false);
+    edge(l.create, l.project_tail, false);
+    edge(l.project, l.associate, false);
+    edge(l.project_tail, l.associate, false);
+  } else {
+    edge(l.create, l.project, false);
+    edge(l.project, l.associate, true);
+  }
   edge(l.associate, l.merge, false);
   if (l.blend >= 0) edge(l.associate, l.blend, true);
   // pre (frame f + 2)
@@ -359,14 +403,15 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
   const int iterations = c.ip->regularization_iterations_per_integration_iteration;
   const bool disable_denoising = iterations == 0;
   const int reg_launches = disable_denoising ? 1 : 2 * iterations;
-  const StepLayout l = MakeLayout(blending, reg_launches);
+  const bool split_project = EnvInt("SM_B200_SPLIT_PROJECT", 1) != 0;
+  const StepLayout l = MakeLayout(blending, reg_launches, split_project);
   const int pdl = EnvInt("SM_B200_GRAPH_PDL", 1);
   std::vector<KernelLaunch> launches(l.count);
 
   cudaStream_t gs = r->graph_stream;
   SM_CUDA(cudaEventRecord(r->entry_event, stream));
   SM_CUDA(cudaStreamWaitEvent(gs, r->entry_event, 0));
-  if (c.on_host) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->entry_event, 0));
+  if (c.depth_ring) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->entry_event, 0));
   int uploaded_until = c.first - half - 1;
   const int it0 = c.first - 2;
 
@@ -380,23 +425,22 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
   for (int it = it0; it < c.last; ++it) {
     const int crit = it, front = it + 1, pre = it + 2;
     // ---- uploads for the pre-processing of this step (host-resident streams) ----
-    if (c.on_host && active(pre)) {
+    if (c.depth_ring && active(pre)) {
       for (int f = uploaded_until + 1; f <= pre + half; ++f) {
         // the slot held frame f - kDepthRing, last read by the pre-processing of frame f - kDepthRing + half
         const int last_reader_step = f - kDepthRing + half - 2;
         if (last_reader_step >= it0) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->iteration_done[(last_reader_step - it0) % kIterationEvents], 0));
-        SM_CUDA(cudaMemcpy2DAsync(r->ring_depth[f % kDepthRing], r->ring_depth_pitch, c.s->depth + c.frame_elems * f,
-                                  W * sizeof(u16), W * sizeof(u16), H, cudaMemcpyHostToDevice, r->upload_stream));
-        c.h2d += c.frame_elems * sizeof(u16);
+        const int st = c.EnqueueRawFrame(f);
+        if (st != SM_OK) return st;
       }
       uploaded_until = pre + half;
-      // the colour slot held frame pre - kColorRing, last read by the step that integrated it
-      const int last_color_step = pre - kColorRing;
-      if (last_color_step >= it0) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->iteration_done[(last_color_step - it0) % kIterationEvents], 0));
-      SM_CUDA(cudaMemcpy2DAsync(r->ring_color[pre % kColorRing], r->ring_color_pitch, c.s->color + 3 * c.frame_elems * pre,
-                                static_cast<size_t>(W) * 3, static_cast<size_t>(W) * 3, H, cudaMemcpyHostToDevice,
-                                r->upload_stream));
-      c.h2d += c.frame_elems * 3;
+      if (c.on_host) {
+        // the colour slot held frame pre - kColorRing, last read by the step that integrated it
+        const int last_color_step = pre - kColorRing;
+        if (last_color_step >= it0) SM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->iteration_done[(last_color_step - it0) % kIterationEvents], 0));
+        const int st = c.EnqueueColorFrame(pre);
+        if (st != SM_OK) return st;
+      }
       SM_CUDA(cudaEventRecord(r->upload_done, r->upload_stream));
       SM_CUDA(cudaStreamWaitEvent(gs, r->upload_done, 0));  // main.cc:995
     }
@@ -407,7 +451,8 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
       const int frame = clamp_frame(crit), set = frame % kSets;
       DeviceState d = c.SetState(set);
       d.smooth = smooth; d.smooth_next = smooth_next;
-      FrameParams f = c.Params(frame, set);
+      if (active(crit)) RecordOperation(r, static_cast<int>(static_cast<u32>(frame) - static_cast<u32>(c.ip->regularization_frame_window_size)));
+      FrameParams f = c.Params(frame, set);  // carries the operation epoch just recorded
       f.skip = active(crit) ? 0 : 1;
       if (active(crit)) r->last_tiebreak = f.tb;
       const FrameKernel kernels[4] = {FK_INTEGRATE, FK_SCAN, FK_UPDATE_NEIGHBORS, FK_CREATE};
@@ -437,9 +482,9 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
       const DeviceState d = c.SetState(set);
       FrameParams f = c.Params(frame, set);
       f.skip = active(front) ? 0 : 1;
-      const FrameKernel kernels[4] = {FK_PROJECT, FK_ASSOCIATE, FK_MERGE, FK_BLEND};
-      const int slots[4] = {l.project, l.associate, l.merge, l.blend};
-      for (int i = 0; i < 4; ++i) {
+      const FrameKernel kernels[5] = {split_project ? FK_PROJECT_MAIN : FK_PROJECT, FK_PROJECT_TAIL, FK_ASSOCIATE, FK_MERGE, FK_BLEND};
+      const int slots[5] = {l.project, l.project_tail, l.associate, l.merge, l.blend};
+      for (int i = 0; i < 5; ++i) {
         if (slots[i] < 0) continue;
         status = DescribeFrameKernel(kernels[i], r->plan, d, f, &launches[slots[i]]);
         if (status != SM_OK) return status;
@@ -487,7 +532,7 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
     }
     SM_CUDA(cudaGraphLaunch(g->exec, gs));
     CountLaunches(static_cast<unsigned long long>(l.count));
-    if (c.on_host) SM_CUDA(cudaEventRecord(r->iteration_done[(it - it0) % kIterationEvents], gs));
+    if (c.depth_ring) SM_CUDA(cudaEventRecord(r->iteration_done[(it - it0) % kIterationEvents], gs));
   }
   r->d.smooth = smooth;
   r->d.smooth_next = smooth_next;
@@ -514,8 +559,9 @@ int StreamRun(sm_reconstruction* r, cudaStream_t stream, const sm_stream_desc* s
   c.first = first_frame; c.last = last_frame;
   c.frame_elems = static_cast<size_t>(c.W) * c.H;
   c.on_host = s->frames_on_host != 0;
+  c.depth_ring = c.on_host || r->median_iterations > 0;
   c.base_slot = r->count_slot;
-  int status = EnsureRunBuffers(r, c.on_host);
+  int status = EnsureRunBuffers(r, c.on_host, c.depth_ring);
   if (status != SM_OK) return status;
   const unsigned long long launches_before = LaunchCount();
   const auto host_t0 = std::chrono::steady_clock::now();

@@ -600,6 +600,63 @@ k_radii(RadiiArgs a, int width, int height, const u16* in, size_t in_pitch, floa
   row_ptr(out, out_pitch, y)[x] = kept;
 }
 
+// ---------------------------------------------------------------------------------------
+// f2: MedianFilterAndDensifyDepthMap (APP/main.cc:207-252), one iteration per launch
+// ---------------------------------------------------------------------------------------
+// The reference runs this on the CPU inside its upload loop (main.cc:927-939, "TODO: Do this on the
+// GPU"): 3x3 window clipped to the image, zeros excluded; with >= 2 valid values the output is
+// their median - for an even count the middle element closer to the float average (IEEE division,
+// host code is not fast-math), the upper one on a tie - otherwise the input pixel. Instead of
+// sorting, every valid value gets its rank (ties by window position), which selects the same
+// elements.
+__global__ void __launch_bounds__(256)
+k_median_densify(int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch) {
+  pdl_prologue();
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= width || y >= height) return;
+  u32 v[9];
+  int n = 0;
+  u32 sum = 0;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int yy = y + dy, xx = x + dx;
+      u32 value = 0;
+      if (yy >= 0 && yy < height && xx >= 0 && xx < width) value = row_ptr(in, in_pitch, yy)[xx];
+      v[(dy + 1) * 3 + dx + 1] = value;
+      n += value != 0 ? 1 : 0;
+      sum += value;
+    }
+  }
+  u16 result = static_cast<u16>(v[4]);
+  if (n >= 2) {
+    u32 lower = 0, upper = 0;  // sorted[n / 2 - 1], sorted[n / 2]
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      if (v[i] == 0) continue;
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        if (j == i || v[j] == 0) continue;
+        rank += (v[j] < v[i] || (v[j] == v[i] && j < i)) ? 1 : 0;
+      }
+      if (rank == n / 2 - 1) lower = v[i];
+      if (rank == n / 2) upper = v[i];
+    }
+    if (n % 2 == 0) {
+      const float average = __fdiv_rn(__uint2float_rn(sum), __int2float_rn(n));  // sum <= 8 * 65535: exact
+      const float prev_diff = fabsf(__fsub_rn(__uint2float_rn(lower), average));
+      const float next_diff = fabsf(__fsub_rn(__uint2float_rn(upper), average));
+      result = static_cast<u16>(prev_diff < next_diff ? lower : upper);
+    } else {
+      result = static_cast<u16>(upper);
+    }
+  }
+  row_ptr(out, out_pitch, y)[x] = result;
+}
+
 // ---- host-side argument construction (mirrors the reference's host wrappers) ------------
 
 BilateralArgs MakeBilateralArgs(float sigma_xy, float sigma_value_factor, u16 value_to_ignore, float radius_factor,
@@ -830,6 +887,30 @@ int StageOutlier(cudaStream_t stream, int other_count, int required_count, float
   return CheckLaunch("outlier");
 }
 
+// `iterations` launches ping-ponging between `out` and `scratch` so that the last one writes `out`;
+// iterations == 0 copies. `in` may alias neither.
+int StageMedianDensify(cudaStream_t stream, int iterations, int width, int height, const u16* in, size_t in_pitch,
+                       u16* out, size_t out_pitch, u16* scratch, size_t scratch_pitch) {
+  if (iterations < 0) return SetError(SM_ERR_INVALID_ARGUMENT, "median_filter_and_densify_iterations < 0");
+  if (iterations == 0) {
+    if (cudaMemcpy2DAsync(out, out_pitch, in, in_pitch, width * sizeof(u16), height, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+      return SetError(SM_ERR_CUDA, "cudaMemcpy2DAsync (median, 0 iterations)");
+    return SM_OK;
+  }
+  if (iterations > 1 && scratch == nullptr) return SetError(SM_ERR_INVALID_ARGUMENT, "median densify: scratch buffer needed for > 1 iteration");
+  const u16* src = in;
+  size_t src_pitch = in_pitch;
+  for (int i = 0; i < iterations; ++i) {
+    const bool to_out = ((iterations - 1 - i) % 2) == 0;  // the last iteration writes `out`
+    u16* dst = to_out ? out : scratch;
+    const size_t dst_pitch = to_out ? out_pitch : scratch_pitch;
+    { LaunchScope scope(stream, KID_MEDIAN_DENSIFY); LaunchKernel(k_median_densify, PixelGrid(width, height), dim3(256), 0, stream, width, height, src, src_pitch, dst, dst_pitch); }
+    src = dst;
+    src_pitch = dst_pitch;
+  }
+  return CheckLaunch("median densify");
+}
+
 int StageErode(cudaStream_t stream, int radius, int width, int height, const u16* in, size_t in_pitch, u16* out,
                size_t out_pitch) {
   if (radius < 0 || radius > kMaxErode) return SetError(SM_ERR_INVALID_ARGUMENT, "radius value is not supported");
@@ -869,6 +950,7 @@ int ConfigurePreprocessKernels(int carveout_percent) {
   cudaFuncSetAttribute(k_erode, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_normals, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_radii, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_median_densify, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaGetLastError();
   return SM_OK;
 }

@@ -72,7 +72,19 @@ struct sm_reconstruction {
   std::vector<uchar3*> ring_color; size_t ring_color_pitch = 0;
   cudaStream_t upload_stream = nullptr;
   cudaEvent_t upload_done = nullptr;
+  // MedianFilterAndDensifyDepthMap passes applied to every raw depth map entering the ring
+  // (APP/main.cc:435 --median_filter_and_densify_iterations, default 0) and their staging buffers
+  int median_iterations = 0;
+  smb::u16* median_stage[2] = {nullptr, nullptr}; size_t median_stage_pitch = 0;
   std::vector<cudaEvent_t> iteration_done;   // frame graph: one event per iteration slot (ring reuse)
+  // delta transfer (transfer.cu): operation counter, per-operation regularisation thresholds, staging
+  smb::u32 op_epoch = 0;
+  uint64_t state_generation = 1;   // bumped by sm_reset / sm_load_state
+  struct Operation { smb::u32 epoch; int stamp_threshold; };
+  std::vector<Operation> op_history;
+  smb::u32* delta_index = nullptr; float* delta_values = nullptr; smb::u32* delta_cursor = nullptr;
+  smb::u32 delta_capacity = 0;
+  smb::u32* delta_host = nullptr; size_t delta_host_capacity = 0;   // pinned, in 32-bit words
   // frame graph (pipeline.cu)
   cudaStream_t graph_stream = nullptr;
   cudaEvent_t graph_exit = nullptr;
@@ -93,6 +105,14 @@ int IntegrateImpl(sm_reconstruction* r, cudaStream_t stream, u32 frame_index, co
                   const float* local_T_global);
 void CountLaunches(unsigned long long n);
 unsigned long long LaunchCount();
+// transfer.cu
+void RecordOperation(sm_reconstruction* r, int stamp_threshold);   // one Integrate() / Regularize(): ++op_epoch
+void FreeTransferBuffers(sm_reconstruction* r);
+int TransferDelta(sm_reconstruction* r, cudaStream_t stream, uint32_t frame_index, sm_transfer_token* token, float* x,
+                  float* y, float* z, float* radius_squared, float* nx, float* ny, float* nz,
+                  uint32_t* last_update_stamp, sm_transfer_stats* stats);
+int UpdateVisualizationBuffers(sm_reconstruction* r, cudaStream_t stream, const sm_visualization_params& p, float* vertex,
+                               uint32_t* neighbor_index, float* normal_vertex);
 // pipeline.cu
 int StreamRun(sm_reconstruction* r, cudaStream_t stream, const sm_stream_desc* s, const sm_preprocess_params* pp,
               const sm_integrate_params* ip, int first_frame, int last_frame, sm_stream_stats* stats);

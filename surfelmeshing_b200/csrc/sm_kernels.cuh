@@ -24,7 +24,7 @@ enum KernelId {
   KID_CLEAR = 0, KID_BILATERAL_OUTLIER, KID_BILATERAL_GENERIC, KID_OUTLIER, KID_ERODE_NORMALS_RADII, KID_ERODE,
   KID_NORMALS, KID_RADII, KID_PROJECT, KID_ASSOCIATE, KID_MERGE, KID_BLEND, KID_INTEGRATE, KID_UPDATE_NEIGHBORS,
   KID_NEW_SURFEL_SCAN, KID_CREATE_SURFELS, KID_REG_ACCUMULATE, KID_REG_STEP, KID_REG_COPY_ONLY,
-  KID_EXPORT_VERTICES, KID_COUNT
+  KID_EXPORT_VERTICES, KID_MEDIAN_DENSIFY, KID_DELTA_SELECT, KID_VIZ_BUFFERS, KID_PROJECT_TAIL, KID_COUNT
 };
 const char* KernelName(int id);
 bool ProfilingEnabled();
@@ -153,6 +153,7 @@ struct FrameParams {
   u32 frame_index;
   int count_slot;        // Counters::surfel_count slot holding the count before this frame
   int skip;              // != 0: the launch is a placeholder of the frame graph, the kernel returns at once
+  u32 op_epoch;          // operation counter of the handle; recorded in row 14 of a surfel when it is merged (transfer.cu)
   TieBreak tb;           // supporting-surfel tie-break (see kSecondaryBit)
   int active_window;     // surfel_integration_active_window_size
   float fx, fy, cx, cy;
@@ -318,6 +319,8 @@ int StageOutlier(cudaStream_t stream, int other_count, int required_count, float
                  u16* out, size_t out_pitch);
 int StageErode(cudaStream_t stream, int radius, int width, int height, const u16* in, size_t in_pitch, u16* out,
                size_t out_pitch);
+int StageMedianDensify(cudaStream_t stream, int iterations, int width, int height, const u16* in, size_t in_pitch,
+                       u16* out, size_t out_pitch, u16* scratch, size_t scratch_pitch);
 int StageNormals(cudaStream_t stream, float observation_angle_threshold_deg, float depth_scaling, float fx, float fy,
                  float cx, float cy, int width, int height, const u16* in, size_t in_pitch, u16* out, size_t out_pitch,
                  float2* normals, size_t normals_pitch);
@@ -333,7 +336,8 @@ struct IntegrateEvents {
 int IntegrateFrame(cudaStream_t stream, const DeviceState& d, const FrameParams& f, bool do_blending,
                    bool rasters_already_cleared, const LaunchPlan& plan, const IntegrateEvents* events);
 // Kernels of one Integrate() as descriptors (stream launches and frame-graph nodes).
-enum FrameKernel { FK_PROJECT = 0, FK_ASSOCIATE, FK_MERGE, FK_BLEND, FK_INTEGRATE, FK_UPDATE_NEIGHBORS, FK_SCAN, FK_CREATE, FK_COUNT };
+enum FrameKernel { FK_PROJECT = 0, FK_ASSOCIATE, FK_MERGE, FK_BLEND, FK_INTEGRATE, FK_UPDATE_NEIGHBORS, FK_SCAN, FK_CREATE,
+                   FK_PROJECT_MAIN, FK_PROJECT_TAIL, FK_COUNT };
 int DescribeFrameKernel(FrameKernel which, const LaunchPlan& plan, const DeviceState& d, const FrameParams& f,
                         KernelLaunch* out);
 int ClearAssociationRasters(cudaStream_t stream, const DeviceState& d);

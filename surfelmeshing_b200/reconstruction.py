@@ -19,7 +19,26 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import IntegrateParams, Library, PreprocessParams, StreamDesc, StreamStats
+from ._lib import (IntegrateParams, Library, PreprocessParams, StreamDesc, StreamStats, TransferStats, TransferToken,
+                   VisualizationParams)
+
+BUFFER_NAMES = ["surfel_x_buffer", "surfel_y_buffer", "surfel_z_buffer", "surfel_radius_squared_buffer",
+                "surfel_normal_x_buffer", "surfel_normal_y_buffer", "surfel_normal_z_buffer",
+                "surfel_last_update_stamp_buffer"]
+
+
+def make_cpu_buffers(max_surfel_count: int, pinned: bool = False) -> dict:
+    """The eight arrays of CUDASurfelBuffersCPU (APP/cuda_surfels_cpu.h:40-73), max_surfel_count long."""
+    out = {}
+    for k in BUFFER_NAMES:
+        dtype = np.uint32 if "stamp" in k else np.float32
+        if pinned:
+            t = torch.empty(max(max_surfel_count, 1), dtype=torch.int32 if "stamp" in k else torch.float32).pin_memory()
+            out[k] = t.numpy().view(dtype)
+            out["_keep_" + k] = t
+        else:
+            out[k] = np.zeros(max(max_surfel_count, 1), dtype=dtype)
+    return out
 
 ROW_NAMES = [
     "x", "y", "z", "smooth_x", "smooth_y", "smooth_z", "confidence", "radius_squared",
@@ -99,6 +118,22 @@ def OutlierDepthMapFusionCUDA(stream, tolerance, input_depth, depth_fx, depth_fy
     H, W = input_depth.shape
     lib.call("outlier_depth_map_fusion", _stream_handle(stream), K, required_count, tolerance, depth_fx, depth_fy,
              depth_cx, depth_cy, W, H, ip, ipitch, ptrs, pitches, mats.ctypes.data_as(C.c_void_p), op, opitch)
+
+
+def MedianFilterAndDensifyDepthMap(stream, iterations, input_depth, output_depth=None, lib: Optional[Library] = None):
+    """APP/main.cc:207-252 (there on the CPU, main.cc:927-939): `iterations` passes of the 3x3
+    zero-excluding median that also fills holes. Returns the output tensor."""
+    lib = lib or _lib.load_product()
+    H, W = input_depth.shape
+    if output_depth is None:
+        output_depth = torch.zeros((H, W), dtype=torch.uint16, device=input_depth.device)
+    scratch = torch.zeros((H, W), dtype=torch.uint16, device=input_depth.device)
+    ip, ipitch = _raster(input_depth)
+    op, opitch = _raster(output_depth)
+    sp, spitch = _raster(scratch)
+    lib.call("median_filter_and_densify_depth_map", _stream_handle(stream), int(iterations), W, H, ip, ipitch, op, opitch,
+             sp, spitch)
+    return output_depth
 
 
 def ErodeDepthMapCUDA(stream, radius, input_depth, output_depth, lib: Optional[Library] = None):
@@ -226,6 +261,33 @@ class CUDASurfelReconstruction:
         buffers["frame_index"] = int(frame_index)
         buffers["surfel_count"] = int(count.value)
         return buffers
+
+    def TransferDeltaToCPU(self, stream, frame_index, buffers: dict, token: TransferToken) -> TransferStats:
+        """sm_transfer_delta_to_cpu: brings `buffers` (filled by the transfer `token` stands for; a fresh
+        TransferToken() = never) up to date; afterwards they equal a full TransferAllToCPU. The arrays
+        must be at least surfels_size() long (the reference allocates max_surfel_count)."""
+        stats = TransferStats()
+        ptrs = [buffers[k].ctypes.data_as(C.c_void_p) for k in BUFFER_NAMES]
+        self.lib.call("transfer_delta_to_cpu", self._h, _stream_handle(stream), int(frame_index), C.byref(token), *ptrs,
+                      C.byref(stats))
+        buffers["frame_index"] = int(frame_index)
+        buffers["surfel_count"] = int(stats.surfel_count)
+        return stats
+
+    def UpdateVisualizationBuffers(self, stream, frame_index, latest_triangulated_frame_index, latest_mesh_surfel_count,
+                                   surfel_integration_active_window_size, visualize_last_update_timestamp,
+                                   visualize_creation_timestamp, visualize_radii, visualize_normals,
+                                   vertex_buffer=None, neighbor_index_buffer=None, normal_vertex_buffer=None,
+                                   point_size_in_floats: int = 4):
+        """cuda_surfel_reconstruction.cc:361-403; the three OpenGL buffers of the reference are plain
+        device tensors here (None = not wanted)."""
+        p = VisualizationParams(int(frame_index), int(latest_triangulated_frame_index), int(latest_mesh_surfel_count),
+                                int(surfel_integration_active_window_size), int(point_size_in_floats),
+                                int(bool(visualize_last_update_timestamp)), int(bool(visualize_creation_timestamp)),
+                                int(bool(visualize_radii)), int(bool(visualize_normals)))
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self.lib.call("update_visualization_buffers", self._h, _stream_handle(stream), C.byref(p), ptr(vertex_buffer),
+                      ptr(neighbor_index_buffer), ptr(normal_vertex_buffer))
 
     def ExportVertices(self, stream, position_buffer: torch.Tensor, color_buffer: torch.Tensor):
         """cuda_surfel_reconstruction.cc:405-410."""

@@ -33,3 +33,12 @@ def reference():
     if not _lib.REF_LIB_PATH.exists():
         pytest.skip("oracle/_ref/libsurfel_ref.so not built (needs /root/reference at build time)")
     return _lib.load_reference_oracle()
+
+
+@pytest.fixture(scope="session")
+def shimref():
+    """Reference host glue linked against the vis:: link shims (oracle/_ref/libsurfel_shimref.so)."""
+    from surfelmeshing_b200 import _lib
+    if not _lib.SHIM_LIB_PATH.exists():
+        pytest.skip("oracle/_ref/libsurfel_shimref.so not built (needs /root/reference at build time)")
+    return _lib.load_shim_oracle()
