@@ -5,11 +5,20 @@
 // method forwards to the C ABI of libsurfel_b200.so (surfel_b200.h). Include this header INSTEAD of
 // "surfel_meshing/cuda_surfel_reconstruction.h" in main.cc and drop cuda_surfel_reconstruction.cc /
 // cuda_surfel_reconstruction_kernels.{cc,cu} from the SurfelMeshing target.
-// It needs the reference's own libvis headers (Eigen, Sophus) and therefore only compiles inside the
-// reference's build tree; it is not built in this repository's image (no Eigen).
+// It needs the reference's own libvis headers (Eigen, Sophus) and therefore only BUILDS inside the
+// reference's tree; in this repository (no Eigen) it is syntax- and type-checked against minimal
+// stand-ins of those headers (tests/stubs/, tests/test_adapter_syntax.py), with a translation unit that
+// makes the calls main.cc makes.
+//
+// Define SURFEL_B200_DELTA_TRANSFER before including to let TransferAllToCPU() use
+// sm_transfer_delta_to_cpu (one token per CUDASurfelBuffersCPU object): the same arrays, a fraction of
+// the PCIe traffic; that variant synchronises the stream itself (main.cc:1261-1287 synchronises right
+// after the call anyway).
 #pragma once
 
-#include <cuda_runtime.h>
+#include <cuda_runtime.h>  // cudaGraphicsMapResources & co. are part of the generic interop API
+
+#include <map>
 
 #include <libvis/camera.h>
 #include <libvis/cuda/cuda_buffer.h>
@@ -26,16 +35,21 @@ class SurfelMeshingRenderWindow;
 
 class CUDASurfelReconstruction {
  public:
-  // The three GL resources and the render window only serve UpdateVisualizationBuffers() and debug
-  // displays (GUI); they are accepted and ignored.
+  // The three GL resources serve UpdateVisualizationBuffers(); the render window only feeds debug
+  // displays of the reference and is ignored.
   CUDASurfelReconstruction(usize max_surfel_count, const PinholeCamera4f& depth_camera,
-                           cudaGraphicsResource_t /*vertex_buffer_resource*/,
-                           cudaGraphicsResource_t /*neighbor_index_buffer_resource*/,
-                           cudaGraphicsResource_t /*normal_vertex_buffer_resource*/,
-                           const shared_ptr<SurfelMeshingRenderWindow>& /*render_window*/) {
+                           cudaGraphicsResource_t vertex_buffer_resource,
+                           cudaGraphicsResource_t neighbor_index_buffer_resource,
+                           cudaGraphicsResource_t normal_vertex_buffer_resource,
+                           const shared_ptr<SurfelMeshingRenderWindow>& /*render_window*/)
+      : vertex_buffer_resource_(vertex_buffer_resource),
+        neighbor_index_buffer_resource_(neighbor_index_buffer_resource),
+        normal_vertex_buffer_resource_(normal_vertex_buffer_resource) {
     Check(sm_create(&handle_, max_surfel_count, depth_camera.width(), depth_camera.height(),
                     depth_camera.parameters()[0], depth_camera.parameters()[1], depth_camera.parameters()[2],
                     depth_camera.parameters()[3]));
+    // The reference records its seven stage-event pairs on every Integrate() (cuda_surfel_reconstruction.cc:131-319).
+    Check(sm_enable_timings(handle_, 1));
   }
   ~CUDASurfelReconstruction() { sm_destroy(handle_); }
   CUDASurfelReconstruction(const CUDASurfelReconstruction&) = delete;
@@ -83,16 +97,59 @@ class CUDASurfelReconstruction {
   void TransferAllToCPU(cudaStream_t stream, u32 frame_index, CUDASurfelsCPU* buffers) {
     CUDASurfelBuffersCPU* b = buffers->write_buffers();
     b->frame_index = frame_index;
+#ifdef SURFEL_B200_DELTA_TRANSFER
+    sm_transfer_stats stats;
+    Check(sm_transfer_delta_to_cpu(handle_, stream, frame_index, &transfer_tokens_[b], b->surfel_x_buffer,
+                                   b->surfel_y_buffer, b->surfel_z_buffer, b->surfel_radius_squared_buffer,
+                                   b->surfel_normal_x_buffer, b->surfel_normal_y_buffer, b->surfel_normal_z_buffer,
+                                   b->surfel_last_update_stamp_buffer, &stats));
+    b->surfel_count = stats.surfel_count;
+#else
     uint64_t count = 0;
     Check(sm_transfer_all_to_cpu(handle_, stream, frame_index, b->surfel_x_buffer, b->surfel_y_buffer,
                                  b->surfel_z_buffer, b->surfel_radius_squared_buffer, b->surfel_normal_x_buffer,
                                  b->surfel_normal_y_buffer, b->surfel_normal_z_buffer,
                                  b->surfel_last_update_stamp_buffer, &count));
     b->surfel_count = count;
+#endif
   }
 
-  // GUI only (CUDA-OpenGL interop): no-op in this drop-in.
-  void UpdateVisualizationBuffers(cudaStream_t, u32, u32, u32, int, bool, bool, bool, bool) {}
+  // cuda_surfel_reconstruction.cc:361-403: the three OpenGL buffers are mapped, filled by ONE sweep
+  // (sm_update_visualization_buffers) and unmapped. Resources that are null are skipped, like there.
+  void UpdateVisualizationBuffers(cudaStream_t stream, u32 frame_index, u32 latest_triangulated_frame_index,
+                                  u32 latest_mesh_surfel_count, int surfel_integration_active_window_size,
+                                  bool visualize_last_update_timestamp, bool visualize_creation_timestamp,
+                                  bool visualize_radii, bool visualize_normals) {
+    sm_visualization_params p;
+    p.frame_index = frame_index;
+    p.latest_triangulated_frame_index = latest_triangulated_frame_index;
+    p.latest_mesh_surfel_count = latest_mesh_surfel_count;
+    p.surfel_integration_active_window_size = surfel_integration_active_window_size;
+    p.point_size_in_floats = 4;  // sizeof(Point3fC3u8) / sizeof(float)
+    p.visualize_last_update_timestamp = visualize_last_update_timestamp;
+    p.visualize_creation_timestamp = visualize_creation_timestamp;
+    p.visualize_radii = visualize_radii;
+    p.visualize_normals = visualize_normals;
+    float* vertex = nullptr;
+    uint32_t* neighbor_index = nullptr;
+    float* normal_vertex = nullptr;
+#ifndef SURFEL_B200_NO_GL_INTEROP
+    cudaGraphicsResource_t resources[3];
+    int count = 0;
+    for (cudaGraphicsResource_t res : {vertex_buffer_resource_, neighbor_index_buffer_resource_, normal_vertex_buffer_resource_})
+      if (res) resources[count++] = res;
+    if (count == 0) return;
+    CheckCuda(cudaGraphicsMapResources(count, resources, stream));
+    size_t bytes = 0;
+    if (vertex_buffer_resource_) CheckCuda(cudaGraphicsResourceGetMappedPointer(reinterpret_cast<void**>(&vertex), &bytes, vertex_buffer_resource_));
+    if (neighbor_index_buffer_resource_) CheckCuda(cudaGraphicsResourceGetMappedPointer(reinterpret_cast<void**>(&neighbor_index), &bytes, neighbor_index_buffer_resource_));
+    if (normal_vertex_buffer_resource_) CheckCuda(cudaGraphicsResourceGetMappedPointer(reinterpret_cast<void**>(&normal_vertex), &bytes, normal_vertex_buffer_resource_));
+    Check(sm_update_visualization_buffers(handle_, stream, &p, vertex, neighbor_index, normal_vertex));
+    CheckCuda(cudaGraphicsUnmapResources(count, resources, stream));
+#else
+    (void)stream; (void)p; (void)vertex; (void)neighbor_index; (void)normal_vertex;
+#endif
+  }
 
   void ExportVertices(cudaStream_t stream, CUDABuffer<float>* position_buffer, CUDABuffer<u8>* color_buffer) {
     Check(sm_export_vertices(handle_, stream, position_buffer->ToCUDA().address(), color_buffer->ToCUDA().address()));
@@ -101,8 +158,7 @@ class CUDASurfelReconstruction {
   void GetTimings(float* data_association, float* surfel_merging, float* measurement_blending, float* integration,
                   float* neighbor_update, float* new_surfel_creation, float* regularization) {
     float t[7] = {0, 0, 0, 0, 0, 0, 0};
-    sm_enable_timings(handle_, 1);  // takes effect from the next Integrate() on
-    if (sm_get_timings(handle_, t) != SM_OK) { for (float& v : t) v = 0; }
+    Check(sm_get_timings(handle_, t));  // of the last Integrate(); timings are on since construction
     *data_association = t[0]; *surfel_merging = t[1]; *measurement_blending = t[2]; *integration = t[3];
     *neighbor_update = t[4]; *new_surfel_creation = t[5]; *regularization = t[6];
   }
@@ -119,7 +175,16 @@ class CUDASurfelReconstruction {
   static void Check(int status) {
     if (status != SM_OK) LOG(FATAL) << "surfel_b200: " << sm_last_error();
   }
+  static void CheckCuda(cudaError_t e) {
+    if (e != cudaSuccess) LOG(FATAL) << "surfel_b200 adapter: " << cudaGetErrorString(e);
+  }
   sm_reconstruction* handle_ = nullptr;
+  cudaGraphicsResource_t vertex_buffer_resource_;
+  cudaGraphicsResource_t neighbor_index_buffer_resource_;
+  cudaGraphicsResource_t normal_vertex_buffer_resource_;
+#ifdef SURFEL_B200_DELTA_TRANSFER
+  std::map<const CUDASurfelBuffersCPU*, sm_transfer_token> transfer_tokens_;  // one per write / read buffer
+#endif
 };
 
 }  // namespace vis

@@ -214,9 +214,13 @@ _shimref: Library | None = None
 
 
 def load_product() -> Library:
+    """The product library. SM_B200_LIB=<path> loads another BUILD OF THE PRODUCT instead (A/B
+    measurements of kernel variants, e.g. variants/lib_r2base.so); it exports the same ABI."""
     global _product
     if _product is None:
-        _product = Library(LIB_PATH, "sm_", product=True)
+        import os
+        override = os.environ.get("SM_B200_LIB")
+        _product = Library(Path(override).resolve() if override else LIB_PATH, "sm_", product=True)
     return _product
 
 

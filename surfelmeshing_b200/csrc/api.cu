@@ -331,6 +331,17 @@ int CreateImpl(sm_reconstruction* r, uint64_t max_surfel_count, int32_t width, i
   std::memset(r->host_counters, 0, sizeof(Counters));
   SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->scratch_B), &r->scratch_B_pitch, width * sizeof(u16), height));
   SM_CUDA(cudaMallocPitch(reinterpret_cast<void**>(&r->blend_src), &r->blend_src_pitch, width * sizeof(u16), height));
+  {
+    // Tile fill of the pre-processing tail: "tma" (default) = one cp.async.bulk.tensor per block through a
+    // descriptor of scratch_B, "vector" = cooperative 128-bit loads (SM_B200_TAIL_FILL, A/B hook).
+    const char* e = std::getenv("SM_B200_TAIL_FILL");
+    const bool want_tma = !(e && std::string(e) == "vector");
+    if (want_tma) {
+      const int status = MakeDepthTensorMap(&r->scratch_B_map, r->scratch_B, r->scratch_B_pitch, width, height);
+      if (status != SM_OK) return status;
+      r->scratch_B_map_valid = true;
+    }
+  }
   for (int i = 0; i < 14; ++i) SM_CUDA(cudaEventCreate(&r->events.ev[i]));
   r->events.enabled = false;
   // Supporting-surfel tie-break defaults; SM_B200_TIEBREAK="wave,early_fraction" overrides.
@@ -493,7 +504,8 @@ int sm_preprocess(sm_reconstruction* r, void* stream, const sm_preprocess_params
                                      r->cx, r->cy, raw_depth, raw_pitch, other_depths, other_pitches,
                                      others_TR_reference, r->scratch_B, r->scratch_B_pitch, out_depth,
                                      out_depth_pitch, reinterpret_cast<float2*>(out_normals), out_normals_pitch,
-                                     out_radius, out_radius_pitch, r->d.assoc, r->d.first_depth, r->d.supported);
+                                     out_radius, out_radius_pitch, r->d.assoc, r->d.first_depth, r->d.supported, nullptr, 0,
+                                     nullptr, nullptr, r->ScratchBMap());
   if (status == SM_OK) r->rasters_cleared = true;
   return status;
 }
@@ -672,6 +684,10 @@ int sm_load_state(sm_reconstruction* r, void* stream_v, const float* host_rows, 
     for (int row : zero_rows) {
       SM_CUDA(cudaMemsetAsync(r->d.surfels + row * r->d.stride, 0, surfels_size * sizeof(float), stream));
     }
+    // bookkeeping rows the library keeps in the reference's unused rows 14 / 15 (sm_kernels.cuh)
+    SM_CUDA(cudaMemsetAsync(r->d.surfels + kRowMergeEpoch * r->d.stride, 0, surfels_size * sizeof(float), stream));
+    const int status = RebuildMetaRow(stream, r->d, surfels_size, r->sm_count);
+    if (status != SM_OK) return status;
   }
   Counters c{};
   for (int i = 0; i < kCountSlots; ++i) c.surfel_count[i] = surfels_size;

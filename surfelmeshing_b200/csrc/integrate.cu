@@ -403,8 +403,13 @@ __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) 
 //      compacts each level into a pixel list,
 //   3. walks the lists level by level (one thread per pixel, one barrier per level) doing the
 //      reference's float arithmetic; the search for level k + 1 runs beside the update of level k.
-constexpr int kBlendTileW = 80, kBlendTileH = 32;  // 8 x 15 = 120 tiles at VGA
-constexpr int kBlendBlock = 512;
+// Tile 32 x 40 (VGA: 20 x 12 = 240 tiles): with the halo of a radius-12 blend the region is 64 x 62 pixels,
+// 61 KB of shared memory, so TWO blocks share an SM and all tiles of a VGA frame are resident at once;
+// both bit rasters of a level search (2 x 124 words) take one pass of the 256 threads. The kernel is a
+// chain of ~11 barrier-separated levels with little work each: what counts is how many tiles are in
+// flight per SM, not the work per tile (round 1: 80 x 32 tiles, 1 block per SM, 120 blocks: 20 us).
+constexpr int kBlendTileW = 32, kBlendTileH = 40;
+constexpr int kBlendBlock = 256;
 constexpr int kMaxBlendRadius = 64;
 
 __host__ __device__ inline int blend_halo_y(int radius) { return radius - 1 > 1 ? radius - 1 : 1; }  // (radius - 2) iterations + the 3x3 start stencil
@@ -475,8 +480,7 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   const int nw = rh * wpr;          // words per bit raster
   float* s_delta = reinterpret_cast<float*>(blend_smem);    // ring 0 (distance_map) deltas
   float* s_ndelta = s_delta + rn16;                          // ring 1 (new_distance_map) deltas
-  u16* s_depth0 = reinterpret_cast<u16*>(s_ndelta + rn16);  // depth as handed in
-  u16* s_depth = s_depth0 + rn16;                            // working depth
+  u16* s_depth = reinterpret_cast<u16*>(s_ndelta + rn16);   // working depth
   u16* s_front = s_depth + rn16;                             // [ring][rn16] pixel lists, level after level, entries (ly << 8) | lx
   u32* s_nodepth = reinterpret_cast<u32*>(s_front + 2 * rn16);  // bit rasters, nw words each
   u32* s_unsupported = s_nodepth + nw;
@@ -529,8 +533,6 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
         else unsupported |= 1u << k;
       }
       const int i = ly * rw + chunk * 16;
-      *reinterpret_cast<uint4*>(s_depth0 + i) = depth.v[0];
-      *reinterpret_cast<uint4*>(s_depth0 + i + 8) = depth.v[1];
       *reinterpret_cast<uint4*>(s_depth + i) = depth.v[0];
       *reinterpret_cast<uint4*>(s_depth + i + 8) = depth.v[1];
     }
@@ -603,10 +605,11 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
     }
   };
 
-  // Start kernel, values: the ring pixels fetch their association record (the only global reads
-  // of the start step, all issued together). The stencils read the depth as handed in (the
-  // reference's in-place write, flagged TODO at :610, can only matter if a blended depth rounds
-  // to 0). The search for level 2 runs beside it.
+  // Start kernel, values: the ring pixels fetch their association record and their depth as handed in
+  // (the only global reads of the start step, all issued together; a pixel can sit on both rings, and
+  // the ring-0 update rewrites the working depth, so the shared copy is not read here). The
+  // reference's in-place write of the start kernel, flagged TODO at :610, can only matter if a
+  // blended depth rounds to 0. The search for level 2 runs beside it.
   if (radius > 2) search_level(2);
   for (int t = threadIdx.x; t < end0 + end1; t += kBlendBlock) {
     const bool surfel_ring = t >= end0;
@@ -614,9 +617,9 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
     const int lx = static_cast<int>(q & 0xFFu), ly = static_cast<int>(q >> 8);
     const int i = ly * rw + lx;
     const PixelAssoc a = d.assoc[(y0 + ly) * d.width + x0 + lx];
+    const float depth_f = u2f(row_ptr(f.depth_pre, f.depth_pre_pitch, y0 + ly)[x0 + lx]);
     const float sum = __uint_as_float(a.w);
     const float rcp_count = frcp(u2f(a.z));
-    const float depth_f = u2f(s_depth0[i]);
     if (surfel_ring) {
       s_ndelta[i] = ffma(sum, rcp_count, -fmul(depth_f, rcp_scaling));
     } else {
@@ -677,7 +680,8 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
   }
 
   SM_BLEND_CLOCK(4);
-  // Write back the changed 8-pixel chunks of the tile interior.
+  // Write back the tile interior (f.depth holds the same values as f.depth_pre so far: tiles that no
+  // ring reaches returned above and keep them).
   constexpr int kChunksPerTileRow = kBlendTileW / 8;
   for (int t = threadIdx.x; t < kBlendTileH * kChunksPerTileRow; t += kBlendBlock) {
     const int row = t / kChunksPerTileRow, chunk = t - row * kChunksPerTileRow;
@@ -685,17 +689,15 @@ __global__ void __launch_bounds__(kBlendBlock) k_blend(DeviceState d, FrameParam
     const int lx = halo_x + chunk * 8, gx = x0 + lx;
     if (gy >= d.height || gx >= d.width) continue;
     const int i = ly * rw + lx;
-    union { uint4 v; u16 e[8]; } now, before;
+    union { uint4 v; u16 e[8]; } now;
     now.v = *reinterpret_cast<const uint4*>(s_depth + i);
-    before.v = *reinterpret_cast<const uint4*>(s_depth0 + i);
-    if (now.v.x == before.v.x && now.v.y == before.v.y && now.v.z == before.v.z && now.v.w == before.v.w) continue;
     u16* out_row = row_ptr(f.depth, f.depth_pitch, gy);
     if (vector_ok && gx + 8 <= d.width) {
       *reinterpret_cast<uint4*>(out_row + gx) = now.v;
     } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        if (gx + k < d.width && now.e[k] != before.e[k]) out_row[gx + k] = now.e[k];
+        if (gx + k < d.width) out_row[gx + k] = now.e[k];
     }
   }
 #ifdef SM_BLEND_CLOCKS
@@ -850,7 +852,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
       SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = 0;
       SM_S(SM_ROW_RADIUS_SQUARED, idx) = -1.0f;
       reinterpret_cast<u8*>(&SM_SU(SM_ROW_COLOR, idx))[3] = 1;
-      SM_SU(SM_ROW_ACCUM_X, idx) = f.op_epoch;  // row 14 is unused by the reference: when it was merged (delta transfer)
+      SM_SU(kRowMeta, idx) = kMetaDetachBit;      // stamp 0, detach flag set
+      SM_SU(kRowMergeEpoch, idx) = f.op_epoch;    // when it was merged (delta transfer)
       return;
     }
     if (!(e.x & kActiveBit)) return;
@@ -863,7 +866,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
     SM_S(SM_ROW_RADIUS_SQUARED, idx) = s.radius_squared;
     SM_S(SM_ROW_NORMAL_X, idx) = s.nx; SM_S(SM_ROW_NORMAL_Y, idx) = s.ny; SM_S(SM_ROW_NORMAL_Z, idx) = s.nz;
     SM_SU(SM_ROW_COLOR, idx) = s.color;
-    if (s.stamped) SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
+    if (s.stamped) {
+      // every path that changes the colour's flag byte also stamps the surfel
+      SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
+      SM_SU(kRowMeta, idx) = f.frame_index | (((s.color >> 24) & 1u) ? kMetaDetachBit : 0u);
+    }
     if (s.replaced) {
       SM_SMOOTH(0, idx) = s.smooth_x; SM_SMOOTH(1, idx) = s.smooth_y; SM_SMOOTH(2, idx) = s.smooth_z;
       SM_SU(SM_ROW_CREATION_STAMP, idx) = f.frame_index;
@@ -1160,6 +1167,7 @@ __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameP
     SM_S(SM_ROW_CONFIDENCE, idx) = 1.0f;
     SM_SU(SM_ROW_CREATION_STAMP, idx) = f.frame_index;
     SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx) = f.frame_index;
+    SM_SU(kRowMeta, idx) = f.frame_index;
     SM_S(SM_ROW_RADIUS_SQUARED, idx) = radius_squared;
     // The reference leaves rows 11-16 and 23 uninitialised; here rows 11-13 and 23 are always
     // zero and the regularisation accumulates in d.gradient, zero between calls (regularize.cu).
@@ -1194,14 +1202,14 @@ __global__ void __launch_bounds__(kBlock) k_export_vertices(DeviceState d, int c
 }  // namespace
 
 namespace {
-// Dynamic shared memory of k_blend: 16 B per region pixel + 11 bit rasters (see the kernel's carve-up).
+// Dynamic shared memory of k_blend: 14 B per region pixel + 11 bit rasters (see the kernel's carve-up).
 size_t BlendSmemBytes(int radius) {
   const size_t rw = kBlendTileW + 2 * blend_halo_x(radius), rh = kBlendTileH + 2 * blend_halo_y(radius);
   const size_t rn16 = (rw * rh + 15) & ~static_cast<size_t>(15);
   const size_t mask_words = rh * ((rw + 31) / 32);
-  return rn16 * 16 + mask_words * 11 * 4 + 16;
+  return rn16 * 14 + mask_words * 11 * 4 + 16;
 }
-constexpr size_t kBlendSmemLimit = 224 * 1024;  // one region per block has to fit an SM (radius <= 25 at the 80x32 tile)
+constexpr size_t kBlendSmemLimit = 224 * 1024;  // one region per block has to fit an SM
 
 #define SM_EV(call)                                                              \
   do {                                                                           \
@@ -1231,7 +1239,7 @@ int DescribeFrameKernel(FrameKernel which, const LaunchPlan& plan, const DeviceS
     case FK_BLEND: {
       const size_t smem = BlendSmemBytes(f.blend_radius);
       if (f.blend_radius < 1 || f.blend_radius > kMaxBlendRadius || smem > kBlendSmemLimit)
-        return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius out of range (1 .. 25)");
+        return SetError(SM_ERR_INVALID_ARGUMENT, "measurement_blending_radius too large for one tile region per SM");
       const dim3 pixel_tiles((d.width + kBlendTileW - 1) / kBlendTileW, (d.height + kBlendTileH - 1) / kBlendTileH);
       out->Reset(reinterpret_cast<const void*>(k_blend), pixel_tiles, dim3(kBlendBlock), smem, KID_BLEND);
       break;

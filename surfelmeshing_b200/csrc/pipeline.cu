@@ -237,7 +237,7 @@ int RunStreams(RunContext& c, cudaStream_t stream, bool pipelined, uint32_t* int
                                    r->assoc_set[set], r->first_depth_set[set], r->supported_set[set],
                                    pipelined ? r->run_depth_pre[set] : nullptr, r->run_depth_pitch,
                                    TimelineSlot(r->d, static_cast<u32>(frame), KID_BILATERAL_OUTLIER),
-                                   TimelineSlot(r->d, static_cast<u32>(frame), KID_ERODE_NORMALS_RADII));
+                                   TimelineSlot(r->d, static_cast<u32>(frame), KID_ERODE_NORMALS_RADII), r->ScratchBMap());
     if (st != SM_OK) return st;
     SM_CUDA(cudaEventRecord(r->pre_done[set], r->pre_stream));
     return SM_OK;
@@ -504,7 +504,7 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
                                   r->run_normals_pitch, r->run_radius[set], r->run_radius_pitch, r->assoc_set[set],
                                   r->first_depth_set[set], r->supported_set[set], r->run_depth_pre[set],
                                   r->run_depth_pitch, TimelineSlot(r->d, static_cast<u32>(frame), KID_BILATERAL_OUTLIER),
-                                  TimelineSlot(r->d, static_cast<u32>(frame), KID_ERODE_NORMALS_RADII));
+                                  TimelineSlot(r->d, static_cast<u32>(frame), KID_ERODE_NORMALS_RADII), r->ScratchBMap());
       if (status != SM_OK) return status;
     }
 

@@ -18,6 +18,8 @@
 // per-stage parity tests). All arithmetic follows the reference's sm_100a SASS op for op
 // (see sm_math.cuh); the u16 outputs are bit-exact.
 
+#include <cuda.h>  // CUtensorMap
+
 #include "sm_kernels.cuh"
 
 namespace smb {
@@ -436,41 +438,111 @@ struct TailArgs {
 
 constexpr int kMaxErode = 3;
 
+// TMA (cp.async.bulk.tensor) + mbarrier primitives for the tile fill below.
+__device__ __forceinline__ u32 smem_u32(const void* p) { return static_cast<u32>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarrier_init(unsigned long long* bar, u32 arrive_count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrive_count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbarrier_arrive_expect_tx(unsigned long long* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarrier_wait(unsigned long long* bar, u32 phase) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// 2-D tiled TMA load: box of the tensor map at element coordinates (x, y) -> dense shared-memory tile;
+// elements outside the tensor arrive as zeros.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+               : "memory");
+}
+
+// Output tile 32 x 16 pixels, 256 threads (two output pixels per thread; the halo stages stride over
+// the block), 8 blocks per SM: all 600 blocks of a VGA frame are resident at once. Halo recompute per
+// output pixel: B 2.4 / E 1.4 / N 1.2 loads-or-pixels (32 x 8 tiles of round 1: 3.0 / 1.7 / 1.3).
+constexpr int kTailTileH = 16;
+constexpr int kTailHaloY = kMaxErode + 2;   // B tile rows above / below the output tile
+constexpr int kTailHaloX = 8;               // >= kMaxErode + 2; 8 keeps every 8-pixel group 16-byte aligned
+constexpr int kTailBW = kTileW + 2 * kTailHaloX;          // 48 pixels = 96 bytes per tile row
+constexpr int kTailBH = kTailTileH + 2 * kTailHaloY;      // 26 rows
+enum { kFillVector = 0, kFillTma = 1 };
+
+// kFill selects how the outlier-filtered input tile (+ halo) reaches shared memory:
+//   kFillTma    one thread issues ONE 2-D TMA box load (cp.async.bulk.tensor, 48 x 26 u16 = 2496 bytes,
+//               out-of-image elements zero-filled by the hardware) and the block waits on an mbarrier:
+//               no per-element index math or bounds tests at all;
+//   kFillVector cooperative 128-bit loads (one aligned 8-pixel group per thread, scalar + bounds-checked
+//               only at the image border).
+// (Round 1 filled a 42 x 18 tile with scalar, bounds-checked u16 loads.)
+template <int kFill>
 __global__ void __launch_bounds__(256, 8)
-k_erode_normals_radii(TailArgs a) {
+k_erode_normals_radii(TailArgs a, const __grid_constant__ CUtensorMap in_map) {
   pdl_prologue();
   if (a.skip) return;
   const TimelineScope timeline_scope(a.timeline);
-  // Tiles (origin relative to the 32 x 8 output tile): B (outlier-filtered input) -5, HV
+  // Tiles (origin relative to the 32 x 16 output tile): B (outlier-filtered input) (-8, -5), HV
   // (row-wise erosion validity) -2 / -(2 + r), E (eroded) -2, N (normals stage) -1.
-  constexpr int HB = kMaxErode + 2;
-  constexpr int BW = kTileW + 2 * HB, BH = kTileH + 2 * HB;   // 42 x 18
-  constexpr int EW = kTileW + 4, EH = kTileH + 4;             // 36 x 12
-  constexpr int HVH = EH + 2 * kMaxErode;                     // 18 rows
-  constexpr int NW = kTileW + 2, NH = kTileH + 2;             // 34 x 10
-  __shared__ u16 sB[BH * BW];
+  constexpr int TH = kTailTileH, HB = kTailHaloY, HBX = kTailHaloX, BW = kTailBW, BH = kTailBH;
+  constexpr int EW = kTileW + 4, EH = TH + 4;                 // 36 x 20
+  constexpr int HVH = EH + 2 * kMaxErode;                     // 26 rows
+  constexpr int NW = kTileW + 2, NH = TH + 2;                 // 34 x 18
+  __shared__ __align__(128) u16 sB[BH * BW];
+  __shared__ __align__(8) unsigned long long fill_barrier;
   __shared__ u8 sHV[HVH * EW];
   __shared__ u16 sE[EH * EW];
   __shared__ u16 sN[NH * NW];
 
   const int r = a.erosion_radius;
   const int tile_x = blockIdx.x * kTileW;
-  const int tile_y = blockIdx.y * kTileH;
+  const int tile_y = blockIdx.y * TH;
 
-  for (int i = threadIdx.x; i < BW * BH; i += 256) {
-    const int ly = i / BW, lx = i - ly * BW;
-    const int gx = tile_x - HB + lx, gy = tile_y - HB + ly;
-    u16 v = 0;
-    if (gx >= 0 && gy >= 0 && gx < a.width && gy < a.height) v = row_ptr(a.in, a.in_pitch, gy)[gx];
-    sB[i] = v;
+  if (kFill == kFillTma) {
+    if (threadIdx.x == 0) mbarrier_init(&fill_barrier, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbarrier_arrive_expect_tx(&fill_barrier, BH * BW * sizeof(u16));
+      tma_load_2d(sB, &in_map, tile_x - HBX, tile_y - HB, &fill_barrier);
+    }
+    mbarrier_wait(&fill_barrier, 0);
+  } else {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a.in) | a.in_pitch) & 15) == 0;
+    constexpr int kVecPerRow = BW / 8;
+    for (int v = threadIdx.x; v < BH * kVecPerRow; v += 256) {
+      const int ly = v / kVecPerRow, lx = (v - ly * kVecPerRow) * 8;
+      const int gx = tile_x - HBX + lx, gy = tile_y - HB + ly;
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      if (gy >= 0 && gy < a.height) {
+        if (aligned && gx >= 0 && gx + 8 <= a.width) {
+          q = __ldg(reinterpret_cast<const uint4*>(row_ptr(a.in, a.in_pitch, gy) + gx));
+        } else {
+          union { uint4 v; u16 e[8]; } t;
+          t.v = q;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (gx + k >= 0 && gx + k < a.width) t.e[k] = row_ptr(a.in, a.in_pitch, gy)[gx + k];
+          q = t.v;
+        }
+      }
+      *reinterpret_cast<uint4*>(&sB[ly * BW + lx]) = q;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   // Erosion (cuda_depth_processing.cu:514-538), separable: row-wise validity, then columns.
+  // E (ex, ey) is image pixel (tile_x - 2 + ex, tile_y - 2 + ey) = sB[(ey - 2 + HB) * BW + ex - 2 + HBX].
   if (r > 0) {
     for (int i = threadIdx.x; i < (EH + 2 * r) * EW; i += 256) {
       const int hy = i / EW, ex = i - hy * EW;
-      const u16* row = &sB[(hy - r + HB - 2) * BW + ex + HB - 2];
+      const u16* row = &sB[(hy - r + HB - 2) * BW + ex + HBX - 2];
       bool valid = true;
       for (int dx = -r; dx <= r; ++dx) valid &= row[dx] != 0;
       sHV[i] = valid;
@@ -479,7 +551,7 @@ k_erode_normals_radii(TailArgs a) {
   }
   for (int i = threadIdx.x; i < EW * EH; i += 256) {
     const int ey = i / EW, ex = i - ey * EW;
-    const u16 center = sB[(ey + HB - 2) * BW + ex + HB - 2];
+    const u16 center = sB[(ey + HB - 2) * BW + ex + HBX - 2];
     u16 v = 0;
     if (center != 0) {
       if (r > 0) {
@@ -513,15 +585,16 @@ k_erode_normals_radii(TailArgs a) {
         v = normals_pixel(a.normals, gx, gy, center, left, right, top, bottom, &normal);
       }
     }
-    const bool interior = lx >= 1 && lx <= kTileW && ly >= 1 && ly <= kTileH;
+    const bool interior = lx >= 1 && lx <= kTileW && ly >= 1 && ly <= TH;
     if (interior && gx < a.width && gy < a.height) row_ptr(a.out_normals, a.out_normals_pitch, gy)[gx] = normal;
     sN[i] = v;
   }
   __syncthreads();
 
-  // Radii on the tile interior.
-  {
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  // Radii on the tile interior: two output pixels per thread.
+#pragma unroll
+  for (int half = 0; half < TH / 8; ++half) {
+    const int lx = threadIdx.x & 31, ly = (threadIdx.x >> 5) + 8 * half;
     const int gx = tile_x + lx, gy = tile_y + ly;
     if (gx < a.width && gy < a.height) {
       const u16 center = sN[(ly + 1) * NW + lx + 1];
@@ -729,7 +802,7 @@ RadiiArgs MakeRadiiArgs(float point_radius_extension_factor, float point_radius_
   return r;
 }
 
-dim3 TileGrid(int width, int height) { return dim3((width + kTileW - 1) / kTileW, (height + kTileH - 1) / kTileH); }
+dim3 TailGrid(int width, int height) { return dim3((width + kTileW - 1) / kTileW, (height + kTailTileH - 1) / kTailTileH); }
 dim3 PixelGrid(int width, int height) { return dim3((width + 31) / 32, (height + 7) / 8); }
 
 // The fused a1 + a2 launch (radius 6) as a descriptor.
@@ -806,11 +879,17 @@ int MakePreprocessArgs(const sm_preprocess_params& p, int width, int height, flo
   return SM_OK;
 }
 
-void DescribeTail(KernelLaunch* k, const TailArgs& t) {
-  static_assert(sizeof(TailArgs) + 16 <= sizeof(k->storage), "KernelLaunch::storage too small");
-  k->Reset(reinterpret_cast<const void*>(k_erode_normals_radii), TileGrid(t.width, t.height), dim3(256), 0,
-           KID_ERODE_NORMALS_RADII);
+// `in_map`: TMA descriptor of the raster t.in (MakeDepthTensorMap) or null -> 128-bit vector fill.
+void DescribeTail(KernelLaunch* k, const TailArgs& t, const TensorMapStorage* in_map) {
+  static_assert(sizeof(TailArgs) + sizeof(CUtensorMap) + 128 <= sizeof(k->storage), "KernelLaunch::storage too small");
+  static_assert(sizeof(TensorMapStorage) == sizeof(CUtensorMap) && alignof(TensorMapStorage) == alignof(CUtensorMap), "TensorMapStorage");
+  static const TensorMapStorage kNoMap = {};
+  const bool tma = in_map != nullptr;
+  k->Reset(tma ? reinterpret_cast<const void*>(k_erode_normals_radii<kFillTma>)
+               : reinterpret_cast<const void*>(k_erode_normals_radii<kFillVector>),
+           TailGrid(t.width, t.height), dim3(256), 0, KID_ERODE_NORMALS_RADII);
   k->Arg(t);
+  k->Arg(tma ? *in_map : kNoMap);
 }
 }  // namespace
 
@@ -821,7 +900,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
                     size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
                     float* clear_first_depth, u8* clear_supported, u16* out_depth_copy,
                     size_t out_depth_copy_pitch, unsigned long long* timeline_bilateral,
-                    unsigned long long* timeline_tail) {
+                    unsigned long long* timeline_tail, const TensorMapStorage* scratch_B_map) {
   BilateralArgs b;
   OutlierArgs o;
   TailArgs t;
@@ -835,7 +914,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
   status = LaunchBilateral(stream, b, &o, scratch_B, scratch_B_pitch);
   if (status != SM_OK) return status;
   KernelLaunch k;
-  DescribeTail(&k, t);
+  DescribeTail(&k, t, scratch_B_map);
   LaunchOnStream(stream, k, true);
   return CheckLaunch("erode/normals/radii");
 }
@@ -847,7 +926,7 @@ int DescribePreprocess(KernelLaunch* bilateral, KernelLaunch* tail, bool skip, c
                        float2* out_normals, size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch,
                        uint4* clear_assoc, float* clear_first_depth, u8* clear_supported, u16* out_depth_copy,
                        size_t out_depth_copy_pitch, unsigned long long* timeline_bilateral,
-                       unsigned long long* timeline_tail) {
+                       unsigned long long* timeline_tail, const TensorMapStorage* scratch_B_map) {
   BilateralArgs b;
   OutlierArgs o;
   TailArgs t;
@@ -863,7 +942,39 @@ int DescribePreprocess(KernelLaunch* bilateral, KernelLaunch* tail, bool skip, c
   b.skip = skip ? 1 : 0;
   t.skip = skip ? 1 : 0;
   DescribeBilateralOutlier(bilateral, b, &o, scratch_B, scratch_B_pitch);
-  DescribeTail(tail, t);
+  DescribeTail(tail, t, scratch_B_map);
+  return SM_OK;
+}
+
+// TMA descriptor of a pitched u16 raster for the tile fill of k_erode_normals_radii: 2-D tiled, box
+// kTailBW x kTailBH elements, no swizzle / interleave, out-of-bounds elements read as zero.
+// cuTensorMapEncodeTiled is a driver entry point: resolved through the runtime (no libcuda link).
+int MakeDepthTensorMap(TensorMapStorage* out, const u16* base, size_t pitch_bytes, int width, int height) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult query;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &query) != cudaSuccess ||
+        query != cudaDriverEntryPointSuccess || fn == nullptr) {
+      cudaGetLastError();
+      return SetError(SM_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    }
+    encode = reinterpret_cast<EncodeTiled>(fn);
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0)
+    return SetError(SM_ERR_INVALID_ARGUMENT, "TMA needs a 16-byte aligned raster and pitch");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(height)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_bytes)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTailBW), static_cast<cuuint32_t>(kTailBH)};
+  const cuuint32_t element_strides[2] = {1, 1};
+  const CUresult res = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<u16*>(base),
+                              dims, strides, box, element_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) return SetError(SM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   return SM_OK;
 }
 
@@ -946,7 +1057,8 @@ int ConfigurePreprocessKernels(int carveout_percent) {
   cudaFuncSetAttribute(k_bilateral_outlier<6, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_bilateral_generic, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_outlier, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
-  cudaFuncSetAttribute(k_erode_normals_radii, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_erode_normals_radii<kFillTma>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+  cudaFuncSetAttribute(k_erode_normals_radii<kFillVector>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_erode, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_normals, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
   cudaFuncSetAttribute(k_radii, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);

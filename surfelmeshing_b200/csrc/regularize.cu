@@ -71,13 +71,13 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
     }
     if ((nbr[0] & nbr[1] & nbr[2] & nbr[3]) == kInvalidIndex) continue;  // no neighbours at all
 
-    // batch 1: detach flags and stamps of the neighbours, and this surfel's own attributes
-    u32 flag_word[4], stamp[4];
+    // batch 1: detach flag + stamp of the neighbours (one gather each: row kRowMeta), and this surfel's
+    // own attributes
+    u32 meta[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const u32 q = nbr[k] != kInvalidIndex ? nbr[k] : i;
-      flag_word[k] = SM_SU(SM_ROW_COLOR, q);
-      stamp[k] = SM_SU(SM_ROW_LAST_UPDATE_STAMP, q);
+      meta[k] = SM_SU(kRowMeta, q);
     }
     const float sx = SM_SMOOTH(0, i), sy = SM_SMOOTH(1, i), sz = SM_SMOOTH(2, i);
     const float nx = SM_S(SM_ROW_NORMAL_X, i), ny = SM_S(SM_ROW_NORMAL_Y, i), nz = SM_S(SM_ROW_NORMAL_Z, i);
@@ -89,11 +89,11 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
     int neighbor_count = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (i < n_remove && nbr[k] != kInvalidIndex && (flag_word[k] >> 24) == 1u) {
+      if (i < n_remove && nbr[k] != kInvalidIndex && (meta[k] & kMetaDetachBit)) {
         nbr[k] = kInvalidIndex;
         SM_SU(SM_ROW_NEIGHBOR0 + k, i) = kInvalidIndex;
       }
-      use[k] = nbr[k] != kInvalidIndex && !outside_window(stamp[k], p);
+      use[k] = nbr[k] != kInvalidIndex && !outside_window(meta[k] & ~kMetaDetachBit, p);
       neighbor_count += use[k] ? 1 : 0;
     }
     if (neighbor_count == 0) continue;
@@ -230,6 +230,21 @@ __global__ void __launch_bounds__(kBlock) k_reg_copy_only(DeviceState d, RegPara
 }
 
 }  // namespace
+
+namespace {
+__global__ void __launch_bounds__(kBlock) k_rebuild_meta(DeviceState d, u32 count) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const u32 flag = (SM_SU(SM_ROW_COLOR, i) >> 24) == 1u ? kMetaDetachBit : 0u;
+    SM_SU(kRowMeta, i) = (SM_SU(SM_ROW_LAST_UPDATE_STAMP, i) & ~kMetaDetachBit) | flag;
+  }
+}
+}  // namespace
+
+int RebuildMetaRow(cudaStream_t stream, const DeviceState& d, u32 count, int sm_count) {
+  if (count == 0) return SM_OK;
+  k_rebuild_meta<<<sm_count * 4, kBlock, 0, stream>>>(d, count);
+  return CheckLaunch("rebuild meta row");
+}
 
 int DescribeRegularize(KernelLaunch* first, KernelLaunch* second, bool skip, const LaunchPlan& plan,
                        const DeviceState& d, bool disable_denoising, u32 frame_index,

@@ -48,6 +48,17 @@ inline Mat3x4 MakeMat3x4(const float* m) {
 // ---- device-side state shared by the Integrate kernels -------------------------------------
 
 constexpr u32 kInvalidIndex = 0xFFFFFFFFu;   // APP/surfel.h:63, kernels.cu:74
+
+// Rows 14-16 of the SoA ("accum", kernels.cuh:66-68) are never touched by the reference. Two of them
+// carry bookkeeping here (sm_dump_state callers treat rows 11-16 and 23 as scratch):
+//   row 14  operation epoch at which the surfel was merged (delta transfer, transfer.cu)
+//   row 15  "meta" = last-update stamp | detach flag << 31: the two per-NEIGHBOUR values the first
+//           regularisation sweep gathers (kernels.cu:1420-1437, :2125-2139) in ONE 4-byte gather
+//           instead of two (stamp row + colour row); rewritten wherever stamp or colour.w change
+//           (k_integrate, k_create_surfels, sm_load_state). Stamps are frame indices < 2^31.
+constexpr int kRowMergeEpoch = SM_ROW_ACCUM_X;
+constexpr int kRowMeta = SM_ROW_ACCUM_Y;
+constexpr u32 kMetaDetachBit = 0x80000000u;
 constexpr int kSegment = 1024;               // surfel slots per list segment (one block-iteration)
 constexpr u32 kActiveBit = 0x80000000u;      // VisEntry.idx: surfel was active at projection time
 
@@ -261,7 +272,7 @@ struct KernelLaunch {
   int kernel_id;                 // KernelId
   int arg_count;
   void* args[4];                 // point into storage
-  alignas(16) unsigned char storage[2304];
+  alignas(64) unsigned char storage[2304];
   size_t used;
   void Reset(const void* f, dim3 g, dim3 b, size_t shared, int id) {
     func = f; grid = g; block = b; smem = shared; kernel_id = id; arg_count = 0; used = 0;
@@ -269,7 +280,7 @@ struct KernelLaunch {
   template <typename T>
   void Arg(const T& v) {
     used = (used + alignof(T) - 1) / alignof(T) * alignof(T);
-    static_assert(alignof(T) <= 16, "argument alignment");
+    static_assert(alignof(T) <= 64, "argument alignment");
     memcpy(storage + used, &v, sizeof(T));   // used + sizeof(T) <= sizeof(storage): checked by the static_asserts at the call sites
     args[arg_count++] = storage + used;
     used += sizeof(T);
@@ -293,6 +304,9 @@ int ConfigureIntegrateKernels(int carveout_percent, LaunchPlan* plan);
 int ConfigureRegularizeKernels(int carveout_percent, LaunchPlan* plan);
 
 // ---- preprocess.cu --------------------------------------------------------------------------
+// Opaque storage of a CUtensorMap (TMA descriptor; cuda.h stays out of this header).
+struct alignas(64) TensorMapStorage { unsigned char bytes[128]; };
+int MakeDepthTensorMap(TensorMapStorage* out, const u16* base, size_t pitch_bytes, int width, int height);
 int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int width, int height, float fx, float fy,
                     float cx, float cy, const u16* raw, size_t raw_pitch, const u16* const* other_depths,
                     const size_t* other_pitches, const float* others_TR_reference, u16* scratch_B,
@@ -300,7 +314,7 @@ int PreprocessFused(cudaStream_t stream, const sm_preprocess_params& p, int widt
                     size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch, uint4* clear_assoc,
                     float* clear_first_depth, u8* clear_supported, u16* out_depth_copy = nullptr,
                     size_t out_depth_copy_pitch = 0, unsigned long long* timeline_bilateral = nullptr,
-                    unsigned long long* timeline_tail = nullptr);
+                    unsigned long long* timeline_tail = nullptr, const TensorMapStorage* scratch_B_map = nullptr);
 // The same two launches as descriptors (frame graph). `skip`: placeholder launches.
 int DescribePreprocess(KernelLaunch* bilateral, KernelLaunch* tail, bool skip, const sm_preprocess_params& p, int width,
                        int height, float fx, float fy, float cx, float cy, const u16* raw, size_t raw_pitch,
@@ -309,7 +323,7 @@ int DescribePreprocess(KernelLaunch* bilateral, KernelLaunch* tail, bool skip, c
                        float2* out_normals, size_t out_normals_pitch, float* out_radius, size_t out_radius_pitch,
                        uint4* clear_assoc, float* clear_first_depth, u8* clear_supported, u16* out_depth_copy,
                        size_t out_depth_copy_pitch, unsigned long long* timeline_bilateral,
-                       unsigned long long* timeline_tail);
+                       unsigned long long* timeline_tail, const TensorMapStorage* scratch_B_map);
 int StageBilateral(cudaStream_t stream, float sigma_xy, float sigma_value_factor, u16 value_to_ignore,
                    float radius_factor, u16 max_depth, float depth_valid_region_radius, int width, int height,
                    const u16* in, size_t in_pitch, u16* out, size_t out_pitch);
@@ -377,6 +391,8 @@ int ExportVertices(cudaStream_t stream, const DeviceState& d, int count_slot, in
 // `remove_replaced_below`: if >= 0, slot of the surfel count below which neighbour links to
 // surfels with the detach flag are dropped first (UpdateNeighborsCUDARemoveReplacedNeighbors
 // fused into the first sweep); -1 = no removal.
+// Rebuilds row kRowMeta from the stamp and colour rows of slots [0, count) (after sm_load_state).
+int RebuildMetaRow(cudaStream_t stream, const DeviceState& d, u32 count, int sm_count);
 int RegularizeSurfels(cudaStream_t stream, DeviceState& d, bool disable_denoising, u32 frame_index,
                       float radius_factor_for_regularization_neighbors, float regularizer_weight,
                       int regularization_frame_window_size, int count_slot, int remove_replaced_below_slot,

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kBlock) k_delta_select(DeviceState d, DeltaArg
       stamp = SM_SU(SM_ROW_LAST_UPDATE_STAMP, i);
       radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, i);
       changed = i >= a.count_at_token || static_cast<int>(stamp) >= a.stamp_threshold ||
-                (radius_squared < 0.f && SM_SU(SM_ROW_ACCUM_X, i) > a.epoch_at_token);
+                (radius_squared < 0.f && SM_SU(kRowMergeEpoch, i) > a.epoch_at_token);
     }
     // warp-aggregated reservation: one atomic per warp, records of a warp stay in slot order
     const unsigned mask = __ballot_sync(0xffffffffu, changed);

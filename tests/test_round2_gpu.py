@@ -7,6 +7,7 @@ import ctypes as C
 import numpy as np
 import pytest
 import torch
+from scipy import ndimage
 
 from oracle import cpu_walk
 from surfelmeshing_b200 import _lib, synthetic as S
@@ -31,6 +32,7 @@ def stream_and_params(width, height, frames, stream_id, sigma=None):
     st = S.make_stream(cam, frames, stream_id=stream_id, sigma_depth=sigma, device="cuda")
     pp = PreprocessParams.defaults()
     pp.depth_valid_region_radius = cam.valid_region_radius()
+    torch.cuda.synchronize()  # the frames are complete before any other stream touches them
     return cam, st, pp, IntegrateParams.defaults()
 
 
@@ -362,10 +364,9 @@ def test_race_bound_rows_inside_the_reference_envelope(product, reference):
         env_links, got_links = link_rows_differ(rb, ra), link_rows_differ(rp, ra)
         assert got_links <= 2 * env_links + 24, (frame, got_links, env_links)
         # --- exact neighbour links away from contested pixels ---
+        # (the integration may move a surfel into the next pixel before its neighbourhood is read: 3 pixels of margin)
         contested_map = (cnt > 1).reshape(cam.height, W)
-        near = contested_map.copy()
-        near[1:, :] |= contested_map[:-1, :]; near[:-1, :] |= contested_map[1:, :]
-        near[:, 1:] |= contested_map[:, :-1]; near[:, :-1] |= contested_map[:, 1:]
+        near = ndimage.binary_dilation(contested_map, structure=np.ones((3, 3), bool), iterations=3)
         # surfels whose primary pixel (recomputed by the CPU walk) has a clean 4-neighbourhood
         clean_px = np.flatnonzero(~near.reshape(-1))
         clean_surfels = np.unique(np.concatenate([sets[p] for p in clean_px if p in sets and len(sets[p]) == 1]

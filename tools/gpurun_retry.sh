@@ -4,7 +4,7 @@ T=$1; LOG=$2; shift 2
 for i in $(seq 1 40); do
   /usr/local/graft/bin/gpurun --timeout $T -- "$@" > $LOG 2>&1
   rc=$?
-  if grep -q "status=transient" $LOG; then sleep 100; continue; fi
+  if grep -q "status=transient" $LOG; then sleep 15; continue; fi
   exit $rc
 done
 exit 3
