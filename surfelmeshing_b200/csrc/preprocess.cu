@@ -447,16 +447,20 @@ __device__ __forceinline__ void mbarrier_init(unsigned long long* bar, u32 arriv
 __device__ __forceinline__ void mbarrier_arrive_expect_tx(unsigned long long* bar, u32 bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Bounded wait: a transfer that never completes (it cannot with a valid descriptor) traps instead of
+// hanging the GPU.
 __device__ __forceinline__ void mbarrier_wait(unsigned long long* bar, u32 phase) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+  for (u32 attempt = 0; attempt < (1u << 22); ++attempt) {
+    u32 done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    if (done) return;
+  }
+  __trap();
 }
 // 2-D tiled TMA load: box of the tensor map at element coordinates (x, y) -> dense shared-memory tile;
 // elements outside the tensor arrive as zeros.
