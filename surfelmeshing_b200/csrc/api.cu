@@ -90,9 +90,9 @@ u32 ModInverse(u32 x, u32 m) {
 
 int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity) {
   if (wave != 0) {
-    // keys are (slot / W) * W + perm(slot % W) < 2^31 - 1
-    const unsigned long long top = (static_cast<unsigned long long>(capacity) / wave + 1) * wave;
-    if (wave < 2 || top >= 0x7FFFFFFFull) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range for this surfel cap");
+    // keys are (slot / W) * 2 W + late * W + perm(slot % W) < 2^32 - 1
+    const unsigned long long top = (static_cast<unsigned long long>(capacity) / wave + 1) * 2ull * wave;
+    if (wave < 2 || top >= 0xFFFFFFFFull) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range for this surfel cap");
     const unsigned long long prime = 2654435761ull;  // > any wave, so gcd(prime % wave, wave) = 1
     cfg->mul = static_cast<u32>(prime % wave);
     if (cfg->mul == 0) cfg->mul = 1;
@@ -110,8 +110,12 @@ TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index) {
   t.mul_inv = cfg.mul_inv;
   t.add = tb_hash(frame_index * 0x9E3779B9u + 0x7F4A7C15u) % cfg.wave;
   t.salt = tb_hash(frame_index ^ 0x85EBCA6Bu);
-  const double scaled = cfg.early_fraction * 4294967296.0;
-  t.early_threshold = scaled <= 0 ? 0u : (scaled >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<u32>(scaled));
+  auto threshold = [](double fraction) {
+    const double scaled = fraction * 4294967296.0;
+    return scaled <= 0 ? 0u : (scaled >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<u32>(scaled));
+  };
+  t.early_threshold = threshold(cfg.early_fraction);
+  t.index_order_threshold = threshold(cfg.index_order_fraction);
   return t;
 }
 
@@ -352,10 +356,16 @@ int CreateImpl(sm_reconstruction* r, uint64_t max_surfel_count, int32_t width, i
       unsigned w = 0; double q = 0;
       if (std::sscanf(e, "%u,%lf", &w, &q) == 2) { wave = w; early = q; }
     }
-    if (wave != 0 && (static_cast<unsigned long long>(d.capacity) / wave + 1) * wave >= 0x7FFFFFFFull) wave = 0;
+    double index_order = kDefaultTieBreakIndexOrderFraction;
+    if (const char* e = std::getenv("SM_B200_TIEBREAK")) {
+      unsigned w = 0; double q = 0, b = 0;
+      if (std::sscanf(e, "%u,%lf,%lf", &w, &q, &b) == 3) index_order = b;
+    }
+    if (wave != 0 && (static_cast<unsigned long long>(d.capacity) / wave + 1) * 2ull * wave >= 0xFFFFFFFFull) wave = 0;
     const int status = SetTieBreakWave(&r->tiebreak, wave, d.capacity);
     if (status != SM_OK) return status;
     r->tiebreak.early_fraction = early;
+    r->tiebreak.index_order_fraction = index_order;
   }
   const int status = ClearAssociationRasters(nullptr, d);
   if (status != SM_OK) return status;
@@ -718,7 +728,7 @@ int sm_download_rasters(sm_reconstruction* r, void* stream_v, uint32_t* supporti
     SM_CUDA(cudaMemcpyAsync(new_surfel_indices, r->d.new_index, sizeof(u32) * P, cudaMemcpyDeviceToHost, stream));
   SM_CUDA(cudaStreamSynchronize(stream));
   for (size_t i = 0; i < P; ++i) {
-    if (supporting_surfels) supporting_surfels[i] = supporting_index(r->last_tiebreak, assoc[i].x);
+    if (supporting_surfels) supporting_surfels[i] = supporting_index(r->last_tiebreak, assoc[i].x, static_cast<u32>(i));
     if (conflicting_surfels) conflicting_surfels[i] = assoc[i].y;
     if (supporting_surfel_counts) supporting_surfel_counts[i] = assoc[i].z;
     if (supporting_surfel_depth_sums) std::memcpy(&supporting_surfel_depth_sums[i], &assoc[i].w, sizeof(float));
@@ -783,6 +793,7 @@ int sm_stream_run(sm_reconstruction* r, void* stream_v, const sm_stream_desc* s,
 // Named tuning / experiment knobs of a handle (no counterpart in the reference):
 //   "tiebreak_wave"            slots per launch wave of the modelled association race (0 = plain rule)
 //   "tiebreak_early_fraction"  fraction of secondary-pixel associations that compete like primary ones
+//   "tiebreak_index_order_fraction"  fraction of the pixels whose supporters are ordered by slot index inside a wave
 //   "median_filter_and_densify_iterations"  sm_stream_run: MedianFilterAndDensifyDepthMap passes over every raw
 //                              depth map on its way into the frame ring (APP/main.cc:435, 927-939; default 0)
 int sm_configure(sm_reconstruction* r, const char* key, double value) {
@@ -795,6 +806,11 @@ int sm_configure(sm_reconstruction* r, const char* key, double value) {
   if (k == "tiebreak_early_fraction") {
     if (!(value >= 0.0 && value <= 1.0)) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_early_fraction must be in [0, 1]");
     r->tiebreak.early_fraction = value;
+    return SM_OK;
+  }
+  if (k == "tiebreak_index_order_fraction") {
+    if (!(value >= 0.0 && value <= 1.0)) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_index_order_fraction must be in [0, 1]");
+    r->tiebreak.index_order_fraction = value;
     return SM_OK;
   }
   if (k == "median_filter_and_densify_iterations") {

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
       PixelAssoc* a = &d.assoc[pp];
       // Reference: atomicCAS(INV -> idx), first come wins. Here: the minimum of a reproducible
       // arrival key (sm_kernels.cuh, kSecondaryBit) - one of the reference's legal outcomes.
-      atomicMin(&a->x, tb_encode(f.tb, idx, k == 1));
+      atomicMin(&a->x, tb_encode(f.tb, idx, k == 1, static_cast<u32>(pp)));
       atomicAdd(&a->z, 1u);
       atomicAdd(reinterpret_cast<float*>(&a->w), z);
       d.supported[pp] = 1;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) 
     const int pp = p.py * d.width + p.px;
     // batch 1
     const PixelGate g = load_pixel_gate(d, f, p.px, p.py);
-    const u32 supported_surfel = supporting_index(f.tb, d.assoc[pp].x);
+    const u32 supported_surfel = supporting_index(f.tb, d.assoc[pp].x, static_cast<u32>(pp));
     const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
     const float snx = SM_S(SM_ROW_NORMAL_X, idx), sny = SM_S(SM_ROW_NORMAL_Y, idx), snz = SM_S(SM_ROW_NORMAL_Z, idx);
     const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
@@ -916,8 +916,8 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
     u32 candidate[4];
 #pragma unroll
     for (int direction = 0; direction < 4; ++direction) {
-      candidate[direction] =
-          supporting_index(f.tb, d.assoc[(y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction]].x);
+      const int candidate_pixel = (y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction];
+      candidate[direction] = supporting_index(f.tb, d.assoc[candidate_pixel].x, static_cast<u32>(candidate_pixel));
     }
     if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) return;  // occluded
     float3 ln;
@@ -1120,7 +1120,7 @@ __global__ void __launch_bounds__(kBlock) k_create_surfels(DeviceState d, FrameP
     for (int direction = 0; direction < 4; ++direction) {
       const int nx_ = x + kDirectionsX[direction], ny_ = y + kDirectionsY[direction];
       const int nseq = ny_ * d.width + nx_;
-      neighbor_index[direction] = supporting_index(f.tb, d.assoc[nseq].x);
+      neighbor_index[direction] = supporting_index(f.tb, d.assoc[nseq].x, static_cast<u32>(nseq));
       neighbor_is_new[direction] = d.new_flag[nseq];
       neighbor_new_index[direction] = d.new_index[nseq];
       neighbor_depth[direction] = row_ptr(f.depth, f.depth_pitch, ny_)[nx_];

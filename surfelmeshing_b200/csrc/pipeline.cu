@@ -403,9 +403,9 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
   const int iterations = c.ip->regularization_iterations_per_integration_iteration;
   const bool disable_denoising = iterations == 0;
   const int reg_launches = disable_denoising ? 1 : 2 * iterations;
-  const bool split_project = EnvInt("SM_B200_SPLIT_PROJECT", 1) != 0;
+  const bool split_project = EnvInt("SM_B200_SPLIT_PROJECT", 0) != 0;
   const StepLayout l = MakeLayout(blending, reg_launches, split_project);
-  const int pdl = EnvInt("SM_B200_GRAPH_PDL", 1);
+  const int pdl = EnvInt("SM_B200_GRAPH_PDL", 0);
   std::vector<KernelLaunch> launches(l.count);
 
   cudaStream_t gs = r->graph_stream;

@@ -29,6 +29,14 @@ namespace {
 #define SM_SMOOTH_NEXT(axis, i) d.smooth_next[static_cast<size_t>(axis) * d.stride + (i)]
 
 constexpr int kBlock = 256;
+// Minimum resident blocks per SM of the two sweeps (0 = whatever the register count gives: 4 and 5).
+// A/B hook (tools/build_variant.sh): more resident warps against spills.
+#ifndef SM_REG_ACCUMULATE_MIN_BLOCKS
+#define SM_REG_ACCUMULATE_MIN_BLOCKS 1
+#endif
+#ifndef SM_REG_STEP_MIN_BLOCKS
+#define SM_REG_STEP_MIN_BLOCKS 1
+#endif
 
 struct RegParams {
   u32 frame_index;
@@ -46,7 +54,7 @@ __device__ __forceinline__ bool outside_window(u32 stamp, const RegParams& p) {
   return static_cast<int>(stamp) < static_cast<int>(p.frame_index - static_cast<u32>(p.window));
 }
 
-__global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegParams p) {
+__global__ void __launch_bounds__(kBlock, SM_REG_ACCUMULATE_MIN_BLOCKS) k_reg_accumulate(DeviceState d, RegParams p) {
   pdl_prologue();
   if (p.skip) return;
   const TimelineScope timeline_scope(d, p.frame_index, KID_REG_ACCUMULATE);
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(kBlock) k_reg_accumulate(DeviceState d, RegPar
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_reg_step(DeviceState d, RegParams p) {
+__global__ void __launch_bounds__(kBlock, SM_REG_STEP_MIN_BLOCKS) k_reg_step(DeviceState d, RegParams p) {
   pdl_prologue();
   if (p.skip) return;
   const TimelineScope timeline_scope(d, p.frame_index, KID_REG_STEP);

@@ -15,11 +15,13 @@ constexpr int kSets = 3;  // buffer sets of the frame pipeline: frames f, f + 1,
 struct TieBreakConfig {
   u32 wave;              // slots per launch wave of the modelled race (0: plain "primary, then lowest index")
   double early_fraction; // fraction of secondary associations that compete like primary ones
+  double index_order_fraction;  // fraction of the pixels that order the supporters of a wave by slot index
   u32 mul, mul_inv;      // derived from wave
 };
 // Defaults (DESIGN.md section 4 has the measurements that picked them).
 constexpr u32 kDefaultTieBreakWave = 0;
 constexpr double kDefaultTieBreakEarlyFraction = 0.0;
+constexpr double kDefaultTieBreakIndexOrderFraction = 0.0;
 TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index);
 int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity);
 

@@ -63,42 +63,52 @@ constexpr int kSegment = 1024;               // surfel slots per list segment (o
 constexpr u32 kActiveBit = 0x80000000u;      // VisEntry.idx: surfel was active at projection time
 
 // PixelAssoc.x while a frame is processed: the arrival key of the winning association. The
-// reference lets the first atomicCAS win (kernels.cu:1688): which of several supporters of a
-// pixel becomes its supporting surfel is a race. The product takes the minimum of a key that
-// orders the associations the way the reference's race does ON AVERAGE and is reproducible:
-//   bit 31      "late": set for most secondary-pixel associations (a reference thread handles its
-//               primary pixel first, so primaries usually arrive first) - all but a pseudo-random
-//               fraction tb.early_fraction of them, which compete like primaries;
-//   bits 0..30  wave * W + perm(slot mod W): slots are grouped into launch waves of W slots (the
-//               reference's 1024-thread blocks are scheduled in slot order, a later wave always
-//               arrives later); inside a wave the order is a per-frame pseudo-random permutation.
-// W = 0 selects the plain rule of round 1 (late = secondary, then lowest slot index).
-// DESIGN.md section 4 has the measurements behind the parameters.
+// reference lets the first atomicCAS win (kernels.cu:1688): which of several supporters of a pixel
+// becomes its supporting surfel is a race. The product takes the minimum of a key that orders the
+// associations the way the reference's race resolves ON AVERAGE (measured, tools/race_stats.py,
+// profiles/r02_race_stats.md) and is reproducible. Most significant first:
+//   wave   slots are grouped into launch waves of W slots (the reference's 1024-thread blocks are
+//          scheduled in slot order; of two supporters in different waves the earlier wave won
+//          18 406 times out of 18 407);
+//   late   set for a secondary-pixel association (a reference thread handles its primary pixel first:
+//          inside a wave a secondary beat a primary in 2.3 % of the contests) - except for a
+//          pseudo-random fraction `early` of them, which compete like primaries;
+//   order  inside a wave: slot order for a pseudo-random fraction of the PIXELS (per frame), a per-frame
+//          pseudo-random permutation of the slots for the others (the lower slot won 72 % of the
+//          same-kind pairs, whatever their distance).
+// W = 0 selects the plain rule of round 1: late (= secondary) first, then lowest slot index.
 constexpr u32 kSecondaryBit = 0x80000000u;
 struct TieBreak {
-  u32 wave;            // W: slots per wave (0: plain rule)
-  u32 mul, mul_inv;    // perm(r) = (r * mul + add) mod W, mul * mul_inv = 1 (mod W)
-  u32 add;             // per frame
-  u32 salt;            // per frame, for the "late" draw
-  u32 early_threshold; // secondary association is NOT late iff hash(slot, salt) < early_threshold
+  u32 wave;             // W: slots per wave (0: plain rule)
+  u32 mul, mul_inv;     // perm(r) = (r * mul + add) mod W, mul * mul_inv = 1 (mod W)
+  u32 add;              // per frame
+  u32 salt;             // per frame, for the two draws
+  u32 early_threshold;  // secondary association is NOT late iff hash(slot ^ salt) < early_threshold
+  u32 index_order_threshold;  // pixel uses slot order iff hash(pixel ^ ~salt) < index_order_threshold
 };
 __host__ __device__ __forceinline__ u32 tb_hash(u32 x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
-__host__ __device__ __forceinline__ u32 tb_encode(const TieBreak& t, u32 idx, bool secondary) {
+__host__ __device__ __forceinline__ bool tb_index_order(const TieBreak& t, u32 pixel) {
+  return tb_hash(pixel ^ ~t.salt) < t.index_order_threshold;
+}
+__host__ __device__ __forceinline__ u32 tb_encode(const TieBreak& t, u32 idx, bool secondary, u32 pixel) {
   if (t.wave == 0) return idx | (secondary ? kSecondaryBit : 0u);
   const u32 w = idx / t.wave, r = idx - w * t.wave;
-  const u32 rp = static_cast<u32>((static_cast<u64>(r) * t.mul + t.add) % t.wave);
+  const u32 rp = tb_index_order(t, pixel) ? r : static_cast<u32>((static_cast<u64>(r) * t.mul + t.add) % t.wave);
   const bool late = secondary && !(tb_hash(idx ^ t.salt) < t.early_threshold);
-  return (w * t.wave + rp) | (late ? kSecondaryBit : 0u);
+  return w * (2u * t.wave) + (late ? t.wave : 0u) + rp;   // < 2^32 - 1: checked by SetTieBreakWave
 }
-__host__ __device__ __forceinline__ u32 supporting_index(const TieBreak& t, u32 key) {
+__host__ __device__ __forceinline__ u32 supporting_index(const TieBreak& t, u32 key, u32 pixel) {
   if (key == kInvalidIndex) return kInvalidIndex;
-  const u32 v = key & ~kSecondaryBit;
-  if (t.wave == 0) return v;
-  const u32 w = v / t.wave, rp = v - w * t.wave;
-  const u32 r = static_cast<u32>((static_cast<u64>(rp + t.wave - t.add) % t.wave) * t.mul_inv % t.wave);
+  if (t.wave == 0) return key & ~kSecondaryBit;
+  const u32 w = key / (2u * t.wave);
+  u32 rem = key - w * (2u * t.wave);
+  if (rem >= t.wave) rem -= t.wave;
+  const u32 r = tb_index_order(t, pixel)
+                    ? rem
+                    : static_cast<u32>((static_cast<u64>(rem + t.wave - t.add) % t.wave) * t.mul_inv % t.wave);
   return w * t.wave + r;
 }
 

@@ -492,7 +492,13 @@ def test_device_timeline_of_the_frame_pipeline(product):
         assert start(f, "k_project") >= end(f, "k_erode_normals_radii")
         if f + 1 < last:
             assert start(f + 1, "k_integrate") >= end(f, "k_reg_step")
-            assert start(f + 1, "k_project") >= end(f, "k_create_surfels")
+            assert start(f + 1, "k_project") >= end(f, "k_integrate")
+            # the segments that hold frame f's new surfels are projected after its creation kernel: by the
+            # one projection launch, or by the tail launch when the frame graph splits the projection
+            split = buf[f + 1, k["k_project_tail"], 0] != never
+            assert start(f + 1, "k_project_tail" if split else "k_project") >= end(f, "k_create_surfels")
+            if split:
+                assert start(f + 1, "k_associate") >= end(f + 1, "k_project_tail")
 
 
 def test_large_frame_stream_properties(product, reference):

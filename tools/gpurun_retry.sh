@@ -1,10 +1,11 @@
 #!/bin/bash
-# usage: tools/gpurun_retry.sh <timeout> <logfile> <command...>  -- retries while the pod answers "busy" (rc 3)
+# usage: tools/gpurun_retry.sh <timeout> <logfile> <command...>  -- retries while the pod answers "busy"
+# (transient) or while an earlier call of this repo is still registered as running
 T=$1; LOG=$2; shift 2
-for i in $(seq 1 40); do
+for i in $(seq 1 200); do
   /usr/local/graft/bin/gpurun --timeout $T -- "$@" > $LOG 2>&1
   rc=$?
-  if grep -q "status=transient" $LOG; then sleep 15; continue; fi
+  if grep -q "status=transient\|already running" $LOG; then sleep 20; continue; fi
   exit $rc
 done
 exit 3

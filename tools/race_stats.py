@@ -96,7 +96,7 @@ def main():
     ap.add_argument("--frames", type=int, default=500)
     ap.add_argument("--sample-every", type=int, default=16)
     ap.add_argument("--cap", type=int, default=5_000_000)
-    ap.add_argument("--free-runs", type=int, default=1)
+    ap.add_argument("--free-runs", type=int, default=2)
     ap.add_argument("--out", default="gpurun_out/race_stats.json")
     args = ap.parse_args()
 
@@ -113,12 +113,12 @@ def main():
     first, last = st.integrated_range()
     K = pp.outlier_filtering_frame_count
 
-    big = 1 << 30
-    variants = [("plain", 0, 0.0)]
-    for q in (0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.7, 1.0):
-        variants.append((f"perm_q{q}", big, q))
-    for q in (0.0, 0.1, 0.2, 0.3, 0.5):
-        variants.append((f"wave_q{q}", REF_WAVE, q))
+    # (name, wave W, early fraction q of the secondaries, fraction b of the pixels in slot order)
+    variants = [("plain", 0, 0.0, 0.0)]
+    for q, b in ((0.0, 0.0), (0.0, 0.44), (0.0, 1.0), (0.02, 0.44), (0.04, 0.0), (0.04, 0.44), (0.04, 1.0), (0.06, 0.44),
+                 (0.10, 0.44)):
+        variants.append((f"wave_q{q}_b{b}", REF_WAVE, q, b))
+    variants.append(("onewave_q0.04_b0.44", 1 << 30, 0.04, 0.44))
 
     def mk(lib=None):
         return R.CUDASurfelReconstruction(args.cap, W, H, cam.fx, cam.fy, cam.cx, cam.cy, lib=lib)
@@ -147,10 +147,11 @@ def main():
             rows, n_before, merges_before = rec_a.dump_state()
             rec_b.load_state(rows, merges_before)
             entry = {"frame": frame, "n_before": int(n_before)}
-            for name, wave, q in variants:
+            for name, wave, q, b in variants:
                 rec_p.load_state(rows, merges_before)
                 rec_p.configure("tiebreak_wave", wave)
                 rec_p.configure("tiebreak_early_fraction", q)
+                rec_p.configure("tiebreak_index_order_fraction", b)
                 rec_p.integrate(None, frame, ip, d0.clone(), n0, r0, st.color[frame], st.global_T_frame[frame],
                                 st.frame_T_global[frame])
                 entry[name] = int(rec_p.surfels_size() - rec_p.surfel_count()) - int(merges_before)
@@ -171,6 +172,11 @@ def main():
     print(f"teacher-forced pass: {time.time() - t0:.1f}s")
     sums = {k: sum(e[k] for e in samples) for k in samples[0] if k not in ("frame", "n_before")}
     print("merge-count sums over the samples:", json.dumps(sums, indent=1))
+    for lo, hi in ((0, REF_WAVE), (REF_WAVE, 1 << 31)):
+        part = [e for e in samples if lo <= e["n_before"] < hi]
+        if part:
+            print(f"  samples with {lo} <= N < {hi}: " + ", ".join(
+                f"{k} {sum(e[k] for e in part) - sum(e['oracle_a'] for e in part):+d}" for k in part[0] if k not in ("frame", "n_before", "oracle_a")))
     print("race statistics:", json.dumps(acc, indent=1))
 
     # ---- free-running totals ----
@@ -180,11 +186,12 @@ def main():
         s_ = rec_a.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp,
                               ip, first, last)
         free[f"oracle_{rep}"] = [int(s_.surfels_size), int(s_.surfel_count)]
-    for name, wave, q in variants:
+    for name, wave, q, b in variants:
         for rep in range(args.free_runs):
             rec_p.reset()
             rec_p.configure("tiebreak_wave", wave)
             rec_p.configure("tiebreak_early_fraction", q)
+            rec_p.configure("tiebreak_index_order_fraction", b)
             s_ = rec_p.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global,
                                   st.others_TR_reference, pp, ip, first, last)
             free[name if rep == 0 else f"{name}_{rep}"] = [int(s_.surfels_size), int(s_.surfel_count)]
