@@ -34,6 +34,7 @@
 // Host side at the end of the file: IntegrateFrame (one stream, stage events) and
 // IntegrateFramePipelined (the frame DAG over the streams of PipelineCtx, sm_kernels.cuh).
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -1424,6 +1425,13 @@ int ConfigureIntegrateKernels(int carveout_percent, LaunchPlan* plan) {
   plan->merge = resident(k_merge, kBlock, 4);
   plan->integrate = resident(k_integrate, kBlock, 3);
   plan->update_neighbors = resident(k_update_neighbors, kBlock, 3);
+  if (const char* pe = std::getenv("SM_B200_OFFCHAIN_GRID_PERCENT")) {  // see ConfigureRegularizeKernels
+    const int percent = std::atoi(pe);
+    if (percent > 0 && percent < 100) {
+      plan->update_neighbors = std::max(sm_count, plan->update_neighbors * percent / 100);
+      plan->merge = std::max(sm_count, plan->merge * percent / 100);
+    }
+  }
   return SM_OK;
 }
 

@@ -298,7 +298,7 @@ struct FrameGraph {
   std::vector<cudaGraphNode_t> nodes;   // same order as the KernelLaunch list of a step
   std::vector<const void*> funcs;
   // what the graph was built for
-  int blending = -1, reg_launches = -1, pdl = -1;
+  int blending = -1, reg_launches = -1, pdl = -1, prio = -1;
   size_t blend_smem = 0;
   dim3 scan_grid;
 };
@@ -352,6 +352,24 @@ int BuildFrameGraph(FrameGraph* g, const StepLayout& l, const std::vector<Kernel
     const cudaKernelNodeParams p = NodeParams(launches[i]);
     SM_CUDA(cudaGraphAddKernelNode(&g->nodes[i], g->graph, nullptr, 0, &p));
     g->funcs[i] = launches[i].func;
+  }
+  // SM_B200_GRAPH_PRIO (A/B hook): launch priorities of the nodes. 1 = the dependency chain that ends a
+  // step (integrate -> create -> project -> associate -> blend) above everything else; 2 = additionally
+  // the pre-processing of frame f + 2 below everything else.
+  if (const int prio = EnvInt("SM_B200_GRAPH_PRIO", 0)) {
+    int least = 0, greatest = 0;
+    SM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    auto set_priority = [&](int node, int priority) -> int {
+      if (node < 0) return SM_OK;
+      cudaKernelNodeAttrValue v = {};
+      v.priority = priority;
+      SM_CUDA(cudaGraphKernelNodeSetAttribute(g->nodes[node], cudaKernelNodeAttributePriority, &v));
+      return SM_OK;
+    };
+    const int mid = (least + greatest) / 2;
+    for (int i = 0; i < l.count; ++i) { const int st = set_priority(i, prio >= 2 ? mid : least); if (st != SM_OK) return st; }
+    for (int node : {l.integrate, l.create, l.project, l.project_tail, l.associate, l.blend}) { const int st = set_priority(node, greatest); if (st != SM_OK) return st; }
+    if (prio >= 2) for (int node : {l.bilateral, l.tail}) { const int st = set_priority(node, least); if (st != SM_OK) return st; }
   }
   std::vector<cudaGraphNode_t> from, to;
   std::vector<cudaGraphEdgeData> data;
@@ -510,8 +528,9 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
 
     // ---- (re)build on the first step or when the shape changed, else update the node arguments ----
     FrameGraph* g = r->graph;
+    const int prio = EnvInt("SM_B200_GRAPH_PRIO", 0);
     bool rebuild = g == nullptr || g->blending != (blending ? 1 : 0) || g->reg_launches != reg_launches || g->pdl != pdl ||
-                   static_cast<int>(g->nodes.size()) != l.count;
+                   g->prio != prio || static_cast<int>(g->nodes.size()) != l.count;
     if (!rebuild) {
       for (int i = 0; i < l.count && !rebuild; ++i) rebuild = g->funcs[i] != launches[i].func;
       if (l.blend >= 0) rebuild = rebuild || g->blend_smem != launches[l.blend].smem;
@@ -520,7 +539,7 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
       if (g) { SM_CUDA(cudaStreamSynchronize(gs)); DestroyFrameGraph(g); r->graph = nullptr; }
       g = new FrameGraph();
       r->graph = g;
-      g->blending = blending ? 1 : 0; g->reg_launches = reg_launches; g->pdl = pdl;
+      g->blending = blending ? 1 : 0; g->reg_launches = reg_launches; g->pdl = pdl; g->prio = prio;
       g->blend_smem = l.blend >= 0 ? launches[l.blend].smem : 0;
       status = BuildFrameGraph(g, l, launches, pdl);
       if (status != SM_OK) return status;

@@ -18,10 +18,14 @@ struct TieBreakConfig {
   double index_order_fraction;  // fraction of the pixels that order the supporters of a wave by slot index
   u32 mul, mul_inv;      // derived from wave
 };
-// Defaults (DESIGN.md section 4 has the measurements that picked them).
-constexpr u32 kDefaultTieBreakWave = 0;
-constexpr double kDefaultTieBreakEarlyFraction = 0.0;
-constexpr double kDefaultTieBreakIndexOrderFraction = 0.0;
+// Defaults (DESIGN.md section 4 / profiles/r02_race_stats.md have the measurements that picked them):
+// wave = the reference's AssociateSurfels launch wave on a B200 (1024-thread blocks, 31 registers ->
+// 2 blocks x 148 SMs = 296 blocks of slots); inside a wave the lower slot won 72 % of the same-kind
+// pairs (-> 44 % of the pixels in slot order, the rest in a random order); 1 % early secondaries puts
+// the merge rate of teacher-forced frames and the free-running totals on the oracle's.
+constexpr u32 kDefaultTieBreakWave = 296 * 1024;
+constexpr double kDefaultTieBreakEarlyFraction = 0.01;
+constexpr double kDefaultTieBreakIndexOrderFraction = 0.44;
 TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index);
 int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity);
 

@@ -164,7 +164,19 @@ DETERMINISTIC_RASTERS = ("first_surfel_depth", "supporting_surfel_counts", "conf
                          "new_surfel_flag_vector", "new_surfel_indices")
 
 
-def compare_integrate(mine_rasters, mine_depth, mine_state, ref_rasters, ref_depth, ref_state, n_before):
+def race_envelope(state_b, state_a, n_before):
+    """What a SECOND run of the oracle (B) differs from the first (A) in, on the race-bound rows of the
+    slots that existed before the frame: (differing merge flags, |merge count difference|, differing
+    neighbour-link rows). The product is held to a multiple of this (compare_integrate)."""
+    rows_b, _, merges_b = state_b
+    rows_a, _, merges_a = state_a
+    flags = int(((rows_b[7, :n_before] < 0) != (rows_a[7, :n_before] < 0)).sum())
+    nb = list(NEIGHBOR_ROWS)
+    links = int((rows_b[nb, :n_before].view(np.uint32) != rows_a[nb, :n_before].view(np.uint32)).any(axis=0).sum())
+    return flags, abs(int(merges_b) - int(merges_a)), links
+
+
+def compare_integrate(mine_rasters, mine_depth, mine_state, ref_rasters, ref_depth, ref_state, n_before, envelope=None):
     """Contract for one teacher-forced Integrate():
     - min-depth raster, supporting counts, conflicting surfels, new-surfel flags + scan indices,
       surfel count: bit-exact;
@@ -175,7 +187,10 @@ def compare_integrate(mine_rasters, mine_depth, mine_state, ref_rasters, ref_dep
     - depth sums: 1e-6 relative (float atomics);
     - per-surfel attributes written by the integration (position, confidence, radius, normal,
       stamps, colour) bit-exact for every surfel whose merge decision agrees (merging reads the
-      supporting surfel, so it inherits its nondeterminism);
+      supporting surfel, so it inherits its nondeterminism): with `envelope` (race_envelope of a second
+      oracle run) the differing merge flags, the merge-count difference and the differing neighbour-link
+      rows stay within 2x the reference's own run-to-run difference (+ a floor of a few units); without
+      one (golden vectors: a single recorded run) within small absolute bounds;
     - smooth positions within 1e-4 relative where neighbour links agree."""
     for k in DETERMINISTIC_RASTERS:
         assert count_mismatch(mine_rasters[k], ref_rasters[k]) == 0, k
@@ -191,14 +206,21 @@ def compare_integrate(mine_rasters, mine_depth, mine_state, ref_rasters, ref_dep
     rows_r, n_r, merges_r = ref_state
     assert n_m == n_r, "surfels_size()"
     same_merge = (rows_m[7] < 0) == (rows_r[7] < 0)
-    assert (~same_merge).sum() <= max(20, 0.01 * n_r), "merge decisions differ only inside the reference's envelope"
-    assert abs(int(merges_m) - int(merges_r)) <= max(20, 0.01 * n_r)
+    nb = list(NEIGHBOR_ROWS)
+    link_rows_differ = int((rows_m[nb, :n_before].view(np.uint32) != rows_r[nb, :n_before].view(np.uint32)).any(axis=0).sum())
+    if envelope is not None:
+        env_flags, env_count, env_links = envelope
+        assert (~same_merge).sum() <= 2 * env_flags + 12, ((~same_merge).sum(), env_flags)
+        assert abs(int(merges_m) - int(merges_r)) <= 2 * env_count + 12, (merges_m, merges_r, env_count)
+        assert link_rows_differ <= 2 * env_links + 24, (link_rows_differ, env_links)
+    else:
+        assert (~same_merge).sum() <= max(20, 0.004 * n_r), "merge decisions differ only inside the reference's envelope"
+        assert abs(int(merges_m) - int(merges_r)) <= max(20, 0.004 * n_r)
+        assert link_rows_differ <= max(40, 0.03 * n_before)
     # a blended-depth pixel that rounds differently (see above) feeds up to a few surfels
     allowed = 4 * int((depth_diff != 0).sum())
     for row in INTEGRATE_ROWS:
         assert count_mismatch(rows_m[row], rows_r[row], same_merge) <= allowed, f"row {row}"
-    links_equal = np.all(rows_m[list(NEIGHBOR_ROWS)].view(np.uint32) == rows_r[list(NEIGHBOR_ROWS)].view(np.uint32), axis=0)
-    assert links_equal.mean() > 0.9
     check_state_invariants(rows_m, n_m)
 
 
@@ -247,6 +269,7 @@ def test_integrate_teacher_forced_live_oracle(product, reference, variant):
         ip.measurement_blending_radius = 5
     rec_p = R.CUDASurfelReconstruction(600_000, W, H, cam_.fx, cam_.fy, cam_.cx, cam_.cy)
     rec_r = R.CUDASurfelReconstruction(600_000, W, H, cam_.fx, cam_.fy, cam_.cx, cam_.cy, lib=reference)
+    rec_b = R.CUDASurfelReconstruction(600_000, W, H, cam_.fx, cam_.fy, cam_.cx, cam_.cy, lib=reference)  # envelope
     first, last = st.integrated_range()
     for frame in range(first, last):
         others = [st.depth[f] for f in other_frames(frame, 8)]
@@ -254,12 +277,14 @@ def test_integrate_teacher_forced_live_oracle(product, reference, variant):
         rec_r.preprocess(None, pp, st.depth[frame], others, st.others_TR_reference[frame], d0, n0, r0)
         rows, n_before, merges = rec_r.dump_state()
         rec_p.load_state(rows, merges)
+        rec_b.load_state(rows, merges)
         dp, dr = d0.clone(), d0.clone()
-        for rec, d in ((rec_p, dp), (rec_r, dr)):
+        for rec, d in ((rec_p, dp), (rec_r, dr), (rec_b, d0.clone())):
             rec.integrate(None, frame, ip, d, n0, r0, st.color[frame], st.global_T_frame[frame], st.frame_T_global[frame])
         torch.cuda.synchronize()
+        state_r = rec_r.dump_state()
         compare_integrate(rec_p.download_rasters(), dp.cpu().numpy(), rec_p.dump_state(), rec_r.download_rasters(),
-                          dr.cpu().numpy(), rec_r.dump_state(), n_before)
+                          dr.cpu().numpy(), state_r, n_before, envelope=race_envelope(rec_b.dump_state(), state_r, n_before))
         assert rec_p.surfel_count() == rec_p.surfels_size() - rec_p.dump_state()[2]
 
 

@@ -18,7 +18,7 @@ from surfelmeshing_b200 import reconstruction as R  # noqa: E402
 from surfelmeshing_b200._lib import IntegrateParams, PreprocessParams  # noqa: E402
 
 KNOBS = ("SM_B200_GRAPH", "SM_B200_GRAPH_PDL", "SM_B200_SPLIT_PROJECT", "SM_B200_TAIL_FILL", "SM_B200_PDL",
-         "SM_B200_CARVEOUT")
+         "SM_B200_CARVEOUT", "SM_B200_GRAPH_PRIO", "SM_B200_OFFCHAIN_GRID_PERCENT", "SM_B200_GRID_PERCENT", "SM_B200_TIEBREAK")
 
 
 def main():

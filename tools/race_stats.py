@@ -115,8 +115,8 @@ def main():
 
     # (name, wave W, early fraction q of the secondaries, fraction b of the pixels in slot order)
     variants = [("plain", 0, 0.0, 0.0)]
-    for q, b in ((0.0, 0.0), (0.0, 0.44), (0.0, 1.0), (0.02, 0.44), (0.04, 0.0), (0.04, 0.44), (0.04, 1.0), (0.06, 0.44),
-                 (0.10, 0.44)):
+    for q, b in ((0.0, 0.0), (0.0, 0.44), (0.0, 1.0), (0.005, 0.44), (0.01, 0.44), (0.015, 0.44), (0.02, 0.44), (0.01, 0.0),
+                 (0.01, 1.0), (0.04, 0.44), (0.10, 0.44)):
         variants.append((f"wave_q{q}_b{b}", REF_WAVE, q, b))
     variants.append(("onewave_q0.04_b0.44", 1 << 30, 0.04, 0.44))
 
