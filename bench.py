@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--sigma-depth", type=float, default=None)
     ap.add_argument("--required-inliers", type=int, default=-1,
                     help="outlier_filtering_required_inliers (-1 = all 8 other frames, the reference's default)")
+    ap.add_argument("--erosion-radius", type=int, default=2, help="depth_erosion_radius (reference default 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
@@ -238,6 +239,7 @@ def main():
     pp = PreprocessParams.defaults()
     pp.depth_valid_region_radius = cam.valid_region_radius()
     pp.outlier_filtering_required_inliers = args.required_inliers
+    pp.depth_erosion_radius = args.erosion_radius
     ip = IntegrateParams.defaults()
     first, last = stream.integrated_range()
     frames_per_step = last - first
@@ -287,8 +289,18 @@ def main():
     kernel_table = None
     if args.impl == "product" and info.rank == 0 and not args.no_roofline:
         peak, peak_src = measured_peaks()
+        # The roofline region is the LAST `tail` frames of a step: there the cloud is at its final size, so the
+        # algorithmic bytes (counters of the last frame) and the mean launch durations (per-kernel CUDA events on
+        # the launching stream) describe the same work. (Over the whole step the cloud grows from 0 to N: bytes of
+        # the last frame over the mean duration of all frames would overstate the bandwidth.)
+        tail = min(40, frames_per_step)
+        rec.reset()
+        if last - tail > first:
+            rec.stream_run(None, stream.depth, stream.color, stream.global_T_frame, stream.frame_T_global,
+                           stream.others_TR_reference, pp, ip, first, last - tail)
         lib.call("profile_kernels", 1)
-        step_device()
+        rec.stream_run(None, stream.depth, stream.color, stream.global_T_frame, stream.frame_T_global,
+                       stream.others_TR_reference, pp, ip, last - tail, last)
         nk = lib.fn["profile_kernel_count"]()
         tot = (torch.zeros(nk, dtype=torch.float64).numpy())
         cnt = np.zeros(nk, dtype=np.uint64)
@@ -311,9 +323,10 @@ def main():
                 name = lib.fn["profile_kernel_name"](i).decode()
                 kernel_table[name] = {"launches": int(cnt[i]), "mean_us": tot[i] / cnt[i] * 1e3,
                                       "share": tot[i] / total_ms}
-        roofline = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "counters": counters}
-        # The same kernels as they run inside the multi-stream frame pipeline: start / end stamps written
-        # by the kernels themselves (sm_timeline_enable), mean over the step.
+        roofline = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "counters": counters,
+                    "region": f"last {tail} frames of a step"}
+        # The same kernels as they run inside the frame graph: start / end stamps written by the kernels
+        # themselves (sm_timeline_enable), mean over the same last frames of a full step.
         frames_pow2 = 1 << (args.frames - 1).bit_length()
         lib.call("timeline_enable", rec._h, frames_pow2)
         step_device()
@@ -321,6 +334,9 @@ def main():
         lib.call("timeline_read", rec._h, stamps_buf.ctypes.data_as(C.POINTER(C.c_uint64)), frames_pow2)
         lib.call("timeline_enable", rec._h, 0)
         launched = stamps_buf[:, :, 0] != np.uint64(0xFFFFFFFFFFFFFFFF)
+        in_region = np.zeros(frames_pow2, dtype=bool)
+        in_region[[f % frames_pow2 for f in range(last - tail, last)]] = True
+        launched &= in_region[:, None]
         for i in range(nk):
             name = lib.fn["profile_kernel_name"](i).decode()
             if launched[:, i].any():
@@ -380,7 +396,7 @@ def main():
                        "frames_per_step": frames_per_step, "surfels_after_step": int(stats.surfels_size),
                        "l2": f"inputs larger than L2 ({stream.depth.numel() * 2 + stream.color.numel():,} B of frames per "
                              f"step), no flush",
-                       "required_inliers": args.required_inliers,
+                       "required_inliers": args.required_inliers, "erosion_radius": args.erosion_radius,
                        "sigma_depth": args.sigma_depth},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": io_bytes[0],

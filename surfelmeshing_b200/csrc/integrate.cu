@@ -303,6 +303,15 @@ __device__ __forceinline__ bool supports_surfel(const DeviceState& d, const Fram
   return true;
 }
 
+// SM_ASSOCIATE_LEVELS (compile-time A/B hook): 1 = one batch of gathers per list entry (round 1); 2 = the
+// depth and min-depth of the (up to two) pixels first - five entries out of six stop at the measurement /
+// conflict / occlusion gates that only need those - and the surfel's normal and radius and the pixels'
+// normals only for the rest. Same decisions (pure predicates; the conflicting-surfel entry is written
+// where the reference writes it).
+#ifndef SM_ASSOCIATE_LEVELS
+#define SM_ASSOCIATE_LEVELS 2
+#endif
+
 __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams f) {
   pdl_prologue();
   if (f.skip) return;
@@ -314,6 +323,7 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
     const Projection p = project(f, d.width, d.height, x, y, z);
     int ox = p.px, oy = p.py;
     const bool has2 = secondary_pixel(p, d.width, d.height, &ox, &oy);
+#if SM_ASSOCIATE_LEVELS == 1
     // one batch of gathers
     const PixelGate g0 = load_pixel_gate(d, f, p.px, p.py);
     const PixelGate g1 = load_pixel_gate(d, f, ox, oy);
@@ -321,11 +331,54 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
     const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
     float3 ln;
     const float dot_angle = facing_dot(f, x, y, z, snx, sny, snz, &ln);
+    bool pass[2] = {true, has2};
+#else
+    // level 1: measurement, conflict and occlusion gates (kernels.cu:1603-1632)
+    PixelGate g0, g1;
+    g0.measurement_depth = fmul(u2f(row_ptr(f.depth_pre, f.depth_pre_pitch, p.py)[p.px]), f.inv_depth_scaling);
+    g1.measurement_depth = fmul(u2f(row_ptr(f.depth_pre, f.depth_pre_pitch, oy)[ox]), f.inv_depth_scaling);
+    g0.first = d.first_depth[p.py * d.width + p.px];
+    g1.first = d.first_depth[oy * d.width + ox];
+    bool pass[2] = {true, has2};
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      if (k == 1 && !has2) break;
+      if (!pass[k]) continue;
+      const PixelGate& g = k == 0 ? g0 : g1;
       const int pp = k == 0 ? p.py * d.width + p.px : oy * d.width + ox;
+      if (!(g.measurement_depth > 0.f)) { pass[k] = false; continue; }
+      if (g.first < fmul(g.measurement_depth, fadd(-f.sensor_noise_factor, 1.0f))) {
+        if (g.first == z) d.assoc[pp].y = idx;  // this surfel is conflicting
+        pass[k] = false;
+        continue;
+      }
+      if (z > fmul(fadd(f.sensor_noise_factor, 1.0f), g.measurement_depth)) pass[k] = false;  // occluded
+    }
+    if (!pass[0] && !pass[1]) return;
+    // level 2: the surfel's normal and radius, the normals of the pixels that are left
+    const float snx = SM_S(SM_ROW_NORMAL_X, idx), sny = SM_S(SM_ROW_NORMAL_Y, idx), snz = SM_S(SM_ROW_NORMAL_Z, idx);
+    const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+    g0.normal = row_ptr(f.normals, f.normals_pitch, pass[0] ? p.py : oy)[pass[0] ? p.px : ox];
+    g1.normal = row_ptr(f.normals, f.normals_pitch, pass[1] ? oy : p.py)[pass[1] ? ox : p.px];
+    float3 ln;
+    const float dot_angle = facing_dot(f, x, y, z, snx, sny, snz, &ln);
+#endif
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!pass[k]) continue;
+      const int pp = k == 0 ? p.py * d.width + p.px : oy * d.width + ox;
+#if SM_ASSOCIATE_LEVELS == 1
       if (!supports_surfel(d, f, k == 0 ? g0 : g1, pp, idx, z, dot_angle, ln)) continue;
+#else
+      {
+        const PixelGate& g = k == 0 ? g0 : g1;
+        if (dot_angle > 0.f) continue;  // kSurfelNormalToViewingDirThreshold = 0
+        if (g.measurement_depth < z) {
+          const float s = normal_z_abs(g.normal.x, g.normal.y);
+          const float dot2 = ffma(-ln.z, s, ffma(ln.x, g.normal.x, fmul(ln.y, g.normal.y)));
+          if (dot2 < f.cos_normal_compatibility_threshold) continue;
+        }
+      }
+#endif
       if (!(surfel_radius_squared > 0.f)) continue;
       PixelAssoc* a = &d.assoc[pp];
       // Reference: atomicCAS(INV -> idx), first come wins. Here: the minimum of a reproducible
@@ -339,11 +392,68 @@ __global__ void __launch_bounds__(kBlock) k_associate(DeviceState d, FrameParams
 }
 
 // a9: merge decision (kernels.cu:1857-1992); applied by k_integrate.
+// A surfel can only be merged if its primary pixel has a measurement that supports it AND that pixel's
+// supporting surfel is another surfel - true for a small fraction of the list. The gates are pure
+// predicates (the one side effect, the conflicting-surfel entry, comes first in the reference too), so
+// they are evaluated cheapest first: level 1 gathers only the surfel's radius and the pixel's depth,
+// min-depth and association record (4 gathers); the 14 row gathers of the surfel and of its merge
+// partner are issued together as level 2, only for the candidates. (Round 1 gathered 11 values for
+// every entry: at BASELINE config 3 the kernel was the longest of the frame.)
+#ifndef SM_MERGE_LEVELS
+#define SM_MERGE_LEVELS 2   // compile-time A/B hook, 1 = round 1's gather order
+#endif
 __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) {
   pdl_prologue();
   if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_MERGE);
   u32 merged_by_thread = 0;
+#if SM_MERGE_LEVELS == 2
+  for_each_visible(d, &d.counters->surfel_count[f.count_slot], [&](size_t pos, const VisEntry& e) {
+    const u32 idx = e.x & ~kActiveBit;  // no active-window test here (kernels.cu:2016)
+    const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
+    const Projection p = project(f, d.width, d.height, x, y, z);
+    const int pp = p.py * d.width + p.px;
+    // level 1
+    const float surfel_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+    const float measurement_depth = fmul(u2f(row_ptr(f.depth_pre, f.depth_pre_pitch, p.py)[p.px]), f.inv_depth_scaling);
+    const float first = d.first_depth[pp];
+    const u32 supporting_key = d.assoc[pp].x;
+    bool merged = false;
+    if (surfel_radius_squared >= 0.f && measurement_depth > 0.f) {
+      if (first < fmul(measurement_depth, fadd(-f.sensor_noise_factor, 1.0f))) {
+        if (first == z) d.assoc[pp].y = idx;  // this surfel is conflicting (kernels.cu:1885-1889)
+      } else if (!(z > fmul(fadd(f.sensor_noise_factor, 1.0f), measurement_depth))) {  // not occluded
+        const u32 q = supporting_index(f.tb, supporting_key, static_cast<u32>(pp));
+        if (q != idx && q != kInvalidIndex) {
+          // level 2: the remaining gates and the comparison with the supporting surfel (kernels.cu:1910-1984)
+          const float snx = SM_S(SM_ROW_NORMAL_X, idx), sny = SM_S(SM_ROW_NORMAL_Y, idx), snz = SM_S(SM_ROW_NORMAL_Z, idx);
+          const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
+          const float2 pixel_normal = row_ptr(f.normals, f.normals_pitch, p.py)[p.px];
+          const float other_radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, q);
+          const float qx = SM_S(SM_ROW_X, q), qy = SM_S(SM_ROW_Y, q), qz = SM_S(SM_ROW_Z, q);
+          const float qnx = SM_S(SM_ROW_NORMAL_X, q), qny = SM_S(SM_ROW_NORMAL_Y, q), qnz = SM_S(SM_ROW_NORMAL_Z, q);
+          float3 ln;
+          const float dot_angle = facing_dot(f, x, y, z, snx, sny, snz, &ln);
+          bool same_surface = !(dot_angle > 0.f);  // kSurfelNormalToViewingDirThreshold = 0
+          if (same_surface && measurement_depth < z) {
+            const float s = normal_z_abs(pixel_normal.x, pixel_normal.y);
+            const float dot2 = ffma(-ln.z, s, ffma(ln.x, pixel_normal.x, fmul(ln.y, pixel_normal.y)));
+            same_surface = !(dot2 < f.cos_normal_compatibility_threshold);
+          }
+          if (same_surface) {
+            const float radius_diff = fmul(surfel_radius_squared, frcp(other_radius_squared));
+            const float distance_squared = squared_norm(fsub(gx, qx), fsub(gy, qy), fsub(gz, qz));
+            merged = !(radius_diff > 1.4400000572204589844f || radius_diff < 0.69444441795349121094f) &&
+                     !(distance_squared > fmul(fadd(surfel_radius_squared, other_radius_squared), 0.03125f)) &&
+                     !(dot3(snx, sny, snz, qnx, qny, qnz) < 0.93968999385833740234f);  // cos 20 deg
+          }
+        }
+      }
+    }
+    d.merge_flag[pos] = merged ? 1 : 0;
+    merged_by_thread += merged ? 1u : 0u;
+  });
+#else  // round 1: one batch of 11 gathers per entry, a second one for the candidates
   for_each_visible(d, &d.counters->surfel_count[f.count_slot], [&](size_t pos, const VisEntry& e) {
     const u32 idx = e.x & ~kActiveBit;  // no active-window test here (kernels.cu:2016)
     const float x = __uint_as_float(e.y), y = __uint_as_float(e.z), z = __uint_as_float(e.w);
@@ -376,6 +486,7 @@ __global__ void __launch_bounds__(kBlock) k_merge(DeviceState d, FrameParams f) 
     d.merge_flag[pos] = merged ? 1 : 0;
     merged_by_thread += merged ? 1u : 0u;
   });
+#endif
   // Block reduction of the merge count (reference: cub::BlockReduce + atomicAdd, :2045-2051).
   merged_by_thread = __reduce_add_sync(0xffffffffu, merged_by_thread);
   __shared__ u32 warp_sums[kBlock / 32];
@@ -824,6 +935,26 @@ __device__ __forceinline__ void integrate_or_conflict(const FrameParams& f, cons
   }
 }
 
+// SM_INTEGRATE_LEVELS (compile-time A/B hook, tools/build_variant.sh): 1 = one batch of gathers per list
+// entry (everything the integration can need); 2 = a light first batch (merge flag, radius, and per pixel
+// the depth, the min-depth and the association record) decides whether either pixel can integrate into
+// or conflict with the surfel, and only then the heavy batch (normal / radius / colour rasters, nine
+// surfel rows) is gathered. Only ~10 % of the listed surfels are changed by a frame: with 2 the kernel
+// moves a third of the bytes (it is the longest kernel of BASELINE config 3), at the price of one more
+// dependent level for the surfels that do integrate.
+#ifndef SM_INTEGRATE_LEVELS
+#define SM_INTEGRATE_LEVELS 2
+#endif
+
+// The gates of integrate_or_conflict that only need the light per-pixel values (kernels.cu:757-800):
+// can this pixel integrate into or conflict with the surfel at all?
+__device__ __forceinline__ bool pixel_can_touch(const FrameParams& f, float measurement_depth, float first, u32 conflicting,
+                                                u32 idx, float cz_) {
+  if (!(measurement_depth > 0.f)) return false;
+  if (first < fmul(measurement_depth, fadd(-f.sensor_noise_factor, 1.0f))) return first == cz_ && conflicting == idx;
+  return !(cz_ > fmul(fadd(f.sensor_noise_factor, 1.0f), measurement_depth));
+}
+
 __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FrameParams f) {
   pdl_prologue();
   if (f.skip) return;
@@ -834,17 +965,31 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
     const Projection p = project(f, d.width, d.height, x, y, z);
     int ox = p.px, oy = p.py;
     const bool has2 = secondary_pixel(p, d.width, d.height, &ox, &oy);
-    // one batch of gathers: the merge decision, both pixels and the surfel
     const u8 merged = d.merge_flag[pos];
-    const PixelMeasurement m0 = load_pixel_measurement(d, f, p.px, p.py);
-    const PixelMeasurement m1 = load_pixel_measurement(d, f, ox, oy);
     SurfelState s;
+    PixelMeasurement m0, m1;
+#if SM_INTEGRATE_LEVELS == 1
+    // one batch of gathers: the merge decision, both pixels and the surfel
+    m0 = load_pixel_measurement(d, f, p.px, p.py);
+    m1 = load_pixel_measurement(d, f, ox, oy);
     s.x = SM_S(SM_ROW_X, idx); s.y = SM_S(SM_ROW_Y, idx); s.z = SM_S(SM_ROW_Z, idx);
     s.confidence = SM_S(SM_ROW_CONFIDENCE, idx);
     s.radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
     s.nx = SM_S(SM_ROW_NORMAL_X, idx); s.ny = SM_S(SM_ROW_NORMAL_Y, idx); s.nz = SM_S(SM_ROW_NORMAL_Z, idx);
     s.color = SM_SU(SM_ROW_COLOR, idx);
     s.creation_stamp = SM_SU(SM_ROW_CREATION_STAMP, idx);
+#else
+    // level 1: the merge decision, the radius and the light per-pixel values
+    const int p0 = p.py * d.width + p.px, p1 = oy * d.width + ox;
+    m0.measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, p.py)[p.px]), f.inv_depth_scaling);
+    m1.measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, oy)[ox]), f.inv_depth_scaling);
+    m0.first = d.first_depth[p0];
+    m1.first = d.first_depth[p1];
+    const PixelAssoc a0 = d.assoc[p0], a1 = d.assoc[p1];
+    m0.conflicting = a0.y; m0.count = a0.z;
+    m1.conflicting = a1.y; m1.count = a1.z;
+    s.radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+#endif
     s.last_update_stamp = 0;
     s.smooth_x = s.smooth_y = s.smooth_z = 0.f;
     s.replaced = false; s.dirty = false; s.stamped = false;
@@ -859,8 +1004,34 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
     }
     if (!(e.x & kActiveBit)) return;
     if (s.radius_squared < 0.f) return;  // kernels.cu:1050
+#if SM_INTEGRATE_LEVELS != 1
+    const bool touch0 = pixel_can_touch(f, m0.measurement_depth, m0.first, m0.conflicting, idx, z);
+    const bool touch1 = has2 && pixel_can_touch(f, m1.measurement_depth, m1.first, m1.conflicting, idx, z);
+    if (!touch0 && !touch1) return;
+    // level 2: the rest of the pixels that can touch the surfel, and the surfel
+    {
+      const int qx0 = touch0 ? p.px : ox, qy0 = touch0 ? p.py : oy;   // unused pixel slots re-read a used one
+      const int qx1 = touch1 ? ox : qx0, qy1 = touch1 ? oy : qy0;
+      m0.normal = row_ptr(f.normals, f.normals_pitch, qy0)[qx0];
+      m1.normal = row_ptr(f.normals, f.normals_pitch, qy1)[qx1];
+      m0.radius_squared = row_ptr(f.radius, f.radius_pitch, qy0)[qx0];
+      m1.radius_squared = row_ptr(f.radius, f.radius_pitch, qy1)[qx1];
+      const uchar3 c0 = row_ptr(f.color, f.color_pitch, qy0)[qx0];
+      const uchar3 c1 = row_ptr(f.color, f.color_pitch, qy1)[qx1];
+      m0.r = c0.x; m0.g = c0.y; m0.b = c0.z;
+      m1.r = c1.x; m1.g = c1.y; m1.b = c1.z;
+      s.x = SM_S(SM_ROW_X, idx); s.y = SM_S(SM_ROW_Y, idx); s.z = SM_S(SM_ROW_Z, idx);
+      s.confidence = SM_S(SM_ROW_CONFIDENCE, idx);
+      s.nx = SM_S(SM_ROW_NORMAL_X, idx); s.ny = SM_S(SM_ROW_NORMAL_Y, idx); s.nz = SM_S(SM_ROW_NORMAL_Z, idx);
+      s.color = SM_SU(SM_ROW_COLOR, idx);
+      s.creation_stamp = SM_SU(SM_ROW_CREATION_STAMP, idx);
+    }
+    if (touch0) integrate_or_conflict(f, m0, p.px, p.py, idx, x, y, z, s);
+    if (touch1) integrate_or_conflict(f, m1, ox, oy, idx, x, y, z, s);
+#else
     integrate_or_conflict(f, m0, p.px, p.py, idx, x, y, z, s);
     if (has2) integrate_or_conflict(f, m1, ox, oy, idx, x, y, z, s);
+#endif
     if (!s.dirty) return;
     SM_S(SM_ROW_X, idx) = s.x; SM_S(SM_ROW_Y, idx) = s.y; SM_S(SM_ROW_Z, idx) = s.z;
     SM_S(SM_ROW_CONFIDENCE, idx) = s.confidence;
@@ -884,12 +1055,55 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
 // ---------------------------------------------------------------------------------------
 // a12: neighbour update (kernels.cu:1197-1380)
 // ---------------------------------------------------------------------------------------
+// SM_UPDATE_EARLY_GATE (compile-time A/B hook): 1 = occlusion gate after a light first batch, 0 = round 1's order.
+#ifndef SM_UPDATE_EARLY_GATE
+#define SM_UPDATE_EARLY_GATE 1
+#endif
 __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, FrameParams f) {
   pdl_prologue();
   if (f.skip) return;
   const TimelineScope timeline_scope(d, f.frame_index, KID_UPDATE_NEIGHBORS);
   for_each_visible(d, &d.counters->surfel_count[f.count_slot], [&](size_t, const VisEntry& e) {
     const u32 idx = e.x & ~kActiveBit;
+    constexpr int kBorder = 1;
+    const int kDirectionsX[4] = {-1, 1, 0, 0};
+    const int kDirectionsY[4] = {0, 0, -1, 1};
+#if SM_UPDATE_EARLY_GATE
+    // batch 1: stamp and position of the surfel (the integration may have moved it: project again) and,
+    // speculatively, the depth at the pixel the list entry projected to BEFORE the integration - almost
+    // always the same pixel. Nine surfels out of ten stop at the occlusion gate that follows (no
+    // measurement at their pixel, or in front of them), so the other eight surfel rows and the five
+    // raster gathers are only issued behind it (batch 2); the gates are pure predicates, their order is free.
+    const Projection cached = project(f, d.width, d.height, __uint_as_float(e.y), __uint_as_float(e.z), __uint_as_float(e.w));
+    const u32 stamp = SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx);
+    const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
+    u16 raw_depth = row_ptr(f.depth, f.depth_pitch, cached.py)[cached.px];
+    if (!is_active(stamp, f.frame_index, f.active_window)) return;
+    const float cz_ = transform_row(f.local_T_global.r2, gx, gy, gz);
+    if (!(cz_ > 0.f)) return;
+    const float cx_ = transform_row(f.local_T_global.r0, gx, gy, gz);
+    const float cy_ = transform_row(f.local_T_global.r1, gx, gy, gz);
+    const float inv_z = frcp(cz_);
+    const int x = f2i_trunc(ffma(fmul(cx_, inv_z), f.fx, f.cx));
+    const int y = f2i_trunc(ffma(fmul(cy_, inv_z), f.fy, f.cy));
+    if (x < kBorder || y < kBorder || x >= d.width - kBorder || y >= d.height - kBorder) return;
+    if (x != cached.px || y != cached.py) raw_depth = row_ptr(f.depth, f.depth_pitch, y)[x];  // the surfel moved into another pixel
+    const float measurement_depth = fmul(u2f(raw_depth), f.inv_depth_scaling);
+    if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) return;  // occluded
+    // batch 2: the rest of the surfel, the pixel's radius and the candidates of the 4-adjacent pixels
+    const float nx = SM_S(SM_ROW_NORMAL_X, idx), ny = SM_S(SM_ROW_NORMAL_Y, idx), nz = SM_S(SM_ROW_NORMAL_Z, idx);
+    const float radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+    u32 neighbor_surfel_indices[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) neighbor_surfel_indices[m] = SM_SU(SM_ROW_NEIGHBOR0 + m, idx);
+    const float observation_radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
+    u32 candidate[4];
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      const int candidate_pixel = (y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction];
+      candidate[direction] = supporting_index(f.tb, d.assoc[candidate_pixel].x, static_cast<u32>(candidate_pixel));
+    }
+#else
     // batch 1: the surfel (its position may have been changed by the integration: project again)
     const u32 stamp = SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx);
     const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
@@ -906,14 +1120,11 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
     const float inv_z = frcp(cz_);
     const int x = f2i_trunc(ffma(fmul(cx_, inv_z), f.fx, f.cx));
     const int y = f2i_trunc(ffma(fmul(cy_, inv_z), f.fy, f.cy));
-    constexpr int kBorder = 1;
     if (x < kBorder || y < kBorder || x >= d.width - kBorder || y >= d.height - kBorder) return;
 
     // batch 2: the pixel and the candidates of the 4-adjacent pixels
     const float measurement_depth = fmul(u2f(row_ptr(f.depth, f.depth_pitch, y)[x]), f.inv_depth_scaling);
     const float observation_radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
-    const int kDirectionsX[4] = {-1, 1, 0, 0};
-    const int kDirectionsY[4] = {0, 0, -1, 1};
     u32 candidate[4];
 #pragma unroll
     for (int direction = 0; direction < 4; ++direction) {
@@ -921,6 +1132,7 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
       candidate[direction] = supporting_index(f.tb, d.assoc[candidate_pixel].x, static_cast<u32>(candidate_pixel));
     }
     if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) return;  // occluded
+#endif
     float3 ln;
     if (facing_dot(f, cx_, cy_, cz_, nx, ny, nz, &ln) > 0.f) return;
     if (radius_squared < 0.f) return;

@@ -1,0 +1,149 @@
+#!/usr/bin/env python
+"""Assembles profiles/r02_bench.md (+ ncu summaries, launch lists) from what the round-2 GPU calls left in
+gpurun_out/. Later calls override earlier ones (c5 > c4 > c3 > c2) wherever both hold the same item."""
+import io
+import json
+import shutil
+import subprocess
+import sys
+from contextlib import redirect_stdout
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+SRC, OUT = ROOT / "gpurun_out", ROOT / "profiles"
+sys.path.insert(0, str(ROOT / "tools"))
+import launch_list_summary  # noqa: E402
+
+
+def load_line(path):
+    try:
+        return json.loads([ln for ln in path.read_text().splitlines() if ln.startswith("{")][-1])
+    except (OSError, IndexError, ValueError):
+        return None
+
+
+def latest(pattern):
+    for call in ("c7", "c6", "c5", "c4", "c3", "c2", "c1"):
+        p = SRC / pattern.format(call=call)
+        if p.exists() and p.stat().st_size > 0:
+            return p
+    return None
+
+
+def launch_table(path):
+    buf = io.StringIO()
+    old = sys.argv
+    sys.argv = ["launch_list_summary.py", str(path)]
+    try:
+        with redirect_stdout(buf):
+            launch_list_summary.main()
+    finally:
+        sys.argv = old
+    return buf.getvalue()
+
+
+def bench_rows(tag, title, lines):
+    p, r = latest("{call}_bench_product" + tag + ".json"), latest("{call}_bench_reference" + tag + ".json")
+    pj, rj = (load_line(p) if p else None), (load_line(r) if r else None)
+    if not pj or not rj:
+        return None, None
+    fp = pj["config"]["frames_per_step"]
+    lines.append(f"| {title} | {pj['value']:.0f} | {pj['e2e']['value']:.0f} | {rj['value']:.0f} | {rj['e2e']['value']:.0f} | "
+                 f"{pj['value'] / rj['value']:.2f}x | {pj['e2e']['value'] / rj['e2e']['value']:.2f}x | "
+                 f"{pj['config']['surfels_after_step']} / {rj['config']['surfels_after_step']} | "
+                 f"{pj['gpu_launches'] / pj['steps'] / fp:.1f} / {rj['gpu_launches'] / rj['steps'] / fp:.1f} |")
+    return pj, rj
+
+
+def kernel_table(pj, lines):
+    rf = pj.get("roofline")
+    if not rf:
+        return
+    c = rf["counters"]
+    lines.append(f"Counters of the last frame: P = {c['P']}, N = {c['N']}, V = {c['V']}, S = {c['S']}, M = {c['M']}, A = {c['A']}, "
+                 f"D = {c.get('D')}. Roofline region: {rf.get('region', 'whole step')}; frame period inside the frame graph "
+                 f"{rf.get('pipelined_frame_period_us', float('nan')):.1f} us.")
+    lines.append(f"`roofline`: kernel `{rf['kernel']}` (longest on the binding dependency cycle `{rf.get('binding_cycle')}`), "
+                 f"{rf['achieved']:.0f} GB/s on {rf['algorithmic_bytes_per_launch'] / 1e6:.1f} MB algorithmic bytes = "
+                 f"{100 * rf['frac']:.1f} % of the measured HBM peak ({rf['peak']:.0f} GB/s); ncu DRAM traffic per launch: {rf['traffic']}.\n")
+    lines.append("| kernel | launches (region) | events us (serial pass) | share | in-graph us (device timeline) | GB/s on algorithmic bytes (events) |")
+    lines.append("|---|---:|---:|---:|---:|---:|")
+    for k, v in pj["kernels"].items():
+        if "mean_us" not in v:
+            continue
+        gbs = f"{v['achieved_gbs']:.0f} ({100 * v['frac_of_hbm_peak']:.1f} %)" if "achieved_gbs" in v else ""
+        lines.append(f"| {k} | {v['launches']} | {v['mean_us']:.2f} | {100 * v['share']:.1f} % | {v.get('pipelined_us', float('nan')):.2f} | {gbs} |")
+    lines.append("")
+
+
+def main():
+    OUT.mkdir(exist_ok=True)
+    L = ["# r02: benchmark lines, A/B runs and ncu evidence (B200)\n",
+         "All numbers from `gpurun` calls of this round (fresh B200 box each, SM clock 1965 MHz, no throttle reason in any line). "
+         "`value` = frames resident in HBM, `e2e` = pinned host frames in (upload stream) + `TransferAllToCPU` out. The reference arm "
+         "is the reference's own kernels rebuilt for sm_100a (`oracle/_ref`).\n",
+         "## Bench lines\n",
+         "| configuration | product value | product e2e | reference value | reference e2e | ratio | e2e ratio | surfels after a step (product / reference) | launches per frame |",
+         "|---|---:|---:|---:|---:|---:|---:|---:|---:|"]
+    c2p, _ = bench_rows("", "C2: VGA, 500 frames, 5 M cap (the headline)", L)
+    c3p, _ = bench_rows("_C3", "C3: 1280x960, 1000 frames, 20 M cap", L)
+    bench_rows("_C5", "C5: VGA, sigma 0.05 m, 2000 frames (the 2 % outlier test removes every pixel: empty cloud in both arms)", L)
+    bench_rows("_C5_req5", "C5, required inliers 5 of 8 (still empty: erosion needs a full 5x5 window)", L)
+    bench_rows("_C5b", "C5b: sigma 0.05 m, required inliers 1, erosion 0: populated cloud under heavy noise", L)
+    L.append("")
+    if c2p:
+        L.append("### C2 kernel table\n")
+        kernel_table(c2p, L)
+        cb = c2p.get("cpu_baseline")
+        if cb:
+            L.append(f"`cpu_baseline`: {cb['value']:.1f} frames/s on {cb['cores']} host cores ({cb['sample']}); runs {cb.get('runs')}, "
+                     f"spread {cb.get('spread')}.\n")
+    if c3p:
+        L.append("### C3 kernel table (the HBM-bound regime)\n")
+        kernel_table(c3p, L)
+    for call, title in (("c1", "call 1 (graph with programmatic edges + split projection as default)"),
+                        ("c2", "call 2 (graph, plain edges, one projection launch as default)"),
+                        ("c4", "call 4 (scheduling hooks)"), ("c5", "call 5"), ("c6", "call 6")):
+        p = SRC / f"{call}_ab.json"
+        if p.exists():
+            L.append(f"## Same-box A/B, {title}\n")
+            L.append("`tools/ab_probe.py`: one process, one stream, 5 timed passes per configuration (+ warm-up), CUDA events.\n")
+            L.append("| configuration | best frames/s | median | host enqueue ms / pass | surfels | launches / pass |")
+            L.append("|---|---:|---:|---:|---:|---:|")
+            for e in json.loads(p.read_text()):
+                knobs = ", ".join(f"{k}={v}" for k, v in e["env"].items()) + (f", lib={e['lib']}" if e["lib"] != "product" else "")
+                L.append(f"| {e['config']} ({knobs or 'defaults'}) | {e['fps_best']:.0f} | {e['fps_median']:.0f} | {e['host_enqueue_ms']:.2f} | "
+                         f"{e['surfels_size']} / {e['surfel_count']} | {e['launches']} |")
+            L.append("")
+    tp = latest("{call}_transfer_probe.json")
+    if tp:
+        j = json.loads(tp.read_text())
+        L.append("## f1: delta `TransferAllToCPU` (`tools/transfer_probe.py`, transfer every 30 frames, pageable target arrays)\n")
+        L.append("| mode | frames/s end to end | time inside the transfer calls (ms) | D2H bytes | transfers |")
+        L.append("|---|---:|---:|---:|---:|")
+        for mode in ("full", "delta"):
+            v = j[mode]
+            L.append(f"| {mode} | {v['frames_per_s']:.0f} | {v['transfer_ms']:.1f} | {v['d2h_bytes']} | {v['transfers']} |")
+        L.append("")
+    for arm, note in (("product", "`-k regex:k_`, frames ~450-480 of one pass of `tools/stream_probe.py --frames 500`"),
+                      ("reference", "`-k regex:Kernel`, the same frames of `--impl reference`")):
+        f = latest("{call}_launches_" + arm + ".csv")
+        if f:
+            shutil.copy(f, OUT / f"r02_launches_{arm}.csv")
+            L.append(f"## ncu launch list, {arm} ({note}; `--metrics gpu__time_duration.sum --clock-control none`: serialised, cold "
+                     f"caches - the SHARE of a kernel is what carries over, not the absolute)\n\nRaw list: `profiles/r02_launches_{arm}.csv`.\n")
+            L.append(launch_table(f))
+    for rep, name, title in (("frame460_C2", "r02_frame460_C2_ncu_full", "C2 stream, frame 460 (N ~ 0.5 M: L2-resident working set)"),
+                             ("frame960_C3", "r02_frame960_C3_ncu_full", "C3 stream, frame 960 (N ~ 3.5 M: HBM-bound regime)")):
+        f = latest("{call}_" + rep + ".ncu-rep")
+        if f:
+            res = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), str(f), str(OUT / name)],
+                                 capture_output=True, text=True)
+            L.append(f"## `ncu --set full`, one launch per kernel: {title}\n\n`profiles/{name}_summary.csv`, `..._traffic.json`.\n\n"
+                     f"```\n{res.stdout}```\n")
+    (OUT / "r02_bench.md").write_text("\n".join(L) + "\n")
+    print(OUT / "r02_bench.md")
+
+
+if __name__ == "__main__":
+    main()
