@@ -108,6 +108,7 @@ TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index) {
   if (cfg.wave == 0) return t;
   t.mul = cfg.mul;
   t.mul_inv = cfg.mul_inv;
+  t.wave_reciprocal = ~0ull / cfg.wave;
   t.add = tb_hash(frame_index * 0x9E3779B9u + 0x7F4A7C15u) % cfg.wave;
   t.salt = tb_hash(frame_index ^ 0x85EBCA6Bu);
   auto threshold = [](double fraction) {

@@ -555,6 +555,11 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
   }
   r->d.smooth = smooth;
   r->d.smooth_next = smooth_next;
+  {  // the handle's rasters / lists are those of the last integrated frame (sm_download_rasters, sm_frame_counters)
+    const DeviceState last_set = c.SetState((c.last - 1) % kSets);
+    r->d.assoc = last_set.assoc; r->d.first_depth = last_set.first_depth; r->d.supported = last_set.supported;
+    r->d.vis = last_set.vis; r->d.seg_count = last_set.seg_count; r->d.merge_flag = last_set.merge_flag;
+  }
   r->count_slot = c.CountSlot(c.last);
   SM_CUDA(cudaEventRecord(r->graph_exit, gs));
   SM_CUDA(cudaStreamWaitEvent(stream, r->graph_exit, 0));

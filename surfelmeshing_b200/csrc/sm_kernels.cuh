@@ -85,7 +85,20 @@ struct TieBreak {
   u32 salt;             // per frame, for the two draws
   u32 early_threshold;  // secondary association is NOT late iff hash(slot ^ salt) < early_threshold
   u32 index_order_threshold;  // pixel uses slot order iff hash(pixel ^ ~salt) < index_order_threshold
+  u64 wave_reciprocal;  // floor((2^64 - 1) / W): division / modulo by W as a multiply (Barrett)
 };
+// x / W and x % W for x < 2^62 without a hardware division (W is a run-time value).
+__host__ __device__ __forceinline__ u64 tb_divide(const TieBreak& t, u64 x, u32* remainder) {
+#if defined(__CUDA_ARCH__)
+  u64 q = __umul64hi(x, t.wave_reciprocal);
+#else
+  u64 q = static_cast<u64>((static_cast<unsigned __int128>(x) * t.wave_reciprocal) >> 64);
+#endif
+  u64 r = x - q * t.wave;
+  while (r >= t.wave) { r -= t.wave; ++q; }   // the truncated reciprocal leaves q at most 2 short
+  *remainder = static_cast<u32>(r);
+  return q;
+}
 __host__ __device__ __forceinline__ u32 tb_hash(u32 x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
@@ -95,20 +108,23 @@ __host__ __device__ __forceinline__ bool tb_index_order(const TieBreak& t, u32 p
 }
 __host__ __device__ __forceinline__ u32 tb_encode(const TieBreak& t, u32 idx, bool secondary, u32 pixel) {
   if (t.wave == 0) return idx | (secondary ? kSecondaryBit : 0u);
-  const u32 w = idx / t.wave, r = idx - w * t.wave;
-  const u32 rp = tb_index_order(t, pixel) ? r : static_cast<u32>((static_cast<u64>(r) * t.mul + t.add) % t.wave);
+  u32 r, rp;
+  const u32 w = static_cast<u32>(tb_divide(t, idx, &r));
+  if (tb_index_order(t, pixel)) rp = r; else tb_divide(t, static_cast<u64>(r) * t.mul + t.add, &rp);
   const bool late = secondary && !(tb_hash(idx ^ t.salt) < t.early_threshold);
   return w * (2u * t.wave) + (late ? t.wave : 0u) + rp;   // < 2^32 - 1: checked by SetTieBreakWave
 }
 __host__ __device__ __forceinline__ u32 supporting_index(const TieBreak& t, u32 key, u32 pixel) {
   if (key == kInvalidIndex) return kInvalidIndex;
   if (t.wave == 0) return key & ~kSecondaryBit;
-  const u32 w = key / (2u * t.wave);
-  u32 rem = key - w * (2u * t.wave);
-  if (rem >= t.wave) rem -= t.wave;
-  const u32 r = tb_index_order(t, pixel)
-                    ? rem
-                    : static_cast<u32>((static_cast<u64>(rem + t.wave - t.add) % t.wave) * t.mul_inv % t.wave);
+  u32 rem;
+  const u32 w2 = static_cast<u32>(tb_divide(t, key, &rem));   // key = (2 w + late) W + perm
+  const u32 w = w2 >> 1;
+  u32 r = rem;
+  if (!tb_index_order(t, pixel)) {
+    const u32 shifted = rem >= t.add ? rem - t.add : rem + t.wave - t.add;
+    tb_divide(t, static_cast<u64>(shifted) * t.mul_inv, &r);
+  }
   return w * t.wave + r;
 }
 

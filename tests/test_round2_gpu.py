@@ -13,6 +13,7 @@ from oracle import cpu_walk
 from surfelmeshing_b200 import _lib, synthetic as S
 from surfelmeshing_b200 import reconstruction as R
 from surfelmeshing_b200._lib import IntegrateParams, PreprocessParams
+from tests.test_parity_gpu import ENVELOPE_FACTOR
 from tests.util import (INTEGRATE_ROWS, INVALID, NEIGHBOR_ROWS, check_state_invariants, count_mismatch, golden_camera,
                         golden_params, other_frames)
 
@@ -315,13 +316,14 @@ def test_race_bound_rows_inside_the_reference_envelope(product, reference):
       - the product's supporting surfel is a member of the pixel's supporter set, computed independently
         from the oracle state by the CPU walk;
       - differing merge flags, merge-count difference and differing neighbour-link rows of the product
-        stay within 2x (+ a small floor) of what oracle B shows against oracle A;
+        stay within ENVELOPE_FACTOR x (+ a small floor) of what oracle B shows against oracle A;
       - neighbour links are EXACT for every surfel whose neighbourhood holds no contested pixel."""
     cam, st, pp, ip = stream_and_params(640, 480, 24, 11)
     first, last = st.integrated_range()
     rec_a, rec_b, rec_p = make(cam, 800_000, reference), make(cam, 800_000, reference), make(cam, 800_000)
     W = cam.width
     exact_checked = 0
+    ratios = []
     for frame in range(first, last):
         d0, n0, r0 = preprocess(rec_a, st, pp, frame)
         rows, n_before, merges = rec_a.dump_state()
@@ -361,10 +363,11 @@ def test_race_bound_rows_inside_the_reference_envelope(product, reference):
 
         env_flags = int((merge_flags(rb) != merge_flags(ra)).sum())
         got_flags = int((merge_flags(rp) != merge_flags(ra)).sum())
-        assert got_flags <= 2 * env_flags + 12, (frame, got_flags, env_flags)
-        assert abs(int(m_p) - int(m_a)) <= 2 * abs(int(m_b) - int(m_a)) + 12, (frame, m_p, m_a, m_b)
+        assert got_flags <= ENVELOPE_FACTOR * env_flags + 12, (frame, got_flags, env_flags)
+        assert abs(int(m_p) - int(m_a)) <= ENVELOPE_FACTOR * abs(int(m_b) - int(m_a)) + 12, (frame, m_p, m_a, m_b)
         env_links, got_links = link_rows_differ(rb, ra), link_rows_differ(rp, ra)
-        assert got_links <= 2 * env_links + 24, (frame, got_links, env_links)
+        assert got_links <= ENVELOPE_FACTOR * env_links + 24, (frame, got_links, env_links)
+        ratios.append((got_flags / max(env_flags, 1), got_links / max(env_links, 1)))
         # --- exact neighbour links away from contested pixels ---
         # (the integration may move a surfel into the next pixel before its neighbourhood is read: 3 pixels of margin)
         contested_map = (cnt > 1).reshape(cam.height, W)
@@ -387,6 +390,7 @@ def test_race_bound_rows_inside_the_reference_envelope(product, reference):
         assert int((links_p[:, exact] != links_a[:, exact]).sum()) <= 2 * env_links // 10 + 4
         check_state_invariants(rp, n_p)
     assert exact_checked > 5000, "the exact neighbour-link comparison covered a meaningful number of surfels"
+    print("product-vs-A over B-vs-A, per frame (merge flags, link rows):", [(round(a, 1), round(b, 1)) for a, b in ratios])
 
 
 def test_free_running_stream_inside_the_reference_envelope(product, reference):

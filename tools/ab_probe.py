@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--host", action="store_true", help="pinned host frames (e2e path)")
     ap.add_argument("--lib", action="append", default=[], help="name=path of another product build")
     ap.add_argument("--config", action="append", default=[],
-                    help="name:KEY=VAL,KEY=VAL[,lib=name]; 'default' is always run first and last")
+                    help="name:KEY=VAL+KEY=VAL[+lib=name]; 'default' is always run first and last")
     ap.add_argument("--out", default="gpurun_out/ab_probe.json")
     args = ap.parse_args()
 
@@ -43,7 +43,7 @@ def main():
     for item in args.config:
         name, _, rest = item.partition(":")
         env, lib = {}, "product"
-        for kv in filter(None, rest.split(",")):
+        for kv in filter(None, rest.split("+")):
             k, v = kv.split("=", 1)
             if k == "lib":
                 lib = v

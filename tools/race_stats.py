@@ -34,6 +34,34 @@ def u16(h, w):
     return torch.zeros((h, w), dtype=torch.uint16, device="cuda")
 
 
+def collect_sets(ev_pixel, ev_key, sup, cnt, frame, store, max_set=6):
+    """Contested pixels of one frame as fixed-width records for an offline fit of the arrival order:
+    frame, pixel, set size, winner position, slots (padded with 0xFFFFFFFF), secondary bits."""
+    order = np.lexsort((ev_key & 0x7FFFFFFF, ev_pixel))
+    px, key = ev_pixel[order], ev_key[order]
+    bounds = np.flatnonzero(np.diff(px)) + 1
+    starts = np.concatenate([[0], bounds])
+    ends = np.concatenate([bounds, [len(px)]])
+    sup = sup.reshape(-1)
+    cnt = cnt.reshape(-1)
+    for s, e in zip(starts, ends):
+        n = e - s
+        if n < 2 or n > max_set or cnt[px[s]] != n:
+            continue
+        idx = key[s:e] & 0x7FFFFFFF
+        hit = np.flatnonzero(idx == sup[px[s]])
+        if len(hit) == 0:
+            continue
+        rec = np.full(max_set, 0xFFFFFFFF, np.uint32)
+        rec[:n] = idx
+        store["frame"].append(frame)
+        store["pixel"].append(int(px[s]))
+        store["n"].append(n)
+        store["winner"].append(int(hit[0]))
+        store["slots"].append(rec)
+        store["secondary"].append(int(sum(((int(key[s + k]) >> 31) & 1) << k for k in range(n))))
+
+
 def winner_stats(ev_pixel, ev_key, sup, cnt, acc):
     """Accumulates, over the multi-supporter pixels whose CPU supporter set has the size the GPU
     counted, who won the reference's race."""
@@ -139,6 +167,7 @@ def main():
                           "pair_one_wave", "pair_one_wave_lower_index_wins", "pair_one_wave_far", "pair_one_wave_near",
                           "pair_one_wave_far_lower_wins", "pair_one_wave_near_lower_wins")}
     samples = []
+    sets = {k: [] for k in ("frame", "pixel", "n", "winner", "slots", "secondary")}
     t0 = time.time()
     for frame in range(first, last):
         d0, n0, r0 = pre(rec_a, frame)
@@ -167,6 +196,13 @@ def main():
                                                       d0.cpu().numpy(), n0.cpu().numpy(), ip.sensor_noise_factor,
                                                       ip.normal_compatibility_threshold_deg, ip.depth_scaling)
             winner_stats(ev_p, ev_k, ras["supporting_surfels"], ras["supporting_surfel_counts"], acc)
+            collect_sets(ev_p, ev_k, ras["supporting_surfels"], ras["supporting_surfel_counts"], frame, sets)
+            # a second look at the same frame from oracle B: is the winner reproducible from run to run?
+            ras_b = rec_b.download_rasters()
+            both = (ras["supporting_surfel_counts"] > 1)
+            acc["contested_pixels_ab"] = acc.get("contested_pixels_ab", 0) + int(both.sum())
+            acc["contested_same_winner_ab"] = acc.get("contested_same_winner_ab", 0) + int(
+                (ras["supporting_surfels"][both] == ras_b["supporting_surfels"][both]).sum())
             samples.append(entry)
             print(json.dumps(entry), flush=True)
     print(f"teacher-forced pass: {time.time() - t0:.1f}s")
@@ -200,6 +236,11 @@ def main():
         print(f"  {k:16s} {v[0]:9d} {v[1]:9d}   merged {v[0] - v[1]:8d}")
     Path(args.out).parent.mkdir(exist_ok=True)
     Path(args.out).write_text(json.dumps({"samples": samples, "sums": sums, "race": acc, "free": free}, indent=1))
+    np.savez_compressed(str(Path(args.out).with_suffix("")) + "_sets.npz", frame=np.array(sets["frame"], np.uint16),
+                        pixel=np.array(sets["pixel"], np.uint32), n=np.array(sets["n"], np.uint8),
+                        winner=np.array(sets["winner"], np.uint8), slots=np.array(sets["slots"], np.uint32),
+                        secondary=np.array(sets["secondary"], np.uint8),
+                        n_before=np.array([[e["frame"], e["n_before"]] for e in samples], np.uint32))
 
 
 if __name__ == "__main__":
