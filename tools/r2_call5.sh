@@ -1,8 +1,23 @@
 #!/bin/bash
-# round 2, GPU call 5: BASELINE configs C3 / C5b (both arms) with the final kernels, ncu captures (C2 + C3 late frame),
-# launch lists, delta-transfer probes, compute-sanitizer passes
+# round 2, GPU call 5: full test suite + smoke, VGA scheduling / kernel A/B, race statistics with the supporter-set
+# dump, bench lines of both arms (C2, C3, C5b), delta-transfer probes, ncu launch lists + full captures,
+# compute-sanitizer passes
 mkdir -p gpurun_out
 PY=python
+timeout 900 $PY -m pytest tests -m gpu -q -s > gpurun_out/c5_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/c5_pytest.log
+tail -30 gpurun_out/c5_pytest.log
+timeout 300 $PY -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/c5_smoke.log 2>&1; tail -2 gpurun_out/c5_smoke.log
+timeout 900 $PY tools/ab_probe.py --lib old4=variants/lib_old4.so --config old4:lib=old4 \
+  --config prio1:SM_B200_GRAPH_PRIO=1 --config prio2:SM_B200_GRAPH_PRIO=2 \
+  --config offchain50:SM_B200_OFFCHAIN_GRID_PERCENT=50 --config offchain75:SM_B200_OFFCHAIN_GRID_PERCENT=75 \
+  --config prio1_offchain50:SM_B200_GRAPH_PRIO=1+SM_B200_OFFCHAIN_GRID_PERCENT=50 \
+  --config plain_tiebreak:SM_B200_TIEBREAK=0,0,0 --config streams_r1:SM_B200_GRAPH=0 \
+  --out gpurun_out/c5_ab.json > gpurun_out/c5_ab.log 2>&1
+cat gpurun_out/c5_ab.log
+timeout 900 $PY tools/race_stats.py --out gpurun_out/c5_race_stats.json > gpurun_out/c5_race.log 2>&1; echo "race rc=$?" >> gpurun_out/c5_race.log
+tail -45 gpurun_out/c5_race.log
+timeout 600 $PY bench.py --steps 5 --warmup 3 > gpurun_out/c5_bench_product.json 2> gpurun_out/c5_bench_product.err
+timeout 600 $PY bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/c5_bench_reference.json 2> gpurun_out/c5_bench_reference.err
 timeout 1500 $PY bench.py --width 1280 --height 960 --frames 1000 --cap 20000000 --steps 3 --warmup 3 --no-cpu-baseline \
    > gpurun_out/c5_bench_product_C3.json 2> gpurun_out/c5_bench_product_C3.err
 timeout 1500 $PY bench.py --impl reference --width 1280 --height 960 --frames 1000 --cap 20000000 --steps 2 --warmup 3 \
