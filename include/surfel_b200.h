@@ -283,6 +283,38 @@ int sm_update_visualization_buffers(sm_reconstruction* r, void* stream, const sm
                                     float* vertex_buffer, uint32_t* neighbor_index_buffer,
                                     float* normal_vertex_buffer);
 
+/* ---- radius-limited k-nearest-neighbour queries for the meshing thread ----
+ * Replaces CompressedOctree::FindNearestSurfelsWithinRadius<include_completed_surfels, include_free_surfels>
+ * (octree.h:471, octree.cc:313-470; callers surfel_meshing.cc:421 <false, true> and :821 <true, false>) for a BATCH of
+ * queries against one snapshot of the cloud: per query the <= max_result_count (<= 64) nearest points with
+ * squared distance <= radius_squared, ascending, the meshing-state filter applied before the cap, exactly what
+ * the octree returns (equal distances, which the octree leaves to its traversal order, come out by ascending
+ * index). All pointers are DEVICE pointers; the calls are asynchronous on `stream`.
+ *
+ *   sm_knn_create   index for up to max_points points (<= 2^26)
+ *   sm_knn_build    bins points [0, point_count) into a hashed uniform grid of `cell_size` (choose it near the
+ *                   largest query radius: a query visits the (2 r / cell_size + 1)^3 cells its ball touches).
+ *                   A point is left out if radius_squared (optional) is <= 0 at its index (merged surfels,
+ *                   kernels.cu:1987) or state (optional) is 255 there.
+ *   sm_knn_build_from_reconstruction   the same over the handle's current surfels: smooth positions (what
+ *                   TransferAllToCPU hands to the meshing thread, cuda_surfel_reconstruction.cc:345-347) of
+ *                   all slots with radius_squared > 0.
+ *   sm_knn_query    state (optional, one byte per point index: 0 free, 1 front, 2 completed, 255 absent; Surfel::
+ *                   MeshingState, surfel.h:67-71) is read at query time, so one index serves both callers.
+ *                   Outputs: [query_count][max_result_count] squared distances (+inf past the count) and indices
+ *                   (0xFFFFFFFF past the count), [query_count] counts. */
+typedef struct sm_knn_index sm_knn_index;
+int sm_knn_create(sm_knn_index** out, uint32_t max_points);
+void sm_knn_destroy(sm_knn_index* k);
+int sm_knn_build(sm_knn_index* k, void* stream, uint32_t point_count, const float* x, const float* y, const float* z,
+                 const float* radius_squared /* may be NULL */, const uint8_t* state /* may be NULL */, float cell_size);
+int sm_knn_build_from_reconstruction(sm_knn_index* k, sm_reconstruction* r, void* stream, float cell_size,
+                                     uint32_t* out_point_count /* may be NULL */);
+int sm_knn_query(sm_knn_index* k, void* stream, uint32_t query_count, const float* qx, const float* qy, const float* qz,
+                 const float* radius_squared, const uint8_t* state /* may be NULL */, int32_t include_completed_surfels,
+                 int32_t include_free_surfels, int32_t max_result_count, float* out_distance_squared,
+                 uint32_t* out_index, int32_t* out_count);
+
 /* Replaces GetTimings(), cuda_surfel_reconstruction.cc:412-429 (milliseconds of
  * the last Integrate: data association, merging, blending, integration,
  * neighbour update, new-surfel creation, regularisation). */

@@ -163,6 +163,11 @@ _PRODUCT_ONLY = {
     "median_filter_and_densify_depth_map": (C.c_int, [_P, _I, _I, _I, _P, _SZ, _P, _SZ, _P, _SZ]),
     "transfer_delta_to_cpu": (C.c_int, [_P, _P, _U32, C.POINTER(TransferToken), _P, _P, _P, _P, _P, _P, _P, _P,
                                         C.POINTER(TransferStats)]),
+    "knn_create": (C.c_int, [C.POINTER(_P), _U32]),
+    "knn_destroy": (None, [_P]),
+    "knn_build": (C.c_int, [_P, _P, _U32, _P, _P, _P, _P, _P, _F]),
+    "knn_build_from_reconstruction": (C.c_int, [_P, _P, _P, _F, C.POINTER(_U32)]),
+    "knn_query": (C.c_int, [_P, _P, _U32, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "timeline_enable": (C.c_int, [_P, _I]),
     "timeline_read": (C.c_int, [_P, C.POINTER(C.c_uint64), _I]),
 }

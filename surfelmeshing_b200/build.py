@@ -20,7 +20,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libsurfel_b200.so"
-SOURCES = ["api.cu", "pipeline.cu", "transfer.cu", "preprocess.cu", "integrate.cu", "regularize.cu"]
+SOURCES = ["api.cu", "pipeline.cu", "transfer.cu", "preprocess.cu", "integrate.cu", "regularize.cu", "knn.cu"]
 HEADERS = ["sm_math.cuh", "sm_kernels.cuh", "sm_handle.cuh", "../../include/surfel_b200.h"]
 
 NVCC_FLAGS = [

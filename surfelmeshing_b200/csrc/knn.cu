@@ -1,0 +1,465 @@
+// knn.cu — batched radius-limited k-nearest-neighbour queries over the surfel cloud.
+//
+// Reference: the CPU meshing thread asks CompressedOctree::FindNearestSurfelsWithinRadius
+// (APP/octree.cc:313-470) for the <= 64 nearest surfels within a squared radius, once per surfel it
+// triangulates (APP/surfel_meshing.cc:421, <false, true>: completed surfels excluded) and once per surfel it resets
+// for remeshing (APP/surfel_meshing.cc:821, <true, false>: free surfels excluded). One query walks a lazily sorted
+// compressed octree on one thread (~3.5 us for 10^4 points on this container's CPU).
+//
+// Here the cloud is binned once per snapshot into a hashed uniform grid (counting sort by bucket: count, exclusive
+// scan, scatter of {x, y, z, index} records, so that a cell is one contiguous run of 16-byte records) and queries run
+// as a batch, one warp per query: the lanes stride over the records of the cells the search ball touches, and the
+// warp keeps the best 64 {distance^2, index} keys sorted across its lanes (two per lane; an insertion is two ballots
+// and two shuffles). Results are what the octree returns: ascending squared distance, `<= radius^2` inclusive, the
+// meshing-state filter applied before the cap; equal distances, which the reference leaves to traversal order, are
+// ordered by index. Squared distances are computed as ((dx*dx + dy*dy) + dz*dz) in fp32 without contraction, the
+// order Eigen's squaredNorm() evaluates, so they agree bit for bit with the reference octree (oracle/_ref/
+// liboctree_ref.so, built from the reference's octree.cc).
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "sm_handle.cuh"
+#include "sm_math.cuh"
+
+struct sm_knn_index {
+  int device = 0;
+  int sm_count = 0;
+  smb::u32 capacity = 0;       // points the index can hold
+  smb::u32 table_size = 0;     // buckets, a power of two
+  smb::u32* bucket_start = nullptr;   // [table_size + 1]: counts, then (after the scan) first record of each bucket
+  smb::u32* bucket_cursor = nullptr;  // [table_size]
+  smb::u32* scan_sums = nullptr;      // one per scan tile
+  smb::u32* point_bucket = nullptr;   // [capacity]
+  float4* records = nullptr;          // [capacity]: x, y, z, index bits, grouped by bucket
+  smb::u32 point_count = 0;           // points offered to the last build (indices are < this)
+  float cell_size = 0.f;
+  float inverse_cell_size = 0.f;
+  bool built = false;
+};
+
+namespace smb {
+
+namespace {
+
+#define SM_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    const cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return SetError(SM_ERR_CUDA, (std::string(#call) + ": " + cudaGetErrorString(e_)).c_str()); \
+  } while (0)
+
+constexpr int kBuildBlock = 256;
+constexpr int kScanBlock = 1024;
+constexpr int kScanPerThread = 4;
+constexpr int kScanTile = kScanBlock * kScanPerThread;
+constexpr int kQueryBlock = 128;           // 4 queries per block, one warp each
+constexpr int kMaxResults = 64;            // kMaxNeighbors / kMaxSurfelCount of the callers (surfel_meshing.cc:669,814)
+constexpr u8 kStateFree = 0;               // Surfel::MeshingState, surfel.h:67-71
+constexpr u8 kStateCompleted = 2;
+constexpr u8 kStateAbsent = 255;           // slot holds no surfel
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+__device__ __forceinline__ int cell_of(float v, float inverse_cell_size) {
+  return __float2int_rd(fmul(v, inverse_cell_size));
+}
+
+__device__ __forceinline__ u32 bucket_of(int cx, int cy, int cz, u32 mask) {
+  u32 h = static_cast<u32>(cx) * 73856093u ^ static_cast<u32>(cy) * 19349663u ^ static_cast<u32>(cz) * 83492791u;
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  return h & mask;
+}
+
+struct BuildArgs {
+  u32 n;
+  const float* x;
+  const float* y;
+  const float* z;
+  const float* radius_squared;   // optional: points with radius^2 <= 0 are left out (merged surfels, kernels.cu:1987)
+  const u8* state;               // optional: points with state 255 are left out
+  float inverse_cell_size;
+  u32 mask;
+  u32* bucket_start;
+  u32* bucket_cursor;
+  u32* point_bucket;
+  float4* records;
+};
+
+__device__ __forceinline__ bool point_present(const BuildArgs& a, u32 i) {
+  if (a.radius_squared && !(a.radius_squared[i] > 0.f)) return false;
+  if (a.state && a.state[i] == kStateAbsent) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(kBuildBlock) k_knn_count(BuildArgs a) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    u32 bucket = 0xFFFFFFFFu;
+    if (point_present(a, i)) {
+      bucket = bucket_of(cell_of(a.x[i], a.inverse_cell_size), cell_of(a.y[i], a.inverse_cell_size),
+                         cell_of(a.z[i], a.inverse_cell_size), a.mask);
+      atomicAdd(&a.bucket_start[bucket], 1u);
+    }
+    a.point_bucket[i] = bucket;
+  }
+}
+
+// Exclusive scan of `values[0, n)` in place, three launches: tile-local scan + tile sums, scan of the sums by
+// one block, add-back. n is at most 2^27 + 1 (table of 2 x 64 M points), so there are at most 32 769 tile sums.
+__global__ void __launch_bounds__(kScanBlock) k_knn_scan_tiles(u32* values, u32 n, u32* sums) {
+  __shared__ u32 warp_totals[kScanBlock / 32];
+  const u32 base = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+  u32 v[kScanPerThread];
+  u32 thread_total = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    v[k] = base + k < n ? values[base + k] : 0u;
+    thread_total += v[k];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 inclusive = thread_total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 up = __shfl_up_sync(kFullMask, inclusive, o);
+    if (lane >= o) inclusive += up;
+  }
+  if (lane == 31) warp_totals[warp] = inclusive;
+  __syncthreads();
+  if (warp == 0) {
+    u32 w = warp_totals[lane];
+    u32 inc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 up = __shfl_up_sync(kFullMask, inc, o);
+      if (lane >= o) inc += up;
+    }
+    warp_totals[lane] = inc - w;
+    if (lane == 31) sums[blockIdx.x] = inc;
+  }
+  __syncthreads();
+  u32 running = warp_totals[warp] + inclusive - thread_total;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    if (base + k < n) values[base + k] = running;
+    running += v[k];
+  }
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_knn_scan_sums(u32* sums, u32 tiles) {
+  __shared__ u32 warp_totals[kScanBlock / 32];
+  __shared__ u32 carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (u32 base = 0; base < tiles; base += kScanBlock) {
+    const u32 i = base + threadIdx.x;
+    const u32 v = i < tiles ? sums[i] : 0u;
+    u32 inclusive = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 up = __shfl_up_sync(kFullMask, inclusive, o);
+      if (lane >= o) inclusive += up;
+    }
+    if (lane == 31) warp_totals[warp] = inclusive;
+    __syncthreads();
+    if (warp == 0) {
+      const u32 w = warp_totals[lane];
+      u32 inc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 up = __shfl_up_sync(kFullMask, inc, o);
+        if (lane >= o) inc += up;
+      }
+      warp_totals[lane] = inc - w;
+    }
+    __syncthreads();
+    const u32 exclusive = carry + warp_totals[warp] + inclusive - v;
+    if (i < tiles) sums[i] = exclusive;
+    __syncthreads();
+    if (threadIdx.x == kScanBlock - 1) carry = exclusive + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_knn_scan_add(u32* values, u32 n, const u32* sums) {
+  const u32 offset = sums[blockIdx.x];
+  const u32 base = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    if (base + k < n) values[base + k] += offset;
+  }
+}
+
+__global__ void __launch_bounds__(kBuildBlock) k_knn_scatter(BuildArgs a) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const u32 bucket = a.point_bucket[i];
+    if (bucket == 0xFFFFFFFFu) continue;
+    const u32 position = a.bucket_start[bucket] + atomicAdd(&a.bucket_cursor[bucket], 1u);
+    a.records[position] = make_float4(a.x[i], a.y[i], a.z[i], __uint_as_float(i));
+  }
+}
+
+struct QueryArgs {
+  u32 query_count;
+  const float* qx;
+  const float* qy;
+  const float* qz;
+  const float* radius_squared;   // per query
+  const u8* state;               // optional, indexed by point index
+  int include_completed;
+  int include_free;
+  int max_result_count;          // 1..64
+  float inverse_cell_size;
+  u32 mask;
+  const u32* bucket_start;
+  const float4* records;
+  float* out_distance_squared;   // [query_count][max_result_count]
+  u32* out_index;                // [query_count][max_result_count]
+  int* out_count;                // [query_count]
+};
+
+// The warp's result list: rank g (0 = nearest) lives in lane g & 31, register g >> 5. Keys are
+// {distance^2 bits, index}: non-negative floats order like their bit patterns, the index breaks ties.
+struct WarpList {
+  unsigned long long e0, e1;
+  __device__ __forceinline__ void insert(unsigned long long key, int lane) {
+    const int rank = __popc(__ballot_sync(kFullMask, e0 < key)) + __popc(__ballot_sync(kFullMask, e1 < key));
+    const unsigned long long up0 = __shfl_up_sync(kFullMask, e0, 1);
+    unsigned long long up1 = __shfl_up_sync(kFullMask, e1, 1);
+    const unsigned long long last0 = __shfl_sync(kFullMask, e0, 31);
+    if (lane == 0) up1 = last0;
+    if (lane == rank) e0 = key; else if (lane > rank) e0 = up0;
+    if (lane + 32 == rank) e1 = key; else if (lane + 32 > rank) e1 = up1;
+  }
+  __device__ __forceinline__ unsigned long long at(int rank) const {
+    const unsigned long long a = __shfl_sync(kFullMask, e0, rank & 31);
+    const unsigned long long b = __shfl_sync(kFullMask, e1, rank & 31);
+    return rank < 32 ? a : b;
+  }
+};
+
+// Past this many cells per query the warp walks all records instead (bounded work for a radius far above the cell size).
+constexpr long long kMaxCellsPerQuery = 1024;
+
+struct QueryState {
+  WarpList list;
+  int count;
+  unsigned long long threshold;   // keys >= threshold cannot enter the first max_result_count ranks
+};
+
+template <bool kCheckCell>
+__device__ __forceinline__ void scan_records(const QueryArgs& a, QueryState& s, u32 begin, u32 end, int cx, int cy, int cz,
+                                             float px, float py, float pz, float radius_squared, int lane) {
+  for (u32 base = begin; base < end; base += 32) {
+    const u32 e = base + lane;
+    unsigned long long key = kEmptyKey;
+    if (e < end) {
+      const float4 record = a.records[e];
+      // Several cells can share a bucket: a record counts only while its own cell is the one visited.
+      if (!kCheckCell || (cell_of(record.x, a.inverse_cell_size) == cx && cell_of(record.y, a.inverse_cell_size) == cy &&
+                          cell_of(record.z, a.inverse_cell_size) == cz)) {
+        const float dx = fsub(record.x, px), dy = fsub(record.y, py), dz = fsub(record.z, pz);
+        const float distance_squared = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+        if (distance_squared <= radius_squared) {
+          const u32 index = __float_as_uint(record.w);
+          bool wanted = true;
+          if (a.state) {
+            const u8 state = a.state[index];
+            wanted = state != kStateAbsent && (a.include_completed || state != kStateCompleted) &&
+                     (a.include_free || state != kStateFree);
+          }
+          if (wanted) key = (static_cast<unsigned long long>(__float_as_uint(distance_squared)) << 32) | index;
+        }
+      }
+    }
+    unsigned candidates = __ballot_sync(kFullMask, key < s.threshold);
+    while (candidates) {
+      const int source = __ffs(candidates) - 1;
+      candidates &= candidates - 1;
+      const unsigned long long candidate = __shfl_sync(kFullMask, key, source);
+      if (candidate < s.threshold) {   // the threshold may have dropped since the ballot
+        s.list.insert(candidate, lane);
+        s.count = min(s.count + 1, kMaxResults);
+        if (s.count >= a.max_result_count) s.threshold = s.list.at(a.max_result_count - 1);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kQueryBlock) k_knn_query(QueryArgs a) {
+  const int lane = threadIdx.x & 31;
+  const u32 warps_per_grid = gridDim.x * (kQueryBlock / 32);
+  for (u32 q = blockIdx.x * (kQueryBlock / 32) + (threadIdx.x >> 5); q < a.query_count; q += warps_per_grid) {
+    const float px = a.qx[q], py = a.qy[q], pz = a.qz[q];
+    const float radius_squared = a.radius_squared[q];
+    QueryState s{{kEmptyKey, kEmptyKey}, 0, kEmptyKey};
+    if (radius_squared >= 0.f) {
+      // Cells the ball can touch. Everything is rounded outwards: a record whose fp32 distance passes the
+      // test lies inside [p - reach, p + reach] on every axis, and cell_of() is monotone.
+      const float reach = __fmul_ru(__fsqrt_ru(radius_squared), 1.00001f);
+      const int x0 = cell_of(__fsub_rd(px, reach), a.inverse_cell_size), x1 = cell_of(__fadd_ru(px, reach), a.inverse_cell_size);
+      const int y0 = cell_of(__fsub_rd(py, reach), a.inverse_cell_size), y1 = cell_of(__fadd_ru(py, reach), a.inverse_cell_size);
+      const int z0 = cell_of(__fsub_rd(pz, reach), a.inverse_cell_size), z1 = cell_of(__fadd_ru(pz, reach), a.inverse_cell_size);
+      const long long nx = static_cast<long long>(x1) - x0 + 1, ny = static_cast<long long>(y1) - y0 + 1,
+                      nz = static_cast<long long>(z1) - z0 + 1;
+      if (nx > kMaxCellsPerQuery || ny > kMaxCellsPerQuery || nz > kMaxCellsPerQuery || nx * ny * nz > kMaxCellsPerQuery) {
+        scan_records<false>(a, s, 0, a.bucket_start[a.mask + 1], 0, 0, 0, px, py, pz, radius_squared, lane);
+      } else {
+        for (int cz = z0; cz <= z1; ++cz) {
+          for (int cy = y0; cy <= y1; ++cy) {
+            for (int cx = x0; cx <= x1; ++cx) {
+              const u32 bucket = bucket_of(cx, cy, cz, a.mask);
+              scan_records<true>(a, s, a.bucket_start[bucket], a.bucket_start[bucket + 1], cx, cy, cz, px, py, pz,
+                                 radius_squared, lane);
+            }
+          }
+        }
+      }
+    }
+    const int found = min(s.count, a.max_result_count);
+    const size_t out = static_cast<size_t>(q) * a.max_result_count;
+    if (lane < a.max_result_count) {
+      const bool valid = lane < found;
+      a.out_distance_squared[out + lane] = valid ? __uint_as_float(static_cast<u32>(s.list.e0 >> 32)) : __int_as_float(0x7F800000);
+      a.out_index[out + lane] = valid ? static_cast<u32>(s.list.e0) : 0xFFFFFFFFu;
+    }
+    if (lane + 32 < a.max_result_count) {
+      const bool valid = lane + 32 < found;
+      a.out_distance_squared[out + lane + 32] = valid ? __uint_as_float(static_cast<u32>(s.list.e1 >> 32)) : __int_as_float(0x7F800000);
+      a.out_index[out + lane + 32] = valid ? static_cast<u32>(s.list.e1) : 0xFFFFFFFFu;
+    }
+    if (lane == 0) a.out_count[q] = found;
+  }
+}
+
+u32 NextPowerOfTwo(u32 v) {
+  u32 p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+void FreeIndex(sm_knn_index* k) {
+  cudaFree(k->bucket_start);
+  cudaFree(k->bucket_cursor);
+  cudaFree(k->scan_sums);
+  cudaFree(k->point_bucket);
+  cudaFree(k->records);
+  delete k;
+}
+
+int CreateIndex(sm_knn_index* k, u32 max_points) {
+  SM_CUDA(cudaGetDevice(&k->device));
+  SM_CUDA(cudaDeviceGetAttribute(&k->sm_count, cudaDevAttrMultiProcessorCount, k->device));
+  k->capacity = max_points;
+  k->table_size = NextPowerOfTwo(std::max<u32>(1024u, 2u * max_points));
+  const u32 tiles = (k->table_size + 1 + kScanTile - 1) / kScanTile;
+  SM_CUDA(cudaMalloc(&k->bucket_start, sizeof(u32) * (static_cast<size_t>(k->table_size) + 1)));
+  SM_CUDA(cudaMalloc(&k->bucket_cursor, sizeof(u32) * static_cast<size_t>(k->table_size)));
+  SM_CUDA(cudaMalloc(&k->scan_sums, sizeof(u32) * tiles));
+  SM_CUDA(cudaMalloc(&k->point_bucket, sizeof(u32) * static_cast<size_t>(max_points)));
+  SM_CUDA(cudaMalloc(&k->records, sizeof(float4) * static_cast<size_t>(max_points)));
+  return SM_OK;
+}
+
+}  // namespace
+
+int KnnBuild(sm_knn_index* k, cudaStream_t stream, u32 n, const float* x, const float* y, const float* z,
+             const float* radius_squared, const u8* state, float cell_size) {
+  if (n > k->capacity) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_build: more points than the index was created for");
+  if (!(cell_size > 0.f)) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_build: cell_size must be positive");
+  k->built = false;
+  k->point_count = n;
+  k->cell_size = cell_size;
+  k->inverse_cell_size = 1.f / cell_size;
+  SM_CUDA(cudaMemsetAsync(k->bucket_start, 0, sizeof(u32) * (static_cast<size_t>(k->table_size) + 1), stream));
+  SM_CUDA(cudaMemsetAsync(k->bucket_cursor, 0, sizeof(u32) * static_cast<size_t>(k->table_size), stream));
+  BuildArgs a{n, x, y, z, radius_squared, state, k->inverse_cell_size, k->table_size - 1, k->bucket_start,
+              k->bucket_cursor, k->point_bucket, k->records};
+  const u32 scan_n = k->table_size + 1;
+  const u32 tiles = (scan_n + kScanTile - 1) / kScanTile;
+  if (n > 0) {
+    const int blocks = static_cast<int>(std::min<u32>((n + kBuildBlock - 1) / kBuildBlock, 8u * k->sm_count));
+    k_knn_count<<<blocks, kBuildBlock, 0, stream>>>(a);
+    k_knn_scan_tiles<<<tiles, kScanBlock, 0, stream>>>(k->bucket_start, scan_n, k->scan_sums);
+    k_knn_scan_sums<<<1, kScanBlock, 0, stream>>>(k->scan_sums, tiles);
+    k_knn_scan_add<<<tiles, kScanBlock, 0, stream>>>(k->bucket_start, scan_n, k->scan_sums);
+    k_knn_scatter<<<blocks, kBuildBlock, 0, stream>>>(a);
+  }
+  SM_CUDA(cudaGetLastError());
+  k->built = true;
+  return SM_OK;
+}
+
+int KnnQuery(sm_knn_index* k, cudaStream_t stream, u32 query_count, const float* qx, const float* qy, const float* qz,
+             const float* radius_squared, const u8* state, int include_completed, int include_free,
+             int max_result_count, float* out_distance_squared, u32* out_index, int* out_count) {
+  if (!k->built) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_query: the index has not been built");
+  if (max_result_count < 1 || max_result_count > kMaxResults) {
+    return SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_query: max_result_count must be in [1, 64]");
+  }
+  if (query_count == 0) return SM_OK;
+  QueryArgs a{query_count, qx, qy, qz, radius_squared, state, include_completed, include_free, max_result_count,
+              k->inverse_cell_size, k->table_size - 1, k->bucket_start, k->records, out_distance_squared, out_index,
+              out_count};
+  const u32 needed = (query_count + kQueryBlock / 32 - 1) / (kQueryBlock / 32);
+  const int blocks = static_cast<int>(std::min<u32>(needed, 16u * k->sm_count));
+  k_knn_query<<<blocks, kQueryBlock, 0, stream>>>(a);
+  SM_CUDA(cudaGetLastError());
+  return SM_OK;
+}
+
+}  // namespace smb
+
+extern "C" {
+
+int sm_knn_create(sm_knn_index** out, uint32_t max_points) {
+  if (!out || max_points == 0 || max_points > (1u << 26)) {
+    return smb::SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_create: need out and 1 <= max_points <= 2^26");
+  }
+  sm_knn_index* k = new sm_knn_index;
+  const int status = smb::CreateIndex(k, max_points);
+  if (status != SM_OK) {
+    smb::FreeIndex(k);
+    return status;
+  }
+  *out = k;
+  return SM_OK;
+}
+
+void sm_knn_destroy(sm_knn_index* k) {
+  if (k) smb::FreeIndex(k);
+}
+
+int sm_knn_build(sm_knn_index* k, void* stream, uint32_t point_count, const float* x, const float* y, const float* z,
+                 const float* radius_squared, const uint8_t* state, float cell_size) {
+  if (!k || (point_count && (!x || !y || !z))) return smb::SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_build: null argument");
+  return smb::KnnBuild(k, static_cast<cudaStream_t>(stream), point_count, x, y, z, radius_squared, state, cell_size);
+}
+
+int sm_knn_build_from_reconstruction(sm_knn_index* k, sm_reconstruction* r, void* stream_v, float cell_size,
+                                     uint32_t* out_point_count) {
+  if (!k || !r) return smb::SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_build_from_reconstruction: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  uint32_t n = 0;
+  const int status = sm_surfels_size(r, &n);
+  if (status != SM_OK) return status;
+  if (out_point_count) *out_point_count = n;
+  // The positions the meshing thread sees are the smooth ones (TransferAllToCPU, cuda_surfel_reconstruction.cc:345-347).
+  const size_t st = r->d.stride;
+  return smb::KnnBuild(k, stream, n, r->d.smooth, r->d.smooth + st, r->d.smooth + 2 * st,
+                       r->d.surfels + SM_ROW_RADIUS_SQUARED * st, nullptr, cell_size);
+}
+
+int sm_knn_query(sm_knn_index* k, void* stream, uint32_t query_count, const float* qx, const float* qy, const float* qz,
+                 const float* radius_squared, const uint8_t* state, int32_t include_completed, int32_t include_free,
+                 int32_t max_result_count, float* out_distance_squared, uint32_t* out_index, int32_t* out_count) {
+  if (!k || (query_count && (!qx || !qy || !qz || !radius_squared || !out_distance_squared || !out_index || !out_count))) {
+    return smb::SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_query: null argument");
+  }
+  return smb::KnnQuery(k, static_cast<cudaStream_t>(stream), query_count, qx, qy, qz, radius_squared, state,
+                       include_completed, include_free, max_result_count, out_distance_squared, out_index, out_count);
+}
+
+}  // extern "C"
