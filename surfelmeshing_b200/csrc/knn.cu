@@ -17,6 +17,7 @@
 // liboctree_ref.so, built from the reference's octree.cc).
 
 #include <algorithm>
+#include <climits>
 #include <cstring>
 #include <string>
 
@@ -304,7 +305,9 @@ __global__ void __launch_bounds__(kQueryBlock) k_knn_query(QueryArgs a) {
       const int z0 = cell_of(__fsub_rd(pz, reach), a.inverse_cell_size), z1 = cell_of(__fadd_ru(pz, reach), a.inverse_cell_size);
       const long long nx = static_cast<long long>(x1) - x0 + 1, ny = static_cast<long long>(y1) - y0 + 1,
                       nz = static_cast<long long>(z1) - z0 + 1;
-      if (nx > kMaxCellsPerQuery || ny > kMaxCellsPerQuery || nz > kMaxCellsPerQuery || nx * ny * nz > kMaxCellsPerQuery) {
+      // (also taken when a coordinate saturated: the cell loops below must not run into INT_MAX)
+      if (nx > kMaxCellsPerQuery || ny > kMaxCellsPerQuery || nz > kMaxCellsPerQuery || nx * ny * nz > kMaxCellsPerQuery ||
+          x1 == INT_MAX || y1 == INT_MAX || z1 == INT_MAX) {
         scan_records<false>(a, s, 0, a.bucket_start[a.mask + 1], 0, 0, 0, px, py, pz, radius_squared, lane);
       } else {
         for (int cz = z0; cz <= z1; ++cz) {
