@@ -21,8 +21,12 @@
 // This is a superset of the changed slots, so the arrays end up identical to a full transfer.
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 
 #include "sm_handle.cuh"
 
@@ -222,6 +226,13 @@ void FreeTransferBuffers(sm_reconstruction* r) {
   r->delta_capacity = 0; r->delta_host_capacity = 0;
 }
 
+namespace {
+bool DeltaTimingEnabled() {
+  static const bool enabled = [] { const char* e = std::getenv("SM_B200_DELTA_TIMING"); return e && e[0] == '1'; }();
+  return enabled;
+}
+}  // namespace
+
 int TransferDelta(sm_reconstruction* r, cudaStream_t stream, uint32_t frame_index, sm_transfer_token* token, float* x,
                   float* y, float* z, float* radius_squared, float* nx, float* ny, float* nz,
                   uint32_t* last_update_stamp, sm_transfer_stats* stats) {
@@ -291,14 +302,32 @@ int TransferDelta(sm_reconstruction* r, cudaStream_t stream, uint32_t frame_inde
                                 sizeof(float) * changed, 8, cudaMemcpyDeviceToHost, stream));
       SM_CUDA(cudaStreamSynchronize(stream));
       st.d2h_bytes += sizeof(u32) * words;
-      // scatter into the CUDASurfelBuffersCPU arrays
-      for (int k = 0; k < 7; ++k) {
-        const float* v = host_values + static_cast<size_t>(k) * changed;
-        float* dst = out[k];
-        for (u32 j = 0; j < changed; ++j) dst[host_index[j]] = v[j];
+      // scatter into the CUDASurfelBuffersCPU arrays: the eight arrays are independent, four host threads take two
+      // each once the list is long enough to pay for starting them
+      const auto t_scatter = std::chrono::steady_clock::now();
+      u32* const dst_rows[8] = {reinterpret_cast<u32*>(x), reinterpret_cast<u32*>(y), reinterpret_cast<u32*>(z),
+                                reinterpret_cast<u32*>(radius_squared), reinterpret_cast<u32*>(nx),
+                                reinterpret_cast<u32*>(ny), reinterpret_cast<u32*>(nz), last_update_stamp};
+      const u32* src_rows = reinterpret_cast<const u32*>(host_values);
+      auto scatter_rows = [&](int first_row, int last_row) {
+        for (int k = first_row; k < last_row; ++k) {
+          const u32* v = src_rows + static_cast<size_t>(k) * changed;
+          u32* dst = dst_rows[k];
+          for (u32 j = 0; j < changed; ++j) dst[host_index[j]] = v[j];
+        }
+      };
+      if (changed >= (1u << 16)) {
+        std::thread workers[3];
+        for (int t = 0; t < 3; ++t) workers[t] = std::thread(scatter_rows, 2 * t + 2, 2 * t + 4);
+        scatter_rows(0, 2);
+        for (auto& w : workers) w.join();
+      } else {
+        scatter_rows(0, 8);
       }
-      const u32* sv = reinterpret_cast<const u32*>(host_values + static_cast<size_t>(7) * changed);
-      for (u32 j = 0; j < changed; ++j) last_update_stamp[host_index[j]] = sv[j];
+      if (DeltaTimingEnabled()) {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_scatter).count();
+        fprintf(stderr, "[surfel_b200] delta transfer: %u of %u slots, host scatter %.3f ms\n", changed, n, ms);
+      }
     }
     st.changed_count = changed;
   }
