@@ -89,16 +89,21 @@ u32 ModInverse(u32 x, u32 m) {
 }  // namespace
 
 int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity) {
+  u32 lane_shift = cfg->lane_request;
   if (wave != 0) {
     // keys are (slot / W) * 2 W + late * W + perm(slot % W) < 2^32 - 1
     const unsigned long long top = (static_cast<unsigned long long>(capacity) / wave + 1) * 2ull * wave;
     if (wave < 2 || top >= 0xFFFFFFFFull) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range for this surfel cap");
-    const unsigned long long prime = 2654435761ull;  // > any wave, so gcd(prime % wave, wave) = 1
-    cfg->mul = static_cast<u32>(prime % wave);
+    if (lane_shift > 10) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_lanes must be a power of two <= 1024");
+    if (wave % (1u << lane_shift) != 0 || (wave >> lane_shift) < 2) lane_shift = 0;   // the wave is not made of whole groups
+    const u32 groups = wave >> lane_shift;
+    const unsigned long long prime = 2654435761ull;  // > any wave, so gcd(prime % groups, groups) = 1
+    cfg->mul = static_cast<u32>(prime % groups);
     if (cfg->mul == 0) cfg->mul = 1;
-    cfg->mul_inv = ModInverse(cfg->mul, wave);
+    cfg->mul_inv = ModInverse(cfg->mul, groups);
   }
   cfg->wave = wave;
+  cfg->lane_shift = lane_shift;
   return SM_OK;
 }
 
@@ -106,10 +111,13 @@ TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index) {
   TieBreak t{};
   t.wave = cfg.wave;
   if (cfg.wave == 0) return t;
+  t.lane_shift = cfg.lane_shift;
+  t.groups = cfg.wave >> cfg.lane_shift;
   t.mul = cfg.mul;
   t.mul_inv = cfg.mul_inv;
   t.wave_reciprocal = ~0ull / cfg.wave;
-  t.add = tb_hash(frame_index * 0x9E3779B9u + 0x7F4A7C15u) % cfg.wave;
+  t.group_reciprocal = ~0ull / t.groups;
+  t.add = tb_hash(frame_index * 0x9E3779B9u + 0x7F4A7C15u) % t.groups;
   t.salt = tb_hash(frame_index ^ 0x85EBCA6Bu);
   auto threshold = [](double fraction) {
     const double scaled = fraction * 4294967296.0;
@@ -351,18 +359,19 @@ int CreateImpl(sm_reconstruction* r, uint64_t max_surfel_count, int32_t width, i
   r->events.enabled = false;
   // Supporting-surfel tie-break defaults; SM_B200_TIEBREAK="wave,early_fraction" overrides.
   {
-    u32 wave = kDefaultTieBreakWave;
-    double early = kDefaultTieBreakEarlyFraction;
-    if (const char* e = std::getenv("SM_B200_TIEBREAK")) {
-      unsigned w = 0; double q = 0;
-      if (std::sscanf(e, "%u,%lf", &w, &q) == 2) { wave = w; early = q; }
+    u32 wave = kDefaultTieBreakWave, lanes = 1u << kDefaultTieBreakLaneShift;
+    double early = kDefaultTieBreakEarlyFraction, index_order = kDefaultTieBreakIndexOrderFraction;
+    if (const char* e = std::getenv("SM_B200_TIEBREAK")) {   // "wave,early[,index_order[,lanes]]"
+      unsigned w = 0, l = 0; double q = 0, b = 0;
+      const int got = std::sscanf(e, "%u,%lf,%lf,%u", &w, &q, &b, &l);
+      if (got >= 2) { wave = w; early = q; }
+      if (got >= 3) index_order = b;
+      if (got >= 4) lanes = l;
     }
-    double index_order = kDefaultTieBreakIndexOrderFraction;
-    if (const char* e = std::getenv("SM_B200_TIEBREAK")) {
-      unsigned w = 0; double q = 0, b = 0;
-      if (std::sscanf(e, "%u,%lf,%lf", &w, &q, &b) == 3) index_order = b;
-    }
+    u32 lane_shift = 0;
+    while ((1u << lane_shift) < lanes && lane_shift < 10) ++lane_shift;
     if (wave != 0 && (static_cast<unsigned long long>(d.capacity) / wave + 1) * 2ull * wave >= 0xFFFFFFFFull) wave = 0;
+    r->tiebreak.lane_request = lane_shift;
     const int status = SetTieBreakWave(&r->tiebreak, wave, d.capacity);
     if (status != SM_OK) return status;
     r->tiebreak.early_fraction = early;
@@ -803,6 +812,14 @@ int sm_configure(sm_reconstruction* r, const char* key, double value) {
   if (k == "tiebreak_wave") {
     if (value < 0 || value > 2147483647.0) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range");
     return SetTieBreakWave(&r->tiebreak, static_cast<u32>(value), r->d.capacity);
+  }
+  if (k == "tiebreak_lanes") {   // slots that keep their order inside the shuffled order (1 = none, 32 = a warp)
+    const u32 lanes = static_cast<u32>(value);
+    if (value < 1 || value > 1024 || (lanes & (lanes - 1)) != 0) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_lanes must be a power of two in [1, 1024]");
+    u32 shift = 0;
+    while ((1u << shift) < lanes) ++shift;
+    r->tiebreak.lane_request = shift;
+    return SetTieBreakWave(&r->tiebreak, r->tiebreak.wave, r->d.capacity);
   }
   if (k == "tiebreak_early_fraction") {
     if (!(value >= 0.0 && value <= 1.0)) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_early_fraction must be in [0, 1]");

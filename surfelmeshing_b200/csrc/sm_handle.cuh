@@ -16,18 +16,23 @@ struct TieBreakConfig {
   u32 wave;              // slots per launch wave of the modelled race (0: plain "primary, then lowest index")
   double early_fraction; // fraction of secondary associations that compete like primary ones
   double index_order_fraction;  // fraction of the pixels that order the supporters of a wave by slot index
-  u32 mul, mul_inv;      // derived from wave
+  u32 lane_request;      // log2 of the slots that keep their order in the shuffled order (5: a warp of the reference)
+  u32 lane_shift;        // what is in effect: lane_request, or 0 when the wave is not a multiple of it
+  u32 mul, mul_inv;      // derived from wave and lane_shift
 };
 // Defaults (DESIGN.md section 4 / profiles/r02_race_stats.md have the measurements that picked them):
 // wave = the reference's AssociateSurfels launch wave on a B200 (1024-thread blocks, 31 registers ->
-// 2 blocks x 148 SMs = 296 blocks of slots); inside a wave the lower slot won 72 % of the same-kind
-// pairs (-> 44 % of the pixels in slot order, the rest in a random order); 1 % early secondaries puts
-// the merge rate of teacher-forced frames and the free-running totals on the oracle's.
+// 2 blocks x 148 SMs = 296 blocks of slots); inside a wave and a kind the lower slot won 100 % of the pairs
+// that sit in one warp, ~47 % across the warps of one block and 62 - 67 % across blocks (72 % overall: the
+// warps of a wave in a shuffled order that keeps the lanes of a warp in order, and a quarter of the pixels in
+// plain slot order); 1 % early secondaries puts the merge rate of teacher-forced frames and the
+// free-running totals on the oracle's.
 constexpr u32 kDefaultTieBreakWave = 296 * 1024;
+constexpr u32 kDefaultTieBreakLaneShift = 5;
 constexpr double kDefaultTieBreakEarlyFraction = 0.01;
-constexpr double kDefaultTieBreakIndexOrderFraction = 0.44;
+constexpr double kDefaultTieBreakIndexOrderFraction = 0.25;
 TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index);
-int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity);
+int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity);   // uses cfg->lane_request
 
 struct FrameGraph;  // pipeline.cu
 void DestroyFrameGraph(FrameGraph* g);

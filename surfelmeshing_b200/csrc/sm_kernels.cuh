@@ -80,22 +80,25 @@ constexpr u32 kActiveBit = 0x80000000u;      // VisEntry.idx: surfel was active 
 constexpr u32 kSecondaryBit = 0x80000000u;
 struct TieBreak {
   u32 wave;             // W: slots per wave (0: plain rule)
-  u32 mul, mul_inv;     // perm(r) = (r * mul + add) mod W, mul * mul_inv = 1 (mod W)
+  u32 lane_shift;       // log2 of the slots that keep their order inside the shuffled order (5: a warp of the reference; 0: none)
+  u32 groups;           // W >> lane_shift
+  u32 mul, mul_inv;     // perm(g) = (g * mul + add) mod groups, mul * mul_inv = 1 (mod groups)
   u32 add;              // per frame
   u32 salt;             // per frame, for the two draws
   u32 early_threshold;  // secondary association is NOT late iff hash(slot ^ salt) < early_threshold
   u32 index_order_threshold;  // pixel uses slot order iff hash(pixel ^ ~salt) < index_order_threshold
   u64 wave_reciprocal;  // floor((2^64 - 1) / W): division / modulo by W as a multiply (Barrett)
+  u64 group_reciprocal; // the same for `groups`
 };
-// x / W and x % W for x < 2^62 without a hardware division (W is a run-time value).
-__host__ __device__ __forceinline__ u64 tb_divide(const TieBreak& t, u64 x, u32* remainder) {
+// x / d and x % d for x < 2^62 without a hardware division (d is a run-time value, reciprocal = (2^64 - 1) / d).
+__host__ __device__ __forceinline__ u64 tb_divide(u64 x, u32 d, u64 reciprocal, u32* remainder) {
 #if defined(__CUDA_ARCH__)
-  u64 q = __umul64hi(x, t.wave_reciprocal);
+  u64 q = __umul64hi(x, reciprocal);
 #else
-  u64 q = static_cast<u64>((static_cast<unsigned __int128>(x) * t.wave_reciprocal) >> 64);
+  u64 q = static_cast<u64>((static_cast<unsigned __int128>(x) * reciprocal) >> 64);
 #endif
-  u64 r = x - q * t.wave;
-  while (r >= t.wave) { r -= t.wave; ++q; }   // the truncated reciprocal leaves q at most 2 short
+  u64 r = x - q * d;
+  while (r >= d) { r -= d; ++q; }   // the truncated reciprocal leaves q at most 2 short
   *remainder = static_cast<u32>(r);
   return q;
 }
@@ -106,11 +109,20 @@ __host__ __device__ __forceinline__ u32 tb_hash(u32 x) {
 __host__ __device__ __forceinline__ bool tb_index_order(const TieBreak& t, u32 pixel) {
   return tb_hash(pixel ^ ~t.salt) < t.index_order_threshold;
 }
+// Arrival key of a supporter: wave-major; inside a wave primary before (most) secondary associations; inside a
+// kind either slot order or, per pixel, a shuffled order of the wave's warps in which the lanes of one warp keep
+// their order (two lanes of one warp of the reference issue their compare-and-swap in lane order).
 __host__ __device__ __forceinline__ u32 tb_encode(const TieBreak& t, u32 idx, bool secondary, u32 pixel) {
   if (t.wave == 0) return idx | (secondary ? kSecondaryBit : 0u);
   u32 r, rp;
-  const u32 w = static_cast<u32>(tb_divide(t, idx, &r));
-  if (tb_index_order(t, pixel)) rp = r; else tb_divide(t, static_cast<u64>(r) * t.mul + t.add, &rp);
+  const u32 w = static_cast<u32>(tb_divide(idx, t.wave, t.wave_reciprocal, &r));
+  if (tb_index_order(t, pixel)) {
+    rp = r;
+  } else {
+    u32 gp;
+    tb_divide(static_cast<u64>(r >> t.lane_shift) * t.mul + t.add, t.groups, t.group_reciprocal, &gp);
+    rp = (gp << t.lane_shift) | (r & ((1u << t.lane_shift) - 1u));
+  }
   const bool late = secondary && !(tb_hash(idx ^ t.salt) < t.early_threshold);
   return w * (2u * t.wave) + (late ? t.wave : 0u) + rp;   // < 2^32 - 1: checked by SetTieBreakWave
 }
@@ -118,12 +130,15 @@ __host__ __device__ __forceinline__ u32 supporting_index(const TieBreak& t, u32 
   if (key == kInvalidIndex) return kInvalidIndex;
   if (t.wave == 0) return key & ~kSecondaryBit;
   u32 rem;
-  const u32 w2 = static_cast<u32>(tb_divide(t, key, &rem));   // key = (2 w + late) W + perm
+  const u32 w2 = static_cast<u32>(tb_divide(key, t.wave, t.wave_reciprocal, &rem));   // key = (2 w + late) W + perm
   const u32 w = w2 >> 1;
   u32 r = rem;
   if (!tb_index_order(t, pixel)) {
-    const u32 shifted = rem >= t.add ? rem - t.add : rem + t.wave - t.add;
-    tb_divide(t, static_cast<u64>(shifted) * t.mul_inv, &r);
+    const u32 gp = rem >> t.lane_shift;
+    const u32 shifted = gp >= t.add ? gp - t.add : gp + t.groups - t.add;
+    u32 g;
+    tb_divide(static_cast<u64>(shifted) * t.mul_inv, t.groups, t.group_reciprocal, &g);
+    r = (g << t.lane_shift) | (rem & ((1u << t.lane_shift) - 1u));
   }
   return w * t.wave + r;
 }

@@ -9,15 +9,20 @@ namespace smb { int SetError(int c, const char*) { return c; } }
 int main() {
   TieBreakConfig cfg{};
   // host re-implementation of SetTieBreakWave pieces
-  for (u32 wave : {303104u, 1u << 30, 7u, 1000003u}) {
+  for (int variant = 0; variant < 6; ++variant) {
+    const u32 waves[6] = {303104u, 303104u, 1u << 30, 7u, 1000003u, 4096u};
+    const u32 shifts[6] = {5, 0, 5, 0, 0, 10};
+    const u32 wave = waves[variant], shift = shifts[variant], groups = wave >> shift;
     cfg.wave = wave; cfg.early_fraction = 0.3; cfg.index_order_fraction = 0.44;
-    const unsigned long long prime = 2654435761ull; cfg.mul = prime % wave; if (!cfg.mul) cfg.mul = 1;
+    const unsigned long long prime = 2654435761ull; cfg.mul = prime % groups; if (!cfg.mul) cfg.mul = 1;
     // modular inverse
-    long long t = 0, nt = 1, r = wave, nr = cfg.mul % wave;
+    long long t = 0, nt = 1, r = groups, nr = cfg.mul % groups;
     while (nr) { long long q = r / nr; long long tmp = t - q * nt; t = nt; nt = tmp; tmp = r - q * nr; r = nr; nr = tmp; }
-    if (t < 0) t += wave; cfg.mul_inv = (u32)t;
-    TieBreak tb{}; tb.wave = wave; tb.mul = cfg.mul; tb.mul_inv = cfg.mul_inv; tb.add = 12345 % wave; tb.salt = 0xdeadbeef;
+    if (t < 0) t += groups; cfg.mul_inv = (u32)t;
+    TieBreak tb{}; tb.wave = wave; tb.lane_shift = shift; tb.groups = groups; tb.mul = cfg.mul; tb.mul_inv = cfg.mul_inv;
+    tb.add = 12345 % groups; tb.salt = 0xdeadbeef;
     tb.early_threshold = 0x40000000u; tb.index_order_threshold = 0x70000000u; tb.wave_reciprocal = ~0ull / wave;
+    tb.group_reciprocal = ~0ull / groups;
     unsigned long long bad = 0, n = 0;
     for (u32 idx = 0; idx < 20000000u; idx += 7) for (int sec = 0; sec < 2; ++sec) {
       const u32 pixel = (idx * 2654435761u) % 307200u;
@@ -25,13 +30,19 @@ int main() {
       if (supporting_index(tb, key, pixel) != idx || key == 0xFFFFFFFFu) ++bad;
       // reference formulas with real division
       u32 w = idx / wave, rr = idx % wave;
-      u32 rp = tb_index_order(tb, pixel) ? rr : (u32)(((u64)rr * tb.mul + tb.add) % wave);
+      u32 rp = tb_index_order(tb, pixel) ? rr
+                                         : (u32)(((((u64)(rr >> shift) * tb.mul + tb.add) % groups) << shift) | (rr & ((1u << shift) - 1)));
       bool late = sec && !(tb_hash(idx ^ tb.salt) < tb.early_threshold);
       u32 expect = w * (2u * wave) + (late ? wave : 0u) + rp;
       if (wave < (1u<<30) || idx < wave) if (expect != key) ++bad;
       ++n;
     }
-    printf("wave %u: %llu keys, %llu bad\n", wave, n, bad);
+    // the lanes of one group keep their order under the shuffle
+    if (shift) for (u32 idx = 0; idx + 1 < 5000000u; idx += 13) {
+      if ((idx % wave) >> shift != ((idx + 1) % wave) >> shift || idx / wave != (idx + 1) / wave) continue;
+      for (u32 pixel = 0; pixel < 3; ++pixel) if (!(tb_encode(tb, idx, false, pixel) < tb_encode(tb, idx + 1, false, pixel))) ++bad;
+    }
+    printf("wave %u lanes %u: %llu keys, %llu bad\n", wave, 1u << shift, n, bad);
     if (bad) return 1;
   }
   return 0;

@@ -7,7 +7,7 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 out=$root/variants/build_$name
 mkdir -p $out
 objs=""
-for f in api pipeline transfer preprocess integrate regularize; do
+for f in api pipeline transfer preprocess integrate regularize knn; do
   nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -ftz=true -fmad=false -prec-div=true -prec-sqrt=true \
        -Xcompiler -fPIC "$@" -c $root/surfelmeshing_b200/csrc/$f.cu -o $out/$f.o &
   objs="$objs $out/$f.o"

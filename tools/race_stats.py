@@ -141,12 +141,19 @@ def main():
     first, last = st.integrated_range()
     K = pp.outlier_filtering_frame_count
 
-    # (name, wave W, early fraction q of the secondaries, fraction b of the pixels in slot order)
-    variants = [("plain", 0, 0.0, 0.0)]
-    for q, b in ((0.0, 0.0), (0.0, 0.44), (0.0, 1.0), (0.005, 0.44), (0.01, 0.44), (0.015, 0.44), (0.02, 0.44), (0.01, 0.0),
-                 (0.01, 1.0), (0.04, 0.44), (0.10, 0.44)):
-        variants.append((f"wave_q{q}_b{b}", REF_WAVE, q, b))
-    variants.append(("onewave_q0.04_b0.44", 1 << 30, 0.04, 0.44))
+    # (name, wave W, early fraction q of the secondaries, fraction b of the pixels in slot order, lanes that keep
+    #  their order inside the shuffled order)
+    variants = [("plain", 0, 0.0, 0.0, 1), (f"wave_q0.01_b0.44_l1", REF_WAVE, 0.01, 0.44, 1)]
+    for q, b in ((0.0, 0.25), (0.005, 0.25), (0.01, 0.0), (0.01, 0.15), (0.01, 0.25), (0.01, 0.35), (0.015, 0.25), (0.02, 0.25)):
+        variants.append((f"wave_q{q}_b{b}_l32", REF_WAVE, q, b, 32))
+    variants.append(("wave_q0.01_b0.25_l1024", REF_WAVE, 0.01, 0.25, 1024))
+    variants.append(("onewave_q0.01_b0.25_l32", 1 << 30, 0.01, 0.25, 32))
+
+    def set_variant(rec, wave, q, b, lanes):
+        rec.configure("tiebreak_lanes", lanes)
+        rec.configure("tiebreak_wave", wave)
+        rec.configure("tiebreak_early_fraction", q)
+        rec.configure("tiebreak_index_order_fraction", b)
 
     def mk(lib=None):
         return R.CUDASurfelReconstruction(args.cap, W, H, cam.fx, cam.fy, cam.cx, cam.cy, lib=lib)
@@ -166,7 +173,7 @@ def main():
                           "pair_same_kind_lower_index_wins", "pair_two_waves", "pair_two_waves_lower_wave_wins",
                           "pair_one_wave", "pair_one_wave_lower_index_wins", "pair_one_wave_far", "pair_one_wave_near",
                           "pair_one_wave_far_lower_wins", "pair_one_wave_near_lower_wins")}
-    samples = []
+    samples, agree, flagdiff = [], {}, {}
     sets = {k: [] for k in ("frame", "pixel", "n", "winner", "slots", "secondary")}
     t0 = time.time()
     for frame in range(first, last):
@@ -176,14 +183,15 @@ def main():
             rows, n_before, merges_before = rec_a.dump_state()
             rec_b.load_state(rows, merges_before)
             entry = {"frame": frame, "n_before": int(n_before)}
-            for name, wave, q, b in variants:
+            winners, flags = {}, {}
+            for name, wave, q, b, lanes in variants:
                 rec_p.load_state(rows, merges_before)
-                rec_p.configure("tiebreak_wave", wave)
-                rec_p.configure("tiebreak_early_fraction", q)
-                rec_p.configure("tiebreak_index_order_fraction", b)
+                set_variant(rec_p, wave, q, b, lanes)
                 rec_p.integrate(None, frame, ip, d0.clone(), n0, r0, st.color[frame], st.global_T_frame[frame],
                                 st.frame_T_global[frame])
                 entry[name] = int(rec_p.surfels_size() - rec_p.surfel_count()) - int(merges_before)
+                winners[name] = rec_p.download_rasters()["supporting_surfels"]
+                flags[name] = rec_p.dump_state()[0][7, :n_before] < 0
             rec_b.integrate(None, frame, ip, d0.clone(), n0, r0, st.color[frame], st.global_T_frame[frame],
                             st.frame_T_global[frame])
             entry["oracle_b"] = int(rec_b.surfels_size() - rec_b.surfel_count()) - int(merges_before)
@@ -203,6 +211,15 @@ def main():
             acc["contested_pixels_ab"] = acc.get("contested_pixels_ab", 0) + int(both.sum())
             acc["contested_same_winner_ab"] = acc.get("contested_same_winner_ab", 0) + int(
                 (ras["supporting_surfels"][both] == ras_b["supporting_surfels"][both]).sum())
+            # the per-frame quantities the envelope tests look at: same winner as oracle A on the contested pixels,
+            # merge flags that differ from oracle A's (oracle B gives the reference's own run-to-run figure)
+            flags_a = rec_a.dump_state()[0][7, :n_before] < 0
+            flags_b = rec_b.dump_state()[0][7, :n_before] < 0
+            agree["oracle_b"] = agree.get("oracle_b", 0) + int((ras_b["supporting_surfels"][both] == ras["supporting_surfels"][both]).sum())
+            flagdiff["oracle_b"] = flagdiff.get("oracle_b", 0) + int((flags_b != flags_a).sum())
+            for name in winners:
+                agree[name] = agree.get(name, 0) + int((winners[name][both] == ras["supporting_surfels"][both]).sum())
+                flagdiff[name] = flagdiff.get(name, 0) + int((flags[name] != flags_a).sum())
             samples.append(entry)
             print(json.dumps(entry), flush=True)
     print(f"teacher-forced pass: {time.time() - t0:.1f}s")
@@ -214,6 +231,10 @@ def main():
             print(f"  samples with {lo} <= N < {hi}: " + ", ".join(
                 f"{k} {sum(e[k] for e in part) - sum(e['oracle_a'] for e in part):+d}" for k in part[0] if k not in ("frame", "n_before", "oracle_a")))
     print("race statistics:", json.dumps(acc, indent=1))
+    print("per-frame agreement with oracle A over the sampled frames (contested pixels: %d):" % acc["contested_pixels_ab"])
+    for name in agree:
+        print(f"  {name:28s} same winner {agree[name] / max(acc['contested_pixels_ab'], 1):.4f}   differing merge flags {flagdiff[name]:7d}"
+              f"  ({flagdiff[name] / max(flagdiff['oracle_b'], 1):.2f} x oracle B)")
 
     # ---- free-running totals ----
     free = {}
@@ -222,20 +243,19 @@ def main():
         s_ = rec_a.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp,
                               ip, first, last)
         free[f"oracle_{rep}"] = [int(s_.surfels_size), int(s_.surfel_count)]
-    for name, wave, q, b in variants:
+    for name, wave, q, b, lanes in variants:
         for rep in range(args.free_runs):
             rec_p.reset()
-            rec_p.configure("tiebreak_wave", wave)
-            rec_p.configure("tiebreak_early_fraction", q)
-            rec_p.configure("tiebreak_index_order_fraction", b)
+            set_variant(rec_p, wave, q, b, lanes)
             s_ = rec_p.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global,
                                   st.others_TR_reference, pp, ip, first, last)
             free[name if rep == 0 else f"{name}_{rep}"] = [int(s_.surfels_size), int(s_.surfel_count)]
     print("free-running [surfels_size, surfel_count] after the stream:")
     for k, v in free.items():
-        print(f"  {k:16s} {v[0]:9d} {v[1]:9d}   merged {v[0] - v[1]:8d}")
+        print(f"  {k:28s} {v[0]:9d} {v[1]:9d}   merged {v[0] - v[1]:8d}")
     Path(args.out).parent.mkdir(exist_ok=True)
-    Path(args.out).write_text(json.dumps({"samples": samples, "sums": sums, "race": acc, "free": free}, indent=1))
+    Path(args.out).write_text(json.dumps({"samples": samples, "sums": sums, "race": acc, "free": free, "same_winner_as_oracle_a": agree,
+                                          "differing_merge_flags_vs_oracle_a": flagdiff}, indent=1))
     np.savez_compressed(str(Path(args.out).with_suffix("")) + "_sets.npz", frame=np.array(sets["frame"], np.uint16),
                         pixel=np.array(sets["pixel"], np.uint32), n=np.array(sets["n"], np.uint8),
                         winner=np.array(sets["winner"], np.uint8), slots=np.array(sets["slots"], np.uint32),
