@@ -128,11 +128,17 @@ def timed_steps(info, device, step_fn, warmup, steps):
     return e0.elapsed_time(e1), last
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, width):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed
-    `ncu --set full` capture (profiles/*_traffic.json, written by tools/ncu_summary.py), or None."""
+    `ncu --set full` capture of THIS configuration (profiles/*_C2_*_traffic.json for the 640-wide streams,
+    *_C3_* for the 1280-wide one; written by tools/ncu_summary.py, latest round wins), or None."""
+    tag = {640: "_C2_", 1280: "_C3_"}.get(width)
     best = None
+    if tag is None:
+        return None
     for path in sorted((ROOT / "profiles").glob("*_traffic.json")):
+        if tag not in path.name:
+            continue
         try:
             entry = json.loads(path.read_text())["kernels"].get(kernel)
         except (OSError, ValueError, KeyError):
@@ -363,7 +369,7 @@ def main():
         b = algorithmic_bytes(dom, counters)
         dur = kernel_table[dom]["mean_us"] * 1e-6
         achieved = b / dur / 1e9
-        roofline.update({"kernel": dom, "achieved": achieved, "frac": achieved / peak, "traffic": ncu_traffic(dom),
+        roofline.update({"kernel": dom, "achieved": achieved, "frac": achieved / peak, "traffic": ncu_traffic(dom, cam.width),
                          "algorithmic_bytes_per_launch": b, "mean_launch_us": kernel_table[dom]["mean_us"],
                          "pipelined_launch_us": kernel_table[dom].get("pipelined_us"),
                          "achieved_pipelined": b / (kernel_table[dom].get("pipelined_us", float("nan")) * 1e-6) / 1e9,

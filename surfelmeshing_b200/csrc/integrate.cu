@@ -1059,6 +1059,203 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
 #ifndef SM_UPDATE_EARLY_GATE
 #define SM_UPDATE_EARLY_GATE 1
 #endif
+// SM_UPDATE_COMPACT (compile-time A/B hook): 1 = a block takes one whole list segment (1024 entries, four per
+// thread) at a time, runs the light first batch and its gates for all four entries at once (their loads overlap),
+// compacts the ~10 % that pass the occlusion gate into shared memory and works the heavy batches off densely
+// packed - instead of every warp waiting out three levels of gathers for its two or three surviving lanes.
+#ifndef SM_UPDATE_COMPACT
+#define SM_UPDATE_COMPACT 0
+#endif
+
+#ifndef SM_UPDATE_COMPACT_MIN_BLOCKS
+#define SM_UPDATE_COMPACT_MIN_BLOCKS 3
+#endif
+#if SM_UPDATE_COMPACT
+// Batches 2 and 3 for one surfel that passed the border and occlusion gates (x, y: its pixel after the integration).
+__device__ __forceinline__ void update_neighbors_survivor(const DeviceState& d, const FrameParams& f, u32 idx, int x, int y) {
+  const int kDirectionsX[4] = {-1, 1, 0, 0};
+  const int kDirectionsY[4] = {0, 0, -1, 1};
+  const float gx = SM_S(SM_ROW_X, idx), gy = SM_S(SM_ROW_Y, idx), gz = SM_S(SM_ROW_Z, idx);
+  const float nx = SM_S(SM_ROW_NORMAL_X, idx), ny = SM_S(SM_ROW_NORMAL_Y, idx), nz = SM_S(SM_ROW_NORMAL_Z, idx);
+  const float radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+  u32 neighbor_surfel_indices[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) neighbor_surfel_indices[m] = SM_SU(SM_ROW_NEIGHBOR0 + m, idx);
+  const float observation_radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
+  u32 candidate[4];
+#pragma unroll
+  for (int direction = 0; direction < 4; ++direction) {
+    const int candidate_pixel = (y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction];
+    candidate[direction] = supporting_index(f.tb, d.assoc[candidate_pixel].x, static_cast<u32>(candidate_pixel));
+  }
+  const float cz_ = transform_row(f.local_T_global.r2, gx, gy, gz);
+  const float cx_ = transform_row(f.local_T_global.r0, gx, gy, gz);
+  const float cy_ = transform_row(f.local_T_global.r1, gx, gy, gz);
+  float3 ln;
+  if (facing_dot(f, cx_, cy_, cz_, nx, ny, nz, &ln) > 0.f) return;
+  if (radius_squared < 0.f) return;
+  // kCheckScaleCompatibilityForNeighborAssignment, factor 1.5^2.
+  if (fmul(observation_radius_squared, frcp(radius_squared)) > 2.25f) return;
+  // (see the uncompacted variant below for why nothing can happen unless some candidate is new)
+  bool any_new = false;
+#pragma unroll
+  for (int direction = 0; direction < 4; ++direction) {
+    const u32 q = candidate[direction];
+    if (q == kInvalidIndex || q == idx) { candidate[direction] = kInvalidIndex; continue; }
+    any_new |= q != neighbor_surfel_indices[0] && q != neighbor_surfel_indices[1] &&
+               q != neighbor_surfel_indices[2] && q != neighbor_surfel_indices[3];
+  }
+  if (!any_new) return;
+
+  // batch 3: the current neighbours' positions, positions and normals of the candidates
+  float neighbor_distances_squared[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const u32 q = neighbor_surfel_indices[m];
+    if (q == kInvalidIndex) {
+      neighbor_distances_squared[m] = __int_as_float(0x7f800000);
+    } else {
+      neighbor_distances_squared[m] = squared_norm(fsub(gx, SM_S(SM_ROW_X, q)), fsub(gy, SM_S(SM_ROW_Y, q)),
+                                                   fsub(gz, SM_S(SM_ROW_Z, q)));
+    }
+  }
+  const float max_distance_squared = fmul(radius_squared, f.radius_factor_squared);
+  float cand_distance[4], cand_dot[4];
+#pragma unroll
+  for (int direction = 0; direction < 4; ++direction) {
+    const u32 q = candidate[direction];
+    if (q == kInvalidIndex) continue;
+    cand_distance[direction] = squared_norm(fsub(SM_S(SM_ROW_X, q), gx), fsub(SM_S(SM_ROW_Y, q), gy),
+                                            fsub(SM_S(SM_ROW_Z, q), gz));
+    cand_dot[direction] = dot3(nx, ny, nz, SM_S(SM_ROW_NORMAL_X, q), SM_S(SM_ROW_NORMAL_Y, q), SM_S(SM_ROW_NORMAL_Z, q));
+  }
+  bool changed = false;
+#pragma unroll
+  for (int direction = 0; direction < 4; ++direction) {
+    const u32 q = candidate[direction];
+    if (q == kInvalidIndex) continue;
+    const float distance_squared = cand_distance[direction];
+    if (distance_squared > max_distance_squared) continue;
+    if (cand_dot[direction] <= 0.f) continue;
+    // Already a neighbour, or best (farthest) slot to replace.
+    int best_n = -1;
+    float best_distance_squared = -1.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (q == neighbor_surfel_indices[m]) { best_n = -1; break; }
+      if (neighbor_distances_squared[m] > best_distance_squared) {
+        best_n = m;
+        best_distance_squared = neighbor_distances_squared[m];
+      }
+    }
+    if (best_n >= 0 && distance_squared < best_distance_squared) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        if (m == best_n) { neighbor_surfel_indices[m] = q; neighbor_distances_squared[m] = distance_squared; }
+      }
+      changed = true;
+    }
+  }
+  if (changed) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) SM_SU(SM_ROW_NEIGHBOR0 + m, idx) = neighbor_surfel_indices[m];
+  }
+}
+
+__global__ void __launch_bounds__(kBlock, SM_UPDATE_COMPACT_MIN_BLOCKS) k_update_neighbors(DeviceState d, FrameParams f) {
+  pdl_prologue();
+  if (f.skip) return;
+  const TimelineScope timeline_scope(d, f.frame_index, KID_UPDATE_NEIGHBORS);
+  constexpr int kPerThread = kSegment / kBlock;   // list entries of one segment per thread
+  constexpr int kBorder = 1;
+  __shared__ u32 s_survivor[kSegment];            // surfel index
+  __shared__ u32 s_pixel[kSegment];               // x | y << 16
+  __shared__ u32 s_count;
+  const u32 n = d.counters->surfel_count[f.count_slot];
+  const u32 segments = (n + kSegment - 1) / kSegment;
+  const int lane = threadIdx.x & 31;
+  for (u32 segment = blockIdx.x; segment < segments; segment += gridDim.x) {
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const u32 cnt = d.seg_count[segment];
+    // phase A, loads of all four entries first
+    u32 surfel[kPerThread], stamp[kPerThread];
+    float gx[kPerThread], gy[kPerThread], gz[kPerThread];
+    u16 raw_depth[kPerThread];
+    int cached_px[kPerThread], cached_py[kPerThread];
+    bool live[kPerThread];
+    {
+      VisEntry e[kPerThread];
+#pragma unroll
+      for (int u = 0; u < kPerThread; ++u) {
+        const u32 k = u * kBlock + threadIdx.x;
+        live[u] = k < cnt;
+        if (live[u]) e[u] = d.vis[static_cast<size_t>(segment) * kSegment + k];
+      }
+#pragma unroll
+      for (int u = 0; u < kPerThread; ++u) {
+        if (!live[u]) continue;
+        surfel[u] = e[u].x & ~kActiveBit;
+        const Projection cached = project(f, d.width, d.height, __uint_as_float(e[u].y), __uint_as_float(e[u].z), __uint_as_float(e[u].w));
+        cached_px[u] = cached.px;
+        cached_py[u] = cached.py;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+      if (!live[u]) continue;
+      const u32 idx = surfel[u];
+      stamp[u] = SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx);
+      gx[u] = SM_S(SM_ROW_X, idx); gy[u] = SM_S(SM_ROW_Y, idx); gz[u] = SM_S(SM_ROW_Z, idx);
+      raw_depth[u] = row_ptr(f.depth, f.depth_pitch, cached_py[u])[cached_px[u]];
+    }
+    // gates (pure predicates; the integration may have moved the surfel: project again) and compaction
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+      bool pass = live[u];
+      int x = 0, y = 0;
+      if (pass) pass = is_active(stamp[u], f.frame_index, f.active_window);
+      if (pass) {
+        const float cz_ = transform_row(f.local_T_global.r2, gx[u], gy[u], gz[u]);
+        pass = cz_ > 0.f;
+        if (pass) {
+          const float cx_ = transform_row(f.local_T_global.r0, gx[u], gy[u], gz[u]);
+          const float cy_ = transform_row(f.local_T_global.r1, gx[u], gy[u], gz[u]);
+          const float inv_z = frcp(cz_);
+          x = f2i_trunc(ffma(fmul(cx_, inv_z), f.fx, f.cx));
+          y = f2i_trunc(ffma(fmul(cy_, inv_z), f.fy, f.cy));
+          pass = !(x < kBorder || y < kBorder || x >= d.width - kBorder || y >= d.height - kBorder);
+          if (pass) {
+            u16 depth_here = raw_depth[u];
+            if (x != cached_px[u] || y != cached_py[u]) depth_here = row_ptr(f.depth, f.depth_pitch, y)[x];  // moved into another pixel
+            const float measurement_depth = fmul(u2f(depth_here), f.inv_depth_scaling);
+            pass = !(cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f)));  // not occluded
+          }
+        }
+      }
+      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, pass);
+      if (ballot) {
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(&s_count, static_cast<u32>(__popc(ballot)));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (pass) {
+          const u32 slot = base + __popc(ballot & ((1u << lane) - 1u));
+          s_survivor[slot] = surfel[u];
+          s_pixel[slot] = static_cast<u32>(x) | (static_cast<u32>(y) << 16);
+        }
+      }
+    }
+    __syncthreads();
+    // phase B: the survivors, densely packed
+    const u32 survivors = s_count;
+    for (u32 q = threadIdx.x; q < survivors; q += kBlock) {
+      const u32 pixel = s_pixel[q];
+      update_neighbors_survivor(d, f, s_survivor[q], static_cast<int>(pixel & 0xFFFFu), static_cast<int>(pixel >> 16));
+    }
+    __syncthreads();
+  }
+}
+#else
 __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, FrameParams f) {
   pdl_prologue();
   if (f.skip) return;
@@ -1207,6 +1404,7 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
     }
   });
 }
+#endif  // SM_UPDATE_COMPACT
 
 // ---------------------------------------------------------------------------------------
 // a13: new-surfel flags + stable raster-order scan (single pass, decoupled look-back)
@@ -1637,6 +1835,11 @@ int ConfigureIntegrateKernels(int carveout_percent, LaunchPlan* plan) {
   plan->merge = resident(k_merge, kBlock, 4);
   plan->integrate = resident(k_integrate, kBlock, 3);
   plan->update_neighbors = resident(k_update_neighbors, kBlock, 3);
+#if SM_UPDATE_COMPACT
+  // one list segment per block-iteration: more blocks than are resident, so that the segments of a VGA-sized
+  // cloud (~530) spread over the SMs as blocks retire instead of a few blocks taking two
+  plan->update_neighbors = ScaleGrid(sm_count * 8);
+#endif
   if (const char* pe = std::getenv("SM_B200_OFFCHAIN_GRID_PERCENT")) {  // see ConfigureRegularizeKernels
     const int percent = std::atoi(pe);
     if (percent > 0 && percent < 100) {

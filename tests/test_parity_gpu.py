@@ -164,11 +164,17 @@ DETERMINISTIC_RASTERS = ("first_surfel_depth", "supporting_surfel_counts", "conf
                          "new_surfel_flag_vector", "new_surfel_indices")
 
 
-# Two runs of the reference pick the same winner on ~96 % of the contested pixels (its race is largely
-# reproducible on one GPU); the product's rule reproduces the DISTRIBUTION of the outcomes (DESIGN.md
-# section 4), not the individual pixel, so against one oracle run it differs on more pixels than a second
-# oracle run does: measured 2.3 - 4x on merge flags and neighbour-link rows (profiles/r02_race_stats.md).
-ENVELOPE_FACTOR = 5
+# The nondeterministic rows are held to the reference's OWN run-to-run difference (oracle B against oracle A on the
+# same frame): at most ENVELOPE_FACTOR times that, plus a floor for the frames where two oracle runs happen to agree
+# almost exactly (the first integrated frame: all surfels come from one creation sweep, the reference's race is
+# nearly reproducible there and any other resolution differs by a few units). Measured with the default rule
+# (profiles/r02_race_stats.md): 1.0 - 1.7 x on merge flags, 1.2 - 1.6 x on link rows.
+ENVELOPE_FACTOR = 2
+
+
+def envelope_floors(n_before):
+    """(merge flags / merge count, neighbour-link rows)"""
+    return 12, max(24, n_before // 200)
 
 
 def race_envelope(state_b, state_a, n_before):
@@ -219,15 +225,16 @@ def compare_integrate(mine_rasters, mine_depth, mine_state, ref_rasters, ref_dep
         env_flags, env_count, env_links = envelope
         print(f"envelope: merge flags {int((~same_merge).sum())} vs {env_flags}, merge count {abs(int(merges_m) - int(merges_r))} vs "
               f"{env_count}, link rows {link_rows_differ} vs {env_links} (n = {n_before})")
-        assert (~same_merge).sum() <= ENVELOPE_FACTOR * env_flags + 12, ((~same_merge).sum(), env_flags)
+        flag_floor, link_floor = envelope_floors(n_before)
+        assert (~same_merge).sum() <= ENVELOPE_FACTOR * env_flags + flag_floor, ((~same_merge).sum(), env_flags)
         # (two oracle runs can differ on dozens of flags and still count the same number of merges: the count
         #  envelope is the larger of the two figures)
-        assert abs(int(merges_m) - int(merges_r)) <= ENVELOPE_FACTOR * max(env_count, env_flags) + 12, (merges_m, merges_r, env_count, env_flags)
-        assert link_rows_differ <= ENVELOPE_FACTOR * env_links + 24, (link_rows_differ, env_links)
+        assert abs(int(merges_m) - int(merges_r)) <= ENVELOPE_FACTOR * max(env_count, env_flags) + flag_floor, (merges_m, merges_r, env_count, env_flags)
+        assert link_rows_differ <= ENVELOPE_FACTOR * env_links + link_floor, (link_rows_differ, env_links)
     else:
         assert (~same_merge).sum() <= max(20, 0.004 * n_r), "merge decisions differ only inside the reference's envelope"
         assert abs(int(merges_m) - int(merges_r)) <= max(20, 0.004 * n_r)
-        assert link_rows_differ <= max(40, 0.05 * n_before)
+        assert link_rows_differ <= max(40, 0.04 * n_before)
     # a blended-depth pixel that rounds differently (see above) feeds up to a few surfels
     allowed = 4 * int((depth_diff != 0).sum())
     for row in INTEGRATE_ROWS:

@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--k", type=int, default=64)
     ap.add_argument("--spacing", type=float, default=0.005)
     ap.add_argument("--radius-factor", type=float, default=2.5, help="query radius in units of the point spacing")
-    ap.add_argument("--cell-factor", type=float, default=1.0, help="cell size in units of the query radius")
+    ap.add_argument("--cell-factor", type=float, default=2.0, help="cell size in units of the query radius")
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default=None)

@@ -89,7 +89,8 @@ def main():
     c3p, _ = bench_rows("_C3", "C3: 1280x960, 1000 frames, 20 M cap", L)
     bench_rows("_C5", "C5: VGA, sigma 0.05 m, 2000 frames (the 2 % outlier test removes every pixel: empty cloud in both arms)", L)
     bench_rows("_C5_req5", "C5, required inliers 5 of 8 (still empty: erosion needs a full 5x5 window)", L)
-    bench_rows("_C5b", "C5b: sigma 0.05 m, required inliers 1, erosion 0: populated cloud under heavy noise", L)
+    bench_rows("_C5b_500", "C5b: sigma 0.05 m, required inliers 1, erosion 0, 40 M cap, 500 frames: populated cloud under heavy noise", L)
+    bench_rows("_C5b_2000", "C5b, 2000 frames (with the default 5 M cap both arms overflow: the noisy stream creates ~3 300 surfels per frame)", L)
     L.append("")
     if c2p:
         L.append("### C2 kernel table\n")
@@ -103,7 +104,7 @@ def main():
         kernel_table(c3p, L)
     for call, title in (("c1", "call 1 (graph with programmatic edges + split projection as default)"),
                         ("c2", "call 2 (graph, plain edges, one projection launch as default)"),
-                        ("c4", "call 4 (scheduling hooks)"), ("c5", "call 5"), ("c6", "call 6")):
+                        ("c4", "call 4 (scheduling hooks)"), ("c7", "call 7 (final kernels: light-first-batch gathers, multiply-based key decode)")):
         p = SRC / f"{call}_ab.json"
         if p.exists():
             L.append(f"## Same-box A/B, {title}\n")
@@ -115,16 +116,42 @@ def main():
                 L.append(f"| {e['config']} ({knobs or 'defaults'}) | {e['fps_best']:.0f} | {e['fps_median']:.0f} | {e['host_enqueue_ms']:.2f} | "
                          f"{e['surfels_size']} / {e['surfel_count']} | {e['launches']} |")
             L.append("")
-    tp = latest("{call}_transfer_probe.json")
-    if tp:
+    L.append("## f1: delta `TransferAllToCPU` (`tools/transfer_probe.py`: stream_run in chunks, a hand-off to pageable arrays after each)\n")
+    L.append("| stream | transfer every | mode | frames/s end to end | ms inside the transfer calls | D2H bytes | transfers |")
+    L.append("|---|---:|---|---:|---:|---:|---:|")
+    for pattern, stream, every in (("{call}_transfer_probe.json", "C2 (VGA, 0.54 M surfels)", 30),
+                                   ("{call}_transfer_probe_every5.json", "C2 (VGA, 0.54 M surfels)", 5),
+                                   ("{call}_transfer_probe_hd.json", "1280x960, 400 frames (2.05 M surfels)", 10)):
+        tp = latest(pattern)
+        if not tp:
+            continue
         j = json.loads(tp.read_text())
-        L.append("## f1: delta `TransferAllToCPU` (`tools/transfer_probe.py`, transfer every 30 frames, pageable target arrays)\n")
-        L.append("| mode | frames/s end to end | time inside the transfer calls (ms) | D2H bytes | transfers |")
-        L.append("|---|---:|---:|---:|---:|")
         for mode in ("full", "delta"):
             v = j[mode]
-            L.append(f"| {mode} | {v['frames_per_s']:.0f} | {v['transfer_ms']:.1f} | {v['d2h_bytes']} | {v['transfers']} |")
-        L.append("")
+            L.append(f"| {stream} | {every} | {mode} | {v['frames_per_s']:.0f} | {v['transfer_ms']:.1f} | {v['d2h_bytes']} | {v['transfers']} |")
+    L.append("\nThe delta moves 40 - 50 % fewer bytes (a third of the slots are inside the 30-frame regularisation window at any "
+             "time, so they did change) but is not faster: its host-side scatter of the records into the CUDASurfelBuffersCPU "
+             "arrays (3.3 - 4.0 ms for 0.68 M records on four threads) costs more than the 16 MB it saves on a 25 GB/s link. It "
+             "pays when the consumer uses the changed-slot list instead of its O(N) comparison "
+             "(`surfel_meshing.cc:199-250`), or over a slower link.\n")
+    L.append("## f4: radius k-NN for the meshing thread (`tools/knn_probe.py`)\n")
+    L.append("Synthetic surfel sheet (5 mm spacing), every surfel queries its neighbours within 12.5 mm, k <= 64; the "
+             "reference arm is the reference's own octree (`oracle/_ref/liboctree_ref.so`) on one host thread, the way the "
+             "meshing thread calls it; every sampled query is compared with the GPU answer before a number is printed.\n")
+    L.append("| points = queries | cell size / radius | build ms | query ms | queries/s resident | queries/s end to end (H2D of points + queries, D2H of results) | reference octree queries/s (sample) | end-to-end ratio |")
+    L.append("|---:|---:|---:|---:|---:|---:|---:|---:|")
+    for pattern, cell in (("{call}_knn_probe.json", 1.0), ("{call}_knn_probe_cell20.json", 2.0), ("{call}_knn_probe_cell05.json", 0.5),
+                          ("{call}_knn_probe_4m.json", 1.0)):
+        kp = latest(pattern)
+        if not kp:
+            continue
+        j = json.loads(kp.read_text())
+        ref = j.get("reference_octree", {})
+        pts = j["workload"].split(" ")[0]
+        L.append(f"| {pts} | {cell} | {j['build_ms']:.3f} | {j['query_ms']:.2f} | {j['queries_per_s_resident'] / 1e6:.0f} M | "
+                 f"{j['queries_per_s_e2e'] / 1e6:.1f} M | {ref.get('queries_per_s', 0) / 1e3:.0f} k ({ref.get('sample', '')}) | "
+                 f"{j.get('speedup_e2e_vs_reference_octree', 0):.0f}x |")
+    L.append("")
     for arm, note in (("product", "`-k regex:k_`, frames ~450-480 of one pass of `tools/stream_probe.py --frames 500`"),
                       ("reference", "`-k regex:Kernel`, the same frames of `--impl reference`")):
         f = latest("{call}_launches_" + arm + ".csv")
