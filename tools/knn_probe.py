@@ -36,10 +36,17 @@ def main():
     ap.add_argument("--cell-factor", type=float, default=2.0, help="cell size in units of the query radius")
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--cloud", default="sheet", choices=["sheet", "random"],
+                    help="sheet: a surfel surface; random: uniform points in a cube (BASELINE config 1: the pattern of the "
+                         "reference's octree / triangulation tests), spacing = mean distance to the nearest neighbour")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
 
-    x, y, z = knn_cases.surface_cloud(a.points, 7, spacing=a.spacing)
+    if a.cloud == "random":
+        extent = 0.5 * a.spacing * (a.points ** (1.0 / 3.0)) / 0.554   # nearest-neighbour distance of a Poisson cloud
+        x, y, z = knn_cases.random_cloud(a.points, 7, extent=extent)
+    else:
+        x, y, z = knn_cases.surface_cloud(a.points, 7, spacing=a.spacing)
     rng = np.random.default_rng(8)
     qi = rng.permutation(a.points)[: a.queries] if a.queries <= a.points else rng.integers(0, a.points, a.queries)
     radius = a.radius_factor * a.spacing
@@ -88,7 +95,7 @@ def main():
             e2e_s.append(time.perf_counter() - t0)
 
     result = {
-        "workload": f"{a.points} surfels on a sheet (spacing {a.spacing} m), {len(qi)} queries, radius {radius:.4f} m, "
+        "workload": f"{a.points} surfels {'on a sheet' if a.cloud == 'sheet' else 'uniform in a cube'} (spacing {a.spacing} m), {len(qi)} queries, radius {radius:.4f} m, "
                     f"k <= {a.k}, cell {cell:.4f} m",
         "mean_neighbours_found": float(found.mean()), "queries_at_cap": float((found == a.k).mean()),
         "build_ms": float(np.median(build_ms)), "query_ms": float(np.median(query_ms)),

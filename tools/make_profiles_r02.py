@@ -104,8 +104,10 @@ def main():
         kernel_table(c3p, L)
     for call, title in (("c1", "call 1 (graph with programmatic edges + split projection as default)"),
                         ("c2", "call 2 (graph, plain edges, one projection launch as default)"),
-                        ("c4", "call 4 (scheduling hooks)"), ("c7", "call 7 (final kernels: light-first-batch gathers, multiply-based key decode)")):
-        p = SRC / f"{call}_ab.json"
+                        ("c4", "call 4 (scheduling hooks)"), ("c7", "call 7 (final kernels: light-first-batch gathers, multiply-based key decode)"),
+                        ("c8", "call 8 (k_update_neighbors with block-level survivor compaction, -DSM_UPDATE_COMPACT=1: slower at VGA, kept off)"),
+                        ("c8_hd", "call 8, 1280x960 / 400 frames / 20 M cap (3 passes)")):
+        p = SRC / (f"{call}_ab.json" if not call.endswith("_hd") else f"{call[:-3]}_ab_hd.json")
         if p.exists():
             L.append(f"## Same-box A/B, {title}\n")
             L.append("`tools/ab_probe.py`: one process, one stream, 5 timed passes per configuration (+ warm-up), CUDA events.\n")
