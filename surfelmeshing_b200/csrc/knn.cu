@@ -239,16 +239,60 @@ struct WarpList {
     const unsigned long long b = __shfl_sync(kFullMask, e1, rank & 31);
     return rank < 32 ? a : b;
   }
+  // Bitonic sort of the 64 keys (ascending over ranks 0..63; empty keys are the largest value and end up last).
+  // kHalf: only e0 holds keys (e1 all empty): a 32-key network.
+  template <bool kHalf>
+  __device__ __forceinline__ void sort(int lane) {
+#pragma unroll
+    for (int k = 2; k <= (kHalf ? 32 : 64); k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j >= 1; j >>= 1) {
+        if (j == 32) {   // partner of rank g is g ^ 32: the other register of the same lane (k = 64: ascending)
+          const unsigned long long lo = e0 < e1 ? e0 : e1, hi = e0 < e1 ? e1 : e0;
+          e0 = lo; e1 = hi;
+          continue;
+        }
+        const bool lower = (lane & j) == 0;
+        {
+          const bool ascending = (lane & k) == 0;   // k = 64: lane & 64 == 0
+          const unsigned long long other = __shfl_xor_sync(kFullMask, e0, j);
+          const bool take_min = lower == ascending;
+          e0 = (take_min == (other < e0)) ? other : e0;
+        }
+        if (!kHalf) {
+          const bool ascending = ((lane + 32) & k) == 0;
+          const unsigned long long other = __shfl_xor_sync(kFullMask, e1, j);
+          const bool take_min = lower == ascending;
+          e1 = (take_min == (other < e1)) ? other : e1;
+        }
+      }
+    }
+  }
 };
 
 // Past this many cells per query the warp walks all records instead (bounded work for a radius far above the cell size).
 constexpr long long kMaxCellsPerQuery = 1024;
 
+// A query first APPENDS every record that passes the radius and state tests to a 64-key staging row in shared
+// memory (one ballot and one store per batch of 32 records); most queries end with fewer than 64 candidates and
+// sort them once at the end. Only when the row would overflow does the warp sort what it has into the register
+// list and continue by insertion against the admission threshold.
 struct QueryState {
   WarpList list;
-  int count;
-  unsigned long long threshold;   // keys >= threshold cannot enter the first max_result_count ranks
+  int count;                      // staged keys (staging) or list entries (sorted), <= 64
+  bool staging;
+  unsigned long long threshold;   // sorted mode: keys >= threshold cannot enter the first max_result_count ranks
+  unsigned long long* stage;      // this warp's 64-key row in shared memory
 };
+
+__device__ __forceinline__ void leave_staging(const QueryArgs& a, QueryState& s, int lane) {
+  __syncwarp();
+  s.list.e0 = lane < s.count ? s.stage[lane] : kEmptyKey;
+  s.list.e1 = lane + 32 < s.count ? s.stage[lane + 32] : kEmptyKey;
+  if (s.count <= 32) s.list.sort<true>(lane); else s.list.sort<false>(lane);
+  s.staging = false;
+  if (s.count >= a.max_result_count) s.threshold = s.list.at(a.max_result_count - 1);
+}
 
 template <bool kCheckCell>
 __device__ __forceinline__ void scan_records(const QueryArgs& a, QueryState& s, u32 begin, u32 end, int cx, int cy, int cz,
@@ -276,6 +320,17 @@ __device__ __forceinline__ void scan_records(const QueryArgs& a, QueryState& s, 
       }
     }
     unsigned candidates = __ballot_sync(kFullMask, key < s.threshold);
+    if (candidates == 0) continue;
+    if (s.staging) {
+      const int incoming = __popc(candidates);
+      if (s.count + incoming <= kMaxResults) {
+        if (key < s.threshold) s.stage[s.count + __popc(candidates & ((1u << lane) - 1u))] = key;
+        s.count += incoming;
+        continue;
+      }
+      leave_staging(a, s, lane);
+      candidates = __ballot_sync(kFullMask, key < s.threshold);
+    }
     while (candidates) {
       const int source = __ffs(candidates) - 1;
       candidates &= candidates - 1;
@@ -290,12 +345,13 @@ __device__ __forceinline__ void scan_records(const QueryArgs& a, QueryState& s, 
 }
 
 __global__ void __launch_bounds__(kQueryBlock) k_knn_query(QueryArgs a) {
+  __shared__ unsigned long long s_stage[kQueryBlock / 32][kMaxResults];
   const int lane = threadIdx.x & 31;
   const u32 warps_per_grid = gridDim.x * (kQueryBlock / 32);
   for (u32 q = blockIdx.x * (kQueryBlock / 32) + (threadIdx.x >> 5); q < a.query_count; q += warps_per_grid) {
     const float px = a.qx[q], py = a.qy[q], pz = a.qz[q];
     const float radius_squared = a.radius_squared[q];
-    QueryState s{{kEmptyKey, kEmptyKey}, 0, kEmptyKey};
+    QueryState s{{kEmptyKey, kEmptyKey}, 0, true, kEmptyKey, s_stage[threadIdx.x >> 5]};
     if (radius_squared >= 0.f) {
       // Cells the ball can touch. Everything is rounded outwards: a record whose fp32 distance passes the
       // test lies inside [p - reach, p + reach] on every axis, and cell_of() is monotone.
@@ -321,6 +377,8 @@ __global__ void __launch_bounds__(kQueryBlock) k_knn_query(QueryArgs a) {
         }
       }
     }
+    if (s.staging) leave_staging(a, s, lane);
+    __syncwarp();   // the staging row is reused by this warp's next query
     const int found = min(s.count, a.max_result_count);
     const size_t out = static_cast<size_t>(q) * a.max_result_count;
     if (lane < a.max_result_count) {
