@@ -298,7 +298,7 @@ struct FrameGraph {
   std::vector<cudaGraphNode_t> nodes;   // same order as the KernelLaunch list of a step
   std::vector<const void*> funcs;
   // what the graph was built for
-  int blending = -1, reg_launches = -1, pdl = -1, prio = -1;
+  int blending = -1, reg_launches = -1, pdl = -1, prio = -1, order = -1;
   size_t blend_smem = 0;
   dim3 scan_grid;
 };
@@ -344,6 +344,8 @@ cudaKernelNodeParams NodeParams(const KernelLaunch& k) {
 }
 
 // Builds and instantiates the graph of one step from the launch list of its first use.
+constexpr int kDefaultGraphOrder = 0;
+
 int BuildFrameGraph(FrameGraph* g, const StepLayout& l, const std::vector<KernelLaunch>& launches, int pdl) {
   SM_CUDA(cudaGraphCreate(&g->graph, 0));
   g->nodes.assign(l.count, nullptr);
@@ -409,6 +411,18 @@ int BuildFrameGraph(FrameGraph* g, const StepLayout& l, const std::vector<Kernel
   if (l.blend >= 0) edge(l.associate, l.blend, true);
   // pre (frame f + 2)
   edge(l.bilateral, l.tail, true);
+  // SM_B200_GRAPH_ORDER (bit mask): ordering-only edges. The kernels of a step are launched with grids that fill
+  // the register file, so whichever of two ready kernels gets the SMs first runs alone; these edges let the
+  // chain that ends the step (integrate -> create -> project -> associate -> blend) go first where both are ready:
+  //   1: create before update_neighbors      (both wait for integrate)
+  //   2: associate(f + 1) before the regularisation of frame f
+  //   4: merge(f + 1) before the regularisation of frame f
+  //   8: project(f + 1) before update_neighbors(f)
+  const int order = EnvInt("SM_B200_GRAPH_ORDER", kDefaultGraphOrder);
+  if (order & 1) edge(l.create, l.update, false);
+  if ((order & 2) && l.reg_count > 0) edge(l.associate, l.reg0, false);
+  if ((order & 4) && l.reg_count > 0) edge(l.merge, l.reg0, false);
+  if (order & 8) edge(l.project_tail >= 0 ? l.project_tail : l.project, l.update, false);
   SM_CUDA(cudaGraphAddDependencies_v2(g->graph, from.data(), to.data(), data.data(), from.size()));
   SM_CUDA(cudaGraphInstantiate(&g->exec, g->graph, 0));
   return SM_OK;
@@ -529,8 +543,9 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
     // ---- (re)build on the first step or when the shape changed, else update the node arguments ----
     FrameGraph* g = r->graph;
     const int prio = EnvInt("SM_B200_GRAPH_PRIO", 0);
+    const int order = EnvInt("SM_B200_GRAPH_ORDER", kDefaultGraphOrder);
     bool rebuild = g == nullptr || g->blending != (blending ? 1 : 0) || g->reg_launches != reg_launches || g->pdl != pdl ||
-                   g->prio != prio || static_cast<int>(g->nodes.size()) != l.count;
+                   g->prio != prio || g->order != order || static_cast<int>(g->nodes.size()) != l.count;
     if (!rebuild) {
       for (int i = 0; i < l.count && !rebuild; ++i) rebuild = g->funcs[i] != launches[i].func;
       if (l.blend >= 0) rebuild = rebuild || g->blend_smem != launches[l.blend].smem;
@@ -539,7 +554,7 @@ int RunGraph(RunContext& c, cudaStream_t stream, uint32_t* integrated) {
       if (g) { SM_CUDA(cudaStreamSynchronize(gs)); DestroyFrameGraph(g); r->graph = nullptr; }
       g = new FrameGraph();
       r->graph = g;
-      g->blending = blending ? 1 : 0; g->reg_launches = reg_launches; g->pdl = pdl; g->prio = prio;
+      g->blending = blending ? 1 : 0; g->reg_launches = reg_launches; g->pdl = pdl; g->prio = prio; g->order = order;
       g->blend_smem = l.blend >= 0 ? launches[l.blend].smem : 0;
       status = BuildFrameGraph(g, l, launches, pdl);
       if (status != SM_OK) return status;
