@@ -106,7 +106,10 @@ def main():
                         ("c2", "call 2 (graph, plain edges, one projection launch as default)"),
                         ("c4", "call 4 (scheduling hooks)"), ("c7", "call 7 (final kernels: light-first-batch gathers, multiply-based key decode)"),
                         ("c8", "call 8 (k_update_neighbors with block-level survivor compaction, -DSM_UPDATE_COMPACT=1: slower at VGA, kept off)"),
-                        ("c8_hd", "call 8, 1280x960 / 400 frames / 20 M cap (3 passes)")):
+                        ("c8_hd", "call 8, 1280x960 / 400 frames / 20 M cap (3 passes)"),
+                        ("c8c", "call 8c (ordering-only graph edges, SM_B200_GRAPH_ORDER: 1 create before update_neighbors, 2 associate(f+1) "
+                                "before the regularisation of f, 4 merge(f+1) before it, 8 project(f+1) before update_neighbors(f): all slower, kept off)"),
+                        ("c8c_hd", "call 8c, 1280x960 / 400 frames / 20 M cap (3 passes)")):
         p = SRC / (f"{call}_ab.json" if not call.endswith("_hd") else f"{call[:-3]}_ab_hd.json")
         if p.exists():
             L.append(f"## Same-box A/B, {title}\n")
