@@ -177,6 +177,12 @@ def envelope_floors(n_before):
     return 12, max(24, n_before // 200)
 
 
+def envelope_limit(env, floor):
+    """ENVELOPE_FACTOR x the oracle's own difference, plus four standard deviations of that count (one oracle pair is
+    a single draw: a count of ~50 differing flags scatters by +-7 from run to run), plus the floor."""
+    return ENVELOPE_FACTOR * env + 4.0 * float(np.sqrt(max(env, 1))) + floor
+
+
 def race_envelope(state_b, state_a, n_before):
     """What a SECOND run of the oracle (B) differs from the first (A) in, on the race-bound rows of the
     slots that existed before the frame: (differing merge flags, |merge count difference|, differing
@@ -226,11 +232,11 @@ def compare_integrate(mine_rasters, mine_depth, mine_state, ref_rasters, ref_dep
         print(f"envelope: merge flags {int((~same_merge).sum())} vs {env_flags}, merge count {abs(int(merges_m) - int(merges_r))} vs "
               f"{env_count}, link rows {link_rows_differ} vs {env_links} (n = {n_before})")
         flag_floor, link_floor = envelope_floors(n_before)
-        assert (~same_merge).sum() <= ENVELOPE_FACTOR * env_flags + flag_floor, ((~same_merge).sum(), env_flags)
+        assert (~same_merge).sum() <= envelope_limit(env_flags, flag_floor), ((~same_merge).sum(), env_flags)
         # (two oracle runs can differ on dozens of flags and still count the same number of merges: the count
         #  envelope is the larger of the two figures)
-        assert abs(int(merges_m) - int(merges_r)) <= ENVELOPE_FACTOR * max(env_count, env_flags) + flag_floor, (merges_m, merges_r, env_count, env_flags)
-        assert link_rows_differ <= ENVELOPE_FACTOR * env_links + link_floor, (link_rows_differ, env_links)
+        assert abs(int(merges_m) - int(merges_r)) <= envelope_limit(max(env_count, env_flags), flag_floor), (merges_m, merges_r, env_count, env_flags)
+        assert link_rows_differ <= envelope_limit(env_links, link_floor), (link_rows_differ, env_links)
     else:
         assert (~same_merge).sum() <= max(20, 0.004 * n_r), "merge decisions differ only inside the reference's envelope"
         assert abs(int(merges_m) - int(merges_r)) <= max(20, 0.004 * n_r)

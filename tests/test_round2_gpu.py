@@ -13,7 +13,7 @@ from oracle import cpu_walk
 from surfelmeshing_b200 import _lib, synthetic as S
 from surfelmeshing_b200 import reconstruction as R
 from surfelmeshing_b200._lib import IntegrateParams, PreprocessParams
-from tests.test_parity_gpu import ENVELOPE_FACTOR, envelope_floors
+from tests.test_parity_gpu import ENVELOPE_FACTOR, envelope_floors, envelope_limit
 from tests.util import (INTEGRATE_ROWS, INVALID, NEIGHBOR_ROWS, check_state_invariants, count_mismatch, golden_camera,
                         golden_params, other_frames)
 
@@ -364,10 +364,10 @@ def test_race_bound_rows_inside_the_reference_envelope(product, reference):
         env_flags = int((merge_flags(rb) != merge_flags(ra)).sum())
         got_flags = int((merge_flags(rp) != merge_flags(ra)).sum())
         flag_floor, link_floor = envelope_floors(n_before)
-        assert got_flags <= ENVELOPE_FACTOR * env_flags + flag_floor, (frame, got_flags, env_flags)
-        assert abs(int(m_p) - int(m_a)) <= ENVELOPE_FACTOR * max(abs(int(m_b) - int(m_a)), env_flags) + flag_floor, (frame, m_p, m_a, m_b, env_flags)
+        assert got_flags <= envelope_limit(env_flags, flag_floor), (frame, got_flags, env_flags)
+        assert abs(int(m_p) - int(m_a)) <= envelope_limit(max(abs(int(m_b) - int(m_a)), env_flags), flag_floor), (frame, m_p, m_a, m_b, env_flags)
         env_links, got_links = link_rows_differ(rb, ra), link_rows_differ(rp, ra)
-        assert got_links <= ENVELOPE_FACTOR * env_links + link_floor, (frame, got_links, env_links)
+        assert got_links <= envelope_limit(env_links, link_floor), (frame, got_links, env_links)
         print(f"frame {frame}: merge flags {got_flags} vs {env_flags}, merge count {abs(int(m_p) - int(m_a))} vs {abs(int(m_b) - int(m_a))}, "
               f"link rows {got_links} vs {env_links} (n = {n_before})")
         ratios.append((got_flags / max(env_flags, 1), got_links / max(env_links, 1)))
@@ -400,7 +400,7 @@ def test_free_running_stream_inside_the_reference_envelope(product, reference):
     """BASELINE config 2, full length (500 frames / 492 integrated): the free-running product against the
     free-running oracle. The oracle differs from ITSELF between runs (its races feed back through the
     cloud); the product's deviation from the oracle's mean must stay within 3x the oracle's own spread
-    (+ a floor of 0.05 %) for slots, live surfels and merges."""
+    (+ a floor of 0.1 %: three runs can land within a few dozen of each other) for slots, live surfels and merges."""
     cam, st, pp, ip = stream_and_params(640, 480, 500, 0)
     first, last = st.integrated_range()
     rec_r, rec_p = make(cam, 5_000_000, reference), make(cam, 5_000_000)
@@ -416,4 +416,4 @@ def test_free_running_stream_inside_the_reference_envelope(product, reference):
     for k, name in enumerate(("surfels_size", "surfel_count", "merges")):
         values = [r[k] for r in runs]
         mean, spread = float(np.mean(values)), max(values) - min(values)
-        assert abs(mine[k] - mean) <= 3 * spread + 0.0005 * mean, (name, mine[k], values)
+        assert abs(mine[k] - mean) <= 3 * spread + 0.001 * mean, (name, mine[k], values)
