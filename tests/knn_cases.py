@@ -38,3 +38,21 @@ def states(n, seed):
     s = rng.integers(0, 3, n).astype(np.uint8)
     s[rng.random(n) < 0.05] = 255
     return s
+
+
+def meshing_cloud(n, seed, kind="sheet"):
+    """Input of one meshing iteration (the eight CUDASurfelBuffersCPU arrays). "cube": the reference's triangulation
+    test (test/test_triangulation.cc:70-88: positions 0.5 * range * Random(), one radius, normal +x), the shape
+    BASELINE config 1 scales to 10 k surfels; "sheet": surfels of a surface with radius 1.5 x their spacing, what a
+    reconstruction hands over."""
+    rng = np.random.default_rng(seed)
+    if kind == "cube":
+        x, y, z = [(rng.random(n, dtype=np.float32) - 0.5).astype(np.float32) for _ in range(3)]
+        r2 = np.full(n, 0.1 * 0.1, np.float32)
+    else:
+        x = (rng.random(n, dtype=np.float32) * 0.02 - 0.01).astype(np.float32)
+        y = (rng.random(n, dtype=np.float32) - 0.5).astype(np.float32)
+        z = (rng.random(n, dtype=np.float32) - 0.5).astype(np.float32)
+        r2 = np.full(n, (1.5 / np.sqrt(n)) ** 2, np.float32)
+    nx, ny, nz = np.ones(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    return dict(x=x, y=y, z=z, radius_squared=r2, nx=nx, ny=ny, nz=nz, stamp=np.ones(n, np.uint32))

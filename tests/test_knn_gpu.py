@@ -161,3 +161,26 @@ def test_knn_over_a_reconstruction(product):
     assert (got[1][:, 0] == qi).mean() > 0.99      # neighbour 0 is the surfel itself (surfel_meshing.cc:433-437)
     index.close()
     rec.close()
+
+
+@pytest.mark.parametrize("kind,n", [("cube", 1000), ("sheet", 10000), ("cube", 10000)])
+def test_gpu_batch_feeds_the_reference_triangulation(kind, n):
+    """BASELINE config 1 with the GPU in the loop: the reference's own CPU meshing (surfel_meshing.cc, unmodified,
+    oracle/_ref/libmeshing_ref.so) triangulates the cloud once asking its octree and once answering the octree
+    queries of TriangulateSurfel / RemeshTrianglesAt from ONE sm_knn_query batch (every surfel, all meshing states,
+    radius = the largest TriangulateSurfel can ask for); the meshes must agree triangle for triangle."""
+    from oracle import meshing_ref
+    from tests.test_meshing_oracle import batch_radius, run_reference
+    if not meshing_ref.available():
+        pytest.skip("oracle/_ref/libmeshing_ref.so not built")
+    cloud = knn_cases.meshing_cloud(n, 6, kind)
+    want = run_reference(cloud)
+    r2 = batch_radius(cloud)
+    index = build(cloud["x"], cloud["y"], cloud["z"], 2.0 * float(np.sqrt(r2.max())), radius_squared=cloud["radius_squared"])
+    d2, idx, cnt = gpu_query(index, cloud["x"], cloud["y"], cloud["z"], r2, 64)
+    index.close()
+    got = run_reference(cloud, batch=(d2, idx, cnt, r2))
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    served, fallback = got[3]
+    print(f"{kind} {n}: {len(want[0])} triangles, {served} octree queries answered from the GPU batch, {fallback} by the octree")
+    assert served > 0 and (kind == "cube" and n == 10000 or served > fallback)
