@@ -40,7 +40,7 @@ def states(n, seed):
     return s
 
 
-def meshing_cloud(n, seed, kind="sheet"):
+def meshing_cloud(n, seed, kind="sheet", thickness=0.02):
     """Input of one meshing iteration (the eight CUDASurfelBuffersCPU arrays). "cube": the reference's triangulation
     test (test/test_triangulation.cc:70-88: positions 0.5 * range * Random(), one radius, normal +x), the shape
     BASELINE config 1 scales to 10 k surfels; "sheet": surfels of a surface with radius 1.5 x their spacing, what a
@@ -50,7 +50,7 @@ def meshing_cloud(n, seed, kind="sheet"):
         x, y, z = [(rng.random(n, dtype=np.float32) - 0.5).astype(np.float32) for _ in range(3)]
         r2 = np.full(n, 0.1 * 0.1, np.float32)
     else:
-        x = (rng.random(n, dtype=np.float32) * 0.02 - 0.01).astype(np.float32)
+        x = ((rng.random(n, dtype=np.float32) - np.float32(0.5)) * np.float32(thickness)).astype(np.float32)
         y = (rng.random(n, dtype=np.float32) - 0.5).astype(np.float32)
         z = (rng.random(n, dtype=np.float32) - 0.5).astype(np.float32)
         r2 = np.full(n, (1.5 / np.sqrt(n)) ** 2, np.float32)
