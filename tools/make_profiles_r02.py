@@ -23,7 +23,7 @@ def load_line(path):
 
 
 def latest(pattern):
-    for call in ("c7", "c6", "c5", "c4", "c3", "c2", "c1"):
+    for call in ("c11", "c10", "c9", "c8", "c7", "c6", "c5", "c4", "c3", "c2", "c1"):
         p = SRC / pattern.format(call=call)
         if p.exists() and p.stat().st_size > 0:
             return p
@@ -140,22 +140,47 @@ def main():
              "pays when the consumer uses the changed-slot list instead of its O(N) comparison "
              "(`surfel_meshing.cc:199-250`), or over a slower link.\n")
     L.append("## f4: radius k-NN for the meshing thread (`tools/knn_probe.py`)\n")
-    L.append("Synthetic surfel sheet (5 mm spacing), every surfel queries its neighbours within 12.5 mm, k <= 64; the "
+    L.append("Every point queries its neighbours, k <= 64; the "
              "reference arm is the reference's own octree (`oracle/_ref/liboctree_ref.so`) on one host thread, the way the "
              "meshing thread calls it; every sampled query is compared with the GPU answer before a number is printed.\n")
-    L.append("| points = queries | cell size / radius | build ms | query ms | queries/s resident | queries/s end to end (H2D of points + queries, D2H of results) | reference octree queries/s (sample) | end-to-end ratio |")
-    L.append("|---:|---:|---:|---:|---:|---:|---:|---:|")
-    for pattern, cell in (("{call}_knn_probe.json", 1.0), ("{call}_knn_probe_cell20.json", 2.0), ("{call}_knn_probe_cell05.json", 0.5),
-                          ("{call}_knn_probe_4m.json", 1.0)):
-        kp = latest(pattern)
-        if not kp:
+    L.append("| cloud | points = queries | query radius, cell size | neighbours found (mean) | build ms | query ms | queries/s resident | "
+             "queries/s end to end (H2D of points + queries, D2H of results) | reference octree queries/s (sample) | end-to-end ratio |")
+    L.append("|---|---:|---|---:|---:|---:|---:|---:|---:|---:|")
+    for pattern, label in (("c9_knn_probe.json", "surfel sheet, 5 mm spacing"), ("c8b_knn_probe_cell10.json", "same, cells of one radius"),
+                           ("c8b_knn_probe_r5.json", "same, radius 25 mm (the 64-cap binds for 99 % of the queries)"),
+                           ("c9_knn_probe_random1m.json", "uniform in a cube"),
+                           ("c9_knn_probe_c1.json", "uniform in a cube, BASELINE config 1 size")):
+        kp = SRC / pattern
+        if not kp.exists():
             continue
         j = json.loads(kp.read_text())
         ref = j.get("reference_octree", {})
-        pts = j["workload"].split(" ")[0]
-        L.append(f"| {pts} | {cell} | {j['build_ms']:.3f} | {j['query_ms']:.2f} | {j['queries_per_s_resident'] / 1e6:.0f} M | "
-                 f"{j['queries_per_s_e2e'] / 1e6:.1f} M | {ref.get('queries_per_s', 0) / 1e3:.0f} k ({ref.get('sample', '')}) | "
-                 f"{j.get('speedup_e2e_vs_reference_octree', 0):.0f}x |")
+        w = j["workload"]
+        pts = w.split(" ")[0]
+        geometry = w[w.index("radius"):]
+        L.append(f"| {label} | {pts} | {geometry} | {j['mean_neighbours_found']:.1f} | {j['build_ms']:.3f} | {j['query_ms']:.3f} | "
+                 f"{j['queries_per_s_resident'] / 1e6:.0f} M | {j['queries_per_s_e2e'] / 1e6:.1f} M | "
+                 f"{ref.get('queries_per_s', 0) / 1e3:.0f} k ({ref.get('sample', '')}) | {j.get('speedup_e2e_vs_reference_octree', 0):.0f}x |")
+    L.append("\nThe first version of the query kernel inserted every candidate into the sorted list one by one (call 6: 1 M queries "
+             "in 1.99 ms with cells of 2 r, 3.33 ms with cells of r); staging the candidates in shared memory and sorting once "
+             "(call 8b / 9) brought that to 1.21 ms / 2.68 ms. `profiles/r02_knn_ncu_full_summary.csv` is the `ncu --set full` capture "
+             "of the final kernels.\n")
+    for pattern, title in (("c10_meshing_probe_100k.json", "100 000"), ("c10_meshing_probe_1m.json", "1 000 000")):
+        mp = SRC / pattern
+        if not mp.exists():
+            continue
+        j = json.loads(mp.read_text())
+        if "### One meshing iteration" not in "\n".join(L):
+            L.append("### One meshing iteration of the reference's CPU code (BASELINE config 1 at scale, `tools/meshing_probe.py`)\n")
+            L.append("`IntegrateCUDABuffers -> CheckRemeshing -> Triangulate` of `oracle/_ref/libmeshing_ref.so` (the reference's `surfel_meshing.cc` + "
+                     "`octree.cc`, unmodified) over N fresh surfels, its two octree queries answered by the octree or by one `sm_knn_query` batch.\n")
+            L.append("| surfels | triangles | identical mesh | octree: integrate + check + triangulate (s) | GPU batch: same (s) | batch end to end on the GPU (s) | "
+                     "queries from the batch / left to the octree | iteration speed-up |")
+            L.append("|---:|---:|---|---:|---:|---:|---:|---:|")
+        o, g = j["octree"], j["gpu_batch"]
+        L.append(f"| {title} | {j['triangles']} | {j['identical_mesh']} | {o['integrate_s']:.3f} + {o['check_remeshing_s']:.3f} + {o['triangulate_s']:.3f} = {o['total_s']:.3f} | "
+                 f"{g['integrate_s']:.3f} + {g['check_remeshing_s']:.3f} + {g['triangulate_s']:.3f} = {g['total_s']:.3f} | {j['gpu_batch_end_to_end_s']:.3f} | "
+                 f"{j['queries_answered_from_the_batch']} / {j['queries_left_to_the_octree']} | {j['iteration_speedup']:.2f}x |")
     L.append("")
     for arm, note in (("product", "`-k regex:k_`, frames ~450-480 of one pass of `tools/stream_probe.py --frames 500`"),
                       ("reference", "`-k regex:Kernel`, the same frames of `--impl reference`")):
