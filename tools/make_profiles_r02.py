@@ -91,6 +91,12 @@ def main():
     bench_rows("_C5_req5", "C5, required inliers 5 of 8 (still empty: erosion needs a full 5x5 window)", L)
     bench_rows("_C5b_500", "C5b: sigma 0.05 m, required inliers 1, erosion 0, 40 M cap, 500 frames: populated cloud under heavy noise", L)
     bench_rows("_C5b_2000", "C5b, 2000 frames (with the default 5 M cap both arms overflow: the noisy stream creates ~3 300 surfels per frame)", L)
+    n2p, n2r = load_line(SRC / "c11_bench_product_n2.json"), load_line(SRC / "c11_bench_reference_n2.json")
+    if n2p and n2r:
+        L.append(f"\nReplicas (`bench.py --gpus 2` under torchrun as the driver launches it, one independent C2 stream per GPU, "
+                 f"max-over-ranks timing): product {n2p['value']:.0f} frames/s (e2e {n2p['e2e']['value']:.0f}), reference "
+                 f"{n2r['value']:.0f} (e2e {n2r['e2e']['value']:.0f}); round 1's driver run measured 0.98 scaling efficiency up to 8 GPUs "
+                 f"with the same plumbing (no collective on the data path).")
     L.append("")
     if c2p:
         L.append("### C2 kernel table\n")
