@@ -91,8 +91,8 @@ u32 ModInverse(u32 x, u32 m) {
 int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity) {
   u32 lane_shift = cfg->lane_request;
   if (wave != 0) {
-    // keys are (slot / W) * 2 W + late * W + perm(slot % W) < 2^32 - 1
-    const unsigned long long top = (static_cast<unsigned long long>(capacity) / wave + 1) * 2ull * wave;
+    // keys are ((slot + phase) / W) * 2 W + late * W + perm((slot + phase) % W) < 2^32 - 1, phase < W
+    const unsigned long long top = (static_cast<unsigned long long>(capacity) / wave + 2) * 2ull * wave;
     if (wave < 2 || top >= 0xFFFFFFFFull) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range for this surfel cap");
     if (lane_shift > 10) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_lanes must be a power of two <= 1024");
     if (wave % (1u << lane_shift) != 0 || (wave >> lane_shift) < 2) lane_shift = 0;   // the wave is not made of whole groups
@@ -112,6 +112,7 @@ TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index) {
   t.wave = cfg.wave;
   if (cfg.wave == 0) return t;
   t.lane_shift = cfg.lane_shift;
+  t.wave_offset = cfg.wave_offset;
   t.groups = cfg.wave >> cfg.lane_shift;
   t.mul = cfg.mul;
   t.mul_inv = cfg.mul_inv;
@@ -361,16 +362,19 @@ int CreateImpl(sm_reconstruction* r, uint64_t max_surfel_count, int32_t width, i
   {
     u32 wave = kDefaultTieBreakWave, lanes = 1u << kDefaultTieBreakLaneShift;
     double early = kDefaultTieBreakEarlyFraction, index_order = kDefaultTieBreakIndexOrderFraction;
-    if (const char* e = std::getenv("SM_B200_TIEBREAK")) {   // "wave,early[,index_order[,lanes]]"
-      unsigned w = 0, l = 0; double q = 0, b = 0;
-      const int got = std::sscanf(e, "%u,%lf,%lf,%u", &w, &q, &b, &l);
+    u32 offset = kDefaultTieBreakWaveOffset;
+    if (const char* e = std::getenv("SM_B200_TIEBREAK")) {   // "wave,early[,index_order[,lanes[,wave_offset]]]"
+      unsigned w = 0, l = 0, o = 0; double q = 0, b = 0;
+      const int got = std::sscanf(e, "%u,%lf,%lf,%u,%u", &w, &q, &b, &l, &o);
       if (got >= 2) { wave = w; early = q; }
       if (got >= 3) index_order = b;
       if (got >= 4) lanes = l;
+      if (got >= 5) offset = o ? 1u : 0u;
     }
+    r->tiebreak.wave_offset = offset;
     u32 lane_shift = 0;
     while ((1u << lane_shift) < lanes && lane_shift < 10) ++lane_shift;
-    if (wave != 0 && (static_cast<unsigned long long>(d.capacity) / wave + 1) * 2ull * wave >= 0xFFFFFFFFull) wave = 0;
+    if (wave != 0 && (static_cast<unsigned long long>(d.capacity) / wave + 2) * 2ull * wave >= 0xFFFFFFFFull) wave = 0;
     r->tiebreak.lane_request = lane_shift;
     const int status = SetTieBreakWave(&r->tiebreak, wave, d.capacity);
     if (status != SM_OK) return status;
@@ -812,6 +816,10 @@ int sm_configure(sm_reconstruction* r, const char* key, double value) {
   if (k == "tiebreak_wave") {
     if (value < 0 || value > 2147483647.0) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range");
     return SetTieBreakWave(&r->tiebreak, static_cast<u32>(value), r->d.capacity);
+  }
+  if (k == "tiebreak_wave_offset") {   // 1: wave boundaries at a per-pixel random phase
+    r->tiebreak.wave_offset = value != 0.0 ? 1u : 0u;
+    return SM_OK;
   }
   if (k == "tiebreak_lanes") {   // slots that keep their order inside the shuffled order (1 = none, 32 = a warp)
     const u32 lanes = static_cast<u32>(value);

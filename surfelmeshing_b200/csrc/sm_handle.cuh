@@ -16,6 +16,7 @@ struct TieBreakConfig {
   u32 wave;              // slots per launch wave of the modelled race (0: plain "primary, then lowest index")
   double early_fraction; // fraction of secondary associations that compete like primary ones
   double index_order_fraction;  // fraction of the pixels that order the supporters of a wave by slot index
+  u32 wave_offset;       // 1: per-pixel random phase of the wave boundaries (sm_kernels.cuh: tb_phase)
   u32 lane_request;      // log2 of the slots that keep their order in the shuffled order (5: a warp of the reference)
   u32 lane_shift;        // what is in effect: lane_request, or 0 when the wave is not a multiple of it
   u32 mul, mul_inv;      // derived from wave and lane_shift
@@ -29,6 +30,7 @@ struct TieBreakConfig {
 // free-running totals on the oracle's.
 constexpr u32 kDefaultTieBreakWave = 296 * 1024;
 constexpr u32 kDefaultTieBreakLaneShift = 5;
+constexpr u32 kDefaultTieBreakWaveOffset = 0;
 constexpr double kDefaultTieBreakEarlyFraction = 0.01;
 constexpr double kDefaultTieBreakIndexOrderFraction = 0.25;
 TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index);

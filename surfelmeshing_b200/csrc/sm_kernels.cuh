@@ -87,6 +87,7 @@ struct TieBreak {
   u32 salt;             // per frame, for the two draws
   u32 early_threshold;  // secondary association is NOT late iff hash(slot ^ salt) < early_threshold
   u32 index_order_threshold;  // pixel uses slot order iff hash(pixel ^ ~salt) < index_order_threshold
+  u32 wave_offset;      // 1: the wave boundaries sit at a per-pixel pseudo-random phase (whole groups) instead of at multiples of W
   u64 wave_reciprocal;  // floor((2^64 - 1) / W): division / modulo by W as a multiply (Barrett)
   u64 group_reciprocal; // the same for `groups`
 };
@@ -112,10 +113,20 @@ __host__ __device__ __forceinline__ bool tb_index_order(const TieBreak& t, u32 p
 // Arrival key of a supporter: wave-major; inside a wave primary before (most) secondary associations; inside a
 // kind either slot order or, per pixel, a shuffled order of the wave's warps in which the lanes of one warp keep
 // their order (two lanes of one warp of the reference issue their compare-and-swap in lane order).
+// Phase of the wave boundaries for one pixel, in slots (a whole number of groups). The blocks of the reference's
+// launch do not start in lock step: two supporters d slots apart are ordered by slot with a probability that grows
+// with d and reaches 1 at d = W. Cutting the slot axis into waves at a per-pixel random phase gives exactly that:
+// the pair falls into different waves (ordered) with probability d / W and into one wave (shuffled) otherwise.
+__host__ __device__ __forceinline__ u32 tb_phase(const TieBreak& t, u32 pixel) {
+  if (!t.wave_offset) return 0u;
+  u32 g;
+  tb_divide(tb_hash(pixel ^ t.salt ^ 0x5bd1e995u), t.groups, t.group_reciprocal, &g);
+  return g << t.lane_shift;
+}
 __host__ __device__ __forceinline__ u32 tb_encode(const TieBreak& t, u32 idx, bool secondary, u32 pixel) {
   if (t.wave == 0) return idx | (secondary ? kSecondaryBit : 0u);
   u32 r, rp;
-  const u32 w = static_cast<u32>(tb_divide(idx, t.wave, t.wave_reciprocal, &r));
+  const u32 w = static_cast<u32>(tb_divide(static_cast<u64>(idx) + tb_phase(t, pixel), t.wave, t.wave_reciprocal, &r));
   if (tb_index_order(t, pixel)) {
     rp = r;
   } else {
@@ -140,7 +151,7 @@ __host__ __device__ __forceinline__ u32 supporting_index(const TieBreak& t, u32 
     tb_divide(static_cast<u64>(shifted) * t.mul_inv, t.groups, t.group_reciprocal, &g);
     r = (g << t.lane_shift) | (rem & ((1u << t.lane_shift) - 1u));
   }
-  return w * t.wave + r;
+  return w * t.wave + r - tb_phase(t, pixel);
 }
 
 // Per-pixel association record (the reference keeps four separate rasters,

@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <thread>
 
@@ -316,14 +317,21 @@ int TransferDelta(sm_reconstruction* r, cudaStream_t stream, uint32_t frame_inde
           for (u32 j = 0; j < changed; ++j) dst[host_index[j]] = v[j];
         }
       };
+      bool scattered = false;
       if (changed >= (1u << 16)) {
         std::thread workers[3];
-        for (int t = 0; t < 3; ++t) workers[t] = std::thread(scatter_rows, 2 * t + 2, 2 * t + 4);
+        int started = 0;
+        try {
+          for (; started < 3; ++started) workers[started] = std::thread(scatter_rows, 2 * started + 2, 2 * started + 4);
+        } catch (const std::exception&) {
+          // no thread to be had (resource limit): the rows not handed out are done here
+        }
         scatter_rows(0, 2);
-        for (auto& w : workers) w.join();
-      } else {
-        scatter_rows(0, 8);
+        for (int t = 0; t < started; ++t) workers[t].join();
+        if (started < 3) scatter_rows(2 * started + 2, 8);
+        scattered = true;
       }
+      if (!scattered) scatter_rows(0, 8);
       if (DeltaTimingEnabled()) {
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_scatter).count();
         fprintf(stderr, "[surfel_b200] delta transfer: %u of %u slots, host scatter %.3f ms\n", changed, n, ms);

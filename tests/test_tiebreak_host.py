@@ -20,4 +20,4 @@ def test_tiebreak_key_roundtrip(tmp_path):
     assert build.returncode == 0, build.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0, run.stdout
-    assert run.stdout.count(" 0 bad") == 6, run.stdout
+    assert run.stdout.count(" 0 bad") == 8, run.stdout

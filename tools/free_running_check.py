@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--frames", type=int, default=500)
     ap.add_argument("--cap", type=int, default=5_000_000)
     ap.add_argument("--oracle-runs", type=int, default=3)
-    ap.add_argument("--rule", action="append", default=[], help="'default' or wave,early,index_order,lanes")
+    ap.add_argument("--rule", action="append", default=[], help="'default' or wave,early,index_order,lanes[,phase]")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     cam = S.Camera.tum(a.width, a.height)
@@ -49,7 +49,8 @@ def main():
     rec = R.CUDASurfelReconstruction(a.cap, cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy)
     for rule in a.rule or ["default"]:
         if rule != "default":
-            wave, early, index_order, lanes = rule.split(",")
+            wave, early, index_order, lanes, *rest = rule.split(",")
+            rec.configure("tiebreak_wave_offset", float(rest[0]) if rest else 0.0)
             rec.configure("tiebreak_lanes", float(lanes))
             rec.configure("tiebreak_wave", float(wave))
             rec.configure("tiebreak_early_fraction", float(early))

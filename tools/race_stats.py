@@ -143,13 +143,13 @@ def main():
 
     # (name, wave W, early fraction q of the secondaries, fraction b of the pixels in slot order, lanes that keep
     #  their order inside the shuffled order)
-    variants = [("plain", 0, 0.0, 0.0, 1), (f"wave_q0.01_b0.44_l1", REF_WAVE, 0.01, 0.44, 1)]
-    for q, b in ((0.0, 0.25), (0.005, 0.25), (0.01, 0.0), (0.01, 0.15), (0.01, 0.25), (0.01, 0.35), (0.015, 0.25), (0.02, 0.25)):
-        variants.append((f"wave_q{q}_b{b}_l32", REF_WAVE, q, b, 32))
-    variants.append(("wave_q0.01_b0.25_l1024", REF_WAVE, 0.01, 0.25, 1024))
-    variants.append(("onewave_q0.01_b0.25_l32", 1 << 30, 0.01, 0.25, 32))
+    # (... , per-pixel random phase of the wave boundaries)
+    variants = [("plain", 0, 0.0, 0.0, 1, 0), ("wave_q0.01_b0.25_l32", REF_WAVE, 0.01, 0.25, 32, 0), ("wave_q0.02_b0.25_l32", REF_WAVE, 0.02, 0.25, 32, 0)]
+    for q, b in ((0.01, 0.0), (0.01, 0.1), (0.01, 0.25), (0.02, 0.0), (0.02, 0.1), (0.02, 0.25), (0.03, 0.1)):
+        variants.append((f"wave_q{q}_b{b}_l32_phase", REF_WAVE, q, b, 32, 1))
 
-    def set_variant(rec, wave, q, b, lanes):
+    def set_variant(rec, wave, q, b, lanes, phase):
+        rec.configure("tiebreak_wave_offset", phase)
         rec.configure("tiebreak_lanes", lanes)
         rec.configure("tiebreak_wave", wave)
         rec.configure("tiebreak_early_fraction", q)
@@ -184,9 +184,9 @@ def main():
             rec_b.load_state(rows, merges_before)
             entry = {"frame": frame, "n_before": int(n_before)}
             winners, flags = {}, {}
-            for name, wave, q, b, lanes in variants:
+            for name, wave, q, b, lanes, phase in variants:
                 rec_p.load_state(rows, merges_before)
-                set_variant(rec_p, wave, q, b, lanes)
+                set_variant(rec_p, wave, q, b, lanes, phase)
                 rec_p.integrate(None, frame, ip, d0.clone(), n0, r0, st.color[frame], st.global_T_frame[frame],
                                 st.frame_T_global[frame])
                 entry[name] = int(rec_p.surfels_size() - rec_p.surfel_count()) - int(merges_before)
@@ -243,10 +243,10 @@ def main():
         s_ = rec_a.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp,
                               ip, first, last)
         free[f"oracle_{rep}"] = [int(s_.surfels_size), int(s_.surfel_count)]
-    for name, wave, q, b, lanes in variants:
+    for name, wave, q, b, lanes, phase in variants:
         for rep in range(args.free_runs):
             rec_p.reset()
-            set_variant(rec_p, wave, q, b, lanes)
+            set_variant(rec_p, wave, q, b, lanes, phase)
             s_ = rec_p.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global,
                                   st.others_TR_reference, pp, ip, first, last)
             free[name if rep == 0 else f"{name}_{rep}"] = [int(s_.surfels_size), int(s_.surfel_count)]
