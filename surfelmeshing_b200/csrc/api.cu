@@ -126,6 +126,8 @@ TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index) {
   };
   t.early_threshold = threshold(cfg.early_fraction);
   t.index_order_threshold = threshold(cfg.index_order_fraction);
+  t.early_threshold_later = threshold(cfg.early_fraction_later >= 0 ? cfg.early_fraction_later : cfg.early_fraction);
+  t.index_order_threshold_later = threshold(cfg.index_order_fraction_later >= 0 ? cfg.index_order_fraction_later : cfg.index_order_fraction);
   return t;
 }
 
@@ -380,6 +382,8 @@ int CreateImpl(sm_reconstruction* r, uint64_t max_surfel_count, int32_t width, i
     if (status != SM_OK) return status;
     r->tiebreak.early_fraction = early;
     r->tiebreak.index_order_fraction = index_order;
+    r->tiebreak.early_fraction_later = kDefaultTieBreakEarlyFractionLater;
+    r->tiebreak.index_order_fraction_later = kDefaultTieBreakIndexOrderFractionLater;
   }
   const int status = ClearAssociationRasters(nullptr, d);
   if (status != SM_OK) return status;
@@ -816,6 +820,11 @@ int sm_configure(sm_reconstruction* r, const char* key, double value) {
   if (k == "tiebreak_wave") {
     if (value < 0 || value > 2147483647.0) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range");
     return SetTieBreakWave(&r->tiebreak, static_cast<u32>(value), r->d.capacity);
+  }
+  if (k == "tiebreak_early_fraction_later" || k == "tiebreak_index_order_fraction_later") {   // < 0: same as the first wave
+    if (!(value <= 1.0)) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_*_later must be <= 1 (negative: follow the first wave)");
+    (k == "tiebreak_early_fraction_later" ? r->tiebreak.early_fraction_later : r->tiebreak.index_order_fraction_later) = value;
+    return SM_OK;
   }
   if (k == "tiebreak_wave_offset") {   // 1: wave boundaries at a per-pixel random phase
     r->tiebreak.wave_offset = value != 0.0 ? 1u : 0u;

@@ -16,6 +16,7 @@ struct TieBreakConfig {
   u32 wave;              // slots per launch wave of the modelled race (0: plain "primary, then lowest index")
   double early_fraction; // fraction of secondary associations that compete like primary ones
   double index_order_fraction;  // fraction of the pixels that order the supporters of a wave by slot index
+  double early_fraction_later, index_order_fraction_later;  // the same two for the waves after the first (< 0: same as the first)
   u32 wave_offset;       // 1: per-pixel random phase of the wave boundaries (sm_kernels.cuh: tb_phase)
   u32 lane_request;      // log2 of the slots that keep their order in the shuffled order (5: a warp of the reference)
   u32 lane_shift;        // what is in effect: lane_request, or 0 when the wave is not a multiple of it
@@ -33,6 +34,8 @@ constexpr u32 kDefaultTieBreakLaneShift = 5;
 constexpr u32 kDefaultTieBreakWaveOffset = 0;
 constexpr double kDefaultTieBreakEarlyFraction = 0.01;
 constexpr double kDefaultTieBreakIndexOrderFraction = 0.25;
+constexpr double kDefaultTieBreakEarlyFractionLater = -1.0;
+constexpr double kDefaultTieBreakIndexOrderFractionLater = -1.0;
 TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index);
 int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity);   // uses cfg->lane_request
 

@@ -85,8 +85,11 @@ struct TieBreak {
   u32 mul, mul_inv;     // perm(g) = (g * mul + add) mod groups, mul * mul_inv = 1 (mod groups)
   u32 add;              // per frame
   u32 salt;             // per frame, for the two draws
-  u32 early_threshold;  // secondary association is NOT late iff hash(slot ^ salt) < early_threshold
-  u32 index_order_threshold;  // pixel uses slot order iff hash(pixel ^ ~salt) < index_order_threshold
+  u32 early_threshold;  // secondary association is NOT late iff hash(slot ^ salt) < early_threshold (slots of the first wave)
+  u32 index_order_threshold;  // pixel uses slot order iff hash(pixel ^ ~salt) < index_order_threshold (first wave)
+  u32 early_threshold_later, index_order_threshold_later;  // the same for the later waves: their blocks start one by one as
+                                                           // earlier ones retire, so arrival follows the slot order more closely
+                                                           // and a secondary association of an early block is ahead more often
   u32 wave_offset;      // 1: the wave boundaries sit at a per-pixel pseudo-random phase (whole groups) instead of at multiples of W
   u64 wave_reciprocal;  // floor((2^64 - 1) / W): division / modulo by W as a multiply (Barrett)
   u64 group_reciprocal; // the same for `groups`
@@ -107,8 +110,8 @@ __host__ __device__ __forceinline__ u32 tb_hash(u32 x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
-__host__ __device__ __forceinline__ bool tb_index_order(const TieBreak& t, u32 pixel) {
-  return tb_hash(pixel ^ ~t.salt) < t.index_order_threshold;
+__host__ __device__ __forceinline__ bool tb_index_order(const TieBreak& t, u32 pixel, u32 wave_index) {
+  return tb_hash(pixel ^ ~t.salt) < (wave_index == 0 ? t.index_order_threshold : t.index_order_threshold_later);
 }
 // Arrival key of a supporter: wave-major; inside a wave primary before (most) secondary associations; inside a
 // kind either slot order or, per pixel, a shuffled order of the wave's warps in which the lanes of one warp keep
@@ -127,14 +130,14 @@ __host__ __device__ __forceinline__ u32 tb_encode(const TieBreak& t, u32 idx, bo
   if (t.wave == 0) return idx | (secondary ? kSecondaryBit : 0u);
   u32 r, rp;
   const u32 w = static_cast<u32>(tb_divide(static_cast<u64>(idx) + tb_phase(t, pixel), t.wave, t.wave_reciprocal, &r));
-  if (tb_index_order(t, pixel)) {
+  if (tb_index_order(t, pixel, w)) {
     rp = r;
   } else {
     u32 gp;
     tb_divide(static_cast<u64>(r >> t.lane_shift) * t.mul + t.add, t.groups, t.group_reciprocal, &gp);
     rp = (gp << t.lane_shift) | (r & ((1u << t.lane_shift) - 1u));
   }
-  const bool late = secondary && !(tb_hash(idx ^ t.salt) < t.early_threshold);
+  const bool late = secondary && !(tb_hash(idx ^ t.salt) < (w == 0 ? t.early_threshold : t.early_threshold_later));
   return w * (2u * t.wave) + (late ? t.wave : 0u) + rp;   // < 2^32 - 1: checked by SetTieBreakWave
 }
 __host__ __device__ __forceinline__ u32 supporting_index(const TieBreak& t, u32 key, u32 pixel) {
@@ -144,7 +147,7 @@ __host__ __device__ __forceinline__ u32 supporting_index(const TieBreak& t, u32 
   const u32 w2 = static_cast<u32>(tb_divide(key, t.wave, t.wave_reciprocal, &rem));   // key = (2 w + late) W + perm
   const u32 w = w2 >> 1;
   u32 r = rem;
-  if (!tb_index_order(t, pixel)) {
+  if (!tb_index_order(t, pixel, w)) {
     const u32 gp = rem >> t.lane_shift;
     const u32 shifted = gp >= t.add ? gp - t.add : gp + t.groups - t.add;
     u32 g;

@@ -23,6 +23,7 @@ int main() {
     TieBreak tb{}; tb.wave = wave; tb.lane_shift = shift; tb.groups = groups; tb.mul = cfg.mul; tb.mul_inv = cfg.mul_inv;
     tb.add = 12345 % groups; tb.salt = 0xdeadbeef;
     tb.early_threshold = 0x40000000u; tb.index_order_threshold = 0x70000000u; tb.wave_reciprocal = ~0ull / wave;
+    tb.early_threshold_later = 0x60000000u; tb.index_order_threshold_later = 0x30000000u;
     tb.group_reciprocal = ~0ull / groups;
     tb.wave_offset = offsets[variant];
     unsigned long long bad = 0, n = 0;
@@ -33,9 +34,9 @@ int main() {
       // reference formulas with real division
       const u32 phase = tb.wave_offset ? ((tb_hash(pixel ^ tb.salt ^ 0x5bd1e995u) % groups) << shift) : 0u;
       u32 w = (u32)(((u64)idx + phase) / wave), rr = (u32)(((u64)idx + phase) % wave);
-      u32 rp = tb_index_order(tb, pixel) ? rr
+      u32 rp = tb_index_order(tb, pixel, w) ? rr
                                          : (u32)(((((u64)(rr >> shift) * tb.mul + tb.add) % groups) << shift) | (rr & ((1u << shift) - 1)));
-      bool late = sec && !(tb_hash(idx ^ tb.salt) < tb.early_threshold);
+      bool late = sec && !(tb_hash(idx ^ tb.salt) < (w == 0 ? tb.early_threshold : tb.early_threshold_later));
       u32 expect = w * (2u * wave) + (late ? wave : 0u) + rp;
       if (wave < (1u<<30) || idx < wave) if (expect != key) ++bad;
       ++n;

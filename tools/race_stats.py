@@ -143,17 +143,19 @@ def main():
 
     # (name, wave W, early fraction q of the secondaries, fraction b of the pixels in slot order, lanes that keep
     #  their order inside the shuffled order)
-    # (... , per-pixel random phase of the wave boundaries)
-    variants = [("plain", 0, 0.0, 0.0, 1, 0), ("wave_q0.01_b0.25_l32", REF_WAVE, 0.01, 0.25, 32, 0), ("wave_q0.02_b0.25_l32", REF_WAVE, 0.02, 0.25, 32, 0)]
-    for q, b in ((0.01, 0.0), (0.01, 0.1), (0.01, 0.25), (0.02, 0.0), (0.02, 0.1), (0.02, 0.25), (0.03, 0.1)):
-        variants.append((f"wave_q{q}_b{b}_l32_phase", REF_WAVE, q, b, 32, 1))
+    # name -> knobs (sm_configure "tiebreak_*"): wave W, early fraction q of the secondaries and fraction b of the pixels in
+    # slot order for the first wave / for the later waves (q1, b1; absent = same), lanes that keep their order
+    def rule(wave=REF_WAVE, q=0.01, b=0.25, lanes=32, phase=0, q1=-1.0, b1=-1.0):
+        return {"wave": wave, "early_fraction": q, "index_order_fraction": b, "lanes": lanes, "wave_offset": phase,
+                "early_fraction_later": q1, "index_order_fraction_later": b1}
+    variants = [("plain", rule(wave=0, q=0, b=0, lanes=1)), ("wave_q0.01_b0.25", rule()), ("wave_q0.02_b0.25", rule(q=0.02))]
+    for q1, b1 in ((0.03, -1.0), (0.04, -1.0), (0.06, -1.0), (0.03, 0.45), (0.04, 0.45), (0.06, 0.45), (0.04, 0.7), (0.08, 0.7)):
+        variants.append((f"wave_q0.01_b0.25_later_q{q1}_b{b1 if b1 >= 0 else 'same'}", rule(q1=q1, b1=b1)))
 
-    def set_variant(rec, wave, q, b, lanes, phase):
-        rec.configure("tiebreak_wave_offset", phase)
-        rec.configure("tiebreak_lanes", lanes)
-        rec.configure("tiebreak_wave", wave)
-        rec.configure("tiebreak_early_fraction", q)
-        rec.configure("tiebreak_index_order_fraction", b)
+    def set_variant(rec, knobs):
+        for key in ("wave_offset", "lanes", "wave", "early_fraction", "index_order_fraction", "early_fraction_later",
+                    "index_order_fraction_later"):
+            rec.configure("tiebreak_" + key, knobs[key])
 
     def mk(lib=None):
         return R.CUDASurfelReconstruction(args.cap, W, H, cam.fx, cam.fy, cam.cx, cam.cy, lib=lib)
@@ -184,9 +186,9 @@ def main():
             rec_b.load_state(rows, merges_before)
             entry = {"frame": frame, "n_before": int(n_before)}
             winners, flags = {}, {}
-            for name, wave, q, b, lanes, phase in variants:
+            for name, knobs in variants:
                 rec_p.load_state(rows, merges_before)
-                set_variant(rec_p, wave, q, b, lanes, phase)
+                set_variant(rec_p, knobs)
                 rec_p.integrate(None, frame, ip, d0.clone(), n0, r0, st.color[frame], st.global_T_frame[frame],
                                 st.frame_T_global[frame])
                 entry[name] = int(rec_p.surfels_size() - rec_p.surfel_count()) - int(merges_before)
@@ -233,7 +235,7 @@ def main():
     print("race statistics:", json.dumps(acc, indent=1))
     print("per-frame agreement with oracle A over the sampled frames (contested pixels: %d):" % acc["contested_pixels_ab"])
     for name in agree:
-        print(f"  {name:28s} same winner {agree[name] / max(acc['contested_pixels_ab'], 1):.4f}   differing merge flags {flagdiff[name]:7d}"
+        print(f"  {name:44s} same winner {agree[name] / max(acc['contested_pixels_ab'], 1):.4f}   differing merge flags {flagdiff[name]:7d}"
               f"  ({flagdiff[name] / max(flagdiff['oracle_b'], 1):.2f} x oracle B)")
 
     # ---- free-running totals ----
@@ -243,16 +245,16 @@ def main():
         s_ = rec_a.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp,
                               ip, first, last)
         free[f"oracle_{rep}"] = [int(s_.surfels_size), int(s_.surfel_count)]
-    for name, wave, q, b, lanes, phase in variants:
+    for name, knobs in variants:
         for rep in range(args.free_runs):
             rec_p.reset()
-            set_variant(rec_p, wave, q, b, lanes, phase)
+            set_variant(rec_p, knobs)
             s_ = rec_p.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global,
                                   st.others_TR_reference, pp, ip, first, last)
             free[name if rep == 0 else f"{name}_{rep}"] = [int(s_.surfels_size), int(s_.surfel_count)]
     print("free-running [surfels_size, surfel_count] after the stream:")
     for k, v in free.items():
-        print(f"  {k:28s} {v[0]:9d} {v[1]:9d}   merged {v[0] - v[1]:8d}")
+        print(f"  {k:44s} {v[0]:9d} {v[1]:9d}   merged {v[0] - v[1]:8d}")
     Path(args.out).parent.mkdir(exist_ok=True)
     Path(args.out).write_text(json.dumps({"samples": samples, "sums": sums, "race": acc, "free": free, "same_winner_as_oracle_a": agree,
                                           "differing_merge_flags_vs_oracle_a": flagdiff}, indent=1))
