@@ -25,17 +25,21 @@ struct TieBreakConfig {
 // Defaults (DESIGN.md section 4 / profiles/r02_race_stats.md have the measurements that picked them):
 // wave = the reference's AssociateSurfels launch wave on a B200 (1024-thread blocks, 31 registers ->
 // 2 blocks x 148 SMs = 296 blocks of slots); inside a wave and a kind the lower slot won 100 % of the pairs
-// that sit in one warp, ~47 % across the warps of one block and 62 - 67 % across blocks (72 % overall: the
-// warps of a wave in a shuffled order that keeps the lanes of a warp in order, and a quarter of the pixels in
-// plain slot order); 1 % early secondaries puts the merge rate of teacher-forced frames and the
-// free-running totals on the oracle's.
+// that sit in one warp, ~49 % across the warps of one block and 52 - 70 % across blocks (the warps of a wave in a
+// shuffled order that keeps the lanes of a warp in order, and a quarter of the pixels in plain slot order). The
+// blocks of the FIRST wave start together; those of the later waves start one by one as earlier blocks retire, so
+// there arrival follows the slot order more closely (lower slot wins 80 % instead of 70 %) and a secondary
+// association beats a primary one of the same wave 5.4 % of the time instead of 0.6 %: separate fractions for the
+// first and for the later waves (1 % / 3 % early secondaries, 25 % / 45 % of the pixels in slot order) put the
+// per-frame merge flags at 1.2x the reference's own run-to-run difference and the free-running totals of the
+// 500- and 1000-frame VGA streams inside the reference's spread (1280x960: -0.1 % slots).
 constexpr u32 kDefaultTieBreakWave = 296 * 1024;
 constexpr u32 kDefaultTieBreakLaneShift = 5;
 constexpr u32 kDefaultTieBreakWaveOffset = 0;
 constexpr double kDefaultTieBreakEarlyFraction = 0.01;
 constexpr double kDefaultTieBreakIndexOrderFraction = 0.25;
-constexpr double kDefaultTieBreakEarlyFractionLater = -1.0;
-constexpr double kDefaultTieBreakIndexOrderFractionLater = -1.0;
+constexpr double kDefaultTieBreakEarlyFractionLater = 0.03;
+constexpr double kDefaultTieBreakIndexOrderFractionLater = 0.45;
 TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index);
 int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity);   // uses cfg->lane_request
 
