@@ -38,6 +38,19 @@ def pair_table(sets_path):
     prim = np.where(sa, ~low, low)
     out.append(f"\nOne primary and one secondary association in one wave ({int(mixed.sum())} pairs): the primary wins "
                f"{100 * prim[mixed].mean():.1f} % ({100 * prim[mixed & (ra // 1024 == rb // 1024)].mean():.1f} % when both sit in one block).")
+    out += ["\nThe first wave (its 296 blocks start together) against the second (its blocks start one by one as blocks of the "
+            "first retire):\n", "| wave | same-kind pairs | lower slot wins | mixed pairs | secondary wins | ... when its block is > 32 blocks "
+            "ahead of the primary's | ... 1 - 32 blocks ahead | ... in the same or a later block |", "|---|---:|---:|---:|---:|---:|---:|---:|"]
+    sec_block = np.where(sa, ra, rb) // 1024
+    prim_block = np.where(sa, rb, ra) // 1024
+    lead = prim_block - sec_block
+    for w in (0, 1):
+        sk, mx = same_wave & (wave_a == w), mixed & (wave_a == w)
+        if sk.sum() == 0 or mx.sum() == 0:
+            continue
+        cell = lambda m: f"{100 * (1 - prim[m].mean()):.1f} %" if m.sum() else "-"
+        out.append(f"| {w} | {int(sk.sum())} | {100 * low[sk].mean():.1f} % | {int(mx.sum())} | {cell(mx)} | {cell(mx & (lead > 32))} | "
+                   f"{cell(mx & (lead >= 1) & (lead <= 32))} | {cell(mx & (lead <= 0))} |")
     return out, int(two.sum())
 
 
@@ -49,7 +62,7 @@ def free_table(free, out):
 
 
 def main():
-    src = Path(sys.argv[1] if len(sys.argv) > 1 else ROOT / "gpurun_out" / "c7_race_stats.json")
+    src = Path(sys.argv[1] if len(sys.argv) > 1 else ROOT / "gpurun_out" / "c14_race_stats.json")
     earlier = Path(sys.argv[2]) if len(sys.argv) > 2 else ROOT / "gpurun_out" / "c6_race_stats.json"
     j = json.loads(src.read_text())
     r, samples, free = j["race"], j["samples"], j["free"]
@@ -80,9 +93,9 @@ def main():
             "## The product's rule and its parameters\n",
             "Arrival key, most significant first: launch wave of the slot; a late bit for secondary associations (all but a "
             "pseudo-random fraction q of them); inside a wave, for a fraction b of the pixels (per-frame hash) plain slot order, "
-            "for the rest a per-frame pseudo-random order of the wave's groups of `l` consecutive slots with the slots of a group "
-            "in order (`wave_qQ_bB_lL`; l = 32: a warp of the reference; l = 1: every slot shuffled, the rule before the pair "
-            "table above was measured).\n",
+            "for the rest a per-frame pseudo-random order of the wave's warps (32 consecutive slots) with the lanes of a warp in "
+            "order. `wave_qQ_bB`: one (q, b) for all waves; `..._later_qQ1_bB1`: (Q, B) for the first wave, (Q1, B1) for the later "
+            "ones.\n",
             "### Per-frame agreement with oracle A (what the envelope tests bound)\n",
             "| rule | same winner as oracle A on the contested pixels | differing merge flags over the sampled frames | vs oracle B |",
             "|---|---:|---:|---:|"]
@@ -102,16 +115,47 @@ def main():
         out.append(f"| {k} | {t} | {100 * (t - tot_a) / tot_a:+.2f} % | {dl:+d} | {dh:+d} |")
     out += ["", "### Free-running totals after the 492 integrated frames\n"]
     free_table(free, out)
-    out += ["Chosen default (`csrc/sm_handle.cuh`): waves of 296 x 1024 slots, q = 1 % early secondaries, b = 25 % of the pixels in "
-            "slot order, l = 32: `wave_q0.01_b0.25_l32` above - inside the range of the three oracle runs on slots and live "
-            "surfels and 47 merges (0.04 %) below their lowest count. `tests/test_round2_gpu.py::test_free_running_stream_inside_the_"
-            "reference_envelope` asserts |product - mean(oracle)| <= 3 x the oracle's spread against three fresh oracle runs; "
-            "`...::test_race_bound_rows_inside_the_reference_envelope` and `tests/test_parity_gpu.py` assert the per-frame rows at "
-            "2 x oracle B.\n"]
+    out += ["Chosen default (`csrc/sm_handle.cuh`): waves of 296 x 1024 slots, warps kept intact, (q, b) = (1 %, 25 %) in the first wave "
+            "and (3 %, 45 %) in the later ones: `wave_q0.01_b0.25_later_q0.03_b0.45` above. `tests/test_round2_gpu.py::test_free_running_"
+            "stream_inside_the_reference_envelope` asserts |product - mean(oracle)| <= 3 x the oracle's spread (+ 0.1 %) against three fresh "
+            "oracle runs; `...::test_race_bound_rows_inside_the_reference_envelope` and `tests/test_parity_gpu.py` assert the per-frame rows "
+            "at 2 x oracle B (+ 4 sigma of the count + a floor).\n"]
+    for tag, title in (("vga500", "640x480, 500 frames"), ("vga1000", "640x480, 1000 frames"), ("hd1000", "1280x960, 1000 frames, 20 M cap")):
+        rows = []
+        for call, label in (("c14", "sweep"), ("c15", "final defaults")):
+            f = ROOT / "gpurun_out" / f"{call}_free_{tag}.json"
+            if f.exists():
+                rows.append((label, json.loads(f.read_text())))
+        if not rows:
+            continue
+        out += [f"### Free-running totals, {title} (`tools/free_running_check.py`)\n",
+                "| run | rule (wave, q, b, lanes, phase, q later, b later) | slots | live | merged | deviation from the oracle mean in oracle spreads | relative |",
+                "|---|---|---:|---:|---:|---|---|"]
+        for label, j in rows:
+            sp = j["oracle_spread"]
+            out.append(f"| {label}: three oracle runs | - | " + " / ".join(str(r[0]) for r in j["oracle_runs"]) + " | " +
+                       " / ".join(str(r[1]) for r in j["oracle_runs"]) + " | " + " / ".join(str(r[2]) for r in j["oracle_runs"]) +
+                       f" | spread {sp} | |")
+            for name, v in j["rules"].items():
+                t, d, rel = v["totals"], v["deviation_in_oracle_spreads"], v["relative"]
+                out.append(f"| {label} | {name} | {t[0]} | {t[1]} | {t[2]} | {d[0]:+.1f} / {d[1]:+.1f} / {d[2]:+.1f} | "
+                           f"{100 * rel[0]:+.3f} % / {100 * rel[1]:+.3f} % / {100 * rel[2]:+.3f} % |")
+        out.append("")
+    phase = ROOT / "gpurun_out" / "c13_race_stats.json"
+    if phase.exists():
+        pj = json.loads(phase.read_text())
+        ag, fl, cp = pj["same_winner_as_oracle_a"], pj["differing_merge_flags_vs_oracle_a"], pj["race"]["contested_pixels_ab"]
+        out += ["### Tried and dropped: wave boundaries at a per-pixel random phase (`c13_race_stats.json`)\n",
+                "If the ordering probability grew smoothly with the slot distance, cutting the slot axis into waves at a random phase "
+                "per pixel would model it. It does not: the boundaries at multiples of 303 104 slots are real.\n",
+                "| rule | same winner as oracle A | differing merge flags vs oracle B |", "|---|---:|---:|"]
+        for k in ag:
+            out.append(f"| {k} | {100 * ag[k] / cp:.2f} % | {fl[k] / max(fl['oracle_b'], 1):.2f}x |")
+        out.append("")
     if earlier.exists():
         e = json.loads(earlier.read_text())
         out += [f"### Earlier sweep with every slot shuffled (l = 1; `{earlier.name}`)\n",
-                "`wave_qQ_bB`: the same rule without the warp structure. It matched the free-running totals equally well (the "
+                "`wave_qQ_bB` there: the same rule without the warp structure (every slot of a wave shuffled). It matched the free-running totals equally well (the "
                 "totals depend on the marginal win rates, which both versions reproduce) but differed from oracle A on 1.5 x as "
                 "many merge flags as oracle B does (2.3 - 8 x on single frames), because a quarter of the same-wave contests are "
                 "between lanes of one warp, which the reference resolves the same way every time.\n"]
