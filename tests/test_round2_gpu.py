@@ -399,13 +399,15 @@ def test_race_bound_rows_inside_the_reference_envelope(product, reference):
 def test_free_running_stream_inside_the_reference_envelope(product, reference):
     """BASELINE config 2, full length (500 frames / 492 integrated): the free-running product against the
     free-running oracle. The oracle differs from ITSELF between runs (its races feed back through the
-    cloud); the product's deviation from the oracle's mean must stay within 3x the oracle's own spread
-    (+ a floor of 0.1 %: three runs can land within a few dozen of each other) for slots, live surfels and merges."""
+    cloud); the product's deviation from the oracle's mean must stay within 3x the oracle's own spread over six
+    runs (three runs can land within 60 merges of each other where the run-to-run standard deviation is 150;
+    + a floor of 0.1 %) for slots, live surfels and merges. Measured with the default rule: slots +0.06 %,
+    merges +0.35 % (profiles/r02_race_stats.md)."""
     cam, st, pp, ip = stream_and_params(640, 480, 500, 0)
     first, last = st.integrated_range()
     rec_r, rec_p = make(cam, 5_000_000, reference), make(cam, 5_000_000)
     runs = []
-    for _ in range(3):
+    for _ in range(6):
         rec_r.reset()
         s = rec_r.stream_run(None, st.depth, st.color, st.global_T_frame, st.frame_T_global, st.others_TR_reference, pp,
                              ip, first, last)
