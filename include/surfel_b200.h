@@ -314,6 +314,16 @@ int sm_knn_query(sm_knn_index* k, void* stream, uint32_t query_count, const floa
                  const float* radius_squared, const uint8_t* state /* may be NULL */, int32_t include_completed_surfels,
                  int32_t include_free_surfels, int32_t max_result_count, float* out_distance_squared,
                  uint32_t* out_index, int32_t* out_count);
+/* One neighbour batch for a meshing iteration with HOST arrays on both sides (the CUDASurfelBuffersCPU arrays of the
+ * last TransferAllToCPU, cuda_surfels_cpu.h:40-73): uploads x, y, z, radius_squared [point_count], indexes the points with
+ * radius_squared > 0, asks for every point its <= max_result_count nearest members within radius_factor_squared *
+ * radius_squared[i] (all meshing states; max_neighbor_search_range_increase_factor^2 covers every radius
+ * TriangulateSurfel can ask for, surfel_meshing.cc:323-413) and writes the [point_count][max_result_count] rows and
+ * [point_count] counts to host memory (count 0 for points that are not indexed). cell_size <= 0: twice the largest
+ * query radius. Synchronous; the device staging lives in the index and is reused. */
+int sm_knn_batch_host(sm_knn_index* k, void* stream, uint32_t point_count, const float* x, const float* y, const float* z,
+                      const float* radius_squared, float radius_factor_squared, float cell_size, int32_t max_result_count,
+                      float* out_distance_squared, uint32_t* out_index, int32_t* out_count);
 
 /* Replaces GetTimings(), cuda_surfel_reconstruction.cc:412-429 (milliseconds of
  * the last Integrate: data association, merging, blending, integration,

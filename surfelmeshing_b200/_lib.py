@@ -168,6 +168,7 @@ _PRODUCT_ONLY = {
     "knn_build": (C.c_int, [_P, _P, _U32, _P, _P, _P, _P, _P, _F]),
     "knn_build_from_reconstruction": (C.c_int, [_P, _P, _P, _F, C.POINTER(_U32)]),
     "knn_query": (C.c_int, [_P, _P, _U32, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "knn_batch_host": (C.c_int, [_P, _P, _U32, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P]),
     "timeline_enable": (C.c_int, [_P, _I]),
     "timeline_read": (C.c_int, [_P, C.POINTER(C.c_uint64), _I]),
 }

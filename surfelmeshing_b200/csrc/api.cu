@@ -126,7 +126,9 @@ TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index) {
   };
   t.early_threshold = threshold(cfg.early_fraction);
   t.index_order_threshold = threshold(cfg.index_order_fraction);
-  t.early_threshold_later = threshold(cfg.early_fraction_later >= 0 ? cfg.early_fraction_later : cfg.early_fraction);
+  const double later = cfg.early_fraction_later >= 0 ? cfg.early_fraction_later : cfg.early_fraction;
+  t.early_threshold_later = threshold(later);
+  t.early_threshold_second = threshold(cfg.early_fraction_second >= 0 ? cfg.early_fraction_second : later);
   t.index_order_threshold_later = threshold(cfg.index_order_fraction_later >= 0 ? cfg.index_order_fraction_later : cfg.index_order_fraction);
   return t;
 }
@@ -384,6 +386,7 @@ int CreateImpl(sm_reconstruction* r, uint64_t max_surfel_count, int32_t width, i
     r->tiebreak.index_order_fraction = index_order;
     r->tiebreak.early_fraction_later = kDefaultTieBreakEarlyFractionLater;
     r->tiebreak.index_order_fraction_later = kDefaultTieBreakIndexOrderFractionLater;
+    r->tiebreak.early_fraction_second = kDefaultTieBreakEarlyFractionSecond;
   }
   const int status = ClearAssociationRasters(nullptr, d);
   if (status != SM_OK) return status;
@@ -821,9 +824,11 @@ int sm_configure(sm_reconstruction* r, const char* key, double value) {
     if (value < 0 || value > 2147483647.0) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_wave out of range");
     return SetTieBreakWave(&r->tiebreak, static_cast<u32>(value), r->d.capacity);
   }
-  if (k == "tiebreak_early_fraction_later" || k == "tiebreak_index_order_fraction_later") {   // < 0: same as the first wave
-    if (!(value <= 1.0)) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_*_later must be <= 1 (negative: follow the first wave)");
-    (k == "tiebreak_early_fraction_later" ? r->tiebreak.early_fraction_later : r->tiebreak.index_order_fraction_later) = value;
+  if (k == "tiebreak_early_fraction_later" || k == "tiebreak_index_order_fraction_later" || k == "tiebreak_early_fraction_second") {
+    // < 0: follow the first wave (later) / the later waves (second)
+    if (!(value <= 1.0)) return SetError(SM_ERR_INVALID_ARGUMENT, "tiebreak_*_later / _second must be <= 1 (negative: inherit)");
+    (k == "tiebreak_early_fraction_later" ? r->tiebreak.early_fraction_later
+     : k == "tiebreak_early_fraction_second" ? r->tiebreak.early_fraction_second : r->tiebreak.index_order_fraction_later) = value;
     return SM_OK;
   }
   if (k == "tiebreak_wave_offset") {   // 1: wave boundaries at a per-pixel random phase

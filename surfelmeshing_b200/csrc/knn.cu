@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstring>
 #include <string>
 
@@ -38,6 +39,13 @@ struct sm_knn_index {
   float cell_size = 0.f;
   float inverse_cell_size = 0.f;
   bool built = false;
+  // device staging of sm_knn_batch_host (grown on demand): 4 point rows, results
+  smb::u32 batch_points = 0;
+  int batch_k = 0;
+  float* batch_rows = nullptr;             // [4][batch_points]: x, y, z, radius^2
+  float* batch_distance_squared = nullptr; // [batch_points][batch_k]
+  smb::u32* batch_index = nullptr;
+  int* batch_count = nullptr;
 };
 
 namespace smb {
@@ -208,6 +216,7 @@ struct QueryArgs {
   const float* qy;
   const float* qz;
   const float* radius_squared;   // per query
+  float radius_scale;            // the query radius^2 is radius_squared[q] * radius_scale (1 for sm_knn_query)
   const u8* state;               // optional, indexed by point index
   int include_completed;
   int include_free;
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(kQueryBlock) k_knn_query(QueryArgs a) {
   const u32 warps_per_grid = gridDim.x * (kQueryBlock / 32);
   for (u32 q = blockIdx.x * (kQueryBlock / 32) + (threadIdx.x >> 5); q < a.query_count; q += warps_per_grid) {
     const float px = a.qx[q], py = a.qy[q], pz = a.qz[q];
-    const float radius_squared = a.radius_squared[q];
+    const float radius_squared = fmul(a.radius_squared[q], a.radius_scale);
     QueryState s{{kEmptyKey, kEmptyKey}, 0, true, kEmptyKey, s_stage[threadIdx.x >> 5]};
     if (radius_squared >= 0.f) {
       // Cells the ball can touch. Everything is rounded outwards: a record whose fp32 distance passes the
@@ -407,6 +416,10 @@ void FreeIndex(sm_knn_index* k) {
   cudaFree(k->scan_sums);
   cudaFree(k->point_bucket);
   cudaFree(k->records);
+  cudaFree(k->batch_rows);
+  cudaFree(k->batch_distance_squared);
+  cudaFree(k->batch_index);
+  cudaFree(k->batch_count);
   delete k;
 }
 
@@ -454,20 +467,73 @@ int KnnBuild(sm_knn_index* k, cudaStream_t stream, u32 n, const float* x, const 
 }
 
 int KnnQuery(sm_knn_index* k, cudaStream_t stream, u32 query_count, const float* qx, const float* qy, const float* qz,
-             const float* radius_squared, const u8* state, int include_completed, int include_free,
+             const float* radius_squared, float radius_scale, const u8* state, int include_completed, int include_free,
              int max_result_count, float* out_distance_squared, u32* out_index, int* out_count) {
   if (!k->built) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_query: the index has not been built");
   if (max_result_count < 1 || max_result_count > kMaxResults) {
     return SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_query: max_result_count must be in [1, 64]");
   }
   if (query_count == 0) return SM_OK;
-  QueryArgs a{query_count, qx, qy, qz, radius_squared, state, include_completed, include_free, max_result_count,
+  QueryArgs a{query_count, qx, qy, qz, radius_squared, radius_scale, state, include_completed, include_free, max_result_count,
               k->inverse_cell_size, k->table_size - 1, k->bucket_start, k->records, out_distance_squared, out_index,
               out_count};
   const u32 needed = (query_count + kQueryBlock / 32 - 1) / (kQueryBlock / 32);
   const int blocks = static_cast<int>(std::min<u32>(needed, 16u * k->sm_count));
   k_knn_query<<<blocks, kQueryBlock, 0, stream>>>(a);
   SM_CUDA(cudaGetLastError());
+  return SM_OK;
+}
+
+// sm_knn_batch_host: one neighbour batch for a meshing iteration with host arrays on both sides.
+int KnnBatchHost(sm_knn_index* k, cudaStream_t stream, u32 n, const float* x, const float* y, const float* z,
+                 const float* radius_squared, float radius_factor_squared, float cell_size, int max_result_count,
+                 float* out_distance_squared, u32* out_index, int* out_count) {
+  if (n > k->capacity) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_batch_host: more points than the index was created for");
+  if (max_result_count < 1 || max_result_count > kMaxResults) {
+    return SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_batch_host: max_result_count must be in [1, 64]");
+  }
+  if (!(radius_factor_squared > 0.f)) return SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_batch_host: radius_factor_squared must be positive");
+  if (n == 0) return SM_OK;
+  if (!(cell_size > 0.f)) {   // twice the largest query radius: a ball touches 8 cells
+    float largest = 0.f;
+    for (u32 i = 0; i < n; ++i) largest = std::max(largest, radius_squared[i]);
+    if (!(largest > 0.f)) largest = 1.f;
+    cell_size = 2.f * std::sqrt(largest * radius_factor_squared);
+  }
+  if (k->batch_points < n || k->batch_k < max_result_count) {
+    SM_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(k->batch_rows); cudaFree(k->batch_distance_squared); cudaFree(k->batch_index); cudaFree(k->batch_count);
+    k->batch_rows = nullptr; k->batch_distance_squared = nullptr; k->batch_index = nullptr; k->batch_count = nullptr;
+    k->batch_points = 0;
+    const size_t points = std::min<size_t>(k->capacity, std::max<size_t>(n, 1u << 16));
+    const size_t width = static_cast<size_t>(std::max(max_result_count, k->batch_k));
+    SM_CUDA(cudaMalloc(&k->batch_rows, sizeof(float) * 4 * points));
+    SM_CUDA(cudaMalloc(&k->batch_distance_squared, sizeof(float) * width * points));
+    SM_CUDA(cudaMalloc(&k->batch_index, sizeof(u32) * width * points));
+    SM_CUDA(cudaMalloc(&k->batch_count, sizeof(int) * points));
+    k->batch_points = static_cast<u32>(points);
+    k->batch_k = static_cast<int>(width);
+  }
+  const size_t stride = k->batch_points;
+  float* dx = k->batch_rows;
+  float* dy = dx + stride;
+  float* dz = dy + stride;
+  float* dr = dz + stride;
+  const size_t bytes = sizeof(float) * n;
+  SM_CUDA(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, stream));
+  SM_CUDA(cudaMemcpyAsync(dy, y, bytes, cudaMemcpyHostToDevice, stream));
+  SM_CUDA(cudaMemcpyAsync(dz, z, bytes, cudaMemcpyHostToDevice, stream));
+  SM_CUDA(cudaMemcpyAsync(dr, radius_squared, bytes, cudaMemcpyHostToDevice, stream));
+  int status = KnnBuild(k, stream, n, dx, dy, dz, dr, nullptr, cell_size);
+  if (status != SM_OK) return status;
+  status = KnnQuery(k, stream, n, dx, dy, dz, dr, radius_factor_squared, nullptr, 1, 1, max_result_count,
+                    k->batch_distance_squared, k->batch_index, k->batch_count);
+  if (status != SM_OK) return status;
+  const size_t results = static_cast<size_t>(n) * max_result_count;
+  SM_CUDA(cudaMemcpyAsync(out_distance_squared, k->batch_distance_squared, sizeof(float) * results, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(out_index, k->batch_index, sizeof(u32) * results, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaMemcpyAsync(out_count, k->batch_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+  SM_CUDA(cudaStreamSynchronize(stream));
   return SM_OK;
 }
 
@@ -519,8 +585,18 @@ int sm_knn_query(sm_knn_index* k, void* stream, uint32_t query_count, const floa
   if (!k || (query_count && (!qx || !qy || !qz || !radius_squared || !out_distance_squared || !out_index || !out_count))) {
     return smb::SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_query: null argument");
   }
-  return smb::KnnQuery(k, static_cast<cudaStream_t>(stream), query_count, qx, qy, qz, radius_squared, state,
+  return smb::KnnQuery(k, static_cast<cudaStream_t>(stream), query_count, qx, qy, qz, radius_squared, 1.0f, state,
                        include_completed, include_free, max_result_count, out_distance_squared, out_index, out_count);
+}
+
+int sm_knn_batch_host(sm_knn_index* k, void* stream, uint32_t point_count, const float* x, const float* y, const float* z,
+                      const float* radius_squared, float radius_factor_squared, float cell_size, int32_t max_result_count,
+                      float* out_distance_squared, uint32_t* out_index, int32_t* out_count) {
+  if (!k || (point_count && (!x || !y || !z || !radius_squared || !out_distance_squared || !out_index || !out_count))) {
+    return smb::SetError(SM_ERR_INVALID_ARGUMENT, "sm_knn_batch_host: null argument");
+  }
+  return smb::KnnBatchHost(k, static_cast<cudaStream_t>(stream), point_count, x, y, z, radius_squared, radius_factor_squared,
+                           cell_size, max_result_count, out_distance_squared, out_index, out_count);
 }
 
 }  // extern "C"

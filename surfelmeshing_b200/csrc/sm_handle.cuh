@@ -17,6 +17,7 @@ struct TieBreakConfig {
   double early_fraction; // fraction of secondary associations that compete like primary ones
   double index_order_fraction;  // fraction of the pixels that order the supporters of a wave by slot index
   double early_fraction_later, index_order_fraction_later;  // the same two for the waves after the first (< 0: same as the first)
+  double early_fraction_second;  // early fraction of the second wave alone (< 0: same as the later waves)
   u32 wave_offset;       // 1: per-pixel random phase of the wave boundaries (sm_kernels.cuh: tb_phase)
   u32 lane_request;      // log2 of the slots that keep their order in the shuffled order (5: a warp of the reference)
   u32 lane_shift;        // what is in effect: lane_request, or 0 when the wave is not a multiple of it
@@ -40,6 +41,7 @@ constexpr double kDefaultTieBreakEarlyFraction = 0.01;
 constexpr double kDefaultTieBreakIndexOrderFraction = 0.25;
 constexpr double kDefaultTieBreakEarlyFractionLater = 0.03;
 constexpr double kDefaultTieBreakIndexOrderFractionLater = 0.45;
+constexpr double kDefaultTieBreakEarlyFractionSecond = -1.0;
 TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index);
 int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity);   // uses cfg->lane_request
 

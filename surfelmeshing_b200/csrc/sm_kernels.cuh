@@ -87,6 +87,7 @@ struct TieBreak {
   u32 salt;             // per frame, for the two draws
   u32 early_threshold;  // secondary association is NOT late iff hash(slot ^ salt) < early_threshold (slots of the first wave)
   u32 index_order_threshold;  // pixel uses slot order iff hash(pixel ^ ~salt) < index_order_threshold (first wave)
+  u32 early_threshold_second;                              // the early threshold of the SECOND wave (partly filled at VGA sizes)
   u32 early_threshold_later, index_order_threshold_later;  // the same for the later waves: their blocks start one by one as
                                                            // earlier ones retire, so arrival follows the slot order more closely
                                                            // and a secondary association of an early block is ahead more often
@@ -137,7 +138,8 @@ __host__ __device__ __forceinline__ u32 tb_encode(const TieBreak& t, u32 idx, bo
     tb_divide(static_cast<u64>(r >> t.lane_shift) * t.mul + t.add, t.groups, t.group_reciprocal, &gp);
     rp = (gp << t.lane_shift) | (r & ((1u << t.lane_shift) - 1u));
   }
-  const bool late = secondary && !(tb_hash(idx ^ t.salt) < (w == 0 ? t.early_threshold : t.early_threshold_later));
+  const bool late = secondary && !(tb_hash(idx ^ t.salt) <
+                                   (w == 0 ? t.early_threshold : (w == 1 ? t.early_threshold_second : t.early_threshold_later)));
   return w * (2u * t.wave) + (late ? t.wave : 0u) + rp;   // < 2^32 - 1: checked by SetTieBreakWave
 }
 __host__ __device__ __forceinline__ u32 supporting_index(const TieBreak& t, u32 key, u32 pixel) {

@@ -68,6 +68,22 @@ class SurfelKnnIndex:
         self.point_count = n.value
         return n.value
 
+    def batch_host(self, x, y, z, radius_squared, radius_factor_squared: float, max_result_count: int = 64,
+                   cell_size: float = 0.0, stream=None):
+        """sm_knn_batch_host: numpy arrays in (the CUDASurfelBuffersCPU arrays), numpy arrays out:
+        (distances_squared [N, k] f32, indices [N, k] u32, counts [N] i32)."""
+        import numpy as np
+        arrays = [np.ascontiguousarray(a, np.float32) for a in (x, y, z, radius_squared)]
+        n, k = len(arrays[0]), int(max_result_count)
+        d2 = np.empty((n, k), np.float32)
+        idx = np.empty((n, k), np.uint32)
+        cnt = np.empty((n,), np.int32)
+        self.lib.call("knn_batch_host", self._h, _stream_handle(stream), n, *[C.c_void_p(a.ctypes.data) for a in arrays],
+                      float(radius_factor_squared), float(cell_size), k, C.c_void_p(d2.ctypes.data), C.c_void_p(idx.ctypes.data),
+                      C.c_void_p(cnt.ctypes.data))
+        self.point_count = n
+        return d2, idx, cnt
+
     def FindNearestSurfelsWithinRadius(self, qx, qy, qz, radius_squared, max_result_count: int, state=None,
                                        include_completed_surfels: bool = True, include_free_surfels: bool = True,
                                        stream=None):

@@ -23,7 +23,7 @@ int main() {
     TieBreak tb{}; tb.wave = wave; tb.lane_shift = shift; tb.groups = groups; tb.mul = cfg.mul; tb.mul_inv = cfg.mul_inv;
     tb.add = 12345 % groups; tb.salt = 0xdeadbeef;
     tb.early_threshold = 0x40000000u; tb.index_order_threshold = 0x70000000u; tb.wave_reciprocal = ~0ull / wave;
-    tb.early_threshold_later = 0x60000000u; tb.index_order_threshold_later = 0x30000000u;
+    tb.early_threshold_later = 0x60000000u; tb.index_order_threshold_later = 0x30000000u; tb.early_threshold_second = 0x20000000u;
     tb.group_reciprocal = ~0ull / groups;
     tb.wave_offset = offsets[variant];
     unsigned long long bad = 0, n = 0;
@@ -36,7 +36,7 @@ int main() {
       u32 w = (u32)(((u64)idx + phase) / wave), rr = (u32)(((u64)idx + phase) % wave);
       u32 rp = tb_index_order(tb, pixel, w) ? rr
                                          : (u32)(((((u64)(rr >> shift) * tb.mul + tb.add) % groups) << shift) | (rr & ((1u << shift) - 1)));
-      bool late = sec && !(tb_hash(idx ^ tb.salt) < (w == 0 ? tb.early_threshold : tb.early_threshold_later));
+      bool late = sec && !(tb_hash(idx ^ tb.salt) < (w == 0 ? tb.early_threshold : (w == 1 ? tb.early_threshold_second : tb.early_threshold_later)));
       u32 expect = w * (2u * wave) + (late ? wave : 0u) + rp;
       if (wave < (1u<<30) || idx < wave) if (expect != key) ++bad;
       ++n;

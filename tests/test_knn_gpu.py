@@ -184,3 +184,36 @@ def test_gpu_batch_feeds_the_reference_triangulation(kind, n):
     served, fallback = got[3]
     print(f"{kind} {n}: {len(want[0])} triangles, {served} octree queries answered from the GPU batch, {fallback} by the octree")
     assert served > 0 and (kind == "cube" and n == 10000 or served > fallback)
+
+
+def test_knn_batch_host_matches_the_device_api():
+    """sm_knn_batch_host (host arrays in and out, what a CPU meshing thread holds) returns exactly what build + query on
+    device buffers return, merged points (radius^2 < 0) are neither indexed nor answered, and the reference's
+    triangulation fed with it produces the octree's mesh."""
+    from surfelmeshing_b200.knn import SurfelKnnIndex
+    cloud = knn_cases.meshing_cloud(10000, 8, "sheet")
+    r2_rows = cloud["radius_squared"].copy()
+    r2_rows[::17] = -1.0                                   # merged surfels
+    factor = np.float32(4.0)
+    index = SurfelKnnIndex(20000)
+    d2, idx, cnt = index.batch_host(cloud["x"], cloud["y"], cloud["z"], r2_rows, float(factor), 64)
+    cell = 2.0 * float(np.sqrt(r2_rows.max() * factor))
+    other = build(cloud["x"], cloud["y"], cloud["z"], cell, radius_squared=r2_rows)
+    want = gpu_query(other, cloud["x"], cloud["y"], cloud["z"], (r2_rows * factor).astype(np.float32), 64)
+    other.close()
+    assert_identical((d2, idx, cnt), want)
+    assert (cnt[::17] == 0).all() and not np.isin(idx[idx != 0xFFFFFFFF], np.arange(0, 10000, 17)).any()
+    # a second, smaller batch reuses the staging
+    d2b, idxb, cntb = index.batch_host(cloud["x"][:3000], cloud["y"][:3000], cloud["z"][:3000], r2_rows[:3000], float(factor), 16)
+    assert d2b.shape == (3000, 16) and (cntb <= 16).all() and cntb.max() > 1
+    index.close()
+    from oracle import meshing_ref
+    if meshing_ref.available():
+        from tests.test_meshing_oracle import batch_radius, run_reference
+        cloud["radius_squared"] = np.abs(r2_rows)          # the meshing input itself has no merged surfels here
+        index = SurfelKnnIndex(10000)
+        batch = index.batch_host(cloud["x"], cloud["y"], cloud["z"], cloud["radius_squared"], float(factor), 64)
+        index.close()
+        want_mesh = run_reference(cloud)
+        got_mesh = run_reference(cloud, batch=(*batch, batch_radius(cloud)))
+        assert np.array_equal(got_mesh[0], want_mesh[0]) and np.array_equal(got_mesh[1], want_mesh[1]) and got_mesh[3][0] > 0

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--frames", type=int, default=500)
     ap.add_argument("--cap", type=int, default=5_000_000)
     ap.add_argument("--oracle-runs", type=int, default=3)
-    ap.add_argument("--rule", action="append", default=[], help="'default' or wave,early,index_order,lanes[,phase[,early_later[,index_order_later]]]")
+    ap.add_argument("--rule", action="append", default=[], help="'default' or wave,early,index_order,lanes[,phase[,early_later[,index_order_later[,early_second]]]]")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     cam = S.Camera.tum(a.width, a.height)
@@ -49,9 +49,10 @@ def main():
     rec = R.CUDASurfelReconstruction(a.cap, cam.width, cam.height, cam.fx, cam.fy, cam.cx, cam.cy)
     for rule in a.rule or ["default"]:
         if rule != "default":
-            # wave,early,index_order,lanes[,phase[,early_later[,index_order_later]]]
+            # wave,early,index_order,lanes[,phase[,early_later[,index_order_later[,early_second]]]]
             parts = rule.split(",")
-            wave, early, index_order, lanes, phase, early_later, index_later = [float(v) for v in parts] + [0.0, -1.0, -1.0][len(parts) - 4:]
+            wave, early, index_order, lanes, phase, early_later, index_later, early_second = \
+                [float(v) for v in parts] + [0.0, -1.0, -1.0, -1.0][len(parts) - 4:]
             rec.configure("tiebreak_wave_offset", phase)
             rec.configure("tiebreak_lanes", lanes)
             rec.configure("tiebreak_wave", wave)
@@ -59,6 +60,7 @@ def main():
             rec.configure("tiebreak_index_order_fraction", index_order)
             rec.configure("tiebreak_early_fraction_later", early_later)
             rec.configure("tiebreak_index_order_fraction_later", index_later)
+            rec.configure("tiebreak_early_fraction_second", early_second)
         got = np.array(run(rec))
         dev = (got - mean) / np.maximum(spread, 1)
         result["rules"][rule] = {"totals": got.tolist(), "deviation_in_oracle_spreads": dev.tolist(),

@@ -73,6 +73,14 @@ def main():
         torch.cuda.synchronize()
         if rep:
             gpu_s.append(time.perf_counter() - t0)
+    # the same through the host-array entry point of the C ABI (pageable numpy arrays in and out)
+    host_s = []
+    for rep in range(3):
+        t0 = time.perf_counter()
+        hd2, hidx, hcnt = index.batch_host(cloud["x"], cloud["y"], cloud["z"], cloud["radius_squared"], float(f * f), 64)
+        if rep:
+            host_s.append(time.perf_counter() - t0)
+    assert np.array_equal(hcnt, out_cnt.numpy()) and np.array_equal(hidx, out_idx.numpy().view(np.uint32))
     batch = (out_d2.numpy(), out_idx.numpy().view(np.uint32), out_cnt.numpy(), r2)
     tri_fed, fed_times, fed_stats = run(cloud, batch)
     result = {"workload": f"{n} fresh surfels on a sheet, radius 1.5 x spacing, one meshing iteration of the reference's CPU code",
@@ -80,8 +88,10 @@ def main():
               "octree": cpu_times, "octree_queries": int(stats[1]),
               "gpu_batch": fed_times, "queries_answered_from_the_batch": int(fed_stats[0]), "queries_left_to_the_octree": int(fed_stats[1]),
               "gpu_batch_end_to_end_s": float(np.median(gpu_s)),
+              "gpu_batch_host_api_s": float(np.median(host_s)),
               "mean_neighbours_in_batch_row": float(out_cnt.numpy().mean())}
     result["iteration_speedup"] = cpu_times["total_s"] / (fed_times["total_s"] + result["gpu_batch_end_to_end_s"])
+    result["iteration_speedup_host_api"] = cpu_times["total_s"] / (fed_times["total_s"] + result["gpu_batch_host_api_s"])
     print(json.dumps(result))
     if a.out:
         Path(a.out).write_text(json.dumps(result, indent=1))
