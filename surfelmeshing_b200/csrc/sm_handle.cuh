@@ -31,9 +31,10 @@ struct TieBreakConfig {
 // blocks of the FIRST wave start together; those of the later waves start one by one as earlier blocks retire, so
 // there arrival follows the slot order more closely (lower slot wins 80 % instead of 70 %) and a secondary
 // association beats a primary one of the same wave 5.4 % of the time instead of 0.6 %: separate fractions for the
-// first and for the later waves (1 % / 3 % early secondaries, 25 % / 45 % of the pixels in slot order) put the
-// per-frame merge flags at 1.2x the reference's own run-to-run difference and the free-running totals of the
-// 500- and 1000-frame VGA streams inside the reference's spread (1280x960: -0.1 % slots).
+// first wave, the second (at VGA sizes only partly filled) and the later ones (1 % / 1.5 % / 3 % early secondaries,
+// 25 % / 45 % / 45 % of the pixels in slot order) put the per-frame merge flags at 1.2x the reference's own run-to-run
+// difference and the free-running totals of the 500- and 1000-frame VGA streams inside the reference's spread
+// (1280x960: -0.1 % slots, -0.06 % merges).
 constexpr u32 kDefaultTieBreakWave = 296 * 1024;
 constexpr u32 kDefaultTieBreakLaneShift = 5;
 constexpr u32 kDefaultTieBreakWaveOffset = 0;
@@ -41,7 +42,7 @@ constexpr double kDefaultTieBreakEarlyFraction = 0.01;
 constexpr double kDefaultTieBreakIndexOrderFraction = 0.25;
 constexpr double kDefaultTieBreakEarlyFractionLater = 0.03;
 constexpr double kDefaultTieBreakIndexOrderFractionLater = 0.45;
-constexpr double kDefaultTieBreakEarlyFractionSecond = -1.0;
+constexpr double kDefaultTieBreakEarlyFractionSecond = 0.015;
 TieBreak MakeTieBreak(const TieBreakConfig& cfg, u32 frame_index);
 int SetTieBreakWave(TieBreakConfig* cfg, u32 wave, u32 capacity);   // uses cfg->lane_request
 
