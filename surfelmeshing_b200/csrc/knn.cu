@@ -46,6 +46,9 @@ struct sm_knn_index {
   float* batch_distance_squared = nullptr; // [batch_points][batch_k]
   smb::u32* batch_index = nullptr;
   int* batch_count = nullptr;
+  // pinned bounce buffers of the result download (two chunks in flight) and their events
+  void* bounce[2] = {nullptr, nullptr};
+  cudaEvent_t bounce_ready[2] = {nullptr, nullptr};
 };
 
 namespace smb {
@@ -420,6 +423,10 @@ void FreeIndex(sm_knn_index* k) {
   cudaFree(k->batch_distance_squared);
   cudaFree(k->batch_index);
   cudaFree(k->batch_count);
+  for (int i = 0; i < 2; ++i) {
+    if (k->bounce[i]) cudaFreeHost(k->bounce[i]);
+    if (k->bounce_ready[i]) cudaEventDestroy(k->bounce_ready[i]);
+  }
   delete k;
 }
 
@@ -529,10 +536,42 @@ int KnnBatchHost(sm_knn_index* k, cudaStream_t stream, u32 n, const float* x, co
   status = KnnQuery(k, stream, n, dx, dy, dz, dr, radius_factor_squared, nullptr, 1, 1, max_result_count,
                     k->batch_distance_squared, k->batch_index, k->batch_count);
   if (status != SM_OK) return status;
-  const size_t results = static_cast<size_t>(n) * max_result_count;
-  SM_CUDA(cudaMemcpyAsync(out_distance_squared, k->batch_distance_squared, sizeof(float) * results, cudaMemcpyDeviceToHost, stream));
-  SM_CUDA(cudaMemcpyAsync(out_index, k->batch_index, sizeof(u32) * results, cudaMemcpyDeviceToHost, stream));
-  SM_CUDA(cudaMemcpyAsync(out_count, k->batch_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+  // Results back through two pinned bounce buffers: the copy engine fills one chunk while the host moves the
+  // previous one into the caller's (pageable) arrays - a direct copy into pageable memory runs at a few GB/s.
+  constexpr u32 kChunk = 1u << 16;                                   // queries per chunk
+  const size_t chunk_bytes = static_cast<size_t>(kChunk) * (kMaxResults * 8 + 4);
+  for (int i = 0; i < 2; ++i) {
+    if (!k->bounce[i]) SM_CUDA(cudaMallocHost(&k->bounce[i], chunk_bytes));
+    if (!k->bounce_ready[i]) SM_CUDA(cudaEventCreateWithFlags(&k->bounce_ready[i], cudaEventDisableTiming));
+  }
+  const u32 chunks = (n + kChunk - 1) / kChunk;
+  auto enqueue = [&](u32 c) -> int {
+    const u32 first = c * kChunk, count = std::min(kChunk, n - first);
+    const size_t row = static_cast<size_t>(count) * max_result_count;
+    char* b = static_cast<char*>(k->bounce[c & 1]);
+    SM_CUDA(cudaMemcpyAsync(b, k->batch_distance_squared + static_cast<size_t>(first) * max_result_count, sizeof(float) * row,
+                            cudaMemcpyDeviceToHost, stream));
+    SM_CUDA(cudaMemcpyAsync(b + sizeof(float) * row, k->batch_index + static_cast<size_t>(first) * max_result_count,
+                            sizeof(u32) * row, cudaMemcpyDeviceToHost, stream));
+    SM_CUDA(cudaMemcpyAsync(b + 2 * sizeof(float) * row, k->batch_count + first, sizeof(int) * count, cudaMemcpyDeviceToHost, stream));
+    SM_CUDA(cudaEventRecord(k->bounce_ready[c & 1], stream));
+    return SM_OK;
+  };
+  status = enqueue(0);
+  if (status != SM_OK) return status;
+  for (u32 c = 0; c < chunks; ++c) {
+    if (c + 1 < chunks) {   // buffer (c + 1) & 1 was drained by the host in iteration c - 1
+      status = enqueue(c + 1);
+      if (status != SM_OK) return status;
+    }
+    SM_CUDA(cudaEventSynchronize(k->bounce_ready[c & 1]));
+    const u32 first = c * kChunk, count = std::min(kChunk, n - first);
+    const size_t row = static_cast<size_t>(count) * max_result_count;
+    const char* b = static_cast<const char*>(k->bounce[c & 1]);
+    std::memcpy(out_distance_squared + static_cast<size_t>(first) * max_result_count, b, sizeof(float) * row);
+    std::memcpy(out_index + static_cast<size_t>(first) * max_result_count, b + sizeof(float) * row, sizeof(u32) * row);
+    std::memcpy(out_count + first, b + 2 * sizeof(float) * row, sizeof(int) * count);
+  }
   SM_CUDA(cudaStreamSynchronize(stream));
   return SM_OK;
 }
