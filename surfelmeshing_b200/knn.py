@@ -69,15 +69,22 @@ class SurfelKnnIndex:
         return n.value
 
     def batch_host(self, x, y, z, radius_squared, radius_factor_squared: float, max_result_count: int = 64,
-                   cell_size: float = 0.0, stream=None):
+                   cell_size: float = 0.0, stream=None, out=None):
         """sm_knn_batch_host: numpy arrays in (the CUDASurfelBuffersCPU arrays), numpy arrays out:
-        (distances_squared [N, k] f32, indices [N, k] u32, counts [N] i32)."""
+        (distances_squared [N, k] f32, indices [N, k] u32, counts [N] i32); `out` = such a triple to fill (a meshing
+        thread reuses its arrays from iteration to iteration)."""
         import numpy as np
         arrays = [np.ascontiguousarray(a, np.float32) for a in (x, y, z, radius_squared)]
         n, k = len(arrays[0]), int(max_result_count)
-        d2 = np.empty((n, k), np.float32)
-        idx = np.empty((n, k), np.uint32)
-        cnt = np.empty((n,), np.int32)
+        if out is not None:
+            d2, idx, cnt = out
+            assert d2.shape == (n, k) and idx.shape == (n, k) and cnt.shape == (n,)
+            assert d2.dtype == np.float32 and idx.dtype == np.uint32 and cnt.dtype == np.int32
+            assert d2.flags.c_contiguous and idx.flags.c_contiguous and cnt.flags.c_contiguous
+        else:
+            d2 = np.empty((n, k), np.float32)
+            idx = np.empty((n, k), np.uint32)
+            cnt = np.empty((n,), np.int32)
         self.lib.call("knn_batch_host", self._h, _stream_handle(stream), n, *[C.c_void_p(a.ctypes.data) for a in arrays],
                       float(radius_factor_squared), float(cell_size), k, C.c_void_p(d2.ctypes.data), C.c_void_p(idx.ctypes.data),
                       C.c_void_p(cnt.ctypes.data))

@@ -171,22 +171,25 @@ def main():
              "in 1.99 ms with cells of 2 r, 3.33 ms with cells of r); staging the candidates in shared memory and sorting once "
              "(call 8b / 9) brought that to 1.21 ms / 2.68 ms. `profiles/r02_knn_ncu_full_summary.csv` is the `ncu --set full` capture "
              "of the final kernels.\n")
-    for pattern, title in (("c10_meshing_probe_100k.json", "100 000"), ("c10_meshing_probe_1m.json", "1 000 000")):
-        mp = SRC / pattern
-        if not mp.exists():
+    for pattern, title in (("{call}_meshing_probe_100k.json", "100 000"), ("{call}_meshing_probe_1m.json", "1 000 000")):
+        mp = latest(pattern)
+        if not mp:
             continue
         j = json.loads(mp.read_text())
         if "### One meshing iteration" not in "\n".join(L):
             L.append("### One meshing iteration of the reference's CPU code (BASELINE config 1 at scale, `tools/meshing_probe.py`)\n")
             L.append("`IntegrateCUDABuffers -> CheckRemeshing -> Triangulate` of `oracle/_ref/libmeshing_ref.so` (the reference's `surfel_meshing.cc` + "
                      "`octree.cc`, unmodified) over N fresh surfels, its two octree queries answered by the octree or by one `sm_knn_query` batch.\n")
-            L.append("| surfels | triangles | identical mesh | octree: integrate + check + triangulate (s) | GPU batch: same (s) | batch end to end on the GPU (s) | "
-                     "queries from the batch / left to the octree | iteration speed-up |")
-            L.append("|---:|---:|---|---:|---:|---:|---:|---:|")
+            L.append("| surfels | triangles | identical mesh | octree: integrate + check + triangulate (s) | GPU batch: same (s) | batch end to end on the GPU, "
+                     "pinned arrays (s) | batch through `sm_knn_batch_host`, pageable arrays (s) | queries from the batch / left to the octree | "
+                     "iteration speed-up (pinned / host entry point) |")
+            L.append("|---:|---:|---|---:|---:|---:|---:|---:|---:|")
         o, g = j["octree"], j["gpu_batch"]
         L.append(f"| {title} | {j['triangles']} | {j['identical_mesh']} | {o['integrate_s']:.3f} + {o['check_remeshing_s']:.3f} + {o['triangulate_s']:.3f} = {o['total_s']:.3f} | "
                  f"{g['integrate_s']:.3f} + {g['check_remeshing_s']:.3f} + {g['triangulate_s']:.3f} = {g['total_s']:.3f} | {j['gpu_batch_end_to_end_s']:.3f} | "
-                 f"{j['queries_answered_from_the_batch']} / {j['queries_left_to_the_octree']} | {j['iteration_speedup']:.2f}x |")
+                 f"{j.get('gpu_batch_host_api_s', float('nan')):.3f} | "
+                 f"{j['queries_answered_from_the_batch']} / {j['queries_left_to_the_octree']} | {j['iteration_speedup']:.2f}x / "
+                 f"{j.get('iteration_speedup_host_api', float('nan')):.2f}x |")
     L.append("")
     for arm, note in (("product", "`-k regex:k_`, frames ~450-480 of one pass of `tools/stream_probe.py --frames 500`"),
                       ("reference", "`-k regex:Kernel`, the same frames of `--impl reference`")):
