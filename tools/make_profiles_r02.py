@@ -23,7 +23,7 @@ def load_line(path):
 
 
 def latest(pattern):
-    for call in ("c19", "c18", "c17", "c16", "c15", "c14", "c13", "c12", "c11", "c10", "c9", "c8", "c7", "c6", "c5", "c4", "c3", "c2", "c1"):
+    for call in ("c20", "c19", "c18", "c17", "c16", "c15", "c14", "c13", "c12", "c11", "c10", "c9", "c8", "c7", "c6", "c5", "c4", "c3", "c2", "c1"):
         p = SRC / pattern.format(call=call)
         if p.exists() and p.stat().st_size > 0:
             return p
