@@ -1055,6 +1055,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_integrate(DeviceState d, FramePar
 // ---------------------------------------------------------------------------------------
 // a12: neighbour update (kernels.cu:1197-1380)
 // ---------------------------------------------------------------------------------------
+// SM_UPDATE_ANYNEW_FIRST (compile-time A/B hook, with SM_UPDATE_EARLY_GATE): 1 = the "some candidate is new" gate before
+// the gathers of the other gates.
+#ifndef SM_UPDATE_ANYNEW_FIRST
+#define SM_UPDATE_ANYNEW_FIRST 0
+#endif
 // SM_UPDATE_EARLY_GATE (compile-time A/B hook): 1 = occlusion gate after a light first batch, 0 = round 1's order.
 #ifndef SM_UPDATE_EARLY_GATE
 #define SM_UPDATE_EARLY_GATE 1
@@ -1287,6 +1292,35 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
     if (x != cached.px || y != cached.py) raw_depth = row_ptr(f.depth, f.depth_pitch, y)[x];  // the surfel moved into another pixel
     const float measurement_depth = fmul(u2f(raw_depth), f.inv_depth_scaling);
     if (cz_ > fmul(measurement_depth, fadd(f.sensor_noise_factor, 1.0f))) return;  // occluded
+#if SM_UPDATE_ANYNEW_FIRST
+    // batch 2a: the neighbour list and the candidates of the 4-adjacent pixels. If every usable candidate already is
+    // a neighbour nothing can be inserted (the steady state; see below), whatever the remaining gates say: they are
+    // pure predicates, so this one goes first and the five gathers of batch 2b are only issued behind it.
+    u32 neighbor_surfel_indices[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) neighbor_surfel_indices[m] = SM_SU(SM_ROW_NEIGHBOR0 + m, idx);
+    u32 candidate[4];
+#pragma unroll
+    for (int direction = 0; direction < 4; ++direction) {
+      const int candidate_pixel = (y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction];
+      candidate[direction] = supporting_index(f.tb, d.assoc[candidate_pixel].x, static_cast<u32>(candidate_pixel));
+    }
+    {
+      bool any_new_first = false;
+#pragma unroll
+      for (int direction = 0; direction < 4; ++direction) {
+        const u32 q = candidate[direction];
+        if (q == kInvalidIndex || q == idx) continue;
+        any_new_first |= q != neighbor_surfel_indices[0] && q != neighbor_surfel_indices[1] &&
+                         q != neighbor_surfel_indices[2] && q != neighbor_surfel_indices[3];
+      }
+      if (!any_new_first) return;
+    }
+    // batch 2b: the rest of the surfel and the pixel's radius
+    const float nx = SM_S(SM_ROW_NORMAL_X, idx), ny = SM_S(SM_ROW_NORMAL_Y, idx), nz = SM_S(SM_ROW_NORMAL_Z, idx);
+    const float radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
+    const float observation_radius_squared = row_ptr(f.radius, f.radius_pitch, y)[x];
+#else
     // batch 2: the rest of the surfel, the pixel's radius and the candidates of the 4-adjacent pixels
     const float nx = SM_S(SM_ROW_NORMAL_X, idx), ny = SM_S(SM_ROW_NORMAL_Y, idx), nz = SM_S(SM_ROW_NORMAL_Z, idx);
     const float radius_squared = SM_S(SM_ROW_RADIUS_SQUARED, idx);
@@ -1300,6 +1334,7 @@ __global__ void __launch_bounds__(kBlock) k_update_neighbors(DeviceState d, Fram
       const int candidate_pixel = (y + kDirectionsY[direction]) * d.width + x + kDirectionsX[direction];
       candidate[direction] = supporting_index(f.tb, d.assoc[candidate_pixel].x, static_cast<u32>(candidate_pixel));
     }
+#endif
 #else
     // batch 1: the surfel (its position may have been changed by the integration: project again)
     const u32 stamp = SM_SU(SM_ROW_LAST_UPDATE_STAMP, idx);

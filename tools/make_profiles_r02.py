@@ -115,7 +115,11 @@ def main():
                         ("c8_hd", "call 8, 1280x960 / 400 frames / 20 M cap (3 passes)"),
                         ("c8c", "call 8c (ordering-only graph edges, SM_B200_GRAPH_ORDER: 1 create before update_neighbors, 2 associate(f+1) "
                                 "before the regularisation of f, 4 merge(f+1) before it, 8 project(f+1) before update_neighbors(f): all slower, kept off)"),
-                        ("c8c_hd", "call 8c, 1280x960 / 400 frames / 20 M cap (3 passes)")):
+                        ("c8c_hd", "call 8c, 1280x960 / 400 frames / 20 M cap (3 passes)"),
+                        ("c22", "call 22 (k_update_neighbors: the 'some candidate is new' gate before the other gates' gathers, "
+                                "-DSM_UPDATE_ANYNEW_FIRST=1; `head` = the default build as a variant library; later configurations of one "
+                                "process run up to 5 % slower than the first ones, so each pair is listed twice)"),
+                        ("c22_hd", "call 22, 1280x960 / 400 frames / 20 M cap (3 passes)")):
         p = SRC / (f"{call}_ab.json" if not call.endswith("_hd") else f"{call[:-3]}_ab_hd.json")
         if p.exists():
             L.append(f"## Same-box A/B, {title}\n")
