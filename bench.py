@@ -263,6 +263,7 @@ def main():
     with ClockSampler(info.local_rank) as clocks:
         ms, stats = timed_steps(info, device, step_device, warmup, args.steps)
     ms_max, frames_total = D.aggregate(info, ms, frames_per_step * args.steps, device)
+    ms_per_rank = D.gather_values(info, ms / args.steps, device)
     value = frames_total / (ms_max * 1e-3)
 
     # ---- e2e: host (pinned) frames in, CUDASurfelBuffersCPU arrays out ----
@@ -394,7 +395,8 @@ def main():
     if info.rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": info.world_size, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": ms_max / args.steps, "ms_per_step_per_rank": ms_per_rank,
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"synthetic TUM-fr1/desk-shaped {cam.width}x{cam.height} stream, {args.frames} "
                                    f"frames ({frames_per_step} integrated) per GPU, full preprocess + Integrate(), "

@@ -51,6 +51,16 @@ def barrier(info: RankInfo, device=None):
             dist.barrier()
 
 
+def gather_values(info: RankInfo, value: float, device="cpu"):
+    """The value of every rank, in rank order (diagnostics: how far the replicas spread)."""
+    if not info.is_distributed:
+        return [float(value)]
+    t = torch.zeros(info.world_size, dtype=torch.float64, device=device)
+    t[info.rank] = value
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.tolist()]
+
+
 def aggregate(info: RankInfo, elapsed_ms: float, units: float, device="cpu"):
     """Returns (max elapsed over ranks, total units over ranks): whole-job throughput is
     total units / max time."""
