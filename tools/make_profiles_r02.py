@@ -97,6 +97,12 @@ def main():
                  f"max-over-ranks timing): product {n2p['value']:.0f} frames/s (e2e {n2p['e2e']['value']:.0f}), reference "
                  f"{n2r['value']:.0f} (e2e {n2r['e2e']['value']:.0f}); round 1's driver run measured 0.98 scaling efficiency up to 8 GPUs "
                  f"with the same plumbing (no collective on the data path).")
+    n4p, n4r = load_line(SRC / "c23_bench_product_n4.json"), load_line(SRC / "c23_bench_reference_n4.json")
+    if n4p and n4r:
+        L.append(f"\nThe same at 4 GPUs (GPU call 23, another box): product {n4p['value']:.0f} frames/s ({n4p['ms_per_step']:.1f} ms per step on the "
+                 f"slowest rank against 39.2 ms alone), reference {n4r['value']:.0f} ({n4r['ms_per_step']:.0f} ms per step against 180 ms alone): that box's "
+                 f"host was contended (the reference, which blocks the host twice per frame, ran 2.7x slower per GPU than alone; the product, "
+                 f"which enqueues a pass in 4.5 ms, 15 % slower). `bench.py` now prints every rank's step time (`ms_per_step_per_rank`).")
     L.append("")
     if c2p:
         L.append("### C2 kernel table\n")
