@@ -99,10 +99,20 @@ def main():
                  f"with the same plumbing (no collective on the data path).")
     n4p, n4r = load_line(SRC / "c23_bench_product_n4.json"), load_line(SRC / "c23_bench_reference_n4.json")
     if n4p and n4r:
-        L.append(f"\nThe same at 4 GPUs (GPU call 23, another box): product {n4p['value']:.0f} frames/s ({n4p['ms_per_step']:.1f} ms per step on the "
-                 f"slowest rank against 39.2 ms alone), reference {n4r['value']:.0f} ({n4r['ms_per_step']:.0f} ms per step against 180 ms alone): that box's "
-                 f"host was contended (the reference, which blocks the host twice per frame, ran 2.7x slower per GPU than alone; the product, "
-                 f"which enqueues a pass in 4.5 ms, 15 % slower). `bench.py` now prints every rank's step time (`ms_per_step_per_rank`).")
+        L.append(f"\nThe same at 4 GPUs (GPU call 23, a box whose host was busy): product {n4p['value']:.0f} frames/s ({n4p['ms_per_step']:.1f} ms per step "
+                 f"on the slowest rank against 39.2 ms alone), reference {n4r['value']:.0f} ({n4r['ms_per_step']:.0f} ms per step against 180 ms alone: it blocks "
+                 f"the host twice per frame).")
+    diag = [(n, load_line(SRC / f"c24_{n}.json")) for n in ("graph", "graph_noclocks", "streams", "graph_again")]
+    if all(d for _, d in diag):
+        L.append("\nGPU call 24 (4 GPUs, 128 host cores, load average 17 from other tenants), per-rank step times from `ms_per_step_per_rank`:\n")
+        L.append("| run | frames/s | ms per step, rank 0..3 | replica efficiency vs 12 546 alone |")
+        L.append("|---|---:|---|---:|")
+        names = {"graph": "frame graph (default)", "graph_noclocks": "frame graph, nvidia-smi sampler off (diagnosis)",
+                 "streams": "round 1's stream pipeline (`SM_B200_GRAPH=0`)", "graph_again": "frame graph again"}
+        for n, d in diag:
+            L.append(f"| {names[n]} | {d['value']:.0f} | {', '.join(f'{v:.1f}' for v in d['ms_per_step_per_rank'])} | {d['value'] / (4 * 12546):.2f} |")
+        L.append("\nEvery rank is ~7 % slower than alone (no straggler, the sampler is not the cause); the stream pipeline, whose host side "
+                 "is four times as expensive per frame, loses a third on the same box. Round 1's driver run measured 0.98 at 8 GPUs on an idle box.")
     L.append("")
     if c2p:
         L.append("### C2 kernel table\n")
