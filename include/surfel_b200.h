@@ -390,10 +390,13 @@ int sm_stream_run(sm_reconstruction* r, void* stream, const sm_stream_desc* s,
                   int32_t first_frame, int32_t last_frame, sm_stream_stats* stats);
 
 /* Named tuning knobs of a handle (no counterpart in the reference). Keys:
- *   "tiebreak_wave", "tiebreak_early_fraction": the reproducible rule that picks the supporting
- *   surfel of a pixel with several supporters, where the reference lets the first atomicCAS win
- *   (APP/cuda_surfel_reconstruction_kernels.cu:1688); see DESIGN.md section 4. wave = 0 selects
- *   "primary-pixel association before secondary, then lowest index".
+ *   "tiebreak_wave" (slots per launch wave of the reference's association kernel; 0 = the plain rule "primary-pixel
+ *   association before secondary, then lowest index"), "tiebreak_lanes" (consecutive slots that keep their order: a
+ *   warp), "tiebreak_early_fraction" / "tiebreak_index_order_fraction" (first wave), "tiebreak_early_fraction_second"
+ *   (second wave), "tiebreak_early_fraction_later" / "tiebreak_index_order_fraction_later" (later waves; negative =
+ *   inherit), "tiebreak_wave_offset" (measurement hook): the reproducible rule that picks the supporting surfel of a
+ *   pixel with several supporters, where the reference lets the first atomicCAS win
+ *   (APP/cuda_surfel_reconstruction_kernels.cu:1688); DESIGN.md section 4 has the measurements behind the defaults.
  *   "median_filter_and_densify_iterations": sm_stream_run applies that many
  *   MedianFilterAndDensifyDepthMap passes (APP/main.cc:207-252, 927-939) to every raw depth map
  *   as it enters the device-side frame ring (default 0, as in the reference). */

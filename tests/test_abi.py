@@ -69,3 +69,13 @@ def test_no_cpu_fallback(product):
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(ImportError):
         _lib.Library(tmp_path / "libsurfel_b200.so", "sm_", product=True)
+
+
+def test_every_configure_key_is_documented():
+    """sm_configure accepts named knobs: each key the library tests for appears in the header's description."""
+    source = (ROOT / "surfelmeshing_b200" / "csrc" / "api.cu").read_text()
+    keys = sorted(set(re.findall(r'k == "([a-z_0-9]+)"', source)))
+    assert len(keys) >= 9
+    header = (ROOT / "include" / "surfel_b200.h").read_text()
+    missing = [k for k in keys if f'"{k}"' not in header]
+    assert not missing, missing
