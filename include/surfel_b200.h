@@ -289,7 +289,8 @@ int sm_update_visualization_buffers(sm_reconstruction* r, void* stream, const sm
  * queries against one snapshot of the cloud: per query the <= max_result_count (<= 64) nearest points with
  * squared distance <= radius_squared, ascending, the meshing-state filter applied before the cap, exactly what
  * the octree returns (equal distances, which the octree leaves to its traversal order, come out by ascending
- * index). All pointers are DEVICE pointers; the calls are asynchronous on `stream`.
+ * index). All pointers are DEVICE pointers; the calls are asynchronous on `stream`. An index lives on the CUDA device that
+ * was current at sm_knn_create; that device must be current for every later call on it (as for a reconstruction handle).
  *
  *   sm_knn_create   index for up to max_points points (<= 2^26)
  *   sm_knn_build    bins points [0, point_count) into a hashed uniform grid of `cell_size` (choose it near the
